@@ -1,0 +1,218 @@
+/*
+ * lqo_modem.c -- ORACLE (test infrastructure only; see lqo.h header).
+ * Linear modems (PSK, DPSK, ASK, QAM, BPSK, QPSK), hard decision, and the
+ * qpacketmodem that joins packetizer + modem.  SURVEY.md Appendix A.6.
+ * Scheme numbers reachable through the reference's block API:
+ * /root/reference/lib/flex_tx_impl.cc:77-115, lib/flex_rx_impl.cc:139-178.
+ */
+#include "lqo.h"
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+static unsigned gray_encode_(unsigned s) { return s ^ (s >> 1); }
+static unsigned gray_decode_(unsigned s)
+{
+    unsigned r = s;
+    for (unsigned sh = 1; sh < 32; sh <<= 1) r ^= r >> sh;
+    return r;
+}
+
+int lqo_modem_supported(int ms)
+{
+    return (ms >= LQ_MODEM_PSK2 && ms <= LQ_MODEM_QAM256) || ms == LQ_MODEM_BPSK || ms == LQ_MODEM_QPSK;
+}
+
+unsigned lqo_modem_bps(int ms)
+{
+    if (ms >= LQ_MODEM_PSK2 && ms <= LQ_MODEM_PSK256) return (unsigned)(ms - LQ_MODEM_PSK2 + 1);
+    if (ms >= LQ_MODEM_DPSK2 && ms <= LQ_MODEM_DPSK256) return (unsigned)(ms - LQ_MODEM_DPSK2 + 1);
+    if (ms >= LQ_MODEM_ASK2 && ms <= LQ_MODEM_ASK256) return (unsigned)(ms - LQ_MODEM_ASK2 + 1);
+    if (ms >= LQ_MODEM_QAM4 && ms <= LQ_MODEM_QAM256) return (unsigned)(ms - LQ_MODEM_QAM4 + 2);
+    if (ms == LQ_MODEM_BPSK) return 1;
+    if (ms == LQ_MODEM_QPSK) return 2;
+    return 0;
+}
+
+static int is_psk_(int ms)  { return ms >= LQ_MODEM_PSK2 && ms <= LQ_MODEM_PSK256; }
+static int is_dpsk_(int ms) { return ms >= LQ_MODEM_DPSK2 && ms <= LQ_MODEM_DPSK256; }
+static int is_ask_(int ms)  { return ms >= LQ_MODEM_ASK2 && ms <= LQ_MODEM_ASK256; }
+static int is_qam_(int ms)  { return ms >= LQ_MODEM_QAM4 && ms <= LQ_MODEM_QAM256; }
+
+static lqo_cf cexpj_(float t) { lqo_cf y = { cosf(t), sinf(t) }; return y; }
+
+static lqo_cf modulate_raw_(lqo_modem *q, unsigned s)
+{
+    lqo_cf y = { 0.0f, 0.0f };
+    int ms = q->scheme;
+    if (is_psk_(ms)) {
+        y = cexpj_((float)gray_decode_(s) * 2.0f * q->alpha);
+    } else if (is_ask_(ms)) {
+        y.re = (float)(2 * (int)gray_decode_(s) - (int)q->M + 1) * q->alpha;
+    } else if (is_qam_(ms)) {
+        unsigned si = gray_decode_(s >> q->m_q), sq = gray_decode_(s & ((1u << q->m_q) - 1u));
+        y.re = (float)(2 * (int)si - (int)(1u << q->m_i) + 1) * q->alpha;
+        y.im = (float)(2 * (int)sq - (int)(1u << q->m_q) + 1) * q->alpha;
+    } else if (ms == LQ_MODEM_BPSK) {
+        y.re = s ? -1.0f : 1.0f;
+    } else if (ms == LQ_MODEM_QPSK) {
+        y.re = (s & 1u) ? -(float)M_SQRT1_2 : (float)M_SQRT1_2;
+        y.im = (s & 2u) ? -(float)M_SQRT1_2 : (float)M_SQRT1_2;
+    }
+    return y;
+}
+
+int lqo_modem_init(lqo_modem *q, int ms)
+{
+    memset(q, 0, sizeof *q);
+    if (!lqo_modem_supported(ms)) return -1;
+    q->scheme = ms;
+    q->bps = lqo_modem_bps(ms);
+    q->M = 1u << q->bps;
+    if (is_psk_(ms) || is_dpsk_(ms)) {
+        q->alpha = (float)M_PI / (float)q->M;
+        q->d_phi = (float)M_PI * (1.0f - 1.0f / (float)q->M);
+    } else if (is_ask_(ms)) {
+        static const float c[9] = { 0, 1.0f, 5.0f, 21.0f, 85.0f, 341.0f, 1365.0f, 5461.0f, 21845.0f };
+        q->alpha = 1.0f / sqrtf(c[q->bps]);
+    } else if (is_qam_(ms)) {
+        static const float c[9] = { 0, 0, 2.0f, 6.0f, 10.0f, 26.0f, 42.0f, 106.0f, 170.0f };
+        q->m_i = (q->bps + 1) >> 1;
+        q->m_q = q->bps >> 1;
+        q->alpha = 1.0f / sqrtf(c[q->bps]);
+    }
+    for (unsigned k = 0; k < q->bps && k < 8; k++) q->ref[k] = (float)(1u << k) * q->alpha;
+    if (!is_dpsk_(ms))
+        for (unsigned s = 0; s < q->M; s++) q->map[s] = modulate_raw_(q, s);
+    q->x_hat.re = 1.0f;
+    return 0;
+}
+
+void lqo_modem_reset(lqo_modem *q) { q->dpsk_phi = 0.0f; q->x_hat.re = 1.0f; q->x_hat.im = 0.0f; q->r = q->x_hat; }
+
+lqo_cf lqo_modem_modulate(lqo_modem *q, unsigned s)
+{
+    if (is_dpsk_(q->scheme)) {
+        q->dpsk_phi += (float)gray_decode_(s) * 2.0f * q->alpha;
+        if (q->dpsk_phi > 2.0f * (float)M_PI) q->dpsk_phi -= 2.0f * (float)M_PI;
+        return cexpj_(q->dpsk_phi);
+    }
+    return q->map[s & (q->M - 1u)];
+}
+
+/* successive-approximation slicer over ref[k] = 2^k * alpha */
+static void slice_(float v, unsigned m, const float *ref, unsigned *s_out, float *res)
+{
+    unsigned s = 0, k = m;
+    for (unsigned i = 0; i < m; i++) {
+        s <<= 1;
+        s |= (v > 0.0f);
+        float r = ref[--k];
+        v += (v > 0.0f) ? -r : r;
+    }
+    *s_out = s; *res = v;
+}
+
+unsigned lqo_modem_demodulate(lqo_modem *q, lqo_cf x)
+{
+    int ms = q->scheme;
+    unsigned s = 0, sym = 0;
+    float res;
+    if (is_psk_(ms)) {
+        float theta = atan2f(x.im, x.re) - q->d_phi;
+        if (theta < -(float)M_PI) theta += 2.0f * (float)M_PI;
+        slice_(theta, q->bps, q->ref, &s, &res);
+        sym = gray_encode_(s);
+        q->x_hat = q->map[sym];
+    } else if (is_dpsk_(ms)) {
+        float theta = atan2f(x.im, x.re);
+        float d = theta - q->dpsk_phi;
+        q->dpsk_phi = theta;
+        d -= q->d_phi;
+        if (d > (float)M_PI) d -= 2.0f * (float)M_PI;
+        else if (d < -(float)M_PI) d += 2.0f * (float)M_PI;
+        slice_(d, q->bps, q->ref, &s, &res);
+        sym = gray_encode_(s);
+        q->x_hat = cexpj_(theta - res);
+    } else if (is_ask_(ms)) {
+        slice_(x.re, q->bps, q->ref, &s, &res);
+        sym = gray_encode_(s);
+        q->x_hat = q->map[sym];
+    } else if (is_qam_(ms)) {
+        unsigned si, sq; float ri, rq;
+        slice_(x.re, q->m_i, q->ref, &si, &ri);
+        slice_(x.im, q->m_q, q->ref, &sq, &rq);
+        sym = (gray_encode_(si) << q->m_q) + gray_encode_(sq);
+        q->x_hat.re = x.re - ri;
+        q->x_hat.im = x.im - rq;
+    } else if (ms == LQ_MODEM_BPSK) {
+        sym = (x.re > 0.0f) ? 0u : 1u;
+        q->x_hat = q->map[sym];
+    } else if (ms == LQ_MODEM_QPSK) {
+        sym = ((x.re > 0.0f) ? 0u : 1u) + ((x.im > 0.0f) ? 0u : 2u);
+        q->x_hat = q->map[sym];
+    }
+    q->r = x;
+    return sym;
+}
+
+float lqo_modem_phase_error(const lqo_modem *q)
+{   /* imag( r * conj(x_hat) ) */
+    return fmaf(q->r.im, q->x_hat.re, -(q->r.re * q->x_hat.im));
+}
+
+float lqo_modem_evm(const lqo_modem *q)
+{
+    float dr = q->x_hat.re - q->r.re, di = q->x_hat.im - q->r.im;
+    return sqrtf(fmaf(di, di, dr * dr));
+}
+
+/* ================================================================== qpacketmodem */
+unsigned lqo_qpm_frame_len(unsigned n, int check, int fec0, int fec1, int ms)
+{
+    unsigned bps = lqo_modem_bps(ms);
+    if (!bps) return 0;
+    unsigned bits = 8 * lqo_packetizer_enc_len(n, check, fec0, fec1);
+    return bits / bps + (bits % bps ? 1 : 0);
+}
+
+void lqo_qpm_encode(unsigned n, int check, int fec0, int fec1, int ms, const uint8_t *payload, lqo_cf *frame)
+{
+    unsigned enc_len = lqo_packetizer_enc_len(n, check, fec0, fec1);
+    unsigned nsym = lqo_qpm_frame_len(n, check, fec0, fec1, ms);
+    uint8_t *enc = (uint8_t *)calloc(enc_len + 8, 1);
+    lqo_packetizer_encode(n, check, fec0, fec1, payload, enc);
+    lqo_modem mod;
+    lqo_modem_init(&mod, ms);
+    unsigned bps = mod.bps, nbits = 8 * enc_len;
+    for (unsigned i = 0; i < nsym; i++) {
+        unsigned s = 0;
+        for (unsigned b = 0; b < bps; b++) {
+            unsigned pos = i * bps + b;
+            unsigned bit = (pos < nbits) ? ((enc[pos >> 3] >> (7 - (pos & 7))) & 1u) : 0u; /* zero-padded tail */
+            s = (s << 1) | bit;
+        }
+        frame[i] = lqo_modem_modulate(&mod, s);
+    }
+    free(enc);
+}
+
+int lqo_qpm_decode(unsigned n, int check, int fec0, int fec1, int ms, const lqo_cf *frame, uint8_t *payload)
+{
+    unsigned enc_len = lqo_packetizer_enc_len(n, check, fec0, fec1);
+    unsigned nsym = lqo_qpm_frame_len(n, check, fec0, fec1, ms);
+    uint8_t *enc = (uint8_t *)calloc(enc_len + 8, 1);
+    lqo_modem mod;
+    lqo_modem_init(&mod, ms);
+    unsigned bps = mod.bps, nbits = 8 * enc_len;
+    for (unsigned i = 0; i < nsym; i++) {
+        unsigned s = lqo_modem_demodulate(&mod, frame[i]);
+        for (unsigned b = 0; b < bps; b++) {
+            unsigned pos = i * bps + b;
+            if (pos < nbits && ((s >> (bps - 1 - b)) & 1u)) enc[pos >> 3] |= (uint8_t)(0x80u >> (pos & 7));
+        }
+    }
+    int ok = lqo_packetizer_decode(n, check, fec0, fec1, enc, payload);
+    free(enc);
+    return ok;
+}

@@ -1,0 +1,636 @@
+// lqb_api.cu -- C-ABI (include/lqb200.h) for the receiver and the detector: handle
+// lifetime, device arenas, the per-call plan (which frames go through which kernels) and
+// result gathering.  All arithmetic lives in the kernels; this file only moves data and
+// decides launch shapes.  There is no CPU fallback: without a usable device create() fails.
+#include "../../include/lqb200.h"
+#include "lqb_kernels.h"
+#include "lqb_tables.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+using namespace lqb;
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const char *fmt, const char *a = "")
+{
+    char buf[512];
+    snprintf(buf, sizeof buf, fmt, a);
+    g_err = buf;
+    return code;
+}
+#define CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fail(LQB_ECUDA, "CUDA: %s", cudaGetErrorString(e_)); return LQB_ECUDA; } } while (0)
+#define CUP(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fail(LQB_ECUDA, "CUDA: %s", cudaGetErrorString(e_)); return nullptr; } } while (0)
+
+// grow-only device / pinned buffers
+template <typename T> struct DevBuf {
+    T *p = nullptr; size_t cap = 0;
+    int reserve(size_t n, bool keep = false, cudaStream_t s = 0)
+    {
+        if (n <= cap) return 0;
+        size_t ncap = std::max(n, cap + cap / 2);
+        T *q = nullptr;
+        if (cudaMalloc(&q, ncap * sizeof(T)) != cudaSuccess) return fail(LQB_ENOMEM, "cudaMalloc failed");
+        if (keep && p && cap) { cudaMemcpyAsync(q, p, cap * sizeof(T), cudaMemcpyDeviceToDevice, s); cudaStreamSynchronize(s); }
+        if (p) cudaFree(p);
+        p = q; cap = ncap;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+template <typename T> struct PinBuf {
+    T *p = nullptr; size_t cap = 0;
+    int reserve(size_t n)
+    {
+        if (n <= cap) return 0;
+        size_t ncap = std::max(n, cap + cap / 2);
+        T *q = nullptr;
+        if (cudaMallocHost(&q, ncap * sizeof(T)) != cudaSuccess) return fail(LQB_ENOMEM, "cudaMallocHost failed");
+        if (p) cudaFreeHost(p);
+        p = q; cap = ncap;
+        return 0;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+int build_tables(DevTables &T, float beta, float threshold, float dphi_max)
+{
+    std::memset(&T, 0, sizeof T);
+    auto w512 = twiddles(512), w32 = twiddles(32);
+    std::memcpy(T.W512, w512.data(), sizeof T.W512);
+    std::memcpy(T.W32, w32.data(), sizeof T.W32);
+    auto s = detector_template(beta);
+    std::vector<cf> buf(512, cf{ 0.0f, 0.0f }), S(512);
+    std::copy(s.begin(), s.end(), buf.begin());
+    host_fft(buf.data(), S.data(), 512, +1);
+    for (unsigned i = 0; i < 512; ++i) T.Sc[i] = make_float2(S[i].re, -S[i].im);
+    float s2 = 0.0f;
+    for (unsigned i = 0; i < kSLen; ++i) {
+        T.sconj[i] = make_float2(s[i].re, -s[i].im);
+        s2 += std::fmaf(s[i].im, s[i].im, s[i].re * s[i].re);
+    }
+    T.s2_sum = s2;
+    T.threshold = threshold;
+    T.range = (int)(dphi_max * 512.0f / (2.0f * 3.14159274f));
+    std::memcpy(T.sintab, nco_sintab(), sizeof T.sintab);
+    auto banks = pfb_banks(kRxBeta);
+    std::memcpy(T.banks, banks.data(), sizeof T.banks);
+    cf pil[15];
+    header_pilots(pil);
+    for (unsigned i = 0; i < 15; ++i) T.pilots_conj[i] = make_float2(pil[i].re, -pil[i].im);
+    auto maps = psk_maps();
+    std::memcpy(T.psk_map, maps.data(), sizeof T.psk_map);
+    for (unsigned c = 3; c <= 6; ++c) crc_table(c, T.crc_tab[c]);
+    auto m54 = ilv_maps(54), m27 = ilv_maps(27);
+    for (unsigned p = 0; p < 4; ++p) {
+        for (unsigned i = 0; i < 27; ++i) T.ilv54[p][i] = (uint16_t)m54[p * 27 + i];
+        for (unsigned i = 0; i < 13; ++i) T.ilv27[p][i] = (uint16_t)m27[p * 13 + i];
+    }
+    hamming_dec_tables(T.h84_dec, T.h74_dec);
+    secded_cols(T.secded_col);
+    uint8_t gen[33];
+    gf256_tables(T.gf_exp, T.gf_log, gen);
+    std::memcpy(T.rs_gen, gen, 33);
+    return 0;
+}
+
+bool is_conv(unsigned fs) { return fs == FEC_CONV_V27 || fs == FEC_CONV_V29 || (fs >= FEC_CONV_V27P23 && fs <= FEC_CONV_V29P78); }
+unsigned conv_K(unsigned fs) { return (fs == FEC_CONV_V29 || fs >= FEC_CONV_V29P23) ? 9u : 7u; }
+
+// common per-stream front end shared by rx and det handles
+struct Front {
+    int device = 0;
+    unsigned n_streams = 0, carry_cap = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    DevTables *d_tables = nullptr;
+    StreamState *d_states = nullptr;
+    float2 *d_carry[2] = { nullptr, nullptr };
+    DevBuf<StreamIO> d_io;
+    PinBuf<StreamIO> h_io;
+    DevBuf<float2> d_stage;
+    unsigned *d_count = nullptr;
+    unsigned *h_count = nullptr;
+    std::vector<uint8_t> fed;
+    uint64_t launches = 0;
+
+    int init(int dev, unsigned ns, unsigned cap, void *user_stream, const DevTables &T)
+    {
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return fail(LQB_ENODEV, "no CUDA device available (no CPU fallback exists)");
+        if (dev < 0 || dev >= ndev) return fail(LQB_ENODEV, "device ordinal out of range");
+        cudaDeviceProp prop;
+        CU(cudaGetDeviceProperties(&prop, dev));
+        if (prop.major < 10) return fail(LQB_ENODEV, "device is not sm_100 class; this library carries sm_100a code only");
+        device = dev; n_streams = ns; carry_cap = cap;
+        CU(cudaSetDevice(dev));
+        if (user_stream) stream = (cudaStream_t)user_stream;
+        else { CU(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking)); own_stream = true; }
+        CU(cudaMalloc(&d_tables, sizeof(DevTables)));
+        CU(cudaMemcpy(d_tables, &T, sizeof(DevTables), cudaMemcpyHostToDevice));
+        CU(cudaMalloc(&d_states, (size_t)ns * sizeof(StreamState)));
+        for (int k = 0; k < 2; ++k) CU(cudaMalloc(&d_carry[k], (size_t)ns * cap * sizeof(float2)));
+        CU(cudaMalloc(&d_count, 4 * sizeof(unsigned)));
+        CU(cudaMallocHost(&h_count, 4 * sizeof(unsigned)));
+        fed.assign(ns, 0);
+        return reset(-1);
+    }
+    int reset(int s)
+    {
+        CU(cudaSetDevice(device));
+        StreamState z;
+        std::memset(&z, 0, sizeof z);
+        z.wstart = -256;           // first window = 256 zeros + first 256 samples (qdetector reset state)
+        if (s < 0) {
+            std::vector<StreamState> all(n_streams, z);
+            CU(cudaMemcpyAsync(d_states, all.data(), all.size() * sizeof(StreamState), cudaMemcpyHostToDevice, stream));
+            CU(cudaStreamSynchronize(stream));
+        } else {
+            if ((unsigned)s >= n_streams) return fail(LQB_EINVAL, "stream index out of range");
+            CU(cudaMemcpyAsync(d_states + s, &z, sizeof z, cudaMemcpyHostToDevice, stream));
+            CU(cudaStreamSynchronize(stream));
+        }
+        return 0;
+    }
+    // stage inputs; fills d_io; returns total samples via *total
+    int feed(uint32_t n, const uint32_t *ids, const float *const *iq, const uint64_t *ns, int mem, uint64_t *total, uint64_t *max_n)
+    {
+        if (!n) { *total = 0; *max_n = 0; return 0; }
+        if (n > n_streams) return fail(LQB_EINVAL, "more entries than streams");
+        if (int e = h_io.reserve(n)) return e;
+        if (int e = d_io.reserve(n)) return e;
+        std::fill(fed.begin(), fed.end(), 0);
+        uint64_t tot = 0, mx = 0;
+        for (uint32_t i = 0; i < n; ++i) {
+            uint32_t s = ids ? ids[i] : i;
+            if (s >= n_streams) return fail(LQB_EINVAL, "stream index out of range");
+            if (fed[s]) return fail(LQB_EINVAL, "stream listed twice in one execute");
+            fed[s] = 1;
+            if (ns[i] && !iq[i]) return fail(LQB_EINVAL, "null sample pointer");
+            tot += ns[i]; mx = std::max<uint64_t>(mx, ns[i]);
+        }
+        if (mem == LQB_MEM_HOST) {
+            if (int e = d_stage.reserve(tot + 1)) return e;
+            uint64_t off = 0;
+            uint32_t i = 0;
+            while (i < n) {                         // merge runs that are contiguous in host memory into one copy
+                uint32_t j = i; uint64_t run = ns[i];
+                while (j + 1 < n && iq[j + 1] == iq[j] + 2 * ns[j]) { ++j; run += ns[j]; }
+                if (run) CU(cudaMemcpyAsync(d_stage.p + off, iq[i], run * sizeof(float2), cudaMemcpyHostToDevice, stream));
+                for (uint32_t k = i; k <= j; ++k) {
+                    h_io.p[k].in = d_stage.p + off; h_io.p[k].n_in = ns[k]; h_io.p[k].stream = ids ? ids[k] : k; h_io.p[k].pad = 0;
+                    off += ns[k];
+                }
+                i = j + 1;
+            }
+        } else {
+            for (uint32_t i = 0; i < n; ++i) {
+                h_io.p[i].in = reinterpret_cast<const float2 *>(iq[i]); h_io.p[i].n_in = ns[i];
+                h_io.p[i].stream = ids ? ids[i] : i; h_io.p[i].pad = 0;
+            }
+        }
+        CU(cudaMemcpyAsync(d_io.p, h_io.p, n * sizeof(StreamIO), cudaMemcpyHostToDevice, stream));
+        *total = tot; *max_n = mx;
+        return 0;
+    }
+    void destroy()
+    {
+        cudaSetDevice(device);
+        if (stream) cudaStreamSynchronize(stream);
+        if (d_tables) cudaFree(d_tables);
+        if (d_states) cudaFree(d_states);
+        for (int k = 0; k < 2; ++k) if (d_carry[k]) cudaFree(d_carry[k]);
+        d_io.release(); h_io.release(); d_stage.release();
+        if (d_count) cudaFree(d_count);
+        if (h_count) cudaFreeHost(h_count);
+        if (own_stream && stream) cudaStreamDestroy(stream);
+    }
+};
+
+}  // namespace
+
+// =================================================================== RX handle
+struct lqb_rx_s {
+    Front f;
+    unsigned flags = 0;
+    DevBuf<FrameDesc> d_frames;
+    PinBuf<FrameDesc> h_frames;
+    DevBuf<float2> d_syms;
+    PinBuf<float2> h_syms;
+    DevBuf<unsigned char> d_bufA, d_bufB, d_payload;
+    PinBuf<unsigned char> h_payload;
+    DevBuf<unsigned> d_ilv;
+    size_t ilv_used = 0;
+    std::unordered_map<unsigned, size_t> ilv_cache;
+    DevBuf<unsigned long long> d_dec;
+    DevBuf<unsigned> d_lists;
+    PinBuf<unsigned> h_lists;
+    std::vector<unsigned> order;
+    unsigned n_frames = 0;
+    uint64_t n_valid = 0;
+    cudaEvent_t ev[7] = {};
+    float ms[5] = {};
+};
+
+extern "C" {
+
+const char *lqb_last_error(void) { return g_err.c_str(); }
+int lqb_version(void) { return LQB_VERSION; }
+int lqb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+lqb_rx lqb_rx_create(const lqb_rx_opts *o)
+{
+    if (!o || !o->n_streams) { fail(LQB_EINVAL, "bad options"); return nullptr; }
+    DevTables *T = new DevTables;
+    build_tables(*T, kRxBeta, 0.5f, 0.3f);
+    lqb_rx h = new lqb_rx_s;
+    unsigned cap = o->max_frame_samples ? o->max_frame_samples : 65536u;
+    if (cap < 2048) cap = 2048;
+    int e = h->f.init(o->device, o->n_streams, cap, o->cuda_stream, *T);
+    delete T;
+    if (e) { h->f.destroy(); delete h; return nullptr; }
+    h->flags = o->flags;
+    for (auto &ev : h->ev) cudaEventCreate(&ev);
+    return h;
+}
+
+void lqb_rx_destroy(lqb_rx h)
+{
+    if (!h) return;
+    cudaSetDevice(h->f.device);
+    if (h->f.stream) cudaStreamSynchronize(h->f.stream);
+    h->d_frames.release(); h->h_frames.release(); h->d_syms.release(); h->h_syms.release();
+    h->d_bufA.release(); h->d_bufB.release(); h->d_payload.release(); h->h_payload.release();
+    h->d_ilv.release(); h->d_dec.release(); h->d_lists.release(); h->h_lists.release();
+    for (auto &ev : h->ev) if (ev) cudaEventDestroy(ev);
+    h->f.destroy();
+    delete h;
+}
+
+int lqb_rx_reset(lqb_rx h, int stream)
+{
+    if (!h) return fail(LQB_EINVAL, "null handle");
+    return h->f.reset(stream);
+}
+
+static size_t ilv_offset(lqb_rx h, unsigned n)
+{
+    auto it = h->ilv_cache.find(n);
+    if (it != h->ilv_cache.end()) return it->second;
+    std::vector<uint32_t> maps = ilv_maps(n);
+    size_t off = h->ilv_used;
+    if (h->d_ilv.reserve(off + maps.size() + 4, true, h->f.stream)) return (size_t)-1;
+    if (!maps.empty())
+        cudaMemcpyAsync(h->d_ilv.p + off, maps.data(), maps.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, h->f.stream);
+    cudaStreamSynchronize(h->f.stream);     // maps is a local; finish the copy before it dies
+    h->ilv_used = off + maps.size();
+    h->ilv_cache.emplace(n, off);
+    return off;
+}
+
+int lqb_rx_execute(lqb_rx h, uint32_t n, const uint32_t *ids, const float *const *iq, const uint64_t *ns, int mem)
+{
+    if (!h) return fail(LQB_EINVAL, "null handle");
+    Front &f = h->f;
+    CU(cudaSetDevice(f.device));
+    cudaStream_t st = f.stream;
+    h->n_frames = 0; h->n_valid = 0; h->order.clear();
+    std::memset(h->ms, 0, sizeof h->ms);
+    uint64_t total = 0, max_n = 0;
+    if (int e = f.feed(n, ids, iq, ns, mem, &total, &max_n)) return e;
+    if (!n) return 0;
+
+    // upper bound on frames: a frame spans at least 618 samples
+    size_t max_frames = 0;
+    for (uint32_t i = 0; i < n; ++i) max_frames += (size_t)((ns[i] + f.carry_cap) / 600 + 2);
+    if (int e = h->d_frames.reserve(max_frames)) return e;
+    if (int e = h->h_frames.reserve(max_frames)) return e;
+
+    SeekParams sp;
+    sp.tables = f.d_tables; sp.states = f.d_states; sp.io = f.d_io.p;
+    sp.carry[0] = f.d_carry[0]; sp.carry[1] = f.d_carry[1]; sp.carry_cap = f.carry_cap;
+    sp.det_mode = 0; sp.frames = h->d_frames.p; sp.detections = nullptr;
+    sp.n_out = f.d_count; sp.max_out = (unsigned)max_frames;
+
+    CU(cudaEventRecord(h->ev[0], st));
+    CU(cudaMemsetAsync(f.d_count, 0, sizeof(unsigned), st));
+    launch_seek(sp, n, st); f.launches++;
+    CU(cudaEventRecord(h->ev[1], st));
+    CU(cudaMemcpyAsync(f.h_count, f.d_count, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    unsigned nf = std::min<unsigned>(f.h_count[0], (unsigned)max_frames);
+    FrameDesc *fr = h->h_frames.p;
+    if (nf) {
+        CU(cudaMemcpyAsync(fr, h->d_frames.p, nf * sizeof(FrameDesc), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+
+    // ---------------- plan
+    size_t sym_total = 0, buf_total = 0, pay_total = 0, dec_total = 0, n_tiles = 0;
+    std::vector<unsigned> tile_start(nf + 1, 0), valid, deint[2], blk[2], vit[2], rsb[2];
+    for (unsigned i = 0; i < nf; ++i) {
+        FrameDesc &d = fr[i];
+        tile_start[i] = (unsigned)n_tiles;
+        if (!d.header_valid) continue;
+        valid.push_back(i);
+        d.sym_off = sym_total; sym_total += d.n_sym;
+        unsigned bl = std::max(std::max(d.n1, d.n0), d.k0) + 16;
+        bl = (bl + 15u) & ~15u;
+        d.buf_len = bl; d.buf_off = buf_total; buf_total += bl;
+        d.pay_off = pay_total; pay_total += (d.payload_len + 3u) & ~3u;
+        n_tiles += (d.n_sym + 255) / 256;
+        const unsigned fs[2] = { d.fec0, d.fec1 }, enc[2] = { d.n0, d.n1 }, dl[2] = { d.k0, d.n0 };
+        size_t need_dec = 0;
+        for (int stg = 1; stg >= 0; --stg) {
+            if (fs[stg] != FEC_NONE) {
+                size_t off = ilv_offset(h, enc[stg]);
+                if (off == (size_t)-1) return LQB_ENOMEM;
+                (stg ? d.ilv1_off : d.ilv0_off) = (unsigned)off;
+                deint[stg].push_back(i);
+            }
+            if (is_conv(fs[stg])) {
+                vit[stg].push_back(i);
+                size_t T = (size_t)8 * dl[stg] + conv_K(fs[stg]) - 1, words = conv_K(fs[stg]) == 9 ? 8 : 2;
+                need_dec = std::max(need_dec, (T * words + 1) / 2);
+            } else if (fs[stg] == FEC_RS_M8) {
+                unsigned blocks = (dl[stg] + 222) / 223;
+                for (unsigned b = 0; b < blocks; ++b) { rsb[stg].push_back(i); rsb[stg].push_back(b); }
+            } else {
+                blk[stg].push_back(i);
+            }
+        }
+        d.dec_off = dec_total; dec_total += need_dec;
+    }
+    tile_start[nf] = (unsigned)n_tiles;
+    // group the PLL work list by modulation so warps diverge less
+    std::vector<unsigned> pll = valid;
+    std::stable_sort(pll.begin(), pll.end(), [&](unsigned a, unsigned b) { return fr[a].ms < fr[b].ms; });
+
+    if (nf && !valid.empty()) {
+        if (int e = h->d_syms.reserve(sym_total + 1)) return e;
+        if (int e = h->d_bufA.reserve(buf_total + 16)) return e;
+        if (int e = h->d_bufB.reserve(buf_total + 16)) return e;
+        if (int e = h->d_payload.reserve(pay_total + 16)) return e;
+        if (int e = h->d_dec.reserve(dec_total + 1)) return e;
+        // one list arena: tile_start | pll | valid | deint1 | blk1 | vit1 | rs1 | deint0 | blk0 | vit0 | rs0
+        std::vector<const std::vector<unsigned> *> parts = { &tile_start, &pll, &valid, &deint[1], &blk[1], &vit[1], &rsb[1],
+                                                             &deint[0], &blk[0], &vit[0], &rsb[0] };
+        size_t ltot = 0;
+        std::vector<size_t> loff;
+        for (auto p : parts) { loff.push_back(ltot); ltot += p->size(); }
+        if (int e = h->h_lists.reserve(ltot + 1)) return e;
+        if (int e = h->d_lists.reserve(ltot + 1)) return e;
+        for (size_t k = 0; k < parts.size(); ++k)
+            if (!parts[k]->empty()) std::memcpy(h->h_lists.p + loff[k], parts[k]->data(), parts[k]->size() * sizeof(unsigned));
+        CU(cudaMemcpyAsync(h->d_lists.p, h->h_lists.p, ltot * sizeof(unsigned), cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(h->d_frames.p, fr, nf * sizeof(FrameDesc), cudaMemcpyHostToDevice, st));
+
+        PayloadParams pp;
+        pp.tables = f.d_tables; pp.states = f.d_states; pp.io = f.d_io.p;
+        pp.carry[0] = f.d_carry[0]; pp.carry[1] = f.d_carry[1]; pp.carry_cap = f.carry_cap;
+        pp.frames = h->d_frames.p; pp.n_frames = nf;
+        pp.tile_start = h->d_lists.p + loff[0]; pp.n_tiles = (unsigned)n_tiles;
+        pp.syms = h->d_syms.p; pp.bufA = h->d_bufA.p; pp.bufB = h->d_bufB.p; pp.payload = h->d_payload.p;
+        pp.ilv_maps = h->d_ilv.p; pp.decisions = h->d_dec.p;
+
+        CU(cudaEventRecord(h->ev[2], st));
+        launch_mf(pp, st); f.launches += n_tiles ? 1 : 0;
+        CU(cudaEventRecord(h->ev[3], st));
+        launch_pll(pp, h->d_lists.p + loff[1], (unsigned)pll.size(), st); f.launches++;
+        CU(cudaEventRecord(h->ev[4], st));
+        for (int stg = 1; stg >= 0; --stg) {
+            const size_t base = stg ? 3 : 7;
+            if (!deint[stg].empty()) { launch_deinterleave(pp, h->d_lists.p + loff[base], (unsigned)deint[stg].size(), stg, st); f.launches++; }
+            if (!blk[stg].empty()) { launch_blockfec(pp, h->d_lists.p + loff[base + 1], (unsigned)blk[stg].size(), stg, st); f.launches++; }
+            if (!vit[stg].empty()) { launch_viterbi(pp, h->d_lists.p + loff[base + 2], (unsigned)vit[stg].size(), stg, 7, st); f.launches++; }
+            if (!rsb[stg].empty()) { launch_rs(pp, h->d_lists.p + loff[base + 3], (unsigned)(rsb[stg].size() / 2), stg, st); f.launches++; }
+        }
+        launch_crc(pp, h->d_lists.p + loff[2], (unsigned)valid.size(), st); f.launches++;
+        CU(cudaEventRecord(h->ev[5], st));
+    } else {
+        for (int k = 2; k <= 5; ++k) CU(cudaEventRecord(h->ev[k], st));
+    }
+    launch_carry(sp, n, st); f.launches++;
+    CU(cudaEventRecord(h->ev[6], st));
+
+    // ---------------- gather
+    if (nf && !valid.empty()) {
+        CU(cudaMemcpyAsync(fr, h->d_frames.p, nf * sizeof(FrameDesc), cudaMemcpyDeviceToHost, st));
+        if (!(h->flags & LQB_RX_DEVICE_RESULTS)) {
+            if (int e = h->h_payload.reserve(pay_total + 16)) return e;
+            if (pay_total) CU(cudaMemcpyAsync(h->h_payload.p, h->d_payload.p, pay_total, cudaMemcpyDeviceToHost, st));
+            if (!(h->flags & LQB_RX_NO_FRAMESYMS)) {
+                if (int e = h->h_syms.reserve(sym_total + 1)) return e;
+                if (sym_total) CU(cudaMemcpyAsync(h->h_syms.p, h->d_syms.p, sym_total * sizeof(float2), cudaMemcpyDeviceToHost, st));
+            }
+        }
+    }
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    cudaEventElapsedTime(&h->ms[0], h->ev[0], h->ev[1]);
+    for (int k = 1; k < 4; ++k) cudaEventElapsedTime(&h->ms[k], h->ev[k + 1], h->ev[k + 2]);
+    cudaEventElapsedTime(&h->ms[4], h->ev[0], h->ev[6]);
+
+    h->n_frames = nf;
+    h->order.resize(nf);
+    for (unsigned i = 0; i < nf; ++i) h->order[i] = i;
+    std::sort(h->order.begin(), h->order.end(), [&](unsigned a, unsigned b) {
+        return fr[a].stream != fr[b].stream ? fr[a].stream < fr[b].stream : fr[a].seq < fr[b].seq;
+    });
+    for (unsigned i = 0; i < nf; ++i) h->n_valid += fr[i].payload_valid ? 1 : 0;
+    return 0;
+}
+
+int lqb_rx_execute_dense(lqb_rx h, const float *iq, uint64_t stride, uint64_t ns, int mem)
+{
+    if (!h) return fail(LQB_EINVAL, "null handle");
+    unsigned n = h->f.n_streams;
+    std::vector<const float *> ptr(n);
+    std::vector<uint64_t> len(n, ns);
+    for (unsigned s = 0; s < n; ++s) ptr[s] = iq + 2 * (size_t)s * stride;
+    return lqb_rx_execute(h, n, nullptr, ptr.data(), len.data(), mem);
+}
+
+int lqb_rx_poll(lqb_rx h, lqb_frame_result *out, uint32_t max_out, uint32_t *n_out)
+{
+    if (!h) return fail(LQB_EINVAL, "null handle");
+    unsigned n = std::min<unsigned>(h->n_frames, max_out);
+    const bool host_res = !(h->flags & LQB_RX_DEVICE_RESULTS);
+    for (unsigned k = 0; k < n && out; ++k) {
+        const FrameDesc &d = h->h_frames.p[h->order[k]];
+        lqb_frame_result &r = out[k];
+        std::memset(&r, 0, sizeof r);
+        r.stream = d.stream; r.seq = d.seq; r.sample_index = d.F;
+        std::memcpy(r.header, d.header, 20);
+        r.header_valid = d.header_valid; r.payload_valid = d.payload_valid; r.payload_len = d.payload_len;
+        if (d.header_valid) {
+            r.payload = host_res ? h->h_payload.p + d.pay_off : h->d_payload.p + d.pay_off;
+            if (h->flags & LQB_RX_DEVICE_RESULTS) r.framesyms = reinterpret_cast<const float *>(h->d_syms.p + d.sym_off);
+            else if (!(h->flags & LQB_RX_NO_FRAMESYMS)) r.framesyms = reinterpret_cast<const float *>(h->h_syms.p + d.sym_off);
+            r.num_framesyms = d.n_sym;
+        }
+        r.mod_scheme = d.ms; r.mod_bps = d.bps; r.check = d.check; r.fec0 = d.fec0; r.fec1 = d.fec1;
+        r.evm = d.evm; r.rssi = d.rssi; r.cfo = d.cfo;
+        r.tau_hat = d.tau; r.gamma_hat = d.gamma; r.dphi_hat = d.dphi; r.phi_hat = d.phi; r.rxy = d.rxy;
+        r.flags = d.flags;
+    }
+    if (n_out) *n_out = h->n_frames;
+    return 0;
+}
+
+int lqb_rx_counts(lqb_rx h, uint64_t *frames, uint64_t *valid)
+{
+    if (!h) return fail(LQB_EINVAL, "null handle");
+    if (frames) *frames = h->n_frames;
+    if (valid) *valid = h->n_valid;
+    return 0;
+}
+int lqb_rx_last_timing(lqb_rx h, float ms[5])
+{
+    if (!h) return fail(LQB_EINVAL, "null handle");
+    std::memcpy(ms, h->ms, sizeof h->ms);
+    return 0;
+}
+int lqb_rx_launch_count(lqb_rx h, uint64_t *l)
+{
+    if (!h) return fail(LQB_EINVAL, "null handle");
+    *l = h->f.launches;
+    return 0;
+}
+
+}  // extern "C"
+
+// =================================================================== detector handle
+struct lqb_det_s {
+    Front f;
+    DevBuf<Detection> d_det;
+    PinBuf<Detection> h_det;
+    std::vector<unsigned> order;
+    unsigned n_det = 0;
+    cudaEvent_t ev[2] = {};
+    float ms = 0.0f;
+};
+
+extern "C" {
+
+lqb_det lqb_det_create(const lqb_det_opts *o)
+{
+    if (!o || !o->n_streams) { fail(LQB_EINVAL, "bad options"); return nullptr; }
+    DevTables *T = new DevTables;
+    build_tables(*T, o->beta > 0.0f ? o->beta : 0.3f, o->threshold > 0.0f ? o->threshold : 0.45f, o->dphi_max > 0.0f ? o->dphi_max : 0.3f);
+    lqb_det h = new lqb_det_s;
+    int e = h->f.init(o->device, o->n_streams, 2048, o->cuda_stream, *T);
+    delete T;
+    if (e) { h->f.destroy(); delete h; return nullptr; }
+    for (auto &ev : h->ev) cudaEventCreate(&ev);
+    return h;
+}
+void lqb_det_destroy(lqb_det h)
+{
+    if (!h) return;
+    cudaSetDevice(h->f.device);
+    if (h->f.stream) cudaStreamSynchronize(h->f.stream);
+    h->d_det.release(); h->h_det.release();
+    for (auto &ev : h->ev) if (ev) cudaEventDestroy(ev);
+    h->f.destroy();
+    delete h;
+}
+int lqb_det_reset(lqb_det h, int s) { return h ? h->f.reset(s) : fail(LQB_EINVAL, "null handle"); }
+
+int lqb_det_execute(lqb_det h, uint32_t n, const uint32_t *ids, const float *const *iq, const uint64_t *ns, int mem)
+{
+    if (!h) return fail(LQB_EINVAL, "null handle");
+    Front &f = h->f;
+    CU(cudaSetDevice(f.device));
+    cudaStream_t st = f.stream;
+    h->n_det = 0; h->order.clear();
+    uint64_t total = 0, max_n = 0;
+    if (int e = f.feed(n, ids, iq, ns, mem, &total, &max_n)) return e;
+    if (!n) return 0;
+    size_t max_det = 0;
+    for (uint32_t i = 0; i < n; ++i) max_det += (size_t)((ns[i] + f.carry_cap) / 256 + 2);
+    if (int e = h->d_det.reserve(max_det)) return e;
+    if (int e = h->h_det.reserve(max_det)) return e;
+    SeekParams sp;
+    sp.tables = f.d_tables; sp.states = f.d_states; sp.io = f.d_io.p;
+    sp.carry[0] = f.d_carry[0]; sp.carry[1] = f.d_carry[1]; sp.carry_cap = f.carry_cap;
+    sp.det_mode = 1; sp.frames = nullptr; sp.detections = h->d_det.p;
+    sp.n_out = f.d_count; sp.max_out = (unsigned)max_det;
+    CU(cudaMemsetAsync(f.d_count, 0, sizeof(unsigned), st));
+    CU(cudaEventRecord(h->ev[0], st));
+    launch_seek(sp, n, st); f.launches++;
+    launch_carry(sp, n, st); f.launches++;
+    CU(cudaEventRecord(h->ev[1], st));
+    CU(cudaMemcpyAsync(f.h_count, f.d_count, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    unsigned nd = std::min<unsigned>(f.h_count[0], (unsigned)max_det);
+    if (nd) {
+        CU(cudaMemcpyAsync(h->h_det.p, h->d_det.p, nd * sizeof(Detection), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    CU(cudaGetLastError());
+    cudaEventElapsedTime(&h->ms, h->ev[0], h->ev[1]);
+    h->n_det = nd;
+    h->order.resize(nd);
+    for (unsigned i = 0; i < nd; ++i) h->order[i] = i;
+    const Detection *dd = h->h_det.p;
+    std::sort(h->order.begin(), h->order.end(), [&](unsigned a, unsigned b) {
+        return dd[a].stream != dd[b].stream ? dd[a].stream < dd[b].stream : dd[a].seq < dd[b].seq;
+    });
+    return 0;
+}
+
+int lqb_det_execute_dense(lqb_det h, const float *iq, uint64_t stride, uint64_t ns, int mem)
+{
+    if (!h) return fail(LQB_EINVAL, "null handle");
+    unsigned n = h->f.n_streams;
+    std::vector<const float *> ptr(n);
+    std::vector<uint64_t> len(n, ns);
+    for (unsigned s = 0; s < n; ++s) ptr[s] = iq + 2 * (size_t)s * stride;
+    return lqb_det_execute(h, n, nullptr, ptr.data(), len.data(), mem);
+}
+
+int lqb_det_poll(lqb_det h, lqb_detection *out, uint32_t max_out, uint32_t *n_out)
+{
+    if (!h) return fail(LQB_EINVAL, "null handle");
+    unsigned n = std::min<unsigned>(h->n_det, max_out);
+    for (unsigned k = 0; k < n && out; ++k) {
+        const Detection &d = h->h_det.p[h->order[k]];
+        out[k].stream = d.stream; out[k].seq = d.seq; out[k].sample_index = d.F;
+        out[k].tau_hat = d.tau; out[k].gamma_hat = d.gamma; out[k].dphi_hat = d.dphi; out[k].phi_hat = d.phi; out[k].rxy = d.rxy;
+    }
+    if (n_out) *n_out = h->n_det;
+    return 0;
+}
+int lqb_det_last_timing(lqb_det h, float *ms)
+{
+    if (!h) return fail(LQB_EINVAL, "null handle");
+    *ms = h->ms;
+    return 0;
+}
+
+// =================================================================== host-side tables (no GPU)
+int lqb_tab_interp_taps(float beta, float *h30) { auto h = interp_taps(beta); std::memcpy(h30, h.data(), 30 * sizeof(float)); return 0; }
+int lqb_tab_pfb_banks(float beta, float *b) { auto v = pfb_banks(beta); std::memcpy(b, v.data(), v.size() * sizeof(float)); return 0; }
+int lqb_tab_detector_template(float beta, float *s) { auto v = detector_template(beta); std::memcpy(s, v.data(), v.size() * sizeof(cf)); return 0; }
+int lqb_tab_nco_sintab(float *t) { std::memcpy(t, nco_sintab(), 1024 * sizeof(float)); return 0; }
+int lqb_tab_packet_len(uint32_t n, uint32_t check, uint32_t fec0, uint32_t fec1, uint32_t ms, uint32_t *enc, uint32_t *nsym)
+{
+    if (!modem_supported(ms) || !fec_supported(fec0) || !fec_supported(fec1) || check == 0 || check >= CRC_NUM) return fail(LQB_EINVAL, "unsupported scheme");
+    if (enc) *enc = packetizer_enc_len(n, check, fec0, fec1);
+    if (nsym) *nsym = qpm_frame_len(n, check, fec0, fec1, ms);
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,42 @@
+// lqb_debug.cu -- single-launch hooks that expose kernel building blocks to the unit tests
+// (exported as lqb_dbg_*; not part of the public header).
+#include "lqb_kernels.h"
+#include "lqb_tables.h"
+#include <vector>
+#include <cstring>
+
+namespace lqb {
+
+__global__ void k_dbg_fft512(const float2 *W, const float2 *in, float2 *out, int dir)
+{
+    __shared__ float2 sW[256];
+    __shared__ float2 scr[544];
+    const int lane = threadIdx.x;
+    for (int i = lane; i < 256; i += 32) sW[i] = W[i];
+    __syncwarp();
+    float2 v[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) v[r] = in[fft512_in_index(lane, r)];
+    if (dir > 0) fft512_warp<+1>(v, sW, scr, lane); else fft512_warp<-1>(v, sW, scr, lane);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) out[fft512_out_index(lane, r)] = v[r];
+}
+
+}  // namespace lqb
+
+extern "C" int lqb_dbg_fft512(const float *in_host, float *out_host, int dir)
+{
+    using namespace lqb;
+    auto W = twiddles(512);
+    float2 *dW = nullptr, *din = nullptr, *dout = nullptr;
+    if (cudaMalloc(&dW, 256 * sizeof(float2)) != cudaSuccess) return -19;
+    cudaMalloc(&din, 512 * sizeof(float2));
+    cudaMalloc(&dout, 512 * sizeof(float2));
+    cudaMemcpy(dW, W.data(), 256 * sizeof(float2), cudaMemcpyHostToDevice);
+    cudaMemcpy(din, in_host, 512 * sizeof(float2), cudaMemcpyHostToDevice);
+    k_dbg_fft512<<<1, 32>>>(dW, din, dout, dir);
+    cudaError_t e = cudaDeviceSynchronize();
+    cudaMemcpy(out_host, dout, 512 * sizeof(float2), cudaMemcpyDeviceToHost);
+    cudaFree(dW); cudaFree(din); cudaFree(dout);
+    return e == cudaSuccess ? 0 : -5;
+}

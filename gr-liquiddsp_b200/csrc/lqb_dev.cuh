@@ -1,0 +1,213 @@
+// lqb_dev.cuh -- device-side data layout and arithmetic primitives shared by the kernels.
+//
+// Float discipline: the library is compiled with -fmad=false; fused multiply-adds are
+// written __fmaf_rn() exactly where the algorithm specification (docs/FRAME_FORMAT.md)
+// has one, so every kernel rounds the way the specification says.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "lqb_lens.h"
+
+namespace lqb {
+
+// ------------------------------------------------------------------ constant tables in HBM (one copy per handle)
+struct DevTables {
+    float2   W512[256];        // exp(-j 2 pi k / 512)
+    float2   W32[16];          // exp(-j 2 pi k / 32)
+    float2   Sc[512];          // conj(FFT512(template))
+    float2   sconj[160];       // conj(template), 156 used
+    float    s2_sum, threshold;
+    int      range, pad0;
+    float    sintab[1024];     // NCO sine table
+    float    banks[32 * 28];   // matched-filter bank taps, oldest -> newest
+    float2   pilots_conj[16];  // conj(header pilots), 15 used
+    float2   psk_map[8 * 256]; // PSK-2^b constellation, row b-1
+    uint32_t crc_tab[8][256];  // by liquid crc enum (3..6 used)
+    uint16_t ilv54[4][28];     // header interleaver maps, n = 54 (27 pairs)
+    uint16_t ilv27[4][16];     // n = 27 (13 pairs)
+    uint8_t  h84_dec[256];
+    uint8_t  h74_dec[128];
+    uint8_t  secded_col[64];
+    uint8_t  gf_exp[512];
+    uint8_t  gf_log[256];
+    uint8_t  rs_gen[64];       // 33 used
+};
+
+// ------------------------------------------------------------------ per-stream persistent state
+struct StreamState {
+    long long base;            // absolute index of carry[0]
+    long long G;               // samples with absolute index < G read as zero (reset boundary)
+    long long wstart;          // SEEK: absolute start of the next 512-sample window
+    long long F;               // PENDING: absolute index of the detected frame start
+    long long need_until;      // PENDING: do nothing until samples < need_until are available
+    long long resume;          // out: absolute index from which samples must be carried over
+    unsigned  carry_len;
+    int       mode;            // 0 = SEEK, 1 = PENDING
+    int       offset;          // PENDING: detected CFO bin
+    float     rxy;             // PENDING: detection metric
+    unsigned  seq;             // frames emitted since reset
+    unsigned  dropped;
+    unsigned  carry_sel;       // which of the two carry buffers is current
+    unsigned  pad;
+};
+
+struct StreamIO {              // one entry per stream fed by this execute call
+    const float2      *in;
+    unsigned long long n_in;
+    unsigned           stream;
+    unsigned           pad;
+};
+
+// ------------------------------------------------------------------ frame descriptor (device <-> host)
+struct FrameDesc {
+    long long F, G;
+    unsigned long long sym_off;      // payload symbols: offset into the symbol arena (complex samples)
+    unsigned long long buf_off;      // offset into byte arena A / B (per-frame stride buf_len)
+    unsigned long long pay_off;      // offset into payload output pool
+    unsigned long long dec_off;      // offset into Viterbi decision arena (64-bit words)
+    unsigned stream, seq, io_index, flags;
+    float    tau, gamma, dphi, phi, rxy, mf_scale;
+    unsigned mix_theta0, mix_dtheta, pll_theta0, pll_dtheta;
+    unsigned pfb_index, tau_neg;
+    int      header_valid, payload_valid;
+    unsigned payload_len, ms, bps, check, fec0, fec1;
+    unsigned n_sym, k0, n0, n1;      // k0 = payload+crc bytes, n0 = after fec0, n1 = after fec1
+    unsigned buf_len;                // bytes reserved per byte buffer
+    unsigned ilv1_off, ilv0_off;     // offsets (in uint32 entries) of this frame's interleaver maps
+    float    evm, rssi, cfo, evm_acc;
+    unsigned char header[20];
+    unsigned pad[3];
+};
+
+struct Detection {
+    long long F;
+    unsigned  stream, seq;
+    float     tau, gamma, dphi, phi, rxy;
+    unsigned  pad;
+};
+
+// ------------------------------------------------------------------ arithmetic primitives
+__device__ __forceinline__ float2 cmulf(float2 a, float2 b)
+{
+    float2 y;
+    y.x = __fmaf_rn(-a.y, b.y, __fmul_rn(a.x, b.x));
+    y.y = __fmaf_rn(a.y, b.x, __fmul_rn(a.x, b.y));
+    return y;
+}
+__device__ __forceinline__ float abs2f(float2 a) { return __fmaf_rn(a.y, a.y, __fmul_rn(a.x, a.x)); }
+__device__ __forceinline__ float cabsf_(float2 a) { return __fsqrt_rn(abs2f(a)); }
+
+__device__ __forceinline__ uint32_t nco_constrain_dev(float theta)
+{
+    float p = __fmul_rn(theta, 0.15915494309189535f);
+    float f = __fsub_rn(p, (float)__float2ll_rz(p));
+    if (f < 0.0f) f = __fadd_rn(f, 1.0f);
+    return (uint32_t)__float2ll_rz(__fmul_rn(f, 4294967296.0f));
+}
+__device__ __forceinline__ float2 nco_mix_down(const float *__restrict__ sintab, uint32_t theta, float2 x)
+{
+    unsigned idx = ((theta + (1u << 21)) >> 22) & 0x3ffu;
+    float s = sintab[idx], c = sintab[(idx + 256u) & 0x3ffu];
+    float2 y;                                   // x * (c - j s)
+    y.x = __fmaf_rn(x.y, s, __fmul_rn(x.x, c));
+    y.y = __fmaf_rn(-x.x, s, __fmul_rn(x.y, c));
+    return y;
+}
+__device__ __forceinline__ float nco_get_frequency_dev(uint32_t d_theta)
+{
+    float d = __fmul_rn((float)d_theta, 1.4629180792671596e-09f);
+    return d > 3.14159274f ? __fsub_rn(d, 6.28318548f) : d;
+}
+
+// sample accessor over [carry | new input] with the zero region below G
+struct StreamView {
+    const float2 *carry;
+    const float2 *in;
+    long long     base, G, end;     // end = base + carry_len + n_in (exclusive)
+    unsigned      carry_len;
+    __device__ __forceinline__ float2 at(long long n) const
+    {
+        if (n < G || n >= end) return make_float2(0.0f, 0.0f);
+        long long i = n - base;
+        return (i < (long long)carry_len) ? carry[i] : in[i - carry_len];
+    }
+};
+
+__device__ __forceinline__ unsigned brev4(unsigned r) { return __brev(r) >> 28; }
+__device__ __forceinline__ unsigned brev5(unsigned r) { return __brev(r) >> 27; }
+
+// ------------------------------------------------------------------ 512-point FFT, one warp, 16 points per lane
+// Radix-2 decimation-in-time, identical butterfly order and twiddles to the specification's
+// iterative FFT: stages 1-4 in registers, transpose through shared memory, stages 5-8 in
+// registers, stage 9 against lane^16 with shuffles.
+// In:  v[r] = x[bitrev9((lane << 4) | r)]      Out: v[r] = X[((lane >> 4) << 8) | (r << 4) | (lane & 15)]
+template <int DIR>
+__device__ __forceinline__ void bfly(float2 &lo, float2 &hi, float2 w)
+{
+    const float wi = DIR > 0 ? w.y : -w.y;
+    const float tr = __fmaf_rn(-wi, hi.y, __fmul_rn(w.x, hi.x));
+    const float ti = __fmaf_rn(wi, hi.x, __fmul_rn(w.x, hi.y));
+    const float2 u = lo;
+    lo.x = __fadd_rn(u.x, tr); lo.y = __fadd_rn(u.y, ti);
+    hi.x = __fsub_rn(u.x, tr); hi.y = __fsub_rn(u.y, ti);
+}
+
+template <int DIR>
+__device__ __forceinline__ void fft512_warp(float2 (&v)[16], const float2 *__restrict__ W,
+                                            float2 *__restrict__ scratch /* 544 float2, this warp's */, int lane)
+{
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        const int half = 1 << s;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            if (r & half) continue;
+            const int e = (r & (half - 1)) * (256 >> s);
+            bfly<DIR>(v[r], v[r + half], W[e]);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 16; ++r) scratch[17 * lane + r] = v[r];
+    __syncwarp();
+    const int c = lane & 15, b8 = lane >> 4;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+        const int p = (b8 << 8) | (r << 4) | c;
+        v[r] = scratch[p + (p >> 4)];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        const int half = 1 << s;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            if (r & half) continue;
+            const int e = (c + 16 * (r & (half - 1))) * (16 >> s);
+            bfly<DIR>(v[r], v[r + half], W[e]);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+        float2 o;
+        o.x = __shfl_xor_sync(0xffffffffu, v[r].x, 16);
+        o.y = __shfl_xor_sync(0xffffffffu, v[r].y, 16);
+        float2 lo = b8 ? o : v[r], hi = b8 ? v[r] : o;
+        bfly<DIR>(lo, hi, W[(r << 4) | c]);
+        v[r] = b8 ? hi : lo;
+    }
+}
+
+__device__ __forceinline__ int fft512_out_index(int lane, int r) { return ((lane >> 4) << 8) | (r << 4) | (lane & 15); }
+__device__ __forceinline__ int fft512_in_index(int lane, int r) { return (int)((brev4((unsigned)r) << 5) | brev5((unsigned)lane)); }
+
+__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long k)
+{
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+        unsigned long long o = __shfl_xor_sync(0xffffffffu, k, m);
+        k = o > k ? o : k;
+    }
+    return k;
+}
+
+}  // namespace lqb

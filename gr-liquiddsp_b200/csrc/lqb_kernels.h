@@ -1,0 +1,56 @@
+// lqb_kernels.h -- launch interface between the C-ABI layer (lqb_api.cu) and the kernels.
+#pragma once
+#include "lqb_dev.cuh"
+
+namespace lqb {
+
+struct SeekParams {
+    const DevTables *tables;
+    StreamState     *states;
+    const StreamIO  *io;
+    float2          *carry[2];      // [n_streams][carry_cap] each
+    unsigned         carry_cap;
+    int              det_mode;      // 0: flexframesync discovery, 1: bare qdetector
+    FrameDesc       *frames;        // det_mode 0
+    Detection       *detections;    // det_mode 1
+    unsigned        *n_out;
+    unsigned         max_out;
+};
+
+// work list entry for kernels that run per FEC stage
+struct StageItem { unsigned frame; unsigned pad; };
+
+struct PayloadParams {
+    const DevTables   *tables;
+    const StreamState *states;
+    const StreamIO    *io;
+    const float2      *carry[2];
+    unsigned           carry_cap;
+    FrameDesc         *frames;
+    unsigned           n_frames;
+    // matched filter tiling: tile_start[f] = first tile of frame f (exclusive prefix), n_tiles total
+    const unsigned    *tile_start;
+    unsigned           n_tiles;
+    float2            *syms;        // symbol arena
+    unsigned char     *bufA, *bufB; // byte arenas
+    unsigned char     *payload;     // payload output pool
+    const unsigned    *ilv_maps;    // interleaver map arena
+    unsigned long long *decisions;  // Viterbi decision arena
+};
+
+void launch_seek(const SeekParams &P, unsigned n_io, cudaStream_t s);
+void launch_carry(const SeekParams &P, unsigned n_io, cudaStream_t s);
+
+void launch_mf(const PayloadParams &P, cudaStream_t s);
+void launch_pll(const PayloadParams &P, const unsigned *list, unsigned n, cudaStream_t s);
+// stage = 1: bufA(n1) -> bufB(n0) with fec1;  stage = 0: bufB(n0) -> bufA(k0) with fec0
+void launch_deinterleave(const PayloadParams &P, const unsigned *list, unsigned n, int stage, cudaStream_t s);
+void launch_blockfec(const PayloadParams &P, const unsigned *list, unsigned n, int stage, cudaStream_t s);
+void launch_viterbi(const PayloadParams &P, const unsigned *list, unsigned n, int stage, unsigned K, cudaStream_t s);
+void launch_rs(const PayloadParams &P, const unsigned *blocks /* pairs (frame, block) */, unsigned n_blocks, int stage, cudaStream_t s);
+void launch_crc(const PayloadParams &P, const unsigned *list, unsigned n, cudaStream_t s);
+
+// debug / unit-test hooks (single launches on tiny inputs)
+void launch_dbg_fft512(const DevTables *T, const float2 *in, float2 *out, int dir, cudaStream_t s);
+
+}  // namespace lqb

@@ -1,0 +1,436 @@
+// lqb_rx_fec.cu -- packetizer_decode on the GPU, frame-parallel:
+//   k_deinterleave : the four interleaver passes (CTA per frame, precomputed swap maps)
+//   k_blockfec     : NONE / REP3 / REP5 / Hamming(7,4)(8,4)(12,8) / Golay(24,12) / SECDED
+//   k_viterbi      : K=7 / K=9 rate-1/2 (optionally punctured) hard-input Viterbi, warp per
+//                    codeword: add-compare-select with metrics in shared memory, decisions by
+//                    ballot to HBM, then a shuffle-fed traceback from state 0
+//   k_rs           : RS(255,223) over GF(256)/0x11d, warp per block: 32 syndromes in parallel
+//                    (one per lane), Berlekamp-Massey on lane 0, parallel Chien + Forney
+//   k_crc          : unscramble + CRC/checksum + payload copy-out, warp per frame
+// This is what liquid-dsp's qpacketmodem_decode/packetizer_decode (and libfec underneath)
+// do at the end of flexframesync_execute_rxpayload (reference call site
+// lib/flex_rx_impl.cc:213; schemes named at lib/flex_rx_impl.cc:75-136).
+#include "lqb_dev.cuh"
+#include "lqb_kernels.h"
+
+namespace lqb {
+
+namespace {
+
+struct StageIO { const unsigned char *src; unsigned char *dst; unsigned enc_len, dec_len, fs; };
+
+__device__ __forceinline__ StageIO stage_io(const PayloadParams &P, const FrameDesc &d, int stage)
+{
+    StageIO s;
+    if (stage == 1) { s.src = P.bufA + d.buf_off; s.dst = P.bufB + d.buf_off; s.enc_len = d.n1; s.dec_len = d.n0; s.fs = d.fec1; }
+    else            { s.src = P.bufB + d.buf_off; s.dst = P.bufA + d.buf_off; s.enc_len = d.n0; s.dec_len = d.k0; s.fs = d.fec0; }
+    return s;
+}
+
+// ------------------------------------------------------------------ interleaver
+__global__ void __launch_bounds__(256)
+k_deinterleave(PayloadParams P, const unsigned *__restrict__ list, int stage)
+{
+    const FrameDesc &d = P.frames[list[blockIdx.x]];
+    unsigned char *x = (stage == 1) ? (P.bufA + d.buf_off) : (P.bufB + d.buf_off);
+    const unsigned n = (stage == 1) ? d.n1 : d.n0, n2 = n / 2;
+    const unsigned *maps = P.ilv_maps + ((stage == 1) ? d.ilv1_off : d.ilv0_off);
+    const unsigned masks[4] = { 0xffu, 0x0fu, 0x55u, 0x33u };
+    for (int pass = 3; pass >= 0; --pass) {
+        const unsigned *map = maps + (size_t)pass * n2;
+        const unsigned mask = masks[pass];
+        for (unsigned i = threadIdx.x; i < n2; i += blockDim.x) {
+            unsigned j = map[i];
+            unsigned a = x[2 * j + 1], b = x[2 * i];
+            x[2 * j + 1] = (unsigned char)((a & ~mask) | (b & mask));
+            x[2 * i] = (unsigned char)((a & mask) | (b & ~mask));
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------ block codes
+__device__ __forceinline__ unsigned get_bits(const unsigned char *src, unsigned k, unsigned b)
+{
+    unsigned s = 0;
+    for (unsigned i = 0; i < b; ++i) { unsigned pos = k + i; s = (s << 1) | ((src[pos >> 3] >> (7 - (pos & 7))) & 1u); }
+    return s;
+}
+
+__constant__ unsigned c_golay_P[12] = { 0x8ed, 0x1db, 0x3b5, 0x769, 0xed1, 0xda3, 0xb47, 0x68f, 0xd1d, 0xa3b, 0x477, 0xffe };
+
+__device__ __forceinline__ unsigned golay_mulP(unsigned v)
+{
+    unsigned r = 0;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) r |= ((unsigned)__popc(v & c_golay_P[i]) & 1u) << (11 - i);
+    return r;
+}
+__device__ unsigned golay_decode(unsigned r)
+{
+    const unsigned rp = (r >> 12) & 0xfffu, rm = r & 0xfffu;
+    const unsigned s = rp ^ golay_mulP(rm);
+    if (__popc(s) <= 3) return rm;
+    for (int i = 0; i < 12; ++i)
+        if (__popc(s ^ c_golay_P[i]) <= 2) return rm ^ (1u << (11 - i));
+    const unsigned q = golay_mulP(s);
+    if (__popc(q) <= 3) return rm ^ q;
+    for (int i = 0; i < 12; ++i)
+        if (__popc(q ^ c_golay_P[i]) <= 2) return rm ^ q ^ c_golay_P[i];
+    return rm;
+}
+
+__device__ unsigned h128_decode(unsigned r)
+{
+    const int pos2bit[13] = { -1, 11, 10, 7, 9, 6, 5, 4, 8, 3, 2, 1, 0 };
+    const unsigned d = r & 0xffu, p = (r >> 8) & 0xfu;
+    const unsigned z = ((((unsigned)__popc(d & 0xda) ^ (p >> 3)) & 1u) << 0) | ((((unsigned)__popc(d & 0xb6) ^ (p >> 2)) & 1u) << 1)
+                     | ((((unsigned)__popc(d & 0x71) ^ (p >> 1)) & 1u) << 2) | ((((unsigned)__popc(d & 0x0f) ^ p) & 1u) << 3);
+    if (z >= 1 && z <= 12) r ^= 1u << pos2bit[z];
+    return r & 0xffu;
+}
+
+__device__ void secded_block(const DevTables *T, const unsigned char *src, unsigned char *dst, unsigned nb, unsigned nc, unsigned r)
+{
+    // src: [parity][r data bytes], block of nb data bytes (missing ones are zero); writes r bytes
+    unsigned char blk[8];
+    const unsigned rp = src[0];
+    unsigned p = 0, all = 0, tot = 0;
+    for (unsigned q = 0; q < nb; ++q) { blk[q] = q < r ? src[1 + q] : 0; tot ^= (unsigned)__popc(blk[q]) & 1u; }
+    for (unsigned bit = 0; bit < nb * 8; ++bit)
+        if ((blk[bit >> 3] >> (7 - (bit & 7))) & 1u) { p ^= T->secded_col[bit]; all ^= 1u; }
+    all ^= (unsigned)__popc(p) & 1u;
+    const unsigned calc = p | (all << nc);
+    const unsigned syn = (calc ^ rp) & ((1u << nc) - 1u);
+    tot ^= (unsigned)__popc(rp & ((1u << (nc + 1)) - 1u)) & 1u;
+    if (tot && syn && (syn & (syn - 1)))
+        for (unsigned bit = 0; bit < nb * 8; ++bit)
+            if (T->secded_col[bit] == syn) { blk[bit >> 3] ^= (unsigned char)(0x80u >> (bit & 7)); break; }
+    for (unsigned q = 0; q < r; ++q) dst[q] = blk[q];
+}
+
+__global__ void __launch_bounds__(256)
+k_blockfec(PayloadParams P, const unsigned *__restrict__ list, int stage)
+{
+    const FrameDesc &d = P.frames[list[blockIdx.x]];
+    const StageIO io = stage_io(P, d, stage);
+    const DevTables *T = P.tables;
+    const unsigned n = io.dec_len;
+    const unsigned char *e = io.src;
+    unsigned char *o = io.dst;
+    const unsigned tid = threadIdx.x, nt = blockDim.x;
+    switch (io.fs) {
+    case 1: for (unsigned i = tid; i < n; i += nt) o[i] = e[i]; break;
+    case 2:
+        for (unsigned i = tid; i < n; i += nt) { unsigned a = e[i], b = e[i + n], c = e[i + 2 * n]; o[i] = (unsigned char)((a & b) | (a & c) | (b & c)); }
+        break;
+    case 3:
+        for (unsigned i = tid; i < n; i += nt) {
+            unsigned out = 0;
+            for (unsigned bit = 0; bit < 8; ++bit) {
+                unsigned cnt = 0;
+                for (unsigned r = 0; r < 5; ++r) cnt += (e[i + r * n] >> bit) & 1u;
+                if (cnt >= 3) out |= 1u << bit;
+            }
+            o[i] = (unsigned char)out;
+        }
+        break;
+    case 4:
+        for (unsigned i = tid; i < n; i += nt)
+            o[i] = (unsigned char)((T->h74_dec[get_bits(e, 14 * i, 7)] << 4) | T->h74_dec[get_bits(e, 14 * i + 7, 7)]);
+        break;
+    case 5:
+        for (unsigned i = tid; i < n; i += nt) o[i] = (unsigned char)((T->h84_dec[e[2 * i]] << 4) | T->h84_dec[e[2 * i + 1]]);
+        break;
+    case 6:
+        for (unsigned i = tid; i < n; i += nt) o[i] = (unsigned char)h128_decode(get_bits(e, 12 * i, 12));
+        break;
+    case 7: {
+        const unsigned groups = n / 3, rem = n % 3;
+        for (unsigned g = tid; g < groups; g += nt) {
+            const unsigned char *s = e + 6 * g;
+            unsigned v0 = ((unsigned)s[0] << 16) | ((unsigned)s[1] << 8) | s[2], v1 = ((unsigned)s[3] << 16) | ((unsigned)s[4] << 8) | s[5];
+            unsigned s0 = golay_decode(v0), s1 = golay_decode(v1);
+            o[3 * g] = (unsigned char)(s0 >> 4); o[3 * g + 1] = (unsigned char)(((s0 & 15u) << 4) | (s1 >> 8)); o[3 * g + 2] = (unsigned char)s1;
+        }
+        if (tid < rem) {
+            const unsigned char *s = e + 6 * groups + 3 * tid;
+            o[3 * groups + tid] = (unsigned char)golay_decode(((unsigned)s[0] << 16) | ((unsigned)s[1] << 8) | s[2]);
+        }
+        break;
+    }
+    case 8: case 9: case 10: {
+        const unsigned nb = io.fs == 8 ? 2u : io.fs == 9 ? 4u : 8u, nc = io.fs == 8 ? 5u : io.fs == 9 ? 6u : 7u;
+        const unsigned blocks = (n + nb - 1) / nb;
+        for (unsigned b = tid; b < blocks; b += nt) {
+            unsigned r = (n - b * nb >= nb) ? nb : (n - b * nb);
+            secded_block(T, e + b * (nb + 1), o + b * nb, nb, nc, r);
+        }
+        break;
+    }
+    default: break;
+    }
+}
+
+// ------------------------------------------------------------------ Viterbi (warp per codeword)
+struct ConvSpec { unsigned K, P, poly0, poly1, keep0, keep1; };   // keepR: bit c set if row R keeps column c
+
+__device__ __forceinline__ ConvSpec conv_spec(unsigned fs)
+{
+    ConvSpec c;
+    c.K = 7; c.P = 1; c.poly0 = 0x6d; c.poly1 = 0x4f; c.keep0 = 1; c.keep1 = 1;
+    // puncturing matrices as column bitmasks, column 0 = bit 0
+    const unsigned k27[6][2] = { { 0x3, 0x1 }, { 0x3, 0x5 }, { 0xf, 0x1 }, { 0xb, 0x15 }, { 0x17, 0x29 }, { 0x2f, 0x51 } };
+    const unsigned k29[6][2] = { { 0x3, 0x1 }, { 0x7, 0x1 }, { 0xd, 0x3 }, { 0xb, 0x15 }, { 0x1b, 0x25 }, { 0x6b, 0x15 } };
+    if (fs == 12 || (fs >= 21 && fs <= 26)) { c.K = 9; c.poly0 = 0x1af; c.poly1 = 0x11d; }
+    if (fs >= 15 && fs <= 20) { c.P = fs - 13; c.keep0 = k27[fs - 15][0]; c.keep1 = k27[fs - 15][1]; }
+    if (fs >= 21 && fs <= 26) { c.P = fs - 19; c.keep0 = k29[fs - 21][0]; c.keep1 = k29[fs - 21][1]; }
+    return c;
+}
+
+__device__ __forceinline__ unsigned soft_bit(const unsigned char *enc, unsigned ib) { return ((enc[ib >> 3] >> (7 - (ib & 7))) & 1u) ? 255u : 0u; }
+
+constexpr int kVitWarps = 4;
+
+__global__ void __launch_bounds__(32 * kVitWarps)
+k_viterbi(PayloadParams P, const unsigned *__restrict__ list, unsigned n_list, int stage)
+{
+    __shared__ unsigned metrics[kVitWarps][2][256];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned gi = blockIdx.x * kVitWarps + warp;
+    if (gi >= n_list) return;
+    const FrameDesc &d = P.frames[list[gi]];
+    const StageIO io = stage_io(P, d, stage);
+    const ConvSpec cs = conv_spec(io.fs);
+    const unsigned ns = 1u << (cs.K - 1), half = ns >> 1, words = ns >> 5;
+    const unsigned nbits = 8 * io.dec_len, T = nbits + cs.K - 1;
+    unsigned *dec = reinterpret_cast<unsigned *>(P.decisions + d.dec_off);
+    unsigned (*m)[256] = metrics[warp];
+
+    // kept bits per puncturing period and prefix counts per column
+    unsigned per = 0, pre[8];
+    for (unsigned c = 0; c < cs.P; ++c) { pre[c] = per; per += ((cs.keep0 >> c) & 1u) + ((cs.keep1 >> c) & 1u); }
+
+    for (unsigned s = lane; s < ns; s += 32) m[0][s] = 63u;
+    __syncwarp();
+    if (lane == 0) m[0][0] = 0u;
+    __syncwarp();
+
+    // branch labels for this lane's butterflies (state pair i, i+half -> 2i, 2i+1)
+    unsigned cur = 0;
+    for (unsigned t = 0; t < T; ++t) {
+        const unsigned col = t % cs.P;
+        unsigned ib = (t / cs.P) * per + pre[col];
+        unsigned sym0 = 127u, sym1 = 127u;
+        if ((cs.keep0 >> col) & 1u) { sym0 = soft_bit(io.src, ib); ++ib; }
+        if ((cs.keep1 >> col) & 1u) { sym1 = soft_bit(io.src, ib); }
+        const unsigned *mo = m[cur];
+        unsigned *mn = m[cur ^ 1];
+        for (unsigned q = 0; q < half; q += 32) {
+            const unsigned i = q + lane;
+            const unsigned b0 = (__popc((2 * i) & cs.poly0) & 1) ? 255u : 0u;
+            const unsigned b1 = (__popc((2 * i) & cs.poly1) & 1) ? 255u : 0u;
+            const unsigned metric = (b0 ^ sym0) + (b1 ^ sym1);
+            const unsigned a0 = mo[i], a1 = mo[i + half];
+            unsigned m0 = a0 + metric, m1 = a1 + (510u - metric);
+            const unsigned d0 = (int)(m0 - m1) > 0;
+            mn[2 * i] = d0 ? m1 : m0;
+            m0 = a0 + (510u - metric); m1 = a1 + metric;
+            const unsigned d1 = (int)(m0 - m1) > 0;
+            mn[2 * i + 1] = d1 ? m1 : m0;
+            const unsigned w0 = __ballot_sync(0xffffffffu, d0), w1 = __ballot_sync(0xffffffffu, d1);
+            // decision layout: word 2*(q/32) holds even states 2(q+lane), word 2*(q/32)+1 the odd ones
+            if (lane == 0) { dec[(size_t)t * words + 2 * (q >> 5)] = w0; dec[(size_t)t * words + 2 * (q >> 5) + 1] = w1; }
+        }
+        __syncwarp();
+        cur ^= 1;
+    }
+    __syncwarp();
+    __threadfence_block();
+
+    // traceback from state 0: every lane tracks the state; decision words arrive by shuffle
+    unsigned char *out = io.dst;
+    const unsigned steps_per_blk = 32 / words;
+    unsigned state = 0, byte_acc = 0;
+    for (long long t_hi = (long long)T - 1; t_hi >= 0; t_hi -= steps_per_blk) {
+        // lanes hold words for steps t_hi, t_hi-1, ... : lane l -> step t_hi - l / words, word l % words
+        const long long my_t = t_hi - (long long)(lane / words);
+        unsigned w = 0;
+        if (my_t >= 0) w = dec[(size_t)my_t * words + (lane % words)];
+        for (unsigned k = 0; k < steps_per_blk; ++k) {
+            const long long t = t_hi - k;
+            if (t < 0) break;
+            // state s: pair index i = s >> 1 lives in ballot group q = i / 32 at bit i % 32, odd/even selects the word
+            const unsigned i = state >> 1, wi = 2 * (i >> 5) + (state & 1u);
+            const unsigned word = __shfl_sync(0xffffffffu, w, k * words + wi);
+            const unsigned bit = (word >> (i & 31u)) & 1u;
+            if (t >= (long long)(cs.K - 1)) {
+                const unsigned bi = (unsigned)t - (cs.K - 1);
+                byte_acc |= bit << (7 - (bi & 7u));
+                if ((bi & 7u) == 0) { if (lane == 0) out[bi >> 3] = (unsigned char)byte_acc; byte_acc = 0; }
+            }
+            state = (state >> 1) | (bit << (cs.K - 2));
+        }
+    }
+}
+
+// ------------------------------------------------------------------ Reed-Solomon (warp per 255-byte block)
+constexpr int kRsWarps = 4;
+
+__global__ void __launch_bounds__(32 * kRsWarps)
+k_rs(PayloadParams P, const unsigned *__restrict__ blocks, unsigned n_blocks, int stage)
+{
+    __shared__ unsigned char gexp[512], glog[256];
+    __shared__ unsigned char data[kRsWarps][256];
+    __shared__ unsigned char synd[kRsWarps][32], lam[kRsWarps][36], bb[kRsWarps][36], tt[kRsWarps][36], omg[kRsWarps][32];
+    __shared__ int deg_s[kRsWarps];
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) gexp[i] = P.tables->gf_exp[i];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) glog[i] = P.tables->gf_log[i];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned gi = blockIdx.x * kRsWarps + warp;
+    if (gi >= n_blocks) return;
+    const FrameDesc &d = P.frames[blocks[2 * gi]];
+    const unsigned blk = blocks[2 * gi + 1];
+    const StageIO io = stage_io(P, d, stage);
+    const unsigned n = io.dec_len;
+    const unsigned nblocks = (n + 222) / 223, dec_block = (n + nblocks - 1) / nblocks, enc_block = dec_block + 32, pad = 223 - dec_block;
+    const unsigned nn = 255 - pad;
+    unsigned char *x = data[warp];
+    const unsigned char *src = io.src + (size_t)blk * enc_block;
+    for (unsigned i = lane; i < enc_block; i += 32) x[i] = src[i];
+    __syncwarp();
+
+    // syndrome lane: S_lane = r(alpha^(lane+1)) by Horner from the highest-degree byte
+    unsigned s = x[0];
+    for (unsigned j = 1; j < nn; ++j) s = x[j] ^ (s ? gexp[glog[s] + lane + 1] : 0);
+    synd[warp][lane] = (unsigned char)s;
+    const unsigned any = __ballot_sync(0xffffffffu, s != 0);
+    __syncwarp();
+    if (any) {
+        unsigned char *S = synd[warp], *L = lam[warp], *B = bb[warp], *Tm = tt[warp], *O = omg[warp];
+        if (lane == 0) {
+            for (int i = 0; i < 33; ++i) { L[i] = 0; B[i] = 0; }
+            L[0] = 1; B[0] = 1;
+            unsigned el = 0;
+            for (unsigned r = 1; r <= 32; ++r) {
+                unsigned dsc = 0;
+                for (unsigned i = 0; i < r; ++i) if (L[i] && S[r - i - 1]) dsc ^= gexp[glog[L[i]] + glog[S[r - i - 1]]];
+                if (dsc == 0) {
+                    for (int i = 32; i > 0; --i) B[i] = B[i - 1];
+                    B[0] = 0;
+                } else {
+                    Tm[0] = L[0];
+                    for (int i = 0; i < 32; ++i) Tm[i + 1] = L[i + 1] ^ (B[i] ? gexp[glog[dsc] + glog[B[i]]] : 0);
+                    if (2 * el <= r - 1) {
+                        el = r - el;
+                        const unsigned dinv = 255 - glog[dsc];
+                        for (int i = 0; i <= 32; ++i) B[i] = L[i] ? gexp[glog[L[i]] + dinv] : 0;
+                    } else {
+                        for (int i = 32; i > 0; --i) B[i] = B[i - 1];
+                        B[0] = 0;
+                    }
+                    for (int i = 0; i <= 32; ++i) L[i] = Tm[i];
+                }
+            }
+            int deg = 0;
+            for (int i = 0; i <= 32; ++i) if (L[i]) deg = i;
+            deg_s[warp] = deg;
+            for (int i = 0; i < deg; ++i) {
+                unsigned acc = 0;
+                for (int j = 0; j <= i; ++j) if (S[i - j] && L[j]) acc ^= gexp[glog[S[i - j]] + glog[L[j]]];
+                O[i] = (unsigned char)acc;
+            }
+        }
+        __syncwarp();
+        const int deg = deg_s[warp];
+        // Chien search: lane tests i = lane+1, lane+33, ... ; roots kept in a per-lane bit mask
+        unsigned mine = 0, count = 0;
+        for (unsigned it = 0; it < 8; ++it) {
+            const unsigned i = it * 32 + lane + 1;
+            unsigned q = 1;
+            if (i <= 255) { for (int j = 1; j <= deg; ++j) if (L[j]) q ^= gexp[(glog[L[j]] + i * j) % 255]; }
+            const bool root = (i <= 255) && (q == 0);
+            if (root) mine |= 1u << it;
+            count += __popc(__ballot_sync(0xffffffffu, root));
+        }
+        if ((int)count == deg) {
+            for (unsigned it = 0; it < 8; ++it) {
+                if (!((mine >> it) & 1u)) continue;
+                const unsigned root = it * 32 + lane + 1, loc = root - 1;
+                unsigned num = 0, den = 0;
+                for (int i = 0; i < deg; ++i) if (O[i]) num ^= gexp[(glog[O[i]] + i * root) % 255];
+                const int top = (deg < 31 ? deg : 31) & ~1;
+                for (int i = 0; i <= top; i += 2) if (L[i + 1]) den ^= gexp[(glog[L[i + 1]] + i * root) % 255];
+                if (num != 0 && loc >= pad) x[loc - pad] ^= gexp[(glog[num] + 255 - glog[den]) % 255];
+            }
+        }
+        __syncwarp();
+    }
+    const unsigned n0 = blk * dec_block;
+    const unsigned take = (n - n0 >= dec_block) ? dec_block : (n - n0);
+    unsigned char *dst = io.dst + n0;
+    for (unsigned i = lane; i < take; i += 32) dst[i] = x[i];
+}
+
+// ------------------------------------------------------------------ unscramble + CRC + copy-out (warp per frame)
+__global__ void __launch_bounds__(128)
+k_crc(PayloadParams P, const unsigned *__restrict__ list, unsigned n_list)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned gi = blockIdx.x * 4 + warp;
+    if (gi >= n_list) return;
+    FrameDesc &d = P.frames[list[gi]];
+    unsigned char *buf = P.bufA + d.buf_off;        // k0 bytes: payload + crc, still whitened
+    unsigned char *out = P.payload + d.pay_off;
+    const unsigned plen = d.payload_len, k0 = d.k0, cl = k0 - plen;
+    for (unsigned i = lane; i < k0; i += 32) {
+        unsigned mask = (i & 3u) == 0 ? 0xb4u : (i & 3u) == 1 ? 0x6au : (i & 3u) == 2 ? 0x8bu : 0xc5u;
+        unsigned v = buf[i] ^ mask;
+        buf[i] = (unsigned char)v;
+        if (i < plen) out[i] = (unsigned char)v;
+    }
+    __syncwarp();
+    if (lane == 0) {
+        unsigned key = 0, rx = 0;
+        for (unsigned i = 0; i < cl; ++i) rx = (rx << 8) | buf[plen + i];
+        if (d.check == 2) {
+            unsigned sum = 0;
+            for (unsigned i = 0; i < plen; ++i) sum += buf[i];
+            key = (~sum + 1u) & 0xffu;
+        } else if (d.check >= 3 && d.check <= 6) {
+            const unsigned *tab = P.tables->crc_tab[d.check];
+            unsigned k = 0xffffffffu;
+            for (unsigned i = 0; i < plen; ++i) k = (k >> 8) ^ tab[(k ^ buf[i]) & 0xffu];
+            const unsigned bits = d.check == 3 ? 8u : d.check == 4 ? 16u : d.check == 5 ? 24u : 32u;
+            key = (~k) & (bits == 32 ? 0xffffffffu : ((1u << bits) - 1u));
+        }
+        d.payload_valid = (key == rx) ? 1 : 0;
+    }
+}
+
+}  // namespace
+
+void launch_deinterleave(const PayloadParams &P, const unsigned *list, unsigned n, int stage, cudaStream_t s)
+{
+    if (n) k_deinterleave<<<n, 256, 0, s>>>(P, list, stage);
+}
+void launch_blockfec(const PayloadParams &P, const unsigned *list, unsigned n, int stage, cudaStream_t s)
+{
+    if (n) k_blockfec<<<n, 256, 0, s>>>(P, list, stage);
+}
+void launch_viterbi(const PayloadParams &P, const unsigned *list, unsigned n, int stage, unsigned K, cudaStream_t s)
+{
+    (void)K;
+    if (n) k_viterbi<<<(n + kVitWarps - 1) / kVitWarps, 32 * kVitWarps, 0, s>>>(P, list, n, stage);
+}
+void launch_rs(const PayloadParams &P, const unsigned *blocks, unsigned n_blocks, int stage, cudaStream_t s)
+{
+    if (n_blocks) k_rs<<<(n_blocks + kRsWarps - 1) / kRsWarps, 32 * kRsWarps, 0, s>>>(P, blocks, n_blocks, stage);
+}
+void launch_crc(const PayloadParams &P, const unsigned *list, unsigned n, cudaStream_t s)
+{
+    if (n) k_crc<<<(n + 3) / 4, 128, 0, s>>>(P, list, n);
+}
+
+}  // namespace lqb

@@ -1,0 +1,528 @@
+// lqb_rx_seek.cu -- frame discovery: preamble search (qdetector seek), alignment
+// (tau/gamma/dphi/phi estimation), header matched filter + pilot sync + header decode.
+//
+// Replaces, for a batch of independent streams, the part of liquid-dsp's flexframesync
+// state machine that decides WHERE frames are (reference call site
+// lib/flex_rx_impl.cc:213 -> flexframesync_execute; lib/frame_detector_cc_impl.cc:77 ->
+// qdetector_cccf_execute).  One CTA (4 warps) walks one stream: every 256-sample hop it
+// evaluates the 512-sample window exactly as qdetector does (1 forward FFT + 49 frequency-
+// shifted inverse FFTs, each FFT done by one warp with 16 points per lane), and on a hit
+// runs the serial alignment / header steps before moving its hop grid past the frame.
+// The payload itself is left to the frame-parallel kernels in lqb_rx_payload.cu.
+#include "lqb_dev.cuh"
+#include "lqb_kernels.h"
+
+namespace lqb {
+
+namespace {
+
+constexpr int kThreads = 128;
+constexpr int kWarps = 4;
+constexpr float kPiF = 3.14159274f;     // (float)M_PI
+
+struct SeekShared {
+    float2 Xw[512];           // time-domain window / aligned buffer
+    float2 Xf[512];           // its spectrum (also reused for the CFO spectrum)
+    float2 Sc[512];           // conj(S)
+    float2 W[256];            // twiddles
+    float2 scr[kWarps * 544]; // per-warp FFT transpose scratch; reused flat by the header stage
+    unsigned long long best[kWarps];
+    float  energy[2];
+    float2 y3[3];             // align: y[511], y[0], y[1]
+    // control (written by thread 0)
+    int    trig, idx, off, stop, hv;
+    float  rxy, tau, gamma, dphi, phi, mf_scale;
+    unsigned theta0, dtheta, pfb, tau_neg;
+    unsigned char hbytes[64]; // header: 54 demodulated bytes
+    unsigned char hdec[32];   // decoded header (24 bytes incl. CRC)
+};
+
+// flat offsets inside scr for the align/header stage
+constexpr int kVbuf = 0;      // 640: derotated samples n = 128 .. 616
+constexpr int kHsym = 640;    // 232: header symbols
+constexpr int kZbuf = 1088;   // 512: x * conj(s) for CFO estimation
+constexpr int kVsum = 1600;   // 160: derotated products for the phase estimate
+constexpr int kPil  = 1760;   // 64 : pilot FFT in/out
+
+__device__ __forceinline__ void load_window(SeekShared &sh, const StreamView &sv, long long start, int tid)
+{
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        int i = tid + kThreads * k;
+        sh.Xw[i] = sv.at(start + i);
+    }
+}
+
+// energy of 256 samples as a balanced pairwise tree in index order
+__device__ __forceinline__ float half_energy(const float2 *x, int lane)
+{
+    float e[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) e[q] = abs2f(x[lane * 8 + q]);
+    float a = __fadd_rn(__fadd_rn(__fadd_rn(e[0], e[1]), __fadd_rn(e[2], e[3])),
+                        __fadd_rn(__fadd_rn(e[4], e[5]), __fadd_rn(e[6], e[7])));
+#pragma unroll
+    for (int m = 1; m <= 16; m <<= 1) a = __fadd_rn(a, __shfl_xor_sync(0xffffffffu, a, m));
+    return a;
+}
+
+__device__ __forceinline__ void forward_fft_to(SeekShared &sh, const float2 *src, float2 *dst, int lane)
+{
+    float2 v[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) v[r] = src[fft512_in_index(lane, r)];
+    fft512_warp<+1>(v, sh.W, sh.scr, lane);      // warp 0's scratch
+#pragma unroll
+    for (int r = 0; r < 16; ++r) dst[fft512_out_index(lane, r)] = v[r];
+}
+
+// inverse FFT of Xf .* conj(S shifted by off); leaves y in registers
+__device__ __forceinline__ void cross_ifft(SeekShared &sh, int off, float2 (&v)[16], float2 *scratch, int lane)
+{
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+        int i = fft512_in_index(lane, r);
+        v[r] = cmulf(sh.Xf[i], sh.Sc[(i - off) & 511]);
+    }
+    fft512_warp<-1>(v, sh.W, scratch, lane);
+}
+
+// evaluate the window in sh.Xw; thread 0 publishes trig/idx/off/rxy
+__device__ void eval_window(SeekShared &sh, const DevTables *T, int tid)
+{
+    const int warp = tid >> 5, lane = tid & 31;
+    if (warp < 2) {
+        float e = half_energy(sh.Xw + warp * 256, lane);
+        if (lane == 0) sh.energy[warp] = e;
+    }
+    if (warp == 0) forward_fft_to(sh, sh.Xw, sh.Xf, lane);
+    __syncthreads();
+    const float g0 = __fmul_rn(__fsqrt_rn(__fadd_rn(sh.energy[0], sh.energy[1])), __fsqrt_rn(156.0f / 512.0f));
+    unsigned long long best = 0ull;
+    if (g0 >= 1e-10f) {
+        const int range = T->range;
+        float2 v[16];
+        for (int offi = 3 - warp; offi <= 2 * range; offi += kWarps) {
+            cross_ifft(sh, offi - range, v, sh.scr + warp * 544, lane);
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+                unsigned order = (unsigned)(offi * 512 + fft512_out_index(lane, r));
+                unsigned long long key = ((unsigned long long)__float_as_uint(abs2f(v[r])) << 32) | (0xffffffffu - order);
+                best = key > best ? key : best;
+            }
+        }
+        best = warp_max_u64(best);
+    }
+    if (lane == 0) sh.best[warp] = best;
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long b = sh.best[0];
+        for (int w = 1; w < kWarps; ++w) b = sh.best[w] > b ? sh.best[w] : b;
+        int trig = 0, idx = 0, off = 0;
+        float rxy = 0.0f;
+        if (g0 >= 1e-10f) {
+            float peak2 = __uint_as_float((unsigned)(b >> 32));
+            unsigned order = 0xffffffffu - (unsigned)(b & 0xffffffffu);
+            if (peak2 > 0.0f) { idx = (int)(order & 511u); off = (int)(order >> 9) - T->range; }
+            float g = __fdiv_rn(1.0f, __fmul_rn(__fmul_rn(512.0f, g0), __fsqrt_rn(T->s2_sum)));
+            rxy = __fmul_rn(__fsqrt_rn(peak2), g);
+            trig = (rxy > T->threshold) && (idx < 512 - 156);
+        }
+        sh.trig = trig; sh.idx = idx; sh.off = off; sh.rxy = rxy;
+    }
+    __syncthreads();
+}
+
+// alignment on the 512 samples in sh.Xw (x[F .. F+512)) with CFO bin sh.off
+__device__ void align_frame(SeekShared &sh, const DevTables *T, int tid)
+{
+    const int warp = tid >> 5, lane = tid & 31;
+    float2 *zbuf = sh.scr + kZbuf, *vsum = sh.scr + kVsum;
+    if (warp == 0) forward_fft_to(sh, sh.Xw, sh.Xf, lane);
+    // CFO product (other warps start while warp 0 transforms; zbuf does not alias warp 0's scratch)
+    for (int i = tid; i < 512; i += kThreads)
+        zbuf[i] = (i < 156) ? cmulf(sh.Xw[i], T->sconj[i]) : make_float2(0.0f, 0.0f);
+    __syncthreads();
+    if (warp == 0) {
+        float2 v[16];
+        cross_ifft(sh, sh.off, v, sh.scr, lane);
+        if (lane == 0) sh.y3[1] = v[0];
+        if (lane == 1) sh.y3[2] = v[0];
+        if (lane == 31) sh.y3[0] = v[15];
+        __syncwarp();
+        // CFO spectrum
+#pragma unroll
+        for (int r = 0; r < 16; ++r) v[r] = zbuf[fft512_in_index(lane, r)];
+        fft512_warp<+1>(v, sh.W, sh.scr, lane);
+        unsigned long long best = 0ull;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            int p = fft512_out_index(lane, r);
+            sh.Xf[p] = v[r];
+            unsigned long long key = ((unsigned long long)__float_as_uint(abs2f(v[r])) << 32) | (0xffffffffu - (unsigned)p);
+            best = key > best ? key : best;
+        }
+        best = warp_max_u64(best);
+        if (lane == 0) sh.best[0] = best;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        float yneg = __fsqrt_rn(cabsf_(sh.y3[0])), y0 = __fsqrt_rn(cabsf_(sh.y3[1])), ypos = __fsqrt_rn(cabsf_(sh.y3[2]));
+        float a = __fsub_rn(__fmul_rn(0.5f, __fadd_rn(ypos, yneg)), y0);
+        float b = __fmul_rn(0.5f, __fsub_rn(ypos, yneg));
+        float c = y0;
+        float tau = __fdiv_rn(-b, __fmul_rn(2.0f, a));
+        float g_hat = __fadd_rn(__fadd_rn(__fmul_rn(__fmul_rn(a, tau), tau), __fmul_rn(b, tau)), c);
+        sh.tau = tau;
+        sh.gamma = __fdiv_rn(__fmul_rn(g_hat, g_hat), __fmul_rn(512.0f, T->s2_sum));
+        unsigned long long bb = sh.best[0];
+        float v2 = __uint_as_float((unsigned)(bb >> 32));
+        unsigned i0 = (v2 > 0.0f) ? (0xffffffffu - (unsigned)(bb & 0xffffffffu)) : 0u;
+        float v0 = __fsqrt_rn(v2);
+        float vneg = cabsf_(sh.Xf[(i0 + 511u) & 511u]), vpos = cabsf_(sh.Xf[(i0 + 1u) & 511u]);
+        a = __fsub_rn(__fmul_rn(0.5f, __fadd_rn(vpos, vneg)), v0);
+        b = __fmul_rn(0.5f, __fsub_rn(vpos, vneg));
+        float idx = __fdiv_rn(-b, __fmul_rn(2.0f, a));
+        float index = __fadd_rn((float)i0, idx);
+        float base = (i0 > 256u) ? __fsub_rn(index, 512.0f) : index;
+        sh.dphi = __fdiv_rn(__fmul_rn(__fmul_rn(base, 2.0f), kPiF), 512.0f);
+    }
+    __syncthreads();
+    const float dphi = sh.dphi;
+    for (int i = tid; i < 156; i += kThreads) {
+        float ang = __fmul_rn(-dphi, (float)i);
+        float sn, cs;
+        sincosf(ang, &sn, &cs);
+        vsum[i] = cmulf(zbuf[i], make_float2(cs, sn));
+    }
+    __syncthreads();
+    if (tid == 0) {
+        float mr = 0.0f, mi = 0.0f;
+        for (int i = 0; i < 156; ++i) { mr = __fadd_rn(mr, vsum[i].x); mi = __fadd_rn(mi, vsum[i].y); }
+        sh.phi = atan2f(mi, mr);
+        sh.theta0 = nco_constrain_dev(sh.phi);
+        sh.dtheta = nco_constrain_dev(sh.dphi);
+        if (sh.tau > 0.0f) {
+            sh.pfb = (unsigned)__float2int_rz(__fmul_rn(sh.tau, 32.0f)) % 32u;
+            sh.tau_neg = 0u;
+        } else {
+            sh.pfb = (unsigned)__float2int_rz(__fmul_rn(__fadd_rn(1.0f, sh.tau), 32.0f)) % 32u;
+            sh.tau_neg = 1u;
+        }
+        sh.mf_scale = __fdiv_rn(0.5f, sh.gamma);
+    }
+    __syncthreads();
+}
+
+// in-place interleaver pass on a small byte buffer (serial; header only)
+__device__ void hdr_ilv_pass(unsigned char *x, const uint16_t *map, unsigned n2, unsigned mask)
+{
+    for (unsigned i = 0; i < n2; ++i) {
+        unsigned j = map[i];
+        unsigned a = x[2 * j + 1], b = x[2 * i];
+        x[2 * j + 1] = (unsigned char)((a & ~mask) | (b & mask));
+        x[2 * i] = (unsigned char)((a & mask) | (b & ~mask));
+    }
+}
+
+// header: matched filter over x[F+128 .. F+617), pilot sync, QPSK demod, decode.
+// Publishes sh.hv and the decoded bytes; returns PLL init through pll_theta0/pll_dtheta.
+__device__ void decode_header(SeekShared &sh, const DevTables *T, const StreamView &sv, long long F, int tid,
+                              unsigned *pll_theta0, unsigned *pll_dtheta)
+{
+    float2 *vbuf = sh.scr + kVbuf, *hsym = sh.scr + kHsym, *pil = sh.scr + kPil;
+    const unsigned theta0 = sh.theta0, dtheta = sh.dtheta, tau_neg = sh.tau_neg;
+    for (int m = tid; m < 489; m += kThreads) {
+        unsigned n = 128u + (unsigned)m;
+        vbuf[m] = nco_mix_down(T->sintab, theta0 + n * dtheta, sv.at(F + n));
+    }
+    __syncthreads();
+    const float *h = T->banks + sh.pfb * 28;
+    for (int k = tid; k < 231; k += kThreads) {
+        int nt = 2 * (78 + k) - (int)tau_neg;           // sample index of symbol t = 78 + k
+        const float2 *w = vbuf + (nt - 27 - 128);
+        float ar = 0.0f, ai = 0.0f;
+#pragma unroll 4
+        for (int j = 0; j < 28; ++j) { ar = __fmaf_rn(h[j], w[j].x, ar); ai = __fmaf_rn(h[j], w[j].y, ai); }
+        hsym[k] = make_float2(__fmul_rn(ar, sh.mf_scale), __fmul_rn(ai, sh.mf_scale));
+    }
+    __syncthreads();
+    // ---- pilot sync (thread 0): 15 pilots -> FFT-32 -> residual dphi / phi / gain
+    if (tid == 0) {
+        float2 *bt = pil, *bf = pil + 32;
+        for (int i = 0; i < 32; ++i) bt[i] = (i < 15) ? cmulf(hsym[16 * i], T->pilots_conj[i]) : make_float2(0.0f, 0.0f);
+        for (int i = 0; i < 32; ++i) bf[i] = bt[brev5((unsigned)i)];
+        for (int half = 1; half < 32; half <<= 1) {
+            int step = 16 / half;
+            for (int k = 0; k < 32; k += 2 * half)
+                for (int j = 0; j < half; ++j) bfly<+1>(bf[k + j], bf[k + j + half], T->W32[j * step]);
+        }
+        unsigned i0 = 0; float y0 = 0.0f;
+        for (unsigned i = 0; i < 32; ++i) { float a = cabsf_(bf[i]); if (i == 0 || a > y0) { i0 = i; y0 = a; } }
+        float ypos = cabsf_(bf[(i0 + 1) & 31]), yneg = cabsf_(bf[(i0 + 31) & 31]);
+        float a = __fsub_rn(__fmul_rn(0.5f, __fadd_rn(ypos, yneg)), y0);
+        float b = __fmul_rn(0.5f, __fsub_rn(ypos, yneg));
+        float idx = __fdiv_rn(-b, __fmul_rn(2.0f, a));
+        float index = __fadd_rn((float)i0, idx);
+        float base = (i0 > 16u) ? __fsub_rn(index, 32.0f) : index;
+        float dphi = __fdiv_rn(__fmul_rn(__fmul_rn(base, 2.0f), kPiF), 512.0f);
+        float mr = 0.0f, mi = 0.0f;
+        for (int i = 0; i < 15; ++i) {
+            float ang = __fmul_rn(__fmul_rn(-dphi, (float)i), 16.0f);
+            float sn, cs;
+            sincosf(ang, &sn, &cs);
+            float2 v = cmulf(bt[i], make_float2(cs, sn));
+            mr = __fadd_rn(mr, v.x); mi = __fadd_rn(mi, v.y);
+        }
+        float phi = atan2f(mi, mr);
+        float g_hat = __fdiv_rn(cabsf_(make_float2(mr, mi)), 15.0f);
+        pil[0] = make_float2(dphi, phi);
+        pil[1] = make_float2(__fdiv_rn(1.0f, g_hat), 0.0f);
+        *pll_dtheta = nco_constrain_dev(dphi);
+        *pll_theta0 = nco_constrain_dev(__fadd_rn(phi, __fmul_rn(dphi, 231.0f)));
+    }
+    __syncthreads();
+    // ---- derotate the 216 data symbols and slice QPSK: 4 symbols -> one byte
+    {
+        const float dphi = pil[0].x, phi = pil[0].y, g = pil[1].x;
+        for (int byte = tid; byte < 54; byte += kThreads) {
+            unsigned out = 0;
+            for (int q = 0; q < 4; ++q) {
+                int n = 4 * byte + q;
+                int i = n + n / 15 + 1;                  // position in the pilot-bearing frame
+                float ang = -__fadd_rn(__fmul_rn(dphi, (float)i), phi);
+                float sn, cs;
+                sincosf(ang, &sn, &cs);
+                float2 v = cmulf(hsym[i], make_float2(cs, sn));
+                v.x = __fmul_rn(v.x, g); v.y = __fmul_rn(v.y, g);
+                unsigned s = (v.x > 0.0f ? 0u : 1u) + (v.y > 0.0f ? 0u : 2u);
+                out = (out << 2) | s;
+            }
+            sh.hbytes[byte] = (unsigned char)out;
+        }
+    }
+    __syncthreads();
+    // ---- decode (thread 0): deinterleave(54) -> Hamming(8,4) -> deinterleave(27) -> SECDED(72,64) -> unscramble -> CRC-32
+    if (tid == 0) {
+        unsigned char *e = sh.hbytes, d27[28], *d = sh.hdec;
+        hdr_ilv_pass(e, T->ilv54[3], 27, 0x33); hdr_ilv_pass(e, T->ilv54[2], 27, 0x55);
+        hdr_ilv_pass(e, T->ilv54[1], 27, 0x0f); hdr_ilv_pass(e, T->ilv54[0], 27, 0xff);
+        for (int i = 0; i < 27; ++i) d27[i] = (unsigned char)((T->h84_dec[e[2 * i]] << 4) | T->h84_dec[e[2 * i + 1]]);
+        hdr_ilv_pass(d27, T->ilv27[3], 13, 0x33); hdr_ilv_pass(d27, T->ilv27[2], 13, 0x55);
+        hdr_ilv_pass(d27, T->ilv27[1], 13, 0x0f); hdr_ilv_pass(d27, T->ilv27[0], 13, 0xff);
+        for (int blk = 0; blk < 3; ++blk) {
+            const unsigned char *src = d27 + 9 * blk;
+            unsigned rp = src[0], p = 0, all = 0, tot = 0;
+            unsigned char b8[8];
+            for (int q = 0; q < 8; ++q) { b8[q] = src[1 + q]; tot ^= (unsigned)__popc(b8[q]) & 1u; }
+            for (int bit = 0; bit < 64; ++bit)
+                if ((b8[bit >> 3] >> (7 - (bit & 7))) & 1u) { p ^= T->secded_col[bit]; all ^= 1u; }
+            all ^= (unsigned)__popc(p) & 1u;
+            unsigned calc = p | (all << 7);
+            unsigned syn = (calc ^ rp) & 0x7fu;
+            tot ^= (unsigned)__popc(rp & 0xffu) & 1u;
+            if (tot && syn && (syn & (syn - 1)))
+                for (int bit = 0; bit < 64; ++bit)
+                    if (T->secded_col[bit] == syn) { b8[bit >> 3] ^= (unsigned char)(0x80u >> (bit & 7)); break; }
+            for (int q = 0; q < 8; ++q) d[8 * blk + q] = b8[q];
+        }
+        const unsigned char mask[4] = { 0xb4, 0x6a, 0x8b, 0xc5 };
+        for (int i = 0; i < 24; ++i) d[i] ^= mask[i & 3];
+        unsigned key = 0xffffffffu;
+        for (int i = 0; i < 20; ++i) key = (key >> 8) ^ T->crc_tab[6][(key ^ d[i]) & 0xffu];
+        key = ~key;
+        unsigned rx = ((unsigned)d[20] << 24) | ((unsigned)d[21] << 16) | ((unsigned)d[22] << 8) | d[23];
+        sh.hv = (key == rx);
+    }
+    __syncthreads();
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ the kernel
+__global__ void __launch_bounds__(kThreads, 4)
+k_seek(SeekParams P)
+{
+    __shared__ SeekShared sh;
+    __shared__ StreamState st;
+    __shared__ unsigned pll_theta0, pll_dtheta;
+    const int tid = threadIdx.x;
+    const DevTables *T = P.tables;
+    const StreamIO io = P.io[blockIdx.x];
+
+    for (int i = tid; i < 512; i += kThreads) sh.Sc[i] = T->Sc[i];
+    for (int i = tid; i < 256; i += kThreads) sh.W[i] = T->W512[i];
+    if (tid == 0) st = P.states[io.stream];
+    __syncthreads();
+
+    StreamView sv;
+    sv.carry = P.carry[st.carry_sel] + (size_t)io.stream * P.carry_cap;
+    sv.in = io.in;
+    sv.base = st.base;
+    sv.carry_len = st.carry_len;
+    sv.end = st.base + (long long)st.carry_len + (long long)io.n_in;
+    sv.G = st.G;
+
+    while (true) {
+        // ---------------- SEEK
+        if (st.mode == 0) {
+            if (st.wstart + 512 > sv.end) break;
+            load_window(sh, sv, st.wstart, tid);
+            __syncthreads();
+            eval_window(sh, T, tid);
+            if (!sh.trig) {
+                if (tid == 0) st.wstart += 256;
+                __syncthreads();
+                continue;
+            }
+            if (tid == 0) {
+                st.mode = 1;
+                st.F = st.wstart + sh.idx;
+                st.offset = sh.off;
+                st.rxy = sh.rxy;
+                st.need_until = st.F + 512;
+            }
+            __syncthreads();
+        }
+        // ---------------- PENDING: frame start known
+        if (sv.end < st.need_until) break;
+        const long long F = st.F;
+        load_window(sh, sv, F, tid);
+        if (tid == 0) sh.off = st.offset;
+        __syncthreads();
+        align_frame(sh, T, tid);
+
+        if (P.det_mode) {
+            // frame_detector_cc: report and re-phase the hop grid half a buffer later
+            if (tid == 0) {
+                unsigned slot = atomicAdd(P.n_out, 1u);
+                if (slot < P.max_out) {
+                    Detection d;
+                    d.F = F; d.stream = io.stream; d.seq = st.seq;
+                    d.tau = sh.tau; d.gamma = sh.gamma; d.dphi = sh.dphi; d.phi = sh.phi; d.rxy = st.rxy; d.pad = 0;
+                    P.detections[slot] = d;
+                }
+                st.seq++;
+                st.mode = 0;
+                st.wstart = F + 256;
+            }
+            __syncthreads();
+            continue;
+        }
+
+        const long long hdr_last = F + 616 - (long long)sh.tau_neg;    // sample that completes header symbol 308
+        if (hdr_last + 1 > sv.end) {
+            if (tid == 0) st.need_until = hdr_last + 1;
+            __syncthreads();
+            break;
+        }
+        decode_header(sh, T, sv, F, tid, &pll_theta0, &pll_dtheta);
+
+        // header fields (every thread reads the same shared bytes)
+        const unsigned char *hd = sh.hdec;
+        int hv = sh.hv;
+        unsigned plen = ((unsigned)hd[15] << 8) | hd[16];
+        unsigned ms = hd[17], check = (hd[18] >> 5) & 7u, fec0 = hd[18] & 0x1fu, fec1 = hd[19] & 0x1fu;
+        if (hv) {
+            if (hd[14] != 102) hv = 0;
+            else if (!modem_supported_hd(ms)) hv = 0;
+            else if (check == 0 || check >= 7) hv = 0;
+            else if (!fec_supported_hd(fec0) || !fec_supported_hd(fec1)) hv = 0;
+        }
+        unsigned n_sym = 0, k0 = 0, n0 = 0, n1 = 0;
+        long long last = hdr_last;
+        if (hv) {
+            k0 = plen + crc_len_hd(check);
+            n0 = fec_enc_len_hd(fec0, k0);
+            n1 = fec_enc_len_hd(fec1, n0);
+            unsigned bps = modem_bps_hd(ms);
+            n_sym = (8u * n1 + bps - 1u) / bps;
+            last = F + 2ll * (308ll + (long long)n_sym) - (long long)sh.tau_neg;
+            if (last + 1 > sv.end) {
+                // payload not complete yet: either wait for more samples or drop an oversized frame
+                long long need = last + 1 - (F > sv.G ? F : sv.G);
+                if (need > (long long)P.carry_cap) {
+                    if (tid == 0) {
+                        st.dropped++;
+                        st.mode = 0; st.G = F + 512; st.wstart = st.G - 256;
+                    }
+                    __syncthreads();
+                    sv.G = st.G;
+                    continue;
+                }
+                if (tid == 0) st.need_until = last + 1;
+                __syncthreads();
+                break;
+            }
+        }
+        if (tid == 0) {
+            unsigned slot = atomicAdd(P.n_out, 1u);
+            if (slot < P.max_out) {
+                FrameDesc &d = P.frames[slot];
+                d.F = F; d.G = sv.G;
+                d.sym_off = 0; d.buf_off = 0; d.pay_off = 0; d.dec_off = 0;
+                d.stream = io.stream; d.seq = st.seq; d.io_index = blockIdx.x; d.flags = 0;
+                d.tau = sh.tau; d.gamma = sh.gamma; d.dphi = sh.dphi; d.phi = sh.phi; d.rxy = st.rxy;
+                d.mf_scale = sh.mf_scale;
+                d.mix_theta0 = sh.theta0; d.mix_dtheta = sh.dtheta;
+                d.pll_theta0 = pll_theta0; d.pll_dtheta = pll_dtheta;
+                d.pfb_index = sh.pfb; d.tau_neg = sh.tau_neg;
+                d.header_valid = hv; d.payload_valid = 0;
+                d.payload_len = hv ? plen : 0; d.ms = hv ? ms : 0; d.bps = hv ? modem_bps_hd(ms) : 0;
+                d.check = hv ? check : 0; d.fec0 = hv ? fec0 : 0; d.fec1 = hv ? fec1 : 0;
+                d.n_sym = n_sym; d.k0 = k0; d.n0 = n0; d.n1 = n1;
+                d.buf_len = 0; d.ilv1_off = 0; d.ilv0_off = 0;
+                d.evm = 0.0f; d.evm_acc = 0.0f;
+                d.rssi = __fmul_rn(20.0f, log10f(sh.gamma));
+                d.cfo = nco_get_frequency_dev(sh.dtheta);
+                for (int i = 0; i < 20; ++i) d.header[i] = hd[i];
+            }
+            st.seq++;
+            st.mode = 0;
+            st.G = last + 1;
+            st.wstart = st.G - 256;
+        }
+        __syncthreads();
+        sv.G = st.G;
+    }
+
+    if (tid == 0) {
+        long long r = (st.mode == 0) ? st.wstart : st.F;
+        if (r < st.G) r = st.G;
+        if (r > sv.end) r = sv.end;
+        if (r < sv.base) r = sv.base;
+        st.resume = r;
+        P.states[io.stream] = st;
+    }
+}
+
+// copy the unconsumed tail [resume, end) of every fed stream into the other carry buffer
+__global__ void k_carry(SeekParams P)
+{
+    const StreamIO io = P.io[blockIdx.x];
+    StreamState *sp = P.states + io.stream;
+    __shared__ StreamState st;
+    if (threadIdx.x == 0) st = *sp;
+    __syncthreads();
+    const float2 *old = P.carry[st.carry_sel] + (size_t)io.stream * P.carry_cap;
+    float2 *dst = P.carry[st.carry_sel ^ 1u] + (size_t)io.stream * P.carry_cap;
+    const long long end = st.base + (long long)st.carry_len + (long long)io.n_in;
+    long long n = end - st.resume;
+    if (n > (long long)P.carry_cap) n = P.carry_cap;        // cannot happen (oversized frames are dropped)
+    const long long first = end - n;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+        long long a = first + i - st.base;
+        dst[i] = (a < (long long)st.carry_len) ? old[a] : io.in[a - st.carry_len];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        sp->base = first;
+        sp->carry_len = (unsigned)n;
+        sp->carry_sel = st.carry_sel ^ 1u;
+    }
+}
+
+void launch_seek(const SeekParams &P, unsigned n_io, cudaStream_t s) { k_seek<<<n_io, kThreads, 0, s>>>(P); }
+void launch_carry(const SeekParams &P, unsigned n_io, cudaStream_t s) { k_carry<<<n_io, 256, 0, s>>>(P); }
+
+}  // namespace lqb

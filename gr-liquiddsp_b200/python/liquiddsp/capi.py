@@ -1,0 +1,273 @@
+"""ctypes binding of include/lqb200.h (liblqb200.so).
+
+This is the Python-side stand-in for the SWIG module `liquiddsp_swig` of the reference
+(/root/reference/swig/liquiddsp_swig.i:19-26): it binds exactly the C-ABI the C++ blocks call.
+It never imports anything from oracle/ and has no CPU fallback -- if the CUDA library cannot
+be loaded, importing this module raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.normpath(os.path.join(_HERE, "..", "..", "lib", "liblqb200.so"))
+
+MEM_HOST, MEM_DEVICE = 0, 1
+RX_NO_FRAMESYMS, RX_DEVICE_RESULTS = 1, 2
+
+DECLARED_SYMBOLS = [
+    "lqb_last_error", "lqb_device_count", "lqb_version",
+    "lqb_rx_create", "lqb_rx_destroy", "lqb_rx_reset", "lqb_rx_execute", "lqb_rx_execute_dense",
+    "lqb_rx_poll", "lqb_rx_counts", "lqb_rx_last_timing", "lqb_rx_launch_count",
+    "lqb_tx_create", "lqb_tx_destroy", "lqb_tx_props_init_default", "lqb_tx_frame_len", "lqb_tx_assemble",
+    "lqb_det_create", "lqb_det_destroy", "lqb_det_reset", "lqb_det_execute", "lqb_det_execute_dense",
+    "lqb_det_poll", "lqb_det_last_timing",
+    "lqb_tab_interp_taps", "lqb_tab_pfb_banks", "lqb_tab_detector_template", "lqb_tab_nco_sintab",
+    "lqb_tab_packet_len",
+]
+
+
+class RxOpts(C.Structure):
+    _fields_ = [("device", C.c_int), ("n_streams", C.c_uint32), ("max_frame_samples", C.c_uint32),
+                ("flags", C.c_uint32), ("cuda_stream", C.c_void_p)]
+
+
+class FrameResult(C.Structure):
+    _fields_ = [("stream", C.c_uint32), ("seq", C.c_uint32), ("sample_index", C.c_int64),
+                ("header", C.c_uint8 * 20), ("header_valid", C.c_int32), ("payload_valid", C.c_int32),
+                ("payload_len", C.c_uint32), ("payload", C.c_void_p), ("framesyms", C.c_void_p),
+                ("num_framesyms", C.c_uint32),
+                ("mod_scheme", C.c_uint32), ("mod_bps", C.c_uint32), ("check", C.c_uint32),
+                ("fec0", C.c_uint32), ("fec1", C.c_uint32),
+                ("evm", C.c_float), ("rssi", C.c_float), ("cfo", C.c_float),
+                ("tau_hat", C.c_float), ("gamma_hat", C.c_float), ("dphi_hat", C.c_float),
+                ("phi_hat", C.c_float), ("rxy", C.c_float), ("flags", C.c_uint32)]
+
+
+class TxOpts(C.Structure):
+    _fields_ = [("device", C.c_int), ("flags", C.c_uint32), ("cuda_stream", C.c_void_p)]
+
+
+class TxProps(C.Structure):
+    _fields_ = [("check", C.c_uint32), ("fec0", C.c_uint32), ("fec1", C.c_uint32), ("mod_scheme", C.c_uint32)]
+
+
+class DetOpts(C.Structure):
+    _fields_ = [("device", C.c_int), ("n_streams", C.c_uint32), ("beta", C.c_float), ("threshold", C.c_float),
+                ("dphi_max", C.c_float), ("cuda_stream", C.c_void_p)]
+
+
+class DetectionResult(C.Structure):
+    _fields_ = [("stream", C.c_uint32), ("seq", C.c_uint32), ("sample_index", C.c_int64),
+                ("tau_hat", C.c_float), ("gamma_hat", C.c_float), ("dphi_hat", C.c_float),
+                ("phi_hat", C.c_float), ("rxy", C.c_float)]
+
+
+_lib = None
+
+
+def lib():
+    """Load liblqb200.so (raises OSError when it has not been built)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    L = C.CDLL(LIB_PATH)
+    vp, u32, u64 = C.c_void_p, C.c_uint32, C.c_uint64
+    L.lqb_last_error.restype = C.c_char_p
+    L.lqb_rx_create.restype = vp
+    L.lqb_rx_create.argtypes = [C.POINTER(RxOpts)]
+    L.lqb_rx_destroy.argtypes = [vp]
+    L.lqb_rx_reset.argtypes = [vp, C.c_int]
+    L.lqb_rx_execute.argtypes = [vp, u32, vp, vp, vp, C.c_int]
+    L.lqb_rx_execute_dense.argtypes = [vp, vp, u64, u64, C.c_int]
+    L.lqb_rx_poll.argtypes = [vp, vp, u32, C.POINTER(u32)]
+    L.lqb_rx_counts.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
+    L.lqb_rx_last_timing.argtypes = [vp, C.POINTER(C.c_float)]
+    L.lqb_rx_launch_count.argtypes = [vp, C.POINTER(u64)]
+    if hasattr(L, "lqb_tx_create"):
+        L.lqb_tx_create.restype = vp
+        L.lqb_tx_create.argtypes = [C.POINTER(TxOpts)]
+        L.lqb_tx_destroy.argtypes = [vp]
+        L.lqb_tx_props_init_default.argtypes = [C.POINTER(TxProps)]
+        L.lqb_tx_frame_len.argtypes = [C.POINTER(TxProps), u32, C.POINTER(u32)]
+        L.lqb_tx_assemble.argtypes = [vp, u32, vp, vp, vp, vp, vp, C.c_int]
+    L.lqb_det_create.restype = vp
+    L.lqb_det_create.argtypes = [C.POINTER(DetOpts)]
+    L.lqb_det_destroy.argtypes = [vp]
+    L.lqb_det_reset.argtypes = [vp, C.c_int]
+    L.lqb_det_execute.argtypes = [vp, u32, vp, vp, vp, C.c_int]
+    L.lqb_det_execute_dense.argtypes = [vp, vp, u64, u64, C.c_int]
+    L.lqb_det_poll.argtypes = [vp, vp, u32, C.POINTER(u32)]
+    L.lqb_det_last_timing.argtypes = [vp, C.POINTER(C.c_float)]
+    L.lqb_tab_interp_taps.argtypes = [C.c_float, vp]
+    L.lqb_tab_pfb_banks.argtypes = [C.c_float, vp]
+    L.lqb_tab_detector_template.argtypes = [C.c_float, vp]
+    L.lqb_tab_nco_sintab.argtypes = [vp]
+    L.lqb_tab_packet_len.argtypes = [u32, u32, u32, u32, u32, C.POINTER(u32), C.POINTER(u32)]
+    _lib = L
+    return L
+
+
+class LqbError(RuntimeError):
+    pass
+
+
+def _check(rc):
+    if rc != 0:
+        raise LqbError("lqb error %d: %s" % (rc, lib().lqb_last_error().decode()))
+
+
+def _frame_to_dict(r, host_results=True):
+    d = {k: getattr(r, k) for k, _ in FrameResult._fields_ if k not in ("header", "payload", "framesyms")}
+    d["header"] = bytes(r.header)
+    if host_results and r.header_valid and r.payload:
+        d["payload"] = C.string_at(r.payload, r.payload_len)
+    else:
+        d["payload"] = b""
+    if host_results and r.framesyms and r.num_framesyms:
+        buf = (C.c_float * (2 * r.num_framesyms)).from_address(r.framesyms)
+        d["framesyms"] = np.frombuffer(buf, dtype=np.complex64).copy()
+    else:
+        d["framesyms"] = np.zeros(0, np.complex64)
+    return d
+
+
+class Rx:
+    """Batch flexframesync: n_streams independent channels on one GPU."""
+
+    def __init__(self, n_streams=1, device=0, max_frame_samples=0, flags=0, cuda_stream=None):
+        o = RxOpts(device, n_streams, max_frame_samples, flags, cuda_stream)
+        self._L = lib()
+        self._h = self._L.lqb_rx_create(C.byref(o))
+        if not self._h:
+            raise LqbError("lqb_rx_create failed: " + self._L.lqb_last_error().decode())
+        self.n_streams = n_streams
+        self.flags = flags
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.lqb_rx_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def reset(self, stream=-1):
+        _check(self._L.lqb_rx_reset(self._h, stream))
+
+    def execute(self, chunks, stream_ids=None):
+        """chunks: list of complex64 numpy arrays (host memory), one per listed stream."""
+        n = len(chunks)
+        arrs = [np.ascontiguousarray(c, dtype=np.complex64) for c in chunks]
+        ptrs = (C.c_void_p * n)(*[a.ctypes.data for a in arrs])
+        lens = (C.c_uint64 * n)(*[len(a) for a in arrs])
+        ids = None if stream_ids is None else (C.c_uint32 * n)(*stream_ids)
+        _check(self._L.lqb_rx_execute(self._h, n, ids, ptrs, lens, MEM_HOST))
+
+    def execute_dense_ptr(self, ptr, stride, n_samples, mem):
+        _check(self._L.lqb_rx_execute_dense(self._h, C.c_void_p(ptr), stride, n_samples, mem))
+
+    def execute_dense(self, x2d):
+        x2d = np.ascontiguousarray(x2d, dtype=np.complex64)
+        assert x2d.shape[0] == self.n_streams
+        self.execute_dense_ptr(x2d.ctypes.data, x2d.shape[1], x2d.shape[1], MEM_HOST)
+
+    def counts(self):
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        _check(self._L.lqb_rx_counts(self._h, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
+    def poll(self, raw=False):
+        nf, _ = self.counts()
+        arr = (FrameResult * max(nf, 1))()
+        n = C.c_uint32(0)
+        _check(self._L.lqb_rx_poll(self._h, C.byref(arr), nf, C.byref(n)))
+        if raw:
+            return arr, nf
+        host = not (self.flags & RX_DEVICE_RESULTS)
+        return [_frame_to_dict(arr[i], host) for i in range(nf)]
+
+    def timing(self):
+        ms = (C.c_float * 5)()
+        _check(self._L.lqb_rx_last_timing(self._h, ms))
+        return list(ms)
+
+    def launches(self):
+        v = C.c_uint64(0)
+        _check(self._L.lqb_rx_launch_count(self._h, C.byref(v)))
+        return int(v.value)
+
+
+class Det:
+    """Batch qdetector_cccf with frame_detector_cc's parameters."""
+
+    def __init__(self, n_streams=1, device=0, beta=0.0, threshold=0.0, dphi_max=0.0, cuda_stream=None):
+        o = DetOpts(device, n_streams, beta, threshold, dphi_max, cuda_stream)
+        self._L = lib()
+        self._h = self._L.lqb_det_create(C.byref(o))
+        if not self._h:
+            raise LqbError("lqb_det_create failed: " + self._L.lqb_last_error().decode())
+        self.n_streams = n_streams
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.lqb_det_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def reset(self, stream=-1):
+        _check(self._L.lqb_det_reset(self._h, stream))
+
+    def execute(self, chunks, stream_ids=None):
+        n = len(chunks)
+        arrs = [np.ascontiguousarray(c, dtype=np.complex64) for c in chunks]
+        ptrs = (C.c_void_p * n)(*[a.ctypes.data for a in arrs])
+        lens = (C.c_uint64 * n)(*[len(a) for a in arrs])
+        ids = None if stream_ids is None else (C.c_uint32 * n)(*stream_ids)
+        _check(self._L.lqb_det_execute(self._h, n, ids, ptrs, lens, MEM_HOST))
+
+    def execute_dense_ptr(self, ptr, stride, n_samples, mem):
+        _check(self._L.lqb_det_execute_dense(self._h, C.c_void_p(ptr), stride, n_samples, mem))
+
+    def poll(self):
+        n = C.c_uint32(0)
+        _check(self._L.lqb_det_poll(self._h, None, 0, C.byref(n)))
+        arr = (DetectionResult * max(n.value, 1))()
+        _check(self._L.lqb_det_poll(self._h, C.byref(arr), n.value, C.byref(n)))
+        return [{k: getattr(arr[i], k) for k, _ in DetectionResult._fields_} for i in range(n.value)]
+
+    def timing(self):
+        ms = C.c_float(0)
+        _check(self._L.lqb_det_last_timing(self._h, C.byref(ms)))
+        return float(ms.value)
+
+
+def tab_interp_taps(beta):
+    h = np.zeros(30, np.float32)
+    lib().lqb_tab_interp_taps(beta, h.ctypes.data)
+    return h
+
+
+def tab_pfb_banks(beta):
+    b = np.zeros((32, 28), np.float32)
+    lib().lqb_tab_pfb_banks(beta, b.ctypes.data)
+    return b
+
+
+def tab_detector_template(beta):
+    s = np.zeros(156, np.complex64)
+    lib().lqb_tab_detector_template(beta, s.ctypes.data)
+    return s
+
+
+def tab_nco_sintab():
+    t = np.zeros(1024, np.float32)
+    lib().lqb_tab_nco_sintab(t.ctypes.data)
+    return t
+
+
+def tab_packet_len(n, check, fec0, fec1, ms):
+    a, b = C.c_uint32(0), C.c_uint32(0)
+    _check(lib().lqb_tab_packet_len(n, check, fec0, fec1, ms, C.byref(a), C.byref(b)))
+    return int(a.value), int(b.value)

@@ -1,0 +1,215 @@
+/*
+ * lqb200.h -- C-ABI of the B200-native packet PHY (liblqb200.so).
+ *
+ * This is the drop-in boundary for the one hot path of gvanhoy/gr-liquiddsp:
+ * the liquid-dsp calls made by its three GNU Radio blocks.  Each entry point
+ * below names the reference call site it replaces (paths relative to the
+ * reference repository root):
+ *
+ *   lqb_rx_*   : flexframesync_create / _execute / _destroy and the
+ *                framesync_callback + framesyncstats_s contract
+ *                lib/flex_rx_impl.cc:49 (create), :71 (destroy), :213 (execute),
+ *                :182-201 (callback), lib/flex_rx_impl.h:27-37 (packet_info)
+ *   lqb_tx_*   : flexframegenprops_init_default / flexframegen_create /
+ *                _setprops / _assemble / _getframelen / _write_samples / _destroy
+ *                lib/flex_tx_impl.cc:51-56, :72, :188, :198-201
+ *   lqb_det_*  : msequence_create/advance/destroy, qdetector_cccf_create_linear /
+ *                _set_threshold / _execute / _destroy (and the commented-out getters)
+ *                lib/frame_detector_cc_impl.cc:47-55, :63, :77, :90-93
+ *
+ * Conventions
+ *   - plain C, opaque handles, no exceptions, never exit(): create() returns NULL on
+ *     failure (see lqb_last_error()); every other call returns 0 or a negative LQB_E* code.
+ *   - samples are interleaved complex64 (re, im float pairs) = gr_complex.
+ *   - a handle is single-threaded (GNU Radio's thread-per-block rule); distinct handles
+ *     may be driven from distinct host threads and distinct GPUs.
+ *   - "mem" says where caller buffers live: LQB_MEM_HOST (pageable or pinned host
+ *     memory; the library stages through pinned buffers) or LQB_MEM_DEVICE (device
+ *     pointers on the handle's GPU; zero-copy, work is enqueued on the handle's stream).
+ *   - result buffers returned by *_poll are owned by the handle and stay valid until
+ *     the next *_execute / *_poll / *_destroy on that handle (the lifetime rule the
+ *     reference relies on at lib/flex_rx_impl.cc:192-198).
+ *   - there is no CPU fallback: every compute call fails with LQB_ENODEV when no
+ *     sm_100 device is usable.
+ */
+#ifndef LQB200_H
+#define LQB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LQB_VERSION 100
+
+/* error codes */
+#define LQB_OK        0
+#define LQB_EINVAL   (-22)
+#define LQB_ENOMEM   (-12)
+#define LQB_ENODEV   (-19)
+#define LQB_ECUDA    (-5)
+#define LQB_ERANGE   (-34)
+
+#define LQB_MEM_HOST   0
+#define LQB_MEM_DEVICE 1
+
+/* liquid-dsp wire enums carried in the frame header (only the values the blocks use are named) */
+#define LQB_MODEM_PSK2 1
+#define LQB_MODEM_PSK4 2
+#define LQB_MODEM_PSK8 3
+#define LQB_MODEM_PSK16 4
+#define LQB_MODEM_DPSK2 9
+#define LQB_MODEM_DPSK4 10
+#define LQB_MODEM_DPSK8 11
+#define LQB_MODEM_ASK4 18
+#define LQB_MODEM_QAM16 27
+#define LQB_MODEM_QAM32 28
+#define LQB_MODEM_QAM64 29
+#define LQB_MODEM_QAM128 30
+#define LQB_MODEM_QAM256 31
+#define LQB_MODEM_BPSK 39
+#define LQB_MODEM_QPSK 40
+#define LQB_FEC_NONE 1
+#define LQB_FEC_REP3 2
+#define LQB_FEC_REP5 3
+#define LQB_FEC_HAMMING74 4
+#define LQB_FEC_HAMMING84 5
+#define LQB_FEC_HAMMING128 6
+#define LQB_FEC_GOLAY2412 7
+#define LQB_FEC_SECDED2216 8
+#define LQB_FEC_SECDED3932 9
+#define LQB_FEC_SECDED7264 10
+#define LQB_FEC_CONV_V27 11
+#define LQB_FEC_CONV_V29 12
+#define LQB_FEC_CONV_V27P23 15
+#define LQB_FEC_CONV_V27P34 16
+#define LQB_FEC_CONV_V27P45 17
+#define LQB_FEC_CONV_V27P56 18
+#define LQB_FEC_CONV_V27P67 19
+#define LQB_FEC_CONV_V27P78 20
+#define LQB_FEC_RS_M8 27
+#define LQB_CRC_NONE 1
+#define LQB_CRC_CHECKSUM 2
+#define LQB_CRC_8 3
+#define LQB_CRC_16 4
+#define LQB_CRC_24 5
+#define LQB_CRC_32 6
+
+const char *lqb_last_error(void);          /* thread-local message of the last failure */
+int  lqb_device_count(void);               /* number of usable CUDA devices (0 without a GPU) */
+int  lqb_version(void);
+
+/* ------------------------------------------------------------------ RX (flex_rx / flexframesync) */
+typedef struct lqb_rx_s *lqb_rx;
+
+#define LQB_RX_NO_FRAMESYMS  1u   /* do not copy payload constellation points back to the host */
+#define LQB_RX_DEVICE_RESULTS 2u  /* keep payload bytes on the device too (descriptors only are copied) */
+
+typedef struct {
+    int      device;             /* CUDA device ordinal */
+    uint32_t n_streams;          /* independent channel streams in this batch */
+    uint32_t max_frame_samples;  /* per-stream carry capacity; 0 = 65536. Frames longer than this are dropped */
+    uint32_t flags;              /* LQB_RX_* */
+    void    *cuda_stream;        /* cudaStream_t to enqueue on; NULL = library-owned stream */
+} lqb_rx_opts;
+
+/* mirrors framesync_callback's arguments + framesyncstats_s (lib/flex_rx_impl.cc:182-201),
+ * plus the estimates liquid keeps private (tau, gamma, rxy) and the frame's position */
+typedef struct {
+    uint32_t stream;             /* which channel */
+    uint32_t seq;                /* frame ordinal within that stream since create/reset */
+    int64_t  sample_index;       /* absolute index (per stream) of the first sample of the frame */
+    uint8_t  header[20];         /* 14 user bytes + 6 protocol bytes, as decoded */
+    int32_t  header_valid;
+    int32_t  payload_valid;
+    uint32_t payload_len;
+    const uint8_t *payload;      /* payload_len bytes (NULL when header invalid) */
+    const float   *framesyms;    /* num_framesyms complex points (NULL with LQB_RX_NO_FRAMESYMS / header invalid) */
+    uint32_t num_framesyms;
+    uint32_t mod_scheme, mod_bps, check, fec0, fec1;
+    float    evm;                /* dB */
+    float    rssi;               /* dB */
+    float    cfo;                /* rad/sample */
+    float    tau_hat, gamma_hat, dphi_hat, phi_hat, rxy;
+    uint32_t flags;              /* bit0: frame dropped (longer than max_frame_samples) */
+} lqb_frame_result;
+
+lqb_rx lqb_rx_create(const lqb_rx_opts *opts);
+void   lqb_rx_destroy(lqb_rx h);
+int    lqb_rx_reset(lqb_rx h, int stream /* -1 = all */);
+/* Feed n_samples[i] new samples to stream stream_ids[i] (each stream at most once per call).
+ * iq[i] points at interleaved complex64.  Runs the whole receive chain for every frame that
+ * completes inside the data seen so far; partial frames are carried to the next call. */
+int    lqb_rx_execute(lqb_rx h, uint32_t n, const uint32_t *stream_ids,
+                      const float *const *iq, const uint64_t *n_samples, int mem);
+/* Dense form: all n_streams streams, stream s at iq + 2*s*stride_samples floats, n_samples each */
+int    lqb_rx_execute_dense(lqb_rx h, const float *iq, uint64_t stride_samples, uint64_t n_samples, int mem);
+/* Frames completed by the last execute, ordered by (stream, seq). */
+int    lqb_rx_poll(lqb_rx h, lqb_frame_result *out, uint32_t max_out, uint32_t *n_out);
+/* number of frames completed by the last execute / payloads with a passing check */
+int    lqb_rx_counts(lqb_rx h, uint64_t *frames, uint64_t *valid_payloads);
+/* per-kernel device times (ms) of the last execute, measured with CUDA events on the handle's
+ * stream: [0]=seek/align/header [1]=matched filter [2]=PLL+demod [3]=FEC+CRC [4]=total */
+int    lqb_rx_last_timing(lqb_rx h, float ms[5]);
+int    lqb_rx_launch_count(lqb_rx h, uint64_t *launches);   /* kernels launched since create */
+
+/* ------------------------------------------------------------------ TX (flex_tx / flexframegen) */
+typedef struct lqb_tx_s *lqb_tx;
+typedef struct {
+    int      device;
+    uint32_t flags;
+    void    *cuda_stream;
+} lqb_tx_opts;
+typedef struct { uint32_t check, fec0, fec1, mod_scheme; } lqb_tx_props;   /* flexframegenprops_s */
+
+lqb_tx lqb_tx_create(const lqb_tx_opts *opts);
+void   lqb_tx_destroy(lqb_tx h);
+void   lqb_tx_props_init_default(lqb_tx_props *p);   /* CRC-16, no FEC, QPSK */
+/* samples in a frame: 2*(64 + 231 + payload symbols + 14)   (flexframegen_getframelen) */
+int    lqb_tx_frame_len(const lqb_tx_props *p, uint32_t payload_len, uint32_t *n_samples);
+/* Assemble + write n frames in one launch.  headers[i]: 14 user bytes (NULL = zeros);
+ * payloads[i]: payload_lens[i] bytes; out[i]: room for that frame's samples (complex64). */
+int    lqb_tx_assemble(lqb_tx h, uint32_t n, const lqb_tx_props *props,
+                       const uint8_t *const *headers, const uint8_t *const *payloads,
+                       const uint32_t *payload_lens, float *const *out, int mem);
+
+/* ------------------------------------------------------------------ detector (frame_detector_cc / qdetector_cccf) */
+typedef struct lqb_det_s *lqb_det;
+typedef struct {
+    int      device;
+    uint32_t n_streams;
+    float    beta;        /* 0 = 0.3   (lib/frame_detector_cc_impl.h:36) */
+    float    threshold;   /* 0 = 0.45  (lib/frame_detector_cc_impl.cc:55) */
+    float    dphi_max;    /* 0 = 0.3   (qdetector default range) */
+    void    *cuda_stream;
+} lqb_det_opts;
+typedef struct {
+    uint32_t stream, seq;
+    int64_t  sample_index;
+    float    tau_hat, gamma_hat, dphi_hat, phi_hat, rxy;
+} lqb_detection;
+
+lqb_det lqb_det_create(const lqb_det_opts *opts);
+void    lqb_det_destroy(lqb_det h);
+int     lqb_det_reset(lqb_det h, int stream);
+int     lqb_det_execute(lqb_det h, uint32_t n, const uint32_t *stream_ids,
+                        const float *const *iq, const uint64_t *n_samples, int mem);
+int     lqb_det_execute_dense(lqb_det h, const float *iq, uint64_t stride_samples, uint64_t n_samples, int mem);
+int     lqb_det_poll(lqb_det h, lqb_detection *out, uint32_t max_out, uint32_t *n_out);
+int     lqb_det_last_timing(lqb_det h, float *ms);
+
+/* ------------------------------------------------------------------ host-side tables (no GPU needed) */
+/* exposed so tests can check the product's own filter/table design against the oracle */
+int lqb_tab_interp_taps(float beta, float *h30);
+int lqb_tab_pfb_banks(float beta, float *banks32x28);
+int lqb_tab_detector_template(float beta, float *s156_complex);
+int lqb_tab_nco_sintab(float *tab1024);
+int lqb_tab_packet_len(uint32_t payload_len, uint32_t check, uint32_t fec0, uint32_t fec1,
+                       uint32_t mod_scheme, uint32_t *enc_bytes, uint32_t *n_symbols);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LQB200_H */

@@ -568,10 +568,10 @@ void lqo_flexframesync_execute(lqo_flexframesync q, const lqo_cf *x, unsigned n)
         q->rxy = lqo_qdetector_get_rxy(q->det);
         q->frame_start = idx + 1 - nbuf;        /* may wrap "negative" if the frame began before sample 0 */
         if (q->tau_hat > 0.0f) {
-            q->pfb_index = (unsigned)(q->tau_hat * (float)FF_NPFB) % FF_NPFB;
+            q->pfb_index = (unsigned)(int)(q->tau_hat * (float)FF_NPFB) % FF_NPFB;
             q->mf_counter = 0;
         } else {
-            q->pfb_index = (unsigned)((1.0f + q->tau_hat) * (float)FF_NPFB) % FF_NPFB;
+            q->pfb_index = (unsigned)(int)((1.0f + q->tau_hat) * (float)FF_NPFB) % FF_NPFB;
             q->mf_counter = 1;
         }
         q->mf_scale = 0.5f / q->gamma_hat;

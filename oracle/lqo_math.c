@@ -177,6 +177,7 @@ static lqo_cf *twiddles_(unsigned n)
         w[k].re = (float)cos(a);
         w[k].im = (float)(-sin(a));
     }
+    if (n >= 4) { w[n / 4].re = 0.0f; w[n / 4].im = -1.0f; } /* exact quarter turn (cos(pi/2) is not 0 in double) */
     lqo_cf *expected = NULL;
     if (!__atomic_compare_exchange_n(&cache[lg], &expected, w, 0, __ATOMIC_RELEASE, __ATOMIC_ACQUIRE)) {
         free(w);

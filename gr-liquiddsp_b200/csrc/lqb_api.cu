@@ -241,6 +241,7 @@ struct lqb_rx_s {
 extern "C" {
 
 const char *lqb_last_error(void) { return g_err.c_str(); }
+void lqb_internal_set_error(const char *msg) { g_err = msg ? msg : ""; }
 int lqb_version(void) { return LQB_VERSION; }
 int lqb_device_count(void)
 {

@@ -1,0 +1,543 @@
+// lqb_tx.cu -- batched frame generator (flexframegen) on the GPU and its C-ABI.
+//
+// One CTA assembles one frame: header (CRC-32, whitening, SECDED(72,64), Hamming(8,4),
+// interleaving, QPSK, pilots), payload (CRC, whitening, fec0, interleave, fec1, interleave,
+// bit packing, modulation) and the 2x ARKAISER interpolation -- i.e. what
+// flexframegen_assemble + flexframegen_write_samples do in liquid-dsp.
+// Reference call sites replaced: lib/flex_tx_impl.cc:51-56 (props/create), :188 (setprops),
+// :198-201 (assemble / getframelen / write_samples).
+#include "../../include/lqb200.h"
+#include "lqb_dev.cuh"
+#include "lqb_tables.h"
+
+#include <algorithm>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+extern "C" void lqb_internal_set_error(const char *msg);
+
+namespace lqb {
+
+struct TxTables {
+    float    h[32];            // interpolator taps (30 used)
+    float2   preamble[64];
+    float2   pilots[16];
+    float2   psk_map[8 * 256];
+    uint32_t crc_tab[8][256];
+    uint16_t ilv54[4][28], ilv27[4][16];
+    uint8_t  secded_col[64];
+    uint8_t  gf_exp[512], gf_log[256], rs_gen[64];
+};
+
+struct TxFrame {               // one frame's plan (host-built)
+    unsigned long long pay_off, buf_off, sym_off, out_off;
+    unsigned payload_len, check, fec0, fec1, ms, bps;
+    unsigned k0, n0, n1, n_sym, buf_len, ilv0_off, ilv1_off, n_samples;
+    unsigned char header[16];
+};
+
+namespace {
+
+constexpr int kTxThreads = 256;
+constexpr float kPiF = 3.14159274f;
+constexpr float kTwoPiF = 6.28318548f;
+
+__device__ __forceinline__ unsigned gray_dec(unsigned s) { unsigned r = s; for (unsigned sh = 1; sh < 32; sh <<= 1) r ^= r >> sh; return r; }
+__device__ __forceinline__ unsigned bit_at(const unsigned char *x, long long pos, long long nbits)
+{
+    return (pos >= 0 && pos < nbits) ? ((x[pos >> 3] >> (7 - (pos & 7))) & 1u) : 0u;
+}
+
+__device__ void ilv_forward(unsigned char *x, unsigned n, const unsigned *maps, int tid)
+{
+    const unsigned n2 = n / 2;
+    const unsigned masks[4] = { 0xffu, 0x0fu, 0x55u, 0x33u };
+    for (int pass = 0; pass < 4; ++pass) {
+        const unsigned *map = maps + (size_t)pass * n2;
+        const unsigned mask = masks[pass];
+        for (unsigned i = tid; i < n2; i += kTxThreads) {
+            unsigned j = map[i], a = x[2 * j + 1], b = x[2 * i];
+            x[2 * j + 1] = (unsigned char)((a & ~mask) | (b & mask));
+            x[2 * i] = (unsigned char)((a & mask) | (b & ~mask));
+        }
+        __syncthreads();
+    }
+}
+__device__ void ilv_small(unsigned char *x, const uint16_t *map, unsigned n2, unsigned mask)
+{
+    for (unsigned i = 0; i < n2; ++i) {
+        unsigned j = map[i], a = x[2 * j + 1], b = x[2 * i];
+        x[2 * j + 1] = (unsigned char)((a & ~mask) | (b & mask));
+        x[2 * i] = (unsigned char)((a & mask) | (b & ~mask));
+    }
+}
+
+__device__ unsigned secded_parity(const TxTables *T, const unsigned char *blk, unsigned nb, unsigned nc)
+{
+    unsigned p = 0, all = 0;
+    for (unsigned bit = 0; bit < nb * 8; ++bit)
+        if ((blk[bit >> 3] >> (7 - (bit & 7))) & 1u) { p ^= T->secded_col[bit]; all ^= 1u; }
+    all ^= (unsigned)__popc(p) & 1u;
+    return p | (all << nc);
+}
+
+__constant__ unsigned char c_h84[16] = { 0x00, 0xd2, 0x55, 0x87, 0x99, 0x4b, 0xcc, 0x1e, 0xe1, 0x33, 0xb4, 0x66, 0x78, 0xaa, 0x2d, 0xff };
+__constant__ unsigned c_gP[12] = { 0x8ed, 0x1db, 0x3b5, 0x769, 0xed1, 0xda3, 0xb47, 0x68f, 0xd1d, 0xa3b, 0x477, 0xffe };
+
+__device__ __forceinline__ unsigned golay_encode(unsigned m)
+{
+    unsigned r = 0;
+    for (int i = 0; i < 12; ++i) r |= ((unsigned)__popc(m & c_gP[i]) & 1u) << (11 - i);
+    return (r << 12) | (m & 0xfffu);
+}
+__device__ __forceinline__ unsigned h128_encode(unsigned d)
+{
+    unsigned p = (((unsigned)__popc(d & 0xda) & 1u) << 3) | (((unsigned)__popc(d & 0xb6) & 1u) << 2)
+               | (((unsigned)__popc(d & 0x71) & 1u) << 1) | ((unsigned)__popc(d & 0x0f) & 1u);
+    return (p << 8) | d;
+}
+
+// one FEC stage, src (n bytes) -> dst (enc bytes); whole CTA cooperates
+__device__ void fec_encode(const TxTables *T, unsigned fs, unsigned n, unsigned enc, const unsigned char *src, unsigned char *dst, int tid)
+{
+    switch (fs) {
+    case 1: for (unsigned i = tid; i < n; i += kTxThreads) dst[i] = src[i]; break;
+    case 2: case 3: {
+        const unsigned reps = fs == 2 ? 3u : 5u;
+        for (unsigned i = tid; i < n * reps; i += kTxThreads) dst[i] = src[i % n];
+        break;
+    }
+    case 4:   // Hamming(7,4), bit packed: output bit pos -> codeword pos/7 (two per input byte)
+        for (unsigned o = tid; o < enc; o += kTxThreads) {
+            unsigned v = 0;
+            for (unsigned b = 0; b < 8; ++b) {
+                unsigned pos = 8 * o + b, cw = pos / 7, k = pos % 7, bit = 0;
+                if (cw < 2 * n) {
+                    unsigned nib = (cw & 1u) ? (src[cw >> 1] & 15u) : (src[cw >> 1] >> 4);
+                    bit = ((c_h84[nib] >> 1) >> (6 - k)) & 1u;
+                }
+                v = (v << 1) | bit;
+            }
+            dst[o] = (unsigned char)v;
+        }
+        break;
+    case 5:
+        for (unsigned i = tid; i < n; i += kTxThreads) { dst[2 * i] = c_h84[src[i] >> 4]; dst[2 * i + 1] = c_h84[src[i] & 15u]; }
+        break;
+    case 6:
+        for (unsigned o = tid; o < enc; o += kTxThreads) {
+            unsigned v = 0;
+            for (unsigned b = 0; b < 8; ++b) {
+                unsigned pos = 8 * o + b, cw = pos / 12, k = pos % 12, bit = 0;
+                if (cw < n) bit = (h128_encode(src[cw]) >> (11 - k)) & 1u;
+                v = (v << 1) | bit;
+            }
+            dst[o] = (unsigned char)v;
+        }
+        break;
+    case 7: {
+        const unsigned groups = n / 3, rem = n % 3;
+        for (unsigned g = tid; g < groups; g += kTxThreads) {
+            const unsigned char *s = src + 3 * g;
+            unsigned v0 = golay_encode(((unsigned)s[0] << 4) | (s[1] >> 4)), v1 = golay_encode((((unsigned)s[1] & 15u) << 8) | s[2]);
+            unsigned char *d = dst + 6 * g;
+            d[0] = (unsigned char)(v0 >> 16); d[1] = (unsigned char)(v0 >> 8); d[2] = (unsigned char)v0;
+            d[3] = (unsigned char)(v1 >> 16); d[4] = (unsigned char)(v1 >> 8); d[5] = (unsigned char)v1;
+        }
+        if ((unsigned)tid < rem) {
+            unsigned v = golay_encode(src[3 * groups + tid]);
+            unsigned char *d = dst + 6 * groups + 3 * tid;
+            d[0] = (unsigned char)(v >> 16); d[1] = (unsigned char)(v >> 8); d[2] = (unsigned char)v;
+        }
+        break;
+    }
+    case 8: case 9: case 10: {
+        const unsigned nb = fs == 8 ? 2u : fs == 9 ? 4u : 8u, nc = fs == 8 ? 5u : fs == 9 ? 6u : 7u;
+        const unsigned blocks = (n + nb - 1) / nb;
+        for (unsigned b = tid; b < blocks; b += kTxThreads) {
+            unsigned r = (n - b * nb >= nb) ? nb : (n - b * nb);
+            unsigned char blk[8];
+            for (unsigned q = 0; q < nb; ++q) blk[q] = q < r ? src[b * nb + q] : 0;
+            unsigned char *d = dst + b * (nb + 1);
+            d[0] = (unsigned char)secded_parity(T, blk, nb, nc);
+            for (unsigned q = 0; q < r; ++q) d[1 + q] = blk[q];
+        }
+        break;
+    }
+    case 27: {   // RS(255,223): one warp per block, lane j keeps parity byte j of the LFSR
+        const int warp = tid >> 5, lane = tid & 31;
+        const unsigned blocks = (n + 222) / 223, dec_block = (n + blocks - 1) / blocks, enc_block = dec_block + 32;
+        for (unsigned b = warp; b < blocks; b += kTxThreads / 32) {
+            const unsigned n0 = b * dec_block, take = (n - n0 >= dec_block) ? dec_block : (n - n0);
+            unsigned par = 0;
+            const unsigned g = T->rs_gen[31 - lane];
+            for (unsigned i = 0; i < dec_block; ++i) {
+                const unsigned dbyte = i < take ? src[n0 + i] : 0u;
+                const unsigned fb = dbyte ^ __shfl_sync(0xffffffffu, par, 0);
+                unsigned nxt = __shfl_down_sync(0xffffffffu, par, 1);
+                if (lane == 31) nxt = 0;
+                par = nxt ^ ((fb && g) ? T->gf_exp[T->gf_log[fb] + T->gf_log[g]] : 0u);
+                if (lane == 0) dst[b * enc_block + i] = (unsigned char)dbyte;
+            }
+            dst[b * enc_block + dec_block + lane] = (unsigned char)par;
+        }
+        break;
+    }
+    default: {   // convolutional, thread per output byte
+        unsigned K = 7, P = 1, poly0 = 0x6d, poly1 = 0x4f, keep0 = 1, keep1 = 1;
+        const unsigned k27[6][2] = { { 0x3, 0x1 }, { 0x3, 0x5 }, { 0xf, 0x1 }, { 0xb, 0x15 }, { 0x17, 0x29 }, { 0x2f, 0x51 } };
+        const unsigned k29[6][2] = { { 0x3, 0x1 }, { 0x7, 0x1 }, { 0xd, 0x3 }, { 0xb, 0x15 }, { 0x1b, 0x25 }, { 0x6b, 0x15 } };
+        if (fs == 12 || (fs >= 21 && fs <= 26)) { K = 9; poly0 = 0x1af; poly1 = 0x11d; }
+        if (fs >= 15 && fs <= 20) { P = fs - 13; keep0 = k27[fs - 15][0]; keep1 = k27[fs - 15][1]; }
+        if (fs >= 21 && fs <= 26) { P = fs - 19; keep0 = k29[fs - 21][0]; keep1 = k29[fs - 21][1]; }
+        // (column,row) of the q-th kept bit inside one puncturing period
+        unsigned char kc[16], kr[16];
+        unsigned per = 0;
+        for (unsigned c = 0; c < P; ++c) {
+            if ((keep0 >> c) & 1u) { kc[per] = (unsigned char)c; kr[per] = 0; ++per; }
+            if ((keep1 >> c) & 1u) { kc[per] = (unsigned char)c; kr[per] = 1; ++per; }
+        }
+        const long long nbits = 8ll * n, T_steps = nbits + K - 1;
+        const unsigned long long total = (unsigned long long)(T_steps / P) * per;   // plus a partial period below
+        unsigned long long out_bits = total;
+        for (unsigned c = 0; c < (unsigned)(T_steps % P); ++c) out_bits += ((keep0 >> c) & 1u) + ((keep1 >> c) & 1u);
+        for (unsigned o = tid; o < enc; o += kTxThreads) {
+            unsigned v = 0;
+            for (unsigned b = 0; b < 8; ++b) {
+                const unsigned long long m = 8ull * o + b;
+                unsigned bit = 0;
+                if (m < out_bits) {
+                    const unsigned long long q = m / per;
+                    const unsigned w = (unsigned)(m % per);
+                    const long long t = (long long)(q * P + kc[w]);
+                    unsigned sr = 0;
+                    for (unsigned k = 0; k < K; ++k) sr |= bit_at(src, t - k, nbits) << k;
+                    bit = (unsigned)__popc(sr & (kr[w] ? poly1 : poly0)) & 1u;
+                }
+                v = (v << 1) | bit;
+            }
+            dst[o] = (unsigned char)v;
+        }
+        break;
+    }
+    }
+    __syncthreads();
+}
+
+__device__ float2 modulate(const TxTables *T, unsigned ms, unsigned bps, unsigned s)
+{
+    const unsigned M = 1u << bps;
+    if (ms >= 1 && ms <= 8) return T->psk_map[(bps - 1) * 256 + s];
+    if (ms >= 17 && ms <= 24) {
+        const float c[9] = { 0, 1.0f, 5.0f, 21.0f, 85.0f, 341.0f, 1365.0f, 5461.0f, 21845.0f };
+        const float alpha = __fdiv_rn(1.0f, __fsqrt_rn(c[bps]));
+        return make_float2(__fmul_rn((float)(2 * (int)gray_dec(s) - (int)M + 1), alpha), 0.0f);
+    }
+    if (ms >= 25 && ms <= 31) {
+        const float c[9] = { 0, 0, 2.0f, 6.0f, 10.0f, 26.0f, 42.0f, 106.0f, 170.0f };
+        const float alpha = __fdiv_rn(1.0f, __fsqrt_rn(c[bps]));
+        const unsigned m_i = (bps + 1) >> 1, m_q = bps >> 1;
+        const unsigned si = gray_dec(s >> m_q), sq = gray_dec(s & ((1u << m_q) - 1u));
+        return make_float2(__fmul_rn((float)(2 * (int)si - (int)(1u << m_i) + 1), alpha),
+                           __fmul_rn((float)(2 * (int)sq - (int)(1u << m_q) + 1), alpha));
+    }
+    if (ms == 39) return make_float2(s ? -1.0f : 1.0f, 0.0f);
+    return make_float2((s & 1u) ? -0.707106769f : 0.707106769f, (s & 2u) ? -0.707106769f : 0.707106769f);
+}
+
+__global__ void __launch_bounds__(kTxThreads)
+k_tx(const TxTables *T, const TxFrame *frames, const unsigned char *payloads, unsigned char *bufA, unsigned char *bufB,
+     const unsigned *ilv, float2 *syms, float2 *out)
+{
+    __shared__ float2 hsym[232];
+    __shared__ unsigned char hb[64];
+    const int tid = threadIdx.x;
+    const TxFrame &f = frames[blockIdx.x];
+    unsigned char *A = bufA + f.buf_off, *B = bufB + f.buf_off;
+    float2 *psym = syms + f.sym_off;
+
+    // ---------------- header (thread 0; 20 bytes)
+    if (tid == 0) {
+        unsigned char d[28], e27[28];
+        for (int i = 0; i < 14; ++i) d[i] = f.header[i];
+        d[14] = 102; d[15] = (unsigned char)(f.payload_len >> 8); d[16] = (unsigned char)f.payload_len;
+        d[17] = (unsigned char)f.ms; d[18] = (unsigned char)(((f.check & 7u) << 5) | (f.fec0 & 0x1fu)); d[19] = (unsigned char)(f.fec1 & 0x1fu);
+        unsigned key = 0xffffffffu;
+        for (int i = 0; i < 20; ++i) key = (key >> 8) ^ T->crc_tab[6][(key ^ d[i]) & 0xffu];
+        key = ~key;
+        d[20] = (unsigned char)(key >> 24); d[21] = (unsigned char)(key >> 16); d[22] = (unsigned char)(key >> 8); d[23] = (unsigned char)key;
+        const unsigned char mask[4] = { 0xb4, 0x6a, 0x8b, 0xc5 };
+        for (int i = 0; i < 24; ++i) d[i] ^= mask[i & 3];
+        for (int b = 0; b < 3; ++b) {
+            e27[9 * b] = (unsigned char)secded_parity(T, d + 8 * b, 8, 7);
+            for (int q = 0; q < 8; ++q) e27[9 * b + 1 + q] = d[8 * b + q];
+        }
+        ilv_small(e27, T->ilv27[0], 13, 0xff); ilv_small(e27, T->ilv27[1], 13, 0x0f);
+        ilv_small(e27, T->ilv27[2], 13, 0x55); ilv_small(e27, T->ilv27[3], 13, 0x33);
+        for (int i = 0; i < 27; ++i) { hb[2 * i] = c_h84[e27[i] >> 4]; hb[2 * i + 1] = c_h84[e27[i] & 15u]; }
+        ilv_small(hb, T->ilv54[0], 27, 0xff); ilv_small(hb, T->ilv54[1], 27, 0x0f);
+        ilv_small(hb, T->ilv54[2], 27, 0x55); ilv_small(hb, T->ilv54[3], 27, 0x33);
+    }
+    __syncthreads();
+    for (int i = tid; i < 231; i += kTxThreads) {
+        if ((i & 15) == 0) hsym[i] = T->pilots[i >> 4];
+        else {
+            int n = i - (i >> 4) - 1;                     // data symbol ordinal
+            unsigned s = (hb[n >> 2] >> (6 - 2 * (n & 3))) & 3u;
+            hsym[i] = make_float2((s & 1u) ? -0.707106769f : 0.707106769f, (s & 2u) ? -0.707106769f : 0.707106769f);
+        }
+    }
+
+    // ---------------- payload bytes: CRC, whitening
+    const unsigned plen = f.payload_len, cl = f.k0 - plen;
+    const unsigned char *pay = payloads + f.pay_off;
+    for (unsigned i = tid; i < plen; i += kTxThreads) A[i] = pay[i];
+    __syncthreads();
+    if (tid == 0) {
+        unsigned key = 0;
+        if (f.check == 2) {
+            unsigned sum = 0;
+            for (unsigned i = 0; i < plen; ++i) sum += A[i];
+            key = (~sum + 1u) & 0xffu;
+        } else if (f.check >= 3 && f.check <= 6) {
+            const unsigned *tab = T->crc_tab[f.check];
+            unsigned k = 0xffffffffu;
+            for (unsigned i = 0; i < plen; ++i) k = (k >> 8) ^ tab[(k ^ A[i]) & 0xffu];
+            const unsigned bits = f.check == 3 ? 8u : f.check == 4 ? 16u : f.check == 5 ? 24u : 32u;
+            key = (~k) & (bits == 32 ? 0xffffffffu : ((1u << bits) - 1u));
+        }
+        for (unsigned i = 0; i < cl; ++i) { A[plen + cl - i - 1] = (unsigned char)(key & 0xffu); key >>= 8; }
+    }
+    __syncthreads();
+    for (unsigned i = tid; i < f.k0; i += kTxThreads) {
+        unsigned mask = (i & 3u) == 0 ? 0xb4u : (i & 3u) == 1 ? 0x6au : (i & 3u) == 2 ? 0x8bu : 0xc5u;
+        A[i] ^= (unsigned char)mask;
+    }
+    __syncthreads();
+    // ---------------- fec0 / interleave / fec1 / interleave
+    fec_encode(T, f.fec0, f.k0, f.n0, A, B, tid);
+    if (f.fec0 != 1) ilv_forward(B, f.n0, ilv + f.ilv0_off, tid);
+    fec_encode(T, f.fec1, f.n0, f.n1, B, A, tid);
+    if (f.fec1 != 1) ilv_forward(A, f.n1, ilv + f.ilv1_off, tid);
+
+    // ---------------- bits -> symbols
+    const unsigned bps = f.bps, nbits = 8 * f.n1;
+    if (f.ms >= 9 && f.ms <= 16) {          // DPSK carries phase memory: serial
+        if (tid == 0) {
+            const float alpha = __fdiv_rn(kPiF, (float)(1u << bps));
+            float phi = 0.0f;
+            for (unsigned i = 0; i < f.n_sym; ++i) {
+                unsigned s = 0;
+                for (unsigned b = 0; b < bps; ++b) s = (s << 1) | bit_at(A, (long long)i * bps + b, nbits);
+                phi = __fadd_rn(phi, __fmul_rn(__fmul_rn((float)gray_dec(s), 2.0f), alpha));
+                if (phi > kTwoPiF) phi = __fsub_rn(phi, kTwoPiF);
+                float sn, cs;
+                sincosf(phi, &sn, &cs);
+                psym[i] = make_float2(cs, sn);
+            }
+        }
+    } else {
+        for (unsigned i = tid; i < f.n_sym; i += kTxThreads) {
+            unsigned s = 0;
+            for (unsigned b = 0; b < bps; ++b) s = (s << 1) | bit_at(A, (long long)i * bps + b, nbits);
+            psym[i] = modulate(T, f.ms, bps, s);
+        }
+    }
+    __syncthreads();
+
+    // ---------------- 2x interpolation: out[2t+ph] = sum_n h[ph + 2n] sym[t-n], oldest symbol first
+    const int total_syms = 64 + 231 + (int)f.n_sym + 14;
+    float2 *o = out + f.out_off;
+    for (int m = tid; m < 2 * total_syms; m += kTxThreads) {
+        const int t = m >> 1, ph = m & 1;
+        float ar = 0.0f, ai = 0.0f;
+#pragma unroll
+        for (int n = 14; n >= 0; --n) {
+            const int u = t - n;
+            float2 s = make_float2(0.0f, 0.0f);
+            if (u >= 0) {
+                if (u < 64) s = T->preamble[u];
+                else if (u < 295) s = hsym[u - 64];
+                else if (u < 295 + (int)f.n_sym) s = psym[u - 295];
+            }
+            const float c = T->h[ph + 2 * n];
+            ar = __fmaf_rn(c, s.x, ar); ai = __fmaf_rn(c, s.y, ai);
+        }
+        o[m] = make_float2(ar, ai);
+    }
+}
+
+int tx_fail(int code, const char *msg) { lqb_internal_set_error(msg); return code; }
+
+}  // namespace
+}  // namespace lqb
+
+using namespace lqb;
+
+struct lqb_tx_s {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    TxTables *d_tables = nullptr;
+    TxFrame *d_frames = nullptr; size_t frames_cap = 0;
+    unsigned char *d_pay = nullptr, *d_A = nullptr, *d_B = nullptr; size_t pay_cap = 0, buf_cap = 0, bufB_cap = 0;
+    float2 *d_syms = nullptr, *d_out = nullptr; size_t sym_cap = 0, out_cap = 0;
+    unsigned *d_ilv = nullptr; size_t ilv_cap = 0, ilv_used = 0;
+    std::unordered_map<unsigned, size_t> ilv_cache;
+    std::vector<unsigned> ilv_host;
+    uint64_t launches = 0;
+};
+
+namespace {
+template <typename T> int grow(T *&p, size_t &cap, size_t need)
+{
+    if (need <= cap) return 0;
+    size_t ncap = std::max(need, cap + cap / 2);
+    T *q = nullptr;
+    if (cudaMalloc(&q, ncap * sizeof(T)) != cudaSuccess) return LQB_ENOMEM;
+    if (p) cudaFree(p);
+    p = q; cap = ncap;
+    return 0;
+}
+}  // namespace
+
+extern "C" {
+
+void lqb_tx_props_init_default(lqb_tx_props *p)
+{
+    if (!p) return;
+    p->check = CRC_16; p->fec0 = FEC_NONE; p->fec1 = FEC_NONE; p->mod_scheme = MODEM_QPSK;
+}
+
+int lqb_tx_frame_len(const lqb_tx_props *p, uint32_t payload_len, uint32_t *n_samples)
+{
+    if (!p || !n_samples) return LQB_EINVAL;
+    if (!modem_supported(p->mod_scheme) || !fec_supported(p->fec0) || !fec_supported(p->fec1) || p->check == 0 || p->check >= CRC_NUM || payload_len > 65535)
+        return LQB_EINVAL;
+    *n_samples = 2 * (64 + 231 + qpm_frame_len(payload_len, p->check, p->fec0, p->fec1, p->mod_scheme) + 14);
+    return 0;
+}
+
+lqb_tx lqb_tx_create(const lqb_tx_opts *o)
+{
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { cudaGetLastError(); tx_fail(LQB_ENODEV, "no CUDA device available (no CPU fallback exists)"); return nullptr; }
+    int dev = o ? o->device : 0;
+    if (dev < 0 || dev >= ndev) { tx_fail(LQB_ENODEV, "device ordinal out of range"); return nullptr; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess || prop.major < 10) { tx_fail(LQB_ENODEV, "device is not sm_100 class"); return nullptr; }
+    lqb_tx h = new lqb_tx_s;
+    h->device = dev;
+    cudaSetDevice(dev);
+    if (o && o->cuda_stream) h->stream = (cudaStream_t)o->cuda_stream;
+    else { cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking); h->own_stream = true; }
+    TxTables *T = new TxTables;
+    std::memset(T, 0, sizeof *T);
+    auto taps = interp_taps(kTxBeta);
+    std::memcpy(T->h, taps.data(), 30 * sizeof(float));
+    cf pn[64], pil[15];
+    preamble_pn(pn); header_pilots(pil);
+    for (int i = 0; i < 64; ++i) T->preamble[i] = make_float2(pn[i].re, pn[i].im);
+    for (int i = 0; i < 15; ++i) T->pilots[i] = make_float2(pil[i].re, pil[i].im);
+    auto maps = psk_maps();
+    std::memcpy(T->psk_map, maps.data(), sizeof T->psk_map);
+    for (unsigned c = 3; c <= 6; ++c) crc_table(c, T->crc_tab[c]);
+    auto m54 = ilv_maps(54), m27 = ilv_maps(27);
+    for (unsigned p = 0; p < 4; ++p) {
+        for (unsigned i = 0; i < 27; ++i) T->ilv54[p][i] = (uint16_t)m54[p * 27 + i];
+        for (unsigned i = 0; i < 13; ++i) T->ilv27[p][i] = (uint16_t)m27[p * 13 + i];
+    }
+    secded_cols(T->secded_col);
+    uint8_t gen[33];
+    gf256_tables(T->gf_exp, T->gf_log, gen);
+    std::memcpy(T->rs_gen, gen, 33);
+    cudaError_t e = cudaMalloc(&h->d_tables, sizeof(TxTables));
+    if (e == cudaSuccess) e = cudaMemcpy(h->d_tables, T, sizeof(TxTables), cudaMemcpyHostToDevice);
+    delete T;
+    if (e != cudaSuccess) { tx_fail(LQB_ECUDA, cudaGetErrorString(e)); lqb_tx_destroy(h); return nullptr; }
+    return h;
+}
+
+void lqb_tx_destroy(lqb_tx h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    cudaFree(h->d_tables); cudaFree(h->d_frames); cudaFree(h->d_pay); cudaFree(h->d_A); cudaFree(h->d_B);
+    cudaFree(h->d_syms); cudaFree(h->d_out); cudaFree(h->d_ilv);
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int lqb_tx_assemble(lqb_tx h, uint32_t n, const lqb_tx_props *props, const uint8_t *const *headers,
+                    const uint8_t *const *payloads, const uint32_t *lens, float *const *out, int mem)
+{
+    if (!h || !props || !payloads || !lens || !out) return LQB_EINVAL;
+    if (!n) return 0;
+    if (cudaSetDevice(h->device) != cudaSuccess) return LQB_ECUDA;
+    cudaStream_t st = h->stream;
+    std::vector<TxFrame> fr(n);
+    size_t pay_tot = 0, buf_tot = 0, sym_tot = 0, out_tot = 0;
+    bool new_maps = false;
+    for (uint32_t i = 0; i < n; ++i) {
+        const lqb_tx_props &p = props[i];
+        uint32_t ns = 0;
+        if (int e = lqb_tx_frame_len(&p, lens[i], &ns)) return tx_fail(e, "unsupported props or payload length");
+        if (lens[i] && !payloads[i]) return tx_fail(LQB_EINVAL, "null payload");
+        TxFrame &f = fr[i];
+        std::memset(&f, 0, sizeof f);
+        f.payload_len = lens[i]; f.check = p.check; f.fec0 = p.fec0; f.fec1 = p.fec1; f.ms = p.mod_scheme; f.bps = modem_bps(p.mod_scheme);
+        f.k0 = lens[i] + crc_len(p.check); f.n0 = fec_enc_len(p.fec0, f.k0); f.n1 = fec_enc_len(p.fec1, f.n0);
+        f.n_sym = (8 * f.n1 + f.bps - 1) / f.bps; f.n_samples = ns;
+        f.buf_len = ((std::max(std::max(f.n1, f.n0), f.k0) + 16) + 15u) & ~15u;
+        f.pay_off = pay_tot; pay_tot += (lens[i] + 15u) & ~15u;
+        f.buf_off = buf_tot; buf_tot += f.buf_len;
+        f.sym_off = sym_tot; sym_tot += f.n_sym;
+        f.out_off = out_tot; out_tot += ns;
+        if (headers && headers[i]) std::memcpy(f.header, headers[i], 14);
+        const unsigned encs[2] = { f.n0, f.n1 }, fss[2] = { f.fec0, f.fec1 };
+        for (int s = 0; s < 2; ++s) {
+            if (fss[s] == FEC_NONE) continue;
+            auto it = h->ilv_cache.find(encs[s]);
+            size_t off;
+            if (it == h->ilv_cache.end()) {
+                auto maps = ilv_maps(encs[s]);
+                off = h->ilv_host.size();
+                h->ilv_host.insert(h->ilv_host.end(), maps.begin(), maps.end());
+                h->ilv_cache.emplace(encs[s], off);
+                new_maps = true;
+            } else off = it->second;
+            (s ? f.ilv1_off : f.ilv0_off) = (unsigned)off;
+        }
+    }
+    if (grow(h->d_frames, h->frames_cap, n) || grow(h->d_pay, h->pay_cap, pay_tot + 16) || grow(h->d_A, h->buf_cap, buf_tot + 16)) return tx_fail(LQB_ENOMEM, "cudaMalloc failed");
+    if (grow(h->d_B, h->bufB_cap, buf_tot + 16)) return tx_fail(LQB_ENOMEM, "cudaMalloc failed");
+    if (grow(h->d_syms, h->sym_cap, sym_tot + 1)) return tx_fail(LQB_ENOMEM, "cudaMalloc failed");
+    if (new_maps || !h->d_ilv) {
+        if (grow(h->d_ilv, h->ilv_cap, h->ilv_host.size() + 4)) return tx_fail(LQB_ENOMEM, "cudaMalloc failed");
+        if (!h->ilv_host.empty()) cudaMemcpyAsync(h->d_ilv, h->ilv_host.data(), h->ilv_host.size() * sizeof(unsigned), cudaMemcpyHostToDevice, st);
+    }
+    // outputs: write straight into caller memory when it is device memory and frames are contiguous there
+    bool direct = (mem == LQB_MEM_DEVICE);
+    if (direct) for (uint32_t i = 1; i < n; ++i) if (out[i] != out[i - 1] + 2 * (size_t)fr[i - 1].n_samples) { direct = false; break; }
+    float2 *d_out = nullptr;
+    if (direct) d_out = reinterpret_cast<float2 *>(out[0]);
+    else { if (grow(h->d_out, h->out_cap, out_tot + 1)) return tx_fail(LQB_ENOMEM, "cudaMalloc failed"); d_out = h->d_out; }
+    for (uint32_t i = 0; i < n; ++i)
+        if (lens[i]) cudaMemcpyAsync(h->d_pay + fr[i].pay_off, payloads[i], lens[i], mem == LQB_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(h->d_frames, fr.data(), n * sizeof(TxFrame), cudaMemcpyHostToDevice, st);
+    k_tx<<<n, kTxThreads, 0, st>>>(h->d_tables, h->d_frames, h->d_pay, h->d_A, h->d_B, h->d_ilv, h->d_syms, d_out);
+    h->launches++;
+    if (!direct)
+        for (uint32_t i = 0; i < n; ++i)
+            cudaMemcpyAsync(out[i], d_out + fr[i].out_off, (size_t)fr[i].n_samples * sizeof(float2),
+                            mem == LQB_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) return tx_fail(LQB_ECUDA, cudaGetErrorString(e));
+    return 0;
+}
+
+}  // extern "C"

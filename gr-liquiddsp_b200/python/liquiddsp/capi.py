@@ -271,3 +271,55 @@ def tab_packet_len(n, check, fec0, fec1, ms):
     a, b = C.c_uint32(0), C.c_uint32(0)
     _check(lib().lqb_tab_packet_len(n, check, fec0, fec1, ms, C.byref(a), C.byref(b)))
     return int(a.value), int(b.value)
+
+
+class Tx:
+    """Batch flexframegen: assemble + write many frames per launch."""
+
+    def __init__(self, device=0, cuda_stream=None):
+        o = TxOpts(device, 0, cuda_stream)
+        self._L = lib()
+        self._h = self._L.lqb_tx_create(C.byref(o))
+        if not self._h:
+            raise LqbError("lqb_tx_create failed: " + self._L.lqb_last_error().decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.lqb_tx_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    @staticmethod
+    def frame_len(mod_scheme, check, fec0, fec1, payload_len):
+        p = TxProps(check, fec0, fec1, mod_scheme)
+        n = C.c_uint32(0)
+        _check(lib().lqb_tx_frame_len(C.byref(p), payload_len, C.byref(n)))
+        return int(n.value)
+
+    def assemble(self, props, payloads, headers=None):
+        """props: list of (mod_scheme, check, fec0, fec1); payloads: list of uint8 arrays.
+        Returns a list of complex64 arrays (host)."""
+        n = len(payloads)
+        P = (TxProps * n)(*[TxProps(c, f0, f1, ms) for (ms, c, f0, f1) in props])
+        pls = [np.ascontiguousarray(p, dtype=np.uint8) for p in payloads]
+        lens = (C.c_uint32 * n)(*[len(p) for p in pls])
+        pp = (C.c_void_p * n)(*[p.ctypes.data if len(p) else None for p in pls])
+        hp = None
+        if headers is not None:
+            hs = [np.ascontiguousarray(h, dtype=np.uint8) for h in headers]
+            hp = (C.c_void_p * n)(*[h.ctypes.data for h in hs])
+        outs = [np.zeros(self.frame_len(ms, c, f0, f1, len(p)), np.complex64) for (ms, c, f0, f1), p in zip(props, pls)]
+        op = (C.c_void_p * n)(*[o.ctypes.data for o in outs])
+        _check(self._L.lqb_tx_assemble(self._h, n, P, hp, pp, lens, op, MEM_HOST))
+        return outs
+
+    def assemble_device(self, props, payload_ptrs, payload_lens, out_ptrs, header_ptrs=None):
+        """Device-resident variant: raw device pointers in, frames written to out_ptrs."""
+        n = len(payload_ptrs)
+        P = (TxProps * n)(*[TxProps(c, f0, f1, ms) for (ms, c, f0, f1) in props])
+        lens = (C.c_uint32 * n)(*payload_lens)
+        pp = (C.c_void_p * n)(*payload_ptrs)
+        op = (C.c_void_p * n)(*out_ptrs)
+        hp = None if header_ptrs is None else (C.c_void_p * n)(*header_ptrs)
+        _check(self._L.lqb_tx_assemble(self._h, n, P, hp, pp, lens, op, MEM_DEVICE))

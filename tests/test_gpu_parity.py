@@ -37,7 +37,13 @@ def assert_frames_match(ref, got, syms=True):
         for k in keys:
             assert close(g[k], r[k]), (k, r[k], g[k])
         if syms and r["header_valid"]:
-            assert np.allclose(g["framesyms"], r["framesyms"], rtol=RTOL, atol=1e-4)
+            # constellation points: equal to float rounding, except that a last-bit difference in the
+            # PLL phase (device vs libm sincos/atan2 inside the DPSK loop) can move a symbol across one
+            # step of the 1024-entry NCO table (2 pi / 1024 rad) -- allowed for at most 1 % of symbols
+            err = np.abs(g["framesyms"] - r["framesyms"])
+            mag = np.abs(r["framesyms"])
+            assert np.mean(err > 1e-4 + RTOL * mag) <= 0.01
+            assert np.all(err <= 1e-4 + 0.0075 * mag)
 
 
 def test_fft512_warp_kernel_is_bit_exact_with_the_oracle_fft():

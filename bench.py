@@ -1,0 +1,400 @@
+#!/usr/bin/env python
+"""bench.py -- flex_rx throughput on synthetic multi-channel IQ (BASELINE.json metric).
+
+Workload (config.workload = "flex_rx_1024ch_qpsk_v27_rs8_1500B", BASELINE.json configs[2], the
+configuration the metric "flex_rx Msps & decoded frames/s" is quoted on and the largest that is
+a single-GPU flex_rx case): per GPU 1024 independent channel streams x 1,048,576 samples per
+step; PSK4 + inner v27 + outer RS(255,223), 1500-byte payloads, CRC-24; ~85 % duty; per-stream
+SNR sweep -2..+12 dB in 1 dB steps, CFO U(+-0.02) rad/sample, timing offset U(+-0.5) sample,
+gain U(0.5,1.5).  A step = one pass of the whole receive path over that batch.
+
+  value  : complex input samples consumed per second (Msps), whole job, inputs resident in HBM
+  e2e    : same metric through the reference-facing C-ABI call with HOST buffers (pinned input
+           copied H2D inside the timed region, frame results + payload bytes + constellation
+           points copied D2H inside the timed region)
+  --impl reference : the CPU restatement of liquid-dsp's flexframesync (oracle/) on the host cores
+
+Multi-GPU: channels shard across ranks (weak scaling, 1024 channels per GPU), no data-path
+collective; torch.distributed is used only for the barrier and the max-over-ranks time.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "gr-liquiddsp_b200", "python"))
+
+PSK4, CRC24, V27, RS8 = 2, 5, 11, 27
+PAYLOAD = 1500
+N_DISTINCT = 64
+N_TAU = 8
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--streams", type=int, default=1024, help="channels per GPU")
+    ap.add_argument("--samples", type=int, default=1 << 20, help="samples per channel per step")
+    ap.add_argument("--e2e-samples", type=int, default=1 << 18, help="samples per channel per e2e step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------- synthetic capture
+def clean_frames_ours(torch, dev, seed):
+    """64 distinct cfg-3 frames from the product's GPU frame generator; returns (frames[64, L], payloads)."""
+    from liquiddsp import capi
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    payloads = torch.randint(0, 256, (N_DISTINCT, PAYLOAD), dtype=torch.uint8, generator=g)
+    L = capi.Tx.frame_len(PSK4, CRC24, V27, RS8, PAYLOAD)
+    tx = capi.Tx(device=dev.index, cuda_stream=torch.cuda.current_stream(dev).cuda_stream)
+    d_pay = payloads.to(dev)
+    frames = torch.zeros((N_DISTINCT, L), dtype=torch.complex64, device=dev)
+    tx.assemble_device([(PSK4, CRC24, V27, RS8)] * N_DISTINCT,
+                       [d_pay[i].data_ptr() for i in range(N_DISTINCT)], [PAYLOAD] * N_DISTINCT,
+                       [frames[i].data_ptr() for i in range(N_DISTINCT)])
+    torch.cuda.synchronize(dev)
+    tx.close()
+    return frames, payloads
+
+
+def clean_frames_oracle(torch, seed):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import lqo_py as o
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    payloads = torch.randint(0, 256, (N_DISTINCT, PAYLOAD), dtype=torch.uint8, generator=g)
+    fr = [torch.from_numpy(o.tx_frame(PSK4, CRC24, V27, RS8, payloads[i].numpy())) for i in range(N_DISTINCT)]
+    return torch.stack(fr), payloads
+
+
+def make_capture(torch, frames, S, N, seed, dev, stream_offset=0):
+    """[S, N] complex64 capture on `dev`: frames at a per-stream period, delayed, rotated, scaled, noisy."""
+    L = frames.shape[1]
+    Lp = L + 64
+    # fractional delays: N_TAU classes, applied to every distinct frame in the frequency domain
+    pad = torch.zeros((N_DISTINCT, Lp), dtype=torch.complex64, device=dev)
+    pad[:, 16:16 + L] = frames.to(dev)
+    F = torch.fft.fft(pad, dim=1)
+    f = torch.fft.fftfreq(Lp, device=dev)
+    taus = torch.linspace(-0.5, 0.5, N_TAU, device=dev)
+    variants = torch.fft.ifft(F[None, :, :] * torch.exp(-2j * torch.pi * f[None, None, :] * taus[:, None, None]), dim=2)
+    variants = variants.to(torch.complex64).reshape(-1)            # [N_TAU * N_DISTINCT * Lp]
+    g = torch.Generator(device=dev).manual_seed(seed + 1000 * stream_offset + 17)
+    out = torch.empty((S, N), dtype=torch.complex64, device=dev)
+    sent = 0
+    CH = 32
+    n = torch.arange(N, device=dev, dtype=torch.int64)[None, :]
+    for s0 in range(0, S, CH):
+        s1 = min(S, s0 + CH)
+        sid = torch.arange(s0, s1, device=dev, dtype=torch.int64) + stream_offset
+        gap = 3000 + (sid * 7919) % 4000                            # 3000..6999, mean ~5000 -> ~85 % duty
+        period = Lp + gap
+        lead = (sid * 104729) % period
+        nfr = (N - lead) // period                                  # whole frames only; the tail is noise
+        k = (n - lead[:, None]) // period[:, None]
+        off = (n - lead[:, None]) - k * period[:, None]
+        inside = (n >= lead[:, None]) & (off < Lp) & (k < nfr[:, None])
+        tau_c = (sid % N_TAU)[:, None]
+        which = ((sid[:, None] * 31 + k * 7) % N_DISTINCT)
+        idx = ((tau_c * N_DISTINCT + which) * Lp + off).clamp_(0, variants.numel() - 1)
+        x = torch.where(inside, variants[idx], torch.zeros((), dtype=torch.complex64, device=dev))
+        del k, off, idx, inside
+        cfo = (((sid * 2654435761) % 10007).double() / 10007.0 - 0.5) * 0.04          # U(-0.02, 0.02)
+        gain = 0.5 + ((sid * 40503) % 1009).double() / 1009.0
+        snr_db = -2.0 + (sid % 15).double()
+        ph = torch.remainder(cfo[:, None] * n.double(), 2.0 * torch.pi).float()
+        x = x * torch.polar(gain.float()[:, None].expand_as(ph).contiguous(), ph)
+        nstd = (gain * torch.pow(10.0, -snr_db / 20.0)).float()[:, None] / (2.0 ** 0.5)
+        noise = torch.view_as_complex(torch.randn((s1 - s0, N, 2), generator=g, device=dev, dtype=torch.float32))
+        out[s0:s1] = x + nstd * noise
+        sent += int(nfr.sum().item())
+        del x, ph, noise
+    return out, sent
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            p = [q.strip() for q in ln.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1])); mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- CPU legs (oracle = the checker, never shipped)
+def cpu_rx(capture_host, threads):
+    """Times the oracle flexframesync (oracle/) over [S, N] on `threads` host threads."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import lqo_py as o
+    o.lib()
+    t0 = time.perf_counter()
+    frames, valid = o.rx_many(capture_host, threads)
+    dt = time.perf_counter() - t0
+    return dt, frames, valid
+
+
+def reference_arm(args, rank, world):
+    """--impl reference: liquid-dsp's algorithm (the oracle port) on all host cores, same workload."""
+    if rank != 0:
+        return
+    import torch
+    cores = os.cpu_count() or 1
+    frames, _ = clean_frames_oracle(torch, 1)
+    S = min(args.streams, 4 * cores)
+    N = min(args.samples, 1 << 18)
+    cap, sent = make_capture(torch, frames, S, N, 1, torch.device("cpu"))
+    x = cap.numpy()
+    times, fr, va = [], 0, 0
+    for i in range(args.warmup + args.steps):
+        dt, f, v = cpu_rx(x, cores)
+        if i >= args.warmup:
+            times.append(dt); fr += f; va += v
+    T = sum(times)
+    msps = args.steps * S * N / T / 1e6
+    sample = "%d streams x %d samples per step on %d threads (oracle/ port of liquid-dsp flexframesync, own radix-2 FFT)" % (S, N, cores)
+    print(json.dumps({
+        "impl": "reference", "metric": "flex_rx_msps", "value": msps, "unit": "Msps", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * T / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "flex_rx_1024ch_qpsk_v27_rs8_1500B", "streams_per_gpu": args.streams,
+                   "samples_per_stream_per_step": args.samples, "payload_bytes": PAYLOAD, "mod": "PSK4", "fec0": "v27", "fec1": "rs8"},
+        "decoded_frames_per_s": va / T, "frames_per_s": fr / T,
+        "cpu_baseline": {"value": msps, "unit": "Msps", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": msps, "unit": "Msps", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ----------------------------------------------------------------------------- our arm
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world == 1 and args.gpus > 1:
+        # convenience: relaunch under torchrun, one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from liquiddsp import capi
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    S, N = args.streams, args.samples
+    frames, payloads = clean_frames_ours(torch, dev, 1)
+    cap, sent = make_capture(torch, frames, S, N, 1, dev, stream_offset=rank * S)
+    torch.cuda.synchronize(dev)
+    cs = torch.cuda.current_stream(dev)
+    rx = capi.Rx(S, device=local, max_frame_samples=65536, flags=capi.RX_NO_FRAMESYMS, cuda_stream=cs.cuda_stream)
+
+    def step():
+        rx.execute_dense_ptr(cap.data_ptr(), N, N, capi.MEM_DEVICE)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    clocks = ClockSampler(local)
+    clocks.start()
+    l0 = rx.launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kt = [0.0] * 5
+    work = dict(windows=0, aligns=0, symbols=0, samples=0)
+    fr_tot = va_tot = 0
+    torch.cuda.synchronize(dev)
+    e0.record(cs)
+    for _ in range(args.steps):
+        step()
+        t = rx.timing()
+        kt = [a + b for a, b in zip(kt, t)]
+        w = rx.work()
+        for k in work:
+            work[k] += w[k]
+        f, v = rx.counts()
+        fr_tot += f; va_tot += v
+    e1.record(cs)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    clk = clocks.stop()
+    launches = rx.launches() - l0
+    tt = torch.tensor([ms, float(fr_tot), float(va_tot), float(launches), float(sent)], dtype=torch.float64, device=dev)
+    if world > 1:
+        mx = tt.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = tt.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        ms = float(mx[0]); fr_all, va_all, launches_all, sent_all = float(sm[1]), float(sm[2]), float(sm[3]), float(sm[4])
+    else:
+        fr_all, va_all, launches_all, sent_all = float(fr_tot), float(va_tot), float(launches), float(sent)
+    secs = ms / 1e3
+    value = world * S * N * args.steps / secs / 1e6
+
+    # ---- e2e: host buffers through the same C-ABI call (H2D + all results D2H inside the timed region)
+    e2e = None
+    if not args.no_e2e:
+        Ne = min(args.e2e_samples, N)
+        host = torch.empty((S, Ne), dtype=torch.complex64).pin_memory()
+        host.copy_(cap[:, :Ne])
+        rx2 = capi.Rx(S, device=local, max_frame_samples=65536, flags=0, cuda_stream=cs.cuda_stream)
+        for _ in range(max(1, args.warmup)):
+            rx2.execute_dense_ptr(host.data_ptr(), Ne, Ne, capi.MEM_HOST)
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        d2h = 0
+        t0 = time.perf_counter()
+        e0.record(cs)
+        for _ in range(args.steps):
+            rx2.execute_dense_ptr(host.data_ptr(), Ne, Ne, capi.MEM_HOST)
+            arr, nf = rx2.poll(raw=True)
+            d2h += sum(arr[i].payload_len + 8 * arr[i].num_framesyms + 256 for i in range(nf))
+        e1.record(cs)
+        torch.cuda.synchronize(dev)
+        wall = time.perf_counter() - t0
+        ems = max(e0.elapsed_time(e1), wall * 1e3)
+        te = torch.tensor([ems], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * S * Ne * args.steps / (float(te[0]) / 1e3) / 1e6, "unit": "Msps",
+               "h2d_bytes_per_step": S * Ne * 8, "d2h_bytes_per_step": d2h // max(args.steps, 1),
+               "samples_per_stream_per_step": Ne}
+        rx2.close()
+        del host
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline (per-kernel device times come from CUDA events on the launching stream, summed over the timed steps)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    names = ["seek_align_header", "matched_filter", "pll_demod", "fec_crc"]
+    t_seek, t_mf, t_pll, t_fec = [k / 1e3 for k in kt[:4]]
+    win_bytes = 8.0 * 256.0 * work["windows"]                     # 8 B per new sample a detector window examines
+    win_flops = work["windows"] * (50 * 9 * 256 * 10 + 49 * 512 * 9.0)
+    mf_bytes = 8.0 * (2.0 * work["symbols"]) + 8.0 * work["symbols"]   # 2 samples read + 1 symbol written per symbol
+    fp32_peak = 148 * 128 * 2 * (clk["sm_mhz"] or 1965.0) * 1e6 / 1e12
+    kernels = [
+        {"name": names[0], "ms_per_step": 1e3 * t_seek / args.steps, "bound": "fp32",
+         "hbm_gbs": win_bytes / t_seek / 1e9 if t_seek else None,
+         "hbm_frac": win_bytes / t_seek / 1e9 / hbm_peak if t_seek else None,
+         "fp32_tflops": win_flops / t_seek / 1e12 if t_seek else None,
+         "fp32_frac": win_flops / t_seek / 1e12 / fp32_peak if t_seek else None,
+         "windows_per_step": work["windows"] / args.steps},
+        {"name": names[1], "ms_per_step": 1e3 * t_mf / args.steps, "bound": "hbm",
+         "hbm_gbs": mf_bytes / t_mf / 1e9 if t_mf else None, "hbm_frac": mf_bytes / t_mf / 1e9 / hbm_peak if t_mf else None},
+        {"name": names[2], "ms_per_step": 1e3 * t_pll / args.steps, "bound": "latency",
+         "hbm_gbs": 16.0 * work["symbols"] / t_pll / 1e9 if t_pll else None},
+        {"name": names[3], "ms_per_step": 1e3 * t_fec / args.steps, "bound": "int-alu"},
+    ]
+    dom = max(range(4), key=lambda i: kt[i])
+    step_bytes = 8.0 * S * N * args.steps + 8.0 * work["symbols"]   # every input sample once + symbols written
+    if dom == 1:
+        roof = {"bound": "hbm", "kernel": names[1], "achieved": kernels[1]["hbm_gbs"], "peak": hbm_peak, "unit": "GB/s",
+                "frac": kernels[1]["hbm_frac"], "traffic": None, "peak_source": peak_src}
+    else:
+        ach = win_bytes / t_seek / 1e9 if dom == 0 and t_seek else step_bytes / (kt[4] / 1e3) / 1e9
+        roof = {"bound": "hbm", "kernel": names[dom], "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "note": "dominant kernel is the qdetector search, which is FP32-compute-bound (50 FFT-512 per 256 new samples), "
+                        "not HBM-bound: see kernels[0].fp32_frac; whole-step HBM fraction in step_hbm_frac"}
+    roof["step_hbm_gbs"] = step_bytes / secs / 1e9
+    roof["step_hbm_frac"] = roof["step_hbm_gbs"] / hbm_peak
+
+    # ---- CPU baseline on a bounded sample of the same capture (rank 0, N = 1 only)
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        Sc = min(S, 8 * cores, 256)
+        Nc = N
+        sample = cap[:Sc, :Nc].cpu().numpy()
+        dt, f, v = cpu_rx(sample, cores)
+        cpu = {"value": Sc * Nc / dt / 1e6, "unit": "Msps", "cores": cores, "kind": "port",
+               "decoded_frames_per_s": v / dt,
+               "sample": "first %d streams x %d samples of the same capture, %d threads, %.1f s" % (Sc, Nc, cores, dt)}
+
+    out = {
+        "metric": "flex_rx_msps", "value": value, "unit": "Msps", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "flex_rx_1024ch_qpsk_v27_rs8_1500B", "streams_per_gpu": S, "samples_per_stream_per_step": N,
+                   "payload_bytes": PAYLOAD, "mod": "PSK4", "fec0": "v27", "fec1": "rs8", "check": "crc24",
+                   "snr_db": "-2..+12 per stream", "l2": "inputs (%.1f GB per step) larger than L2" % (S * N * 8 / 1e9)},
+        "decoded_frames_per_s": va_all / secs, "frames_per_s": fr_all / secs,
+        "frames_sent_per_step": sent_all, "frames_found_per_step": fr_all / args.steps, "frames_valid_per_step": va_all / args.steps,
+        "gpu_launches": int(launches_all),
+        "clocks": clk, "e2e": e2e, "roofline": roof, "kernels": kernels, "cpu_baseline": cpu,
+    }
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -236,6 +236,7 @@ struct lqb_rx_s {
     uint64_t n_valid = 0;
     cudaEvent_t ev[7] = {};
     float ms[5] = {};
+    uint64_t work[4] = {};
 };
 
 extern "C" {
@@ -325,12 +326,13 @@ int lqb_rx_execute(lqb_rx h, uint32_t n, const uint32_t *ids, const float *const
     sp.n_out = f.d_count; sp.max_out = (unsigned)max_frames;
 
     CU(cudaEventRecord(h->ev[0], st));
-    CU(cudaMemsetAsync(f.d_count, 0, sizeof(unsigned), st));
+    CU(cudaMemsetAsync(f.d_count, 0, 4 * sizeof(unsigned), st));
     launch_seek(sp, n, st); f.launches++;
     CU(cudaEventRecord(h->ev[1], st));
-    CU(cudaMemcpyAsync(f.h_count, f.d_count, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(f.h_count, f.d_count, 4 * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     unsigned nf = std::min<unsigned>(f.h_count[0], (unsigned)max_frames);
+    h->work[0] = f.h_count[1]; h->work[1] = f.h_count[2]; h->work[2] = 0; h->work[3] = total;
     FrameDesc *fr = h->h_frames.p;
     if (nf) {
         CU(cudaMemcpyAsync(fr, h->d_frames.p, nf * sizeof(FrameDesc), cudaMemcpyDeviceToHost, st));
@@ -374,6 +376,7 @@ int lqb_rx_execute(lqb_rx h, uint32_t n, const uint32_t *ids, const float *const
         d.dec_off = dec_total; dec_total += need_dec;
     }
     tile_start[nf] = (unsigned)n_tiles;
+    h->work[2] = sym_total;
     // group the PLL work list by modulation so warps diverge less
     std::vector<unsigned> pll = valid;
     std::stable_sort(pll.begin(), pll.end(), [&](unsigned a, unsigned b) { return fr[a].ms < fr[b].ms; });
@@ -503,6 +506,12 @@ int lqb_rx_last_timing(lqb_rx h, float ms[5])
     std::memcpy(ms, h->ms, sizeof h->ms);
     return 0;
 }
+int lqb_rx_last_work(lqb_rx h, uint64_t w[4])
+{
+    if (!h) return fail(LQB_EINVAL, "null handle");
+    std::memcpy(w, h->work, sizeof h->work);
+    return 0;
+}
 int lqb_rx_launch_count(lqb_rx h, uint64_t *l)
 {
     if (!h) return fail(LQB_EINVAL, "null handle");
@@ -519,6 +528,7 @@ struct lqb_det_s {
     PinBuf<Detection> h_det;
     std::vector<unsigned> order;
     unsigned n_det = 0;
+    uint64_t windows = 0;
     cudaEvent_t ev[2] = {};
     float ms = 0.0f;
 };
@@ -568,13 +578,14 @@ int lqb_det_execute(lqb_det h, uint32_t n, const uint32_t *ids, const float *con
     sp.carry[0] = f.d_carry[0]; sp.carry[1] = f.d_carry[1]; sp.carry_cap = f.carry_cap;
     sp.det_mode = 1; sp.frames = nullptr; sp.detections = h->d_det.p;
     sp.n_out = f.d_count; sp.max_out = (unsigned)max_det;
-    CU(cudaMemsetAsync(f.d_count, 0, sizeof(unsigned), st));
+    CU(cudaMemsetAsync(f.d_count, 0, 4 * sizeof(unsigned), st));
     CU(cudaEventRecord(h->ev[0], st));
     launch_seek(sp, n, st); f.launches++;
     launch_carry(sp, n, st); f.launches++;
     CU(cudaEventRecord(h->ev[1], st));
-    CU(cudaMemcpyAsync(f.h_count, f.d_count, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(f.h_count, f.d_count, 4 * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    h->windows = f.h_count[1];
     unsigned nd = std::min<unsigned>(f.h_count[0], (unsigned)max_det);
     if (nd) {
         CU(cudaMemcpyAsync(h->h_det.p, h->d_det.p, nd * sizeof(Detection), cudaMemcpyDeviceToHost, st));
@@ -618,6 +629,12 @@ int lqb_det_last_timing(lqb_det h, float *ms)
 {
     if (!h) return fail(LQB_EINVAL, "null handle");
     *ms = h->ms;
+    return 0;
+}
+int lqb_det_last_work(lqb_det h, uint64_t *windows)
+{
+    if (!h) return fail(LQB_EINVAL, "null handle");
+    *windows = h->windows;
     return 0;
 }
 

@@ -355,6 +355,7 @@ k_seek(SeekParams P)
     if (tid == 0) st = P.states[io.stream];
     __syncthreads();
 
+    unsigned n_windows = 0, n_aligns = 0;      // work counters (uniform across the CTA)
     StreamView sv;
     sv.carry = P.carry[st.carry_sel] + (size_t)io.stream * P.carry_cap;
     sv.in = io.in;
@@ -370,6 +371,7 @@ k_seek(SeekParams P)
             load_window(sh, sv, st.wstart, tid);
             __syncthreads();
             eval_window(sh, T, tid);
+            ++n_windows;
             if (!sh.trig) {
                 if (tid == 0) st.wstart += 256;
                 __syncthreads();
@@ -391,6 +393,7 @@ k_seek(SeekParams P)
         if (tid == 0) sh.off = st.offset;
         __syncthreads();
         align_frame(sh, T, tid);
+        ++n_aligns;
 
         if (P.det_mode) {
             // frame_detector_cc: report and re-phase the hop grid half a buffer later
@@ -493,6 +496,8 @@ k_seek(SeekParams P)
         if (r < sv.base) r = sv.base;
         st.resume = r;
         P.states[io.stream] = st;
+        atomicAdd(P.n_out + 1, n_windows);
+        atomicAdd(P.n_out + 2, n_aligns);
     }
 }
 

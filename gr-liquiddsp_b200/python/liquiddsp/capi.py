@@ -19,10 +19,10 @@ RX_NO_FRAMESYMS, RX_DEVICE_RESULTS = 1, 2
 DECLARED_SYMBOLS = [
     "lqb_last_error", "lqb_device_count", "lqb_version",
     "lqb_rx_create", "lqb_rx_destroy", "lqb_rx_reset", "lqb_rx_execute", "lqb_rx_execute_dense",
-    "lqb_rx_poll", "lqb_rx_counts", "lqb_rx_last_timing", "lqb_rx_launch_count",
+    "lqb_rx_poll", "lqb_rx_counts", "lqb_rx_last_timing", "lqb_rx_launch_count", "lqb_rx_last_work",
     "lqb_tx_create", "lqb_tx_destroy", "lqb_tx_props_init_default", "lqb_tx_frame_len", "lqb_tx_assemble",
     "lqb_det_create", "lqb_det_destroy", "lqb_det_reset", "lqb_det_execute", "lqb_det_execute_dense",
-    "lqb_det_poll", "lqb_det_last_timing",
+    "lqb_det_poll", "lqb_det_last_timing", "lqb_det_last_work",
     "lqb_tab_interp_taps", "lqb_tab_pfb_banks", "lqb_tab_detector_template", "lqb_tab_nco_sintab",
     "lqb_tab_packet_len",
 ]
@@ -85,6 +85,8 @@ def lib():
     L.lqb_rx_counts.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
     L.lqb_rx_last_timing.argtypes = [vp, C.POINTER(C.c_float)]
     L.lqb_rx_launch_count.argtypes = [vp, C.POINTER(u64)]
+    L.lqb_rx_last_work.argtypes = [vp, C.POINTER(u64)]
+    L.lqb_det_last_work.argtypes = [vp, C.POINTER(u64)]
     if hasattr(L, "lqb_tx_create"):
         L.lqb_tx_create.restype = vp
         L.lqb_tx_create.argtypes = [C.POINTER(TxOpts)]
@@ -197,6 +199,11 @@ class Rx:
         _check(self._L.lqb_rx_launch_count(self._h, C.byref(v)))
         return int(v.value)
 
+    def work(self):
+        w = (C.c_uint64 * 4)()
+        _check(self._L.lqb_rx_last_work(self._h, w))
+        return dict(windows=int(w[0]), aligns=int(w[1]), symbols=int(w[2]), samples=int(w[3]))
+
 
 class Det:
     """Batch qdetector_cccf with frame_detector_cc's parameters."""
@@ -241,6 +248,11 @@ class Det:
         ms = C.c_float(0)
         _check(self._L.lqb_det_last_timing(self._h, C.byref(ms)))
         return float(ms.value)
+
+    def windows(self):
+        w = C.c_uint64(0)
+        _check(self._L.lqb_det_last_work(self._h, C.byref(w)))
+        return int(w.value)
 
 
 def tab_interp_taps(beta):

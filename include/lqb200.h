@@ -154,6 +154,9 @@ int    lqb_rx_counts(lqb_rx h, uint64_t *frames, uint64_t *valid_payloads);
  * stream: [0]=seek/align/header [1]=matched filter [2]=PLL+demod [3]=FEC+CRC [4]=total */
 int    lqb_rx_last_timing(lqb_rx h, float ms[5]);
 int    lqb_rx_launch_count(lqb_rx h, uint64_t *launches);   /* kernels launched since create */
+/* work done by the last execute: [0] 512-sample detector windows evaluated, [1] frame alignments,
+ * [2] payload symbols matched-filtered/demodulated, [3] input samples consumed */
+int    lqb_rx_last_work(lqb_rx h, uint64_t work[4]);
 
 /* ------------------------------------------------------------------ TX (flex_tx / flexframegen) */
 typedef struct lqb_tx_s *lqb_tx;
@@ -199,6 +202,7 @@ int     lqb_det_execute(lqb_det h, uint32_t n, const uint32_t *stream_ids,
 int     lqb_det_execute_dense(lqb_det h, const float *iq, uint64_t stride_samples, uint64_t n_samples, int mem);
 int     lqb_det_poll(lqb_det h, lqb_detection *out, uint32_t max_out, uint32_t *n_out);
 int     lqb_det_last_timing(lqb_det h, float *ms);
+int     lqb_det_last_work(lqb_det h, uint64_t *windows);   /* detector windows evaluated by the last execute */
 
 /* ------------------------------------------------------------------ host-side tables (no GPU needed) */
 /* exposed so tests can check the product's own filter/table design against the oracle */

@@ -186,6 +186,22 @@ static lqo_cf *twiddles_(unsigned n)
     return w;
 }
 
+static const unsigned short *bitrev_(unsigned n, unsigned lg)
+{
+    static unsigned short *cache[16];
+    unsigned short *t = __atomic_load_n(&cache[lg], __ATOMIC_ACQUIRE);
+    if (t) return t;
+    t = (unsigned short *)malloc(n * sizeof(unsigned short));
+    for (unsigned i = 0; i < n; i++) {
+        unsigned r = 0;
+        for (unsigned b = 0; b < lg; b++) r |= ((i >> b) & 1u) << (lg - 1 - b);
+        t[i] = (unsigned short)r;
+    }
+    unsigned short *expected = NULL;
+    if (!__atomic_compare_exchange_n(&cache[lg], &expected, t, 0, __ATOMIC_RELEASE, __ATOMIC_ACQUIRE)) { free(t); t = expected; }
+    return t;
+}
+
 void lqo_fft(const lqo_cf *in, lqo_cf *out, unsigned n, int dir)
 {
     unsigned lg = 0;
@@ -193,11 +209,8 @@ void lqo_fft(const lqo_cf *in, lqo_cf *out, unsigned n, int dir)
     const lqo_cf *W = twiddles_(n);
     lqo_cf tmp[512];
     lqo_cf *a = (in == out) ? tmp : out;
-    for (unsigned i = 0; i < n; i++) {
-        unsigned r = 0;
-        for (unsigned b = 0; b < lg; b++) r |= ((i >> b) & 1u) << (lg - 1 - b);
-        a[i] = in[r];
-    }
+    const unsigned short *rev = bitrev_(n, lg);
+    for (unsigned i = 0; i < n; i++) a[i] = in[rev[i]];
     for (unsigned s = 1; s <= lg; s++) {
         unsigned m = 1u << s, half = m >> 1, step = n / m;
         for (unsigned k = 0; k < n; k += m) {

@@ -229,7 +229,7 @@ struct lqb_rx_s {
     size_t ilv_used = 0;
     std::unordered_map<unsigned, size_t> ilv_cache;
     DevBuf<unsigned long long> d_dec;
-    DevBuf<unsigned> d_lists;
+    DevBuf<unsigned> d_lists, d_tilemap;
     PinBuf<unsigned> h_lists;
     std::vector<unsigned> order;
     unsigned n_frames = 0;
@@ -274,7 +274,7 @@ void lqb_rx_destroy(lqb_rx h)
     if (h->f.stream) cudaStreamSynchronize(h->f.stream);
     h->d_frames.release(); h->h_frames.release(); h->d_syms.release(); h->h_syms.release();
     h->d_bufA.release(); h->d_bufB.release(); h->d_payload.release(); h->h_payload.release();
-    h->d_ilv.release(); h->d_dec.release(); h->d_lists.release(); h->h_lists.release();
+    h->d_ilv.release(); h->d_dec.release(); h->d_lists.release(); h->h_lists.release(); h->d_tilemap.release();
     for (auto &ev : h->ev) if (ev) cudaEventDestroy(ev);
     h->f.destroy();
     delete h;
@@ -341,13 +341,14 @@ int lqb_rx_execute(lqb_rx h, uint32_t n, const uint32_t *ids, const float *const
 
     // ---------------- plan
     size_t sym_total = 0, buf_total = 0, pay_total = 0, dec_total = 0, n_tiles = 0;
-    std::vector<unsigned> tile_start(nf + 1, 0), valid, deint[2], blk[2], vit[2], rsb[2];
+    std::vector<unsigned> tile_start(nf + 1, 0), valid, deint[2], blk[2], vit[2], vit9[2], rsb[2];
+    size_t tmax7[2] = { 0, 0 };
     for (unsigned i = 0; i < nf; ++i) {
         FrameDesc &d = fr[i];
         tile_start[i] = (unsigned)n_tiles;
         if (!d.header_valid) continue;
         valid.push_back(i);
-        d.sym_off = sym_total; sym_total += d.n_sym;
+        d.sym_off = sym_total; sym_total += (d.n_sym + 1u) & ~1u;      // even: 16-byte aligned symbol rows
         unsigned bl = std::max(std::max(d.n1, d.n0), d.k0) + 16;
         bl = (bl + 15u) & ~15u;
         d.buf_len = bl; d.buf_off = buf_total; buf_total += bl;
@@ -363,9 +364,9 @@ int lqb_rx_execute(lqb_rx h, uint32_t n, const uint32_t *ids, const float *const
                 deint[stg].push_back(i);
             }
             if (is_conv(fs[stg])) {
-                vit[stg].push_back(i);
-                size_t T = (size_t)8 * dl[stg] + conv_K(fs[stg]) - 1, words = conv_K(fs[stg]) == 9 ? 8 : 2;
-                need_dec = std::max(need_dec, (T * words + 1) / 2);
+                size_t T = (size_t)8 * dl[stg] + conv_K(fs[stg]) - 1;
+                if (conv_K(fs[stg]) == 7) { vit[stg].push_back(i); tmax7[stg] = std::max(tmax7[stg], T); }   // [step][thread] arena
+                else { vit9[stg].push_back(i); need_dec = std::max(need_dec, T * 4); }                      // 8 words per step
             } else if (fs[stg] == FEC_RS_M8) {
                 unsigned blocks = (dl[stg] + 222) / 223;
                 for (unsigned b = 0; b < blocks; ++b) { rsb[stg].push_back(i); rsb[stg].push_back(b); }
@@ -376,6 +377,10 @@ int lqb_rx_execute(lqb_rx h, uint32_t n, const uint32_t *ids, const float *const
         d.dec_off = dec_total; dec_total += need_dec;
     }
     tile_start[nf] = (unsigned)n_tiles;
+    // K=7 frames share one [step][thread] decision arena at the front; K=9 frames follow with private slices
+    const size_t dec7 = std::max(tmax7[0] * vit[0].size(), tmax7[1] * vit[1].size());
+    for (unsigned i = 0; i < nf; ++i) fr[i].dec_off += dec7;
+    dec_total += dec7;
     h->work[2] = sym_total;
     // group the PLL work list by modulation so warps diverge less
     std::vector<unsigned> pll = valid;
@@ -387,9 +392,10 @@ int lqb_rx_execute(lqb_rx h, uint32_t n, const uint32_t *ids, const float *const
         if (int e = h->d_bufB.reserve(buf_total + 16)) return e;
         if (int e = h->d_payload.reserve(pay_total + 16)) return e;
         if (int e = h->d_dec.reserve(dec_total + 1)) return e;
+        if (int e = h->d_tilemap.reserve(n_tiles + 1)) return e;
         // one list arena: tile_start | pll | valid | deint1 | blk1 | vit1 | rs1 | deint0 | blk0 | vit0 | rs0
         std::vector<const std::vector<unsigned> *> parts = { &tile_start, &pll, &valid, &deint[1], &blk[1], &vit[1], &rsb[1],
-                                                             &deint[0], &blk[0], &vit[0], &rsb[0] };
+                                                             &deint[0], &blk[0], &vit[0], &rsb[0], &vit9[1], &vit9[0] };
         size_t ltot = 0;
         std::vector<size_t> loff;
         for (auto p : parts) { loff.push_back(ltot); ltot += p->size(); }
@@ -404,12 +410,12 @@ int lqb_rx_execute(lqb_rx h, uint32_t n, const uint32_t *ids, const float *const
         pp.tables = f.d_tables; pp.states = f.d_states; pp.io = f.d_io.p;
         pp.carry[0] = f.d_carry[0]; pp.carry[1] = f.d_carry[1]; pp.carry_cap = f.carry_cap;
         pp.frames = h->d_frames.p; pp.n_frames = nf;
-        pp.tile_start = h->d_lists.p + loff[0]; pp.n_tiles = (unsigned)n_tiles;
+        pp.tile_start = h->d_lists.p + loff[0]; pp.n_tiles = (unsigned)n_tiles; pp.tile_frame = h->d_tilemap.p;
         pp.syms = h->d_syms.p; pp.bufA = h->d_bufA.p; pp.bufB = h->d_bufB.p; pp.payload = h->d_payload.p;
         pp.ilv_maps = h->d_ilv.p; pp.decisions = h->d_dec.p;
 
         CU(cudaEventRecord(h->ev[2], st));
-        launch_mf(pp, st); f.launches += n_tiles ? 1 : 0;
+        launch_mf(pp, st); f.launches += n_tiles ? 2 : 0;
         CU(cudaEventRecord(h->ev[3], st));
         launch_pll(pp, h->d_lists.p + loff[1], (unsigned)pll.size(), st); f.launches++;
         CU(cudaEventRecord(h->ev[4], st));
@@ -418,6 +424,7 @@ int lqb_rx_execute(lqb_rx h, uint32_t n, const uint32_t *ids, const float *const
             if (!deint[stg].empty()) { launch_deinterleave(pp, h->d_lists.p + loff[base], (unsigned)deint[stg].size(), stg, st); f.launches++; }
             if (!blk[stg].empty()) { launch_blockfec(pp, h->d_lists.p + loff[base + 1], (unsigned)blk[stg].size(), stg, st); f.launches++; }
             if (!vit[stg].empty()) { launch_viterbi(pp, h->d_lists.p + loff[base + 2], (unsigned)vit[stg].size(), stg, 7, st); f.launches++; }
+            if (!vit9[stg].empty()) { launch_viterbi(pp, h->d_lists.p + loff[stg ? 11 : 12], (unsigned)vit9[stg].size(), stg, 9, st); f.launches++; }
             if (!rsb[stg].empty()) { launch_rs(pp, h->d_lists.p + loff[base + 3], (unsigned)(rsb[stg].size() / 2), stg, st); f.launches++; }
         }
         launch_crc(pp, h->d_lists.p + loff[2], (unsigned)valid.size(), st); f.launches++;

@@ -10,14 +10,17 @@ namespace lqb {
 __global__ void k_dbg_fft512(const float2 *W, const float2 *in, float2 *out, int dir)
 {
     __shared__ float2 sW[256];
+    __shared__ float2 sWc[240];
     __shared__ float2 scr[544];
     const int lane = threadIdx.x;
     for (int i = lane; i < 256; i += 32) sW[i] = W[i];
     __syncwarp();
+    fft512_fill_compact(sWc, sW, lane, 32);
+    __syncwarp();
     float2 v[16];
 #pragma unroll
     for (int r = 0; r < 16; ++r) v[r] = in[fft512_in_index(lane, r)];
-    if (dir > 0) fft512_warp<+1>(v, sW, scr, lane); else fft512_warp<-1>(v, sW, scr, lane);
+    if (dir > 0) fft512_warp<+1>(v, sW, sWc, scr, lane); else fft512_warp<-1>(v, sW, sWc, scr, lane);
 #pragma unroll
     for (int r = 0; r < 16; ++r) out[fft512_out_index(lane, r)] = v[r];
 }

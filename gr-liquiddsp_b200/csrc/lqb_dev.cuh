@@ -87,6 +87,8 @@ struct Detection {
 };
 
 // ------------------------------------------------------------------ arithmetic primitives
+// (A packed-pair variant built on sm_100's FFMA2/FMUL2/FADD2 is bit-identical but measured 10 % slower
+// in the detector kernel -- see profiles/r01_notes.md -- so the scalar forms stay.)
 __device__ __forceinline__ float2 cmulf(float2 a, float2 b)
 {
     float2 y;
@@ -99,10 +101,12 @@ __device__ __forceinline__ float cabsf_(float2 a) { return __fsqrt_rn(abs2f(a));
 
 __device__ __forceinline__ uint32_t nco_constrain_dev(float theta)
 {
+    // identical to: p = theta/(2 pi); f = p - trunc(p); f < 0 ? f + 1; (uint32)(int64)(f * 2^32)
+    // (truncf == (float)(int64)p for |p| < 2^63; f == 1.0 -- a tiny negative plus one -- wraps to 0)
     float p = __fmul_rn(theta, 0.15915494309189535f);
-    float f = __fsub_rn(p, (float)__float2ll_rz(p));
+    float f = __fsub_rn(p, truncf(p));
     if (f < 0.0f) f = __fadd_rn(f, 1.0f);
-    return (uint32_t)__float2ll_rz(__fmul_rn(f, 4294967296.0f));
+    return f >= 1.0f ? 0u : __float2uint_rz(__fmul_rn(f, 4294967296.0f));
 }
 __device__ __forceinline__ float2 nco_mix_down(const float *__restrict__ sintab, uint32_t theta, float2 x)
 {
@@ -151,9 +155,27 @@ __device__ __forceinline__ void bfly(float2 &lo, float2 &hi, float2 w)
     lo.x = __fadd_rn(u.x, tr); lo.y = __fadd_rn(u.y, ti);
     hi.x = __fsub_rn(u.x, tr); hi.y = __fsub_rn(u.y, ti);
 }
-
+// twiddle 1 and the exact quarter turn (0,-1) / (0,+1): the products are exact, only the adds remain
+__device__ __forceinline__ void bfly_one(float2 &lo, float2 &hi)
+{
+    const float2 u = lo, t = hi;
+    lo.x = __fadd_rn(u.x, t.x); lo.y = __fadd_rn(u.y, t.y);
+    hi.x = __fsub_rn(u.x, t.x); hi.y = __fsub_rn(u.y, t.y);
+}
 template <int DIR>
-__device__ __forceinline__ void fft512_warp(float2 (&v)[16], const float2 *__restrict__ W,
+__device__ __forceinline__ void bfly_quarter(float2 &lo, float2 &hi)
+{
+    const float2 t = DIR > 0 ? make_float2(hi.y, -hi.x) : make_float2(-hi.y, hi.x);
+    const float2 u = lo;
+    lo.x = __fadd_rn(u.x, t.x); lo.y = __fadd_rn(u.y, t.y);
+    hi.x = __fsub_rn(u.x, t.x); hi.y = __fsub_rn(u.y, t.y);
+}
+
+// W  : 256 twiddles exp(-j 2 pi k / 512) (stages 1-4 read compile-time entries, stage 9 reads 16 r + c)
+// Wc : per-stage compact copies for stages 5-8 so that the 16 lanes of a half-warp read consecutive
+//      words (bank-conflict free): Wc[16 (2^s - 1) + j] = W[j * (16 >> s)], s = 0..3, j < 16 * 2^s
+template <int DIR>
+__device__ __forceinline__ void fft512_warp(float2 (&v)[16], const float2 *__restrict__ W, const float2 *__restrict__ Wc,
                                             float2 *__restrict__ scratch /* 544 float2, this warp's */, int lane)
 {
 #pragma unroll
@@ -163,7 +185,9 @@ __device__ __forceinline__ void fft512_warp(float2 (&v)[16], const float2 *__res
         for (int r = 0; r < 16; ++r) {
             if (r & half) continue;
             const int e = (r & (half - 1)) * (256 >> s);
-            bfly<DIR>(v[r], v[r + half], W[e]);
+            if (e == 0) bfly_one(v[r], v[r + half]);
+            else if (e == 128) bfly_quarter<DIR>(v[r], v[r + half]);
+            else bfly<DIR>(v[r], v[r + half], W[e]);
         }
     }
 #pragma unroll
@@ -182,8 +206,7 @@ __device__ __forceinline__ void fft512_warp(float2 (&v)[16], const float2 *__res
 #pragma unroll
         for (int r = 0; r < 16; ++r) {
             if (r & half) continue;
-            const int e = (c + 16 * (r & (half - 1))) * (16 >> s);
-            bfly<DIR>(v[r], v[r + half], W[e]);
+            bfly<DIR>(v[r], v[r + half], Wc[16 * (half - 1) + c + 16 * (r & (half - 1))]);
         }
     }
 #pragma unroll
@@ -194,6 +217,16 @@ __device__ __forceinline__ void fft512_warp(float2 (&v)[16], const float2 *__res
         float2 lo = b8 ? o : v[r], hi = b8 ? v[r] : o;
         bfly<DIR>(lo, hi, W[(r << 4) | c]);
         v[r] = b8 ? hi : lo;
+    }
+}
+
+// fill the compact stage tables from the full table (any number of threads; caller synchronises)
+__device__ __forceinline__ void fft512_fill_compact(float2 *Wc, const float2 *W, int tid, int nthreads)
+{
+    for (int i = tid; i < 240; i += nthreads) {
+        int s = (i >= 112) ? 3 : (i >= 48) ? 2 : (i >= 16) ? 1 : 0;
+        int j = i - 16 * ((1 << s) - 1);
+        Wc[i] = W[j * (16 >> s)];
     }
 }
 

@@ -31,6 +31,7 @@ struct PayloadParams {
     // matched filter tiling: tile_start[f] = first tile of frame f (exclusive prefix), n_tiles total
     const unsigned    *tile_start;
     unsigned           n_tiles;
+    unsigned          *tile_frame;  // [n_tiles] tile -> frame index (filled on the device)
     float2            *syms;        // symbol arena
     unsigned char     *bufA, *bufB; // byte arenas
     unsigned char     *payload;     // payload output pool

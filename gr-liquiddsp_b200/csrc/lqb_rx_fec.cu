@@ -274,6 +274,101 @@ k_viterbi(PayloadParams P, const unsigned *__restrict__ list, unsigned n_list, i
     }
 }
 
+
+// ------------------------------------------------------------------ Viterbi K=7, one thread per codeword
+// All 64 path metrics live in registers (two banks, ping-pong over an unrolled pair of trellis
+// steps), so a step is 32 fully unrolled butterflies of plain integer add / min / compare with
+// compile-time branch labels and no inter-thread traffic.  The 64 decision bits of a step go to
+// HBM as one 8-byte word laid out [step][thread] (coalesced across the warp); the traceback reads
+// them back the same way, so its loads do not depend on the state being traced.
+__device__ __forceinline__ void acs27(const unsigned (&mo)[64], unsigned (&mn)[64], unsigned sym0, unsigned sym1, unsigned &d0, unsigned &d1)
+{
+    unsigned A[4];
+#pragma unroll
+    for (int l = 0; l < 4; ++l) A[l] = (((l & 1) ? 255u : 0u) ^ sym0) + (((l & 2) ? 255u : 0u) ^ sym1);
+    unsigned lo = 0, hi = 0;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        const int lab = (__popc((2 * i) & 0x6d) & 1) | ((__popc((2 * i) & 0x4f) & 1) << 1);
+        const unsigned a = A[lab], b = A[3 - lab];
+        unsigned m0 = mo[i] + a, m1 = mo[i + 32] + b;
+        unsigned dcs = m0 > m1 ? 1u : 0u;
+        mn[2 * i] = m0 > m1 ? m1 : m0;
+        if (2 * i < 32) lo |= dcs << (2 * i); else hi |= dcs << (2 * i - 32);
+        m0 = mo[i] + b; m1 = mo[i + 32] + a;
+        dcs = m0 > m1 ? 1u : 0u;
+        mn[2 * i + 1] = m0 > m1 ? m1 : m0;
+        if (2 * i + 1 < 32) lo |= dcs << (2 * i + 1); else hi |= dcs << (2 * i + 1 - 32);
+    }
+    d0 = lo; d1 = hi;
+}
+
+__global__ void __launch_bounds__(64)
+k_viterbi27(PayloadParams P, const unsigned *__restrict__ list, unsigned n_list, int stage, uint2 *__restrict__ dec)
+{
+    const unsigned gi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gi >= n_list) return;
+    const FrameDesc &d = P.frames[list[gi]];
+    const StageIO io = stage_io(P, d, stage);
+    const ConvSpec cs = conv_spec(io.fs);
+    const unsigned nbits = 8 * io.dec_len, T = nbits + 6;
+    unsigned per = 0, pre[8];
+    for (unsigned c = 0; c < cs.P; ++c) { pre[c] = per; per += ((cs.keep0 >> c) & 1u) + ((cs.keep1 >> c) & 1u); }
+    const unsigned char *enc = io.src;
+
+    unsigned ma[64], mb[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) ma[i] = 63u;
+    ma[0] = 0u;
+    unsigned col = 0, q = 0;                       // t = q * P + col
+    auto symbols = [&](unsigned &s0, unsigned &s1) {
+        unsigned ib = q * per + pre[col];
+        s0 = 127u; s1 = 127u;
+        if ((cs.keep0 >> col) & 1u) { s0 = soft_bit(enc, ib); ++ib; }
+        if ((cs.keep1 >> col) & 1u) { s1 = soft_bit(enc, ib); }
+        if (++col == cs.P) { col = 0; ++q; }
+    };
+    unsigned t = 0;
+    for (; t + 1 < T; t += 2) {
+        unsigned s0, s1, d0, d1;
+        symbols(s0, s1);
+        acs27(ma, mb, s0, s1, d0, d1);
+        dec[(size_t)t * n_list + gi] = make_uint2(d0, d1);
+        symbols(s0, s1);
+        acs27(mb, ma, s0, s1, d0, d1);
+        dec[(size_t)(t + 1) * n_list + gi] = make_uint2(d0, d1);
+    }
+    if (t < T) {
+        unsigned s0, s1, d0, d1;
+        symbols(s0, s1);
+        acs27(ma, mb, s0, s1, d0, d1);
+        dec[(size_t)t * n_list + gi] = make_uint2(d0, d1);
+    }
+    // traceback from state 0; bit shifted out at step t entered at t - 6
+    unsigned char *out = io.dst;
+    unsigned state = 0, byte_acc = 0;
+    long long tt = (long long)T - 1;
+    while (tt >= 0) {
+        uint2 w[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) w[k] = (tt - k >= 0) ? dec[(size_t)(tt - k) * n_list + gi] : make_uint2(0u, 0u);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const long long ts = tt - k;
+            if (ts < 0) break;
+            const unsigned word = (state & 32u) ? w[k].y : w[k].x;
+            const unsigned bit = (word >> (state & 31u)) & 1u;
+            if (ts >= 6) {
+                const unsigned bi = (unsigned)ts - 6u;
+                byte_acc |= bit << (7 - (bi & 7u));
+                if ((bi & 7u) == 0) { out[bi >> 3] = (unsigned char)byte_acc; byte_acc = 0; }
+            }
+            state = (state >> 1) | (bit << 5);
+        }
+        tt -= 8;
+    }
+}
+
 // ------------------------------------------------------------------ Reed-Solomon (warp per 255-byte block)
 constexpr int kRsWarps = 4;
 
@@ -421,8 +516,9 @@ void launch_blockfec(const PayloadParams &P, const unsigned *list, unsigned n, i
 }
 void launch_viterbi(const PayloadParams &P, const unsigned *list, unsigned n, int stage, unsigned K, cudaStream_t s)
 {
-    (void)K;
-    if (n) k_viterbi<<<(n + kVitWarps - 1) / kVitWarps, 32 * kVitWarps, 0, s>>>(P, list, n, stage);
+    if (!n) return;
+    if (K == 7) k_viterbi27<<<(n + 63) / 64, 64, 0, s>>>(P, list, n, stage, reinterpret_cast<uint2 *>(P.decisions));
+    else k_viterbi<<<(n + kVitWarps - 1) / kVitWarps, 32 * kVitWarps, 0, s>>>(P, list, n, stage);
 }
 void launch_rs(const PayloadParams &P, const unsigned *blocks, unsigned n_blocks, int stage, cudaStream_t s)
 {

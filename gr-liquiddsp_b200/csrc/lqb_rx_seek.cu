@@ -16,8 +16,14 @@ namespace lqb {
 
 namespace {
 
-constexpr int kThreads = 128;
-constexpr int kWarps = 4;
+#ifndef LQB_SEEK_WARPS
+#define LQB_SEEK_WARPS 4
+#endif
+#ifndef LQB_SEEK_MINB
+#define LQB_SEEK_MINB 4
+#endif
+constexpr int kWarps = LQB_SEEK_WARPS;
+constexpr int kThreads = 32 * kWarps;
 constexpr float kPiF = 3.14159274f;     // (float)M_PI
 
 struct SeekShared {
@@ -25,7 +31,8 @@ struct SeekShared {
     float2 Xf[512];           // its spectrum (also reused for the CFO spectrum)
     float2 Sc[512];           // conj(S)
     float2 W[256];            // twiddles
-    float2 scr[kWarps * 544]; // per-warp FFT transpose scratch; reused flat by the header stage
+    float2 Wc[240];           // per-stage compact twiddles (stages 5-8)
+    float2 scr[(kWarps * 544 > 1824) ? kWarps * 544 : 1824]; // per-warp FFT transpose scratch; reused flat by the header stage
     unsigned long long best[kWarps];
     float  energy[2];
     float2 y3[3];             // align: y[511], y[0], y[1]
@@ -47,7 +54,7 @@ constexpr int kPil  = 1760;   // 64 : pilot FFT in/out
 __device__ __forceinline__ void load_window(SeekShared &sh, const StreamView &sv, long long start, int tid)
 {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < 512 / kThreads; ++k) {
         int i = tid + kThreads * k;
         sh.Xw[i] = sv.at(start + i);
     }
@@ -71,7 +78,7 @@ __device__ __forceinline__ void forward_fft_to(SeekShared &sh, const float2 *src
     float2 v[16];
 #pragma unroll
     for (int r = 0; r < 16; ++r) v[r] = src[fft512_in_index(lane, r)];
-    fft512_warp<+1>(v, sh.W, sh.scr, lane);      // warp 0's scratch
+    fft512_warp<+1>(v, sh.W, sh.Wc, sh.scr, lane);      // warp 0's scratch
 #pragma unroll
     for (int r = 0; r < 16; ++r) dst[fft512_out_index(lane, r)] = v[r];
 }
@@ -84,7 +91,7 @@ __device__ __forceinline__ void cross_ifft(SeekShared &sh, int off, float2 (&v)[
         int i = fft512_in_index(lane, r);
         v[r] = cmulf(sh.Xf[i], sh.Sc[(i - off) & 511]);
     }
-    fft512_warp<-1>(v, sh.W, scratch, lane);
+    fft512_warp<-1>(v, sh.W, sh.Wc, scratch, lane);
 }
 
 // evaluate the window in sh.Xw; thread 0 publishes trig/idx/off/rxy
@@ -102,15 +109,21 @@ __device__ void eval_window(SeekShared &sh, const DevTables *T, int tid)
     if (g0 >= 1e-10f) {
         const int range = T->range;
         float2 v[16];
-        for (int offi = 3 - warp; offi <= 2 * range; offi += kWarps) {
+        // per-lane running maximum; strict '>' keeps the earliest (offset, lag) on ties within the lane
+        float bv = 0.0f;
+        unsigned border = 0;
+        for (int offi = kWarps - 1 - warp; offi <= 2 * range; offi += kWarps) {
             cross_ifft(sh, offi - range, v, sh.scr + warp * 544, lane);
+            const unsigned obase = (unsigned)(offi * 512 + fft512_out_index(lane, 0));
 #pragma unroll
             for (int r = 0; r < 16; ++r) {
-                unsigned order = (unsigned)(offi * 512 + fft512_out_index(lane, r));
-                unsigned long long key = ((unsigned long long)__float_as_uint(abs2f(v[r])) << 32) | (0xffffffffu - order);
-                best = key > best ? key : best;
+                const float a2 = abs2f(v[r]);
+                const bool gt = a2 > bv;
+                bv = gt ? a2 : bv;
+                border = gt ? obase + 16u * r : border;
             }
         }
+        best = ((unsigned long long)__float_as_uint(bv) << 32) | (0xffffffffu - border);
         best = warp_max_u64(best);
     }
     if (lane == 0) sh.best[warp] = best;
@@ -153,7 +166,7 @@ __device__ void align_frame(SeekShared &sh, const DevTables *T, int tid)
         // CFO spectrum
 #pragma unroll
         for (int r = 0; r < 16; ++r) v[r] = zbuf[fft512_in_index(lane, r)];
-        fft512_warp<+1>(v, sh.W, sh.scr, lane);
+        fft512_warp<+1>(v, sh.W, sh.Wc, sh.scr, lane);
         unsigned long long best = 0ull;
 #pragma unroll
         for (int r = 0; r < 16; ++r) {
@@ -340,7 +353,7 @@ __device__ void decode_header(SeekShared &sh, const DevTables *T, const StreamVi
 }  // namespace
 
 // ------------------------------------------------------------------ the kernel
-__global__ void __launch_bounds__(kThreads, 4)
+__global__ void __launch_bounds__(kThreads, LQB_SEEK_MINB)
 k_seek(SeekParams P)
 {
     __shared__ SeekShared sh;
@@ -353,6 +366,8 @@ k_seek(SeekParams P)
     for (int i = tid; i < 512; i += kThreads) sh.Sc[i] = T->Sc[i];
     for (int i = tid; i < 256; i += kThreads) sh.W[i] = T->W512[i];
     if (tid == 0) st = P.states[io.stream];
+    __syncthreads();
+    fft512_fill_compact(sh.Wc, sh.W, tid, kThreads);
     __syncthreads();
 
     unsigned n_windows = 0, n_aligns = 0;      // work counters (uniform across the CTA)

@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.normpath(os.path.join(_HERE, "..", "..", "lib", "liblqb200.so"))
+LIB_PATH = os.environ.get("LQB_LIB") or os.path.normpath(os.path.join(_HERE, "..", "..", "lib", "liblqb200.so"))
 
 MEM_HOST, MEM_DEVICE = 0, 1
 RX_NO_FRAMESYMS, RX_DEVICE_RESULTS = 1, 2

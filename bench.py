@@ -258,8 +258,8 @@ def main():
     clocks.start()
     l0 = rx.launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kt = [0.0] * 5
-    work = dict(windows=0, aligns=0, symbols=0, samples=0)
+    kt = [0.0] * 6
+    work = dict(windows=0, aligns=0, symbols=0, samples=0, exact_windows=0, coarse_tiles=0)
     fr_tot = va_tot = 0
     torch.cuda.synchronize(dev)
     e0.record(cs)
@@ -336,8 +336,12 @@ def main():
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     names = ["seek_align_header", "matched_filter", "pll_demod", "fec_crc"]
     t_seek, t_mf, t_pll, t_fec = [k / 1e3 for k in kt[:4]]
+    t_coarse = kt[5] / 1e3
     win_bytes = 8.0 * 256.0 * work["windows"]                     # 8 B per new sample a detector window examines
-    win_flops = work["windows"] * (50 * 9 * 256 * 10 + 49 * 512 * 9.0)
+    win_flops = work["exact_windows"] * (50 * 9 * 256 * 10 + 49 * 512 * 9.0)
+    # tensor-core pre-filter: 128 lags x 320 (K) x 112 (N) x 2 flop per tile, fp16 in / fp32 accumulate
+    tc_flops = work["coarse_tiles"] * 128.0 * 320.0 * 112.0 * 2.0
+    tc_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
     mf_bytes = 8.0 * (2.0 * work["symbols"]) + 8.0 * work["symbols"]   # 2 samples read + 1 symbol written per symbol
     fp32_peak = 148 * 128 * 2 * (clk["sm_mhz"] or 1965.0) * 1e6 / 1e12
     kernels = [
@@ -346,7 +350,11 @@ def main():
          "hbm_frac": win_bytes / t_seek / 1e9 / hbm_peak if t_seek else None,
          "fp32_tflops": win_flops / t_seek / 1e12 if t_seek else None,
          "fp32_frac": win_flops / t_seek / 1e12 / fp32_peak if t_seek else None,
-         "windows_per_step": work["windows"] / args.steps},
+         "windows_per_step": work["windows"] / args.steps, "exact_windows_per_step": work["exact_windows"] / args.steps,
+         "prefilter_ms_per_step": 1e3 * t_coarse / args.steps,
+         "prefilter_tensor_tflops": tc_flops / t_coarse / 1e12 if t_coarse else None,
+         "prefilter_tensor_frac": tc_flops / t_coarse / 1e12 / tc_peak if t_coarse else None,
+         "prefilter_hbm_gbs": (8.0 * work["samples"]) / t_coarse / 1e9 if t_coarse else None},
         {"name": names[1], "ms_per_step": 1e3 * t_mf / args.steps, "bound": "hbm",
          "hbm_gbs": mf_bytes / t_mf / 1e9 if t_mf else None, "hbm_frac": mf_bytes / t_mf / 1e9 / hbm_peak if t_mf else None},
         {"name": names[2], "ms_per_step": 1e3 * t_pll / args.steps, "bound": "latency",

@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <unordered_map>
@@ -119,6 +120,15 @@ struct Front {
     unsigned *h_count = nullptr;
     std::vector<uint8_t> fed;
     uint64_t launches = 0;
+    // tensor-core pre-filter (lqb_rx_coarse.cu)
+    bool coarse_ok = false;
+    void *d_bmat = nullptr;
+    DevBuf<float> d_m8, d_e8;
+    DevBuf<unsigned> d_tpre;
+    PinBuf<unsigned> h_tpre;
+    StreamState *h_states = nullptr;      // pinned host mirror of d_states (carry lengths for tile planning)
+    float coarse_ms = 0.0f;
+    cudaEvent_t cev[2] = { nullptr, nullptr };
 
     int init(int dev, unsigned ns, unsigned cap, void *user_stream, const DevTables &T)
     {
@@ -138,7 +148,18 @@ struct Front {
         for (int k = 0; k < 2; ++k) CU(cudaMalloc(&d_carry[k], (size_t)ns * cap * sizeof(float2)));
         CU(cudaMalloc(&d_count, 4 * sizeof(unsigned)));
         CU(cudaMallocHost(&h_count, 4 * sizeof(unsigned)));
+        CU(cudaMallocHost(&h_states, (size_t)ns * sizeof(StreamState)));
+        CU(cudaEventCreate(&cev[0])); CU(cudaEventCreate(&cev[1]));
         fed.assign(ns, 0);
+        if (T.range == 24 && !getenv("LQB_NO_COARSE")) {
+            std::vector<float> sre(kSLen), sim(kSLen);
+            for (unsigned i = 0; i < kSLen; ++i) { sre[i] = T.sconj[i].x; sim[i] = -T.sconj[i].y; }
+            std::vector<unsigned short> bm;
+            build_coarse_bmat(sre.data(), sim.data(), 24, bm);
+            CU(cudaMalloc(&d_bmat, bm.size() * sizeof(unsigned short)));
+            CU(cudaMemcpy(d_bmat, bm.data(), bm.size() * sizeof(unsigned short), cudaMemcpyHostToDevice));
+            coarse_ok = true;
+        }
         return reset(-1);
     }
     int reset(int s)
@@ -148,11 +169,12 @@ struct Front {
         std::memset(&z, 0, sizeof z);
         z.wstart = -256;           // first window = 256 zeros + first 256 samples (qdetector reset state)
         if (s < 0) {
-            std::vector<StreamState> all(n_streams, z);
-            CU(cudaMemcpyAsync(d_states, all.data(), all.size() * sizeof(StreamState), cudaMemcpyHostToDevice, stream));
+            for (unsigned i = 0; i < n_streams; ++i) h_states[i] = z;
+            CU(cudaMemcpyAsync(d_states, h_states, (size_t)n_streams * sizeof(StreamState), cudaMemcpyHostToDevice, stream));
             CU(cudaStreamSynchronize(stream));
         } else {
             if ((unsigned)s >= n_streams) return fail(LQB_EINVAL, "stream index out of range");
+            h_states[s] = z;
             CU(cudaMemcpyAsync(d_states + s, &z, sizeof z, cudaMemcpyHostToDevice, stream));
             CU(cudaStreamSynchronize(stream));
         }
@@ -199,6 +221,37 @@ struct Front {
         *total = tot; *max_n = mx;
         return 0;
     }
+    // plan and launch the pre-filter for the streams just fed; fills the coarse fields of sp
+    int run_coarse(uint32_t n, const uint64_t *ns, SeekParams &sp)
+    {
+        sp.coarse = 0; sp.tile_prefix = nullptr; sp.m8 = nullptr; sp.e8 = nullptr;
+        coarse_ms = 0.0f;
+        if (!coarse_ok || !n) return 0;
+        if (int e = h_tpre.reserve(n + 1)) return e;
+        if (int e = d_tpre.reserve(n + 1)) return e;
+        uint64_t tiles = 0;
+        for (uint32_t i = 0; i < n; ++i) {
+            h_tpre.p[i] = (unsigned)tiles;
+            const uint64_t L = (uint64_t)h_states[h_io.p[i].stream].carry_len + ns[i];
+            tiles += (L + 127) / 128;
+        }
+        h_tpre.p[n] = (unsigned)tiles;
+        if (tiles == 0 || tiles > 0xfffffff0ull / 16) return 0;
+        if (int e = d_m8.reserve(tiles * 16 + 64)) return e;
+        if (int e = d_e8.reserve(tiles * 16 + 64)) return e;
+        CU(cudaMemcpyAsync(d_tpre.p, h_tpre.p, (n + 1) * sizeof(unsigned), cudaMemcpyHostToDevice, stream));
+        CoarseParams cp;
+        cp.states = d_states; cp.io = d_io.p; cp.carry[0] = d_carry[0]; cp.carry[1] = d_carry[1]; cp.carry_cap = carry_cap;
+        cp.tile_prefix = d_tpre.p; cp.n_io = n; cp.n_tiles = (unsigned)tiles; cp.bmat = d_bmat; cp.m8 = d_m8.p; cp.e8 = d_e8.p;
+        CU(cudaEventRecord(cev[0], stream));
+        launch_coarse(cp, stream); launches++;
+        CU(cudaEventRecord(cev[1], stream));
+        sp.coarse = 1; sp.tile_prefix = d_tpre.p; sp.m8 = d_m8.p; sp.e8 = d_e8.p;
+        return 0;
+    }
+    // refresh the host mirror of the stream states (call after launch_carry, before the final sync)
+    int mirror_states() { CU(cudaMemcpyAsync(h_states, d_states, (size_t)n_streams * sizeof(StreamState), cudaMemcpyDeviceToHost, stream)); return 0; }
+
     void destroy()
     {
         cudaSetDevice(device);
@@ -207,6 +260,10 @@ struct Front {
         if (d_states) cudaFree(d_states);
         for (int k = 0; k < 2; ++k) if (d_carry[k]) cudaFree(d_carry[k]);
         d_io.release(); h_io.release(); d_stage.release();
+        d_m8.release(); d_e8.release(); d_tpre.release(); h_tpre.release();
+        if (d_bmat) cudaFree(d_bmat);
+        if (h_states) cudaFreeHost(h_states);
+        for (auto &e : cev) if (e) cudaEventDestroy(e);
         if (d_count) cudaFree(d_count);
         if (h_count) cudaFreeHost(h_count);
         if (own_stream && stream) cudaStreamDestroy(stream);
@@ -235,8 +292,8 @@ struct lqb_rx_s {
     unsigned n_frames = 0;
     uint64_t n_valid = 0;
     cudaEvent_t ev[7] = {};
-    float ms[5] = {};
-    uint64_t work[4] = {};
+    float ms[6] = {};
+    uint64_t work[6] = {};
 };
 
 extern "C" {
@@ -326,13 +383,14 @@ int lqb_rx_execute(lqb_rx h, uint32_t n, const uint32_t *ids, const float *const
     sp.n_out = f.d_count; sp.max_out = (unsigned)max_frames;
 
     CU(cudaEventRecord(h->ev[0], st));
+    if (int e = f.run_coarse(n, ns, sp)) return e;
     CU(cudaMemsetAsync(f.d_count, 0, 4 * sizeof(unsigned), st));
     launch_seek(sp, n, st); f.launches++;
     CU(cudaEventRecord(h->ev[1], st));
     CU(cudaMemcpyAsync(f.h_count, f.d_count, 4 * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     unsigned nf = std::min<unsigned>(f.h_count[0], (unsigned)max_frames);
-    h->work[0] = f.h_count[1]; h->work[1] = f.h_count[2]; h->work[2] = 0; h->work[3] = total;
+    h->work[0] = f.h_count[1]; h->work[1] = f.h_count[2]; h->work[2] = 0; h->work[3] = total; h->work[4] = f.h_count[3]; h->work[5] = f.coarse_ok ? (uint64_t)f.h_tpre.p[n] : 0;
     FrameDesc *fr = h->h_frames.p;
     if (nf) {
         CU(cudaMemcpyAsync(fr, h->d_frames.p, nf * sizeof(FrameDesc), cudaMemcpyDeviceToHost, st));
@@ -433,6 +491,7 @@ int lqb_rx_execute(lqb_rx h, uint32_t n, const uint32_t *ids, const float *const
         for (int k = 2; k <= 5; ++k) CU(cudaEventRecord(h->ev[k], st));
     }
     launch_carry(sp, n, st); f.launches++;
+    if (int e = f.mirror_states()) return e;
     CU(cudaEventRecord(h->ev[6], st));
 
     // ---------------- gather
@@ -452,6 +511,8 @@ int lqb_rx_execute(lqb_rx h, uint32_t n, const uint32_t *ids, const float *const
     cudaEventElapsedTime(&h->ms[0], h->ev[0], h->ev[1]);
     for (int k = 1; k < 4; ++k) cudaEventElapsedTime(&h->ms[k], h->ev[k + 1], h->ev[k + 2]);
     cudaEventElapsedTime(&h->ms[4], h->ev[0], h->ev[6]);
+    h->ms[5] = 0.0f;
+    if (sp.coarse) cudaEventElapsedTime(&h->ms[5], f.cev[0], f.cev[1]);
 
     h->n_frames = nf;
     h->order.resize(nf);
@@ -507,13 +568,13 @@ int lqb_rx_counts(lqb_rx h, uint64_t *frames, uint64_t *valid)
     if (valid) *valid = h->n_valid;
     return 0;
 }
-int lqb_rx_last_timing(lqb_rx h, float ms[5])
+int lqb_rx_last_timing(lqb_rx h, float ms[6])
 {
     if (!h) return fail(LQB_EINVAL, "null handle");
     std::memcpy(ms, h->ms, sizeof h->ms);
     return 0;
 }
-int lqb_rx_last_work(lqb_rx h, uint64_t w[4])
+int lqb_rx_last_work(lqb_rx h, uint64_t w[6])
 {
     if (!h) return fail(LQB_EINVAL, "null handle");
     std::memcpy(w, h->work, sizeof h->work);
@@ -585,10 +646,12 @@ int lqb_det_execute(lqb_det h, uint32_t n, const uint32_t *ids, const float *con
     sp.carry[0] = f.d_carry[0]; sp.carry[1] = f.d_carry[1]; sp.carry_cap = f.carry_cap;
     sp.det_mode = 1; sp.frames = nullptr; sp.detections = h->d_det.p;
     sp.n_out = f.d_count; sp.max_out = (unsigned)max_det;
-    CU(cudaMemsetAsync(f.d_count, 0, 4 * sizeof(unsigned), st));
     CU(cudaEventRecord(h->ev[0], st));
+    if (int e = f.run_coarse(n, ns, sp)) return e;
+    CU(cudaMemsetAsync(f.d_count, 0, 4 * sizeof(unsigned), st));
     launch_seek(sp, n, st); f.launches++;
     launch_carry(sp, n, st); f.launches++;
+    if (int e = f.mirror_states()) return e;
     CU(cudaEventRecord(h->ev[1], st));
     CU(cudaMemcpyAsync(f.h_count, f.d_count, 4 * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));

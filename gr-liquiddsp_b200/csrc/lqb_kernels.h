@@ -1,6 +1,7 @@
 // lqb_kernels.h -- launch interface between the C-ABI layer (lqb_api.cu) and the kernels.
 #pragma once
 #include "lqb_dev.cuh"
+#include <vector>
 
 namespace lqb {
 
@@ -15,6 +16,22 @@ struct SeekParams {
     Detection       *detections;    // det_mode 1
     unsigned        *n_out;
     unsigned         max_out;
+    // tensor-core pre-filter results (lqb_rx_coarse.cu); coarse == 0 disables the shortcut
+    int              coarse;
+    const unsigned  *tile_prefix;   // [n_io + 1] first 128-lag tile of each fed stream
+    const float     *m8;            // per 8 lags: max over lags and CFO bins of |C|^2
+    const float     *e8;            // per 8 samples: energy
+};
+
+struct CoarseParams {
+    const StreamState *states;
+    const StreamIO    *io;
+    const float2      *carry[2];
+    unsigned           carry_cap;
+    const unsigned    *tile_prefix; // [n_io + 1]
+    unsigned           n_io, n_tiles;
+    const void        *bmat;        // fp16 B operand in shared-memory layout (71680 bytes)
+    float             *m8, *e8;     // [n_tiles * 16]
 };
 
 // work list entry for kernels that run per FEC stage
@@ -40,6 +57,8 @@ struct PayloadParams {
 };
 
 void launch_seek(const SeekParams &P, unsigned n_io, cudaStream_t s);
+void launch_coarse(const CoarseParams &P, cudaStream_t s);
+void build_coarse_bmat(const float *s_re, const float *s_im, int range, std::vector<unsigned short> &out);
 void launch_carry(const SeekParams &P, unsigned n_io, cudaStream_t s);
 
 void launch_mf(const PayloadParams &P, cudaStream_t s);

@@ -146,6 +146,52 @@ __device__ void eval_window(SeekShared &sh, const DevTables *T, int tid)
     __syncthreads();
 }
 
+// Pre-filter test for the window starting r0 samples after the carry base: true when the tensor-core
+// correlation bound proves that no lag < 356 can exceed the threshold, i.e. the exact evaluation
+// could not trigger.  m8 = max |C|^2 per 8 lags (fp16 operands, error <= 1.4e-3 ||x_156|| ||s||),
+// e8 = energy per 8 samples.  Energy below uses only blocks fully inside the window (a lower bound,
+// so the rxy bound errs high); the superset sum guards the error term.
+__device__ bool coarse_rules_out(SeekShared &sh, const SeekParams &P, const DevTables *T, unsigned long long coff, long long r0, int tid)
+{
+    const int warp = tid >> 5, lane = tid & 31;
+    const long long b0 = r0 >> 3, b1 = (r0 + 355) >> 3;             // lag blocks touching [r0, r0+356)
+    const long long e0 = (r0 + 7) >> 3, e1 = ((r0 + 512) >> 3) - 1; // sample blocks inside [r0, r0+512)
+    const long long u0 = r0 >> 3, u1 = (r0 + 511) >> 3;             // sample blocks touching it
+    float m = 0.0f, el = 0.0f, eu = 0.0f;
+    for (long long b = b0 + tid; b <= b1; b += kThreads) m = fmaxf(m, P.m8[coff + b]);
+    for (long long b = u0 + tid; b <= u1; b += kThreads) {
+        const float e = P.e8[coff + b];
+        eu += e;
+        if (b >= e0 && b <= e1) el += e;
+    }
+#pragma unroll
+    for (int k = 16; k >= 1; k >>= 1) {
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, k));
+        el += __shfl_xor_sync(0xffffffffu, el, k);
+        eu += __shfl_xor_sync(0xffffffffu, eu, k);
+    }
+    __syncthreads();                       // protect the reduction scratch against the previous use
+    float *red = reinterpret_cast<float *>(sh.best);
+    if (lane == 0) red[warp] = m;
+    __shared__ float red_el[kWarps], red_eu[kWarps];
+    if (lane == 0) { red_el[warp] = el; red_eu[warp] = eu; }
+    __syncthreads();
+    if (tid == 0) {
+        float mm = 0.0f, l = 0.0f, u = 0.0f;
+        for (int w = 0; w < kWarps; ++w) { mm = fmaxf(mm, red[w]); l += red_el[w]; u += red_eu[w]; }
+        int skip = 0;
+        if (l > 0.0f && u <= 4.0f * l) {
+            const float ub = sqrtf(mm) / (sqrtf(l) * sqrtf(156.0f / 512.0f) * sqrtf(T->s2_sum));
+            skip = ub < T->threshold - 0.008f;
+        }
+        sh.trig = skip;
+    }
+    __syncthreads();
+    const bool r = sh.trig != 0;
+    __syncthreads();
+    return r;
+}
+
 // alignment on the 512 samples in sh.Xw (x[F .. F+512)) with CFO bin sh.off
 __device__ void align_frame(SeekShared &sh, const DevTables *T, int tid)
 {
@@ -370,7 +416,8 @@ k_seek(SeekParams P)
     fft512_fill_compact(sh.Wc, sh.W, tid, kThreads);
     __syncthreads();
 
-    unsigned n_windows = 0, n_aligns = 0;      // work counters (uniform across the CTA)
+    unsigned n_windows = 0, n_aligns = 0, n_exact = 0;      // work counters (uniform across the CTA)
+    const unsigned long long coff = P.coarse ? (unsigned long long)P.tile_prefix[blockIdx.x] * 16ull : 0ull;
     StreamView sv;
     sv.carry = P.carry[st.carry_sel] + (size_t)io.stream * P.carry_cap;
     sv.in = io.in;
@@ -383,10 +430,16 @@ k_seek(SeekParams P)
         // ---------------- SEEK
         if (st.mode == 0) {
             if (st.wstart + 512 > sv.end) break;
+            ++n_windows;
+            if (P.coarse && st.wstart >= st.G && coarse_rules_out(sh, P, T, coff, st.wstart - sv.base, tid)) {
+                if (tid == 0) st.wstart += 256;
+                __syncthreads();
+                continue;
+            }
+            ++n_exact;
             load_window(sh, sv, st.wstart, tid);
             __syncthreads();
             eval_window(sh, T, tid);
-            ++n_windows;
             if (!sh.trig) {
                 if (tid == 0) st.wstart += 256;
                 __syncthreads();
@@ -513,6 +566,7 @@ k_seek(SeekParams P)
         P.states[io.stream] = st;
         atomicAdd(P.n_out + 1, n_windows);
         atomicAdd(P.n_out + 2, n_aligns);
+        atomicAdd(P.n_out + 3, n_exact);
     }
 }
 

@@ -190,7 +190,7 @@ class Rx:
         return [_frame_to_dict(arr[i], host) for i in range(nf)]
 
     def timing(self):
-        ms = (C.c_float * 5)()
+        ms = (C.c_float * 6)()
         _check(self._L.lqb_rx_last_timing(self._h, ms))
         return list(ms)
 
@@ -200,9 +200,10 @@ class Rx:
         return int(v.value)
 
     def work(self):
-        w = (C.c_uint64 * 4)()
+        w = (C.c_uint64 * 6)()
         _check(self._L.lqb_rx_last_work(self._h, w))
-        return dict(windows=int(w[0]), aligns=int(w[1]), symbols=int(w[2]), samples=int(w[3]))
+        return dict(windows=int(w[0]), aligns=int(w[1]), symbols=int(w[2]), samples=int(w[3]),
+                    exact_windows=int(w[4]), coarse_tiles=int(w[5]))
 
 
 class Det:

@@ -151,12 +151,14 @@ int    lqb_rx_poll(lqb_rx h, lqb_frame_result *out, uint32_t max_out, uint32_t *
 /* number of frames completed by the last execute / payloads with a passing check */
 int    lqb_rx_counts(lqb_rx h, uint64_t *frames, uint64_t *valid_payloads);
 /* per-kernel device times (ms) of the last execute, measured with CUDA events on the handle's
- * stream: [0]=seek/align/header [1]=matched filter [2]=PLL+demod [3]=FEC+CRC [4]=total */
-int    lqb_rx_last_timing(lqb_rx h, float ms[5]);
+ * stream: [0]=pre-filter+seek/align/header [1]=matched filter [2]=PLL+demod [3]=FEC+CRC [4]=total
+ * [5]=tensor-core pre-filter alone (included in [0]) */
+int    lqb_rx_last_timing(lqb_rx h, float ms[6]);
 int    lqb_rx_launch_count(lqb_rx h, uint64_t *launches);   /* kernels launched since create */
-/* work done by the last execute: [0] 512-sample detector windows evaluated, [1] frame alignments,
- * [2] payload symbols matched-filtered/demodulated, [3] input samples consumed */
-int    lqb_rx_last_work(lqb_rx h, uint64_t work[4]);
+/* work done by the last execute: [0] 512-sample detector windows visited, [1] frame alignments,
+ * [2] payload symbols matched-filtered/demodulated, [3] input samples consumed,
+ * [4] windows that needed the exact 50-FFT evaluation, [5] 128-lag pre-filter tiles */
+int    lqb_rx_last_work(lqb_rx h, uint64_t work[6]);
 
 /* ------------------------------------------------------------------ TX (flex_tx / flexframegen) */
 typedef struct lqb_tx_s *lqb_tx;

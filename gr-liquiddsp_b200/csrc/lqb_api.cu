@@ -224,9 +224,10 @@ struct Front {
     // plan and launch the pre-filter for the streams just fed; fills the coarse fields of sp
     int run_coarse(uint32_t n, const uint64_t *ns, SeekParams &sp)
     {
-        sp.coarse = 0; sp.tile_prefix = nullptr; sp.m8 = nullptr; sp.e8 = nullptr;
+        sp.coarse = 0; sp.tile_prefix = nullptr; sp.m8 = nullptr; sp.e8 = nullptr; sp.bmat = d_bmat;
         coarse_ms = 0.0f;
         if (!coarse_ok || !n) return 0;
+        if (!getenv("LQB_COARSE_SEPARATE")) { sp.coarse = 2; h_tpre.reserve(n + 1); h_tpre.p[n] = 0; return 0; }   // fused in k_seek
         if (int e = h_tpre.reserve(n + 1)) return e;
         if (int e = d_tpre.reserve(n + 1)) return e;
         uint64_t tiles = 0;
@@ -512,7 +513,7 @@ int lqb_rx_execute(lqb_rx h, uint32_t n, const uint32_t *ids, const float *const
     for (int k = 1; k < 4; ++k) cudaEventElapsedTime(&h->ms[k], h->ev[k + 1], h->ev[k + 2]);
     cudaEventElapsedTime(&h->ms[4], h->ev[0], h->ev[6]);
     h->ms[5] = 0.0f;
-    if (sp.coarse) cudaEventElapsedTime(&h->ms[5], f.cev[0], f.cev[1]);
+    if (sp.coarse == 1) cudaEventElapsedTime(&h->ms[5], f.cev[0], f.cev[1]);
 
     h->n_frames = nf;
     h->order.resize(nf);

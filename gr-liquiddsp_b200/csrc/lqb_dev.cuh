@@ -131,7 +131,7 @@ struct StreamView {
     unsigned      carry_len;
     __device__ __forceinline__ float2 at(long long n) const
     {
-        if (n < G || n >= end) return make_float2(0.0f, 0.0f);
+        if (n < G || n >= end || n < base) return make_float2(0.0f, 0.0f);
         long long i = n - base;
         return (i < (long long)carry_len) ? carry[i] : in[i - carry_len];
     }

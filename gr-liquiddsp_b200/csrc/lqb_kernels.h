@@ -17,7 +17,8 @@ struct SeekParams {
     unsigned        *n_out;
     unsigned         max_out;
     // tensor-core pre-filter results (lqb_rx_coarse.cu); coarse == 0 disables the shortcut
-    int              coarse;
+    int              coarse;        // 0: off, 1: separate pre-filter kernel results in m8/e8, 2: fused in k_seek
+    const void      *bmat;          // fp16 B operand (coarse == 2)
     const unsigned  *tile_prefix;   // [n_io + 1] first 128-lag tile of each fed stream
     const float     *m8;            // per 8 lags: max over lags and CFO bins of |C|^2
     const float     *e8;            // per 8 samples: energy

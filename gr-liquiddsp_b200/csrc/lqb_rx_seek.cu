@@ -11,6 +11,7 @@
 // The payload itself is left to the frame-parallel kernels in lqb_rx_payload.cu.
 #include "lqb_dev.cuh"
 #include "lqb_kernels.h"
+#include "lqb_tc.cuh"
 
 namespace lqb {
 
@@ -20,7 +21,7 @@ namespace {
 #define LQB_SEEK_WARPS 4
 #endif
 #ifndef LQB_SEEK_MINB
-#define LQB_SEEK_MINB 4
+#define LQB_SEEK_MINB 2
 #endif
 constexpr int kWarps = LQB_SEEK_WARPS;
 constexpr int kThreads = 32 * kWarps;
@@ -40,6 +41,11 @@ struct SeekShared {
     int    trig, idx, off, stop, hv;
     float  rxy, tau, gamma, dphi, phi, mf_scale;
     unsigned theta0, dtheta, pfb, tau_neg;
+    // fused tensor-core pre-filter
+    uint64_t tc_bar;
+    unsigned tmem_base;
+    float tc_wmax[kWarps], tc_wsum[kWarps], tc_red[2 * kWarps];
+    float tc_scale2, tc_energy, tc_m0, tc_m1;
     unsigned char hbytes[64]; // header: 54 demodulated bytes
     unsigned char hdec[32];   // decoded header (24 bytes incl. CRC)
 };
@@ -144,6 +150,140 @@ __device__ void eval_window(SeekShared &sh, const DevTables *T, int tid)
         sh.trig = trig; sh.idx = idx; sh.off = off; sh.rxy = rxy;
     }
     __syncthreads();
+}
+
+
+// ------------------------------------------------------------------ fused tensor-core correlation block
+// Correlates n_t * 128 consecutive lags starting at absolute sample a0 against the template at all
+// 49 CFO bins on the tensor cores (fp16 operands, fp32 accumulation in TMEM; same implicit-Hankel
+// operand trick as lqb_rx_coarse.cu) and leaves max_b |C|^2 per lag in rowmax[]; also returns the
+// exact-input energy of the staged samples with absolute index in [e_lo, e_hi).
+// scr layout while this runs: Z[2][416*16] | xs[2][432] halfs | rowmax[256] floats.
+constexpr int kTcRows = 2 * 128 + 160;          // 416 rows of 16 bytes per component
+constexpr int kTcZBytes = kTcRows * 16;         // 6656
+constexpr int kTcSamp = kTcRows + 8;            // 424 staged samples
+
+__device__ void tc_block(SeekShared &sh, const unsigned char *Bsm, const StreamView &sv, long long a0, int n_t,
+                         long long e_lo, long long e_hi, unsigned &phase, int tid)
+{
+    using namespace tc;
+    const int warp = tid >> 5, lane = tid & 31;
+    unsigned char *Z = reinterpret_cast<unsigned char *>(sh.scr);
+    __half *xs = reinterpret_cast<__half *>(Z + 2 * kTcZBytes);
+    float *rowmax = reinterpret_cast<float *>(Z + 2 * kTcZBytes + 2 * 432 * sizeof(__half));
+    const int n_samp = 128 * n_t + 168;
+    // ---- stage samples: magnitude max (tile scale) and window-half energy from the exact inputs
+    float2 v[4];
+    float mx = 0.0f, en = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int i = tid + kThreads * k;
+        const long long n = a0 + i;
+        v[k] = (i < n_samp) ? sv.at(n) : make_float2(0.0f, 0.0f);
+        mx = fmaxf(mx, fmaxf(fabsf(v[k].x), fabsf(v[k].y)));
+        if (i < n_samp && n >= e_lo && n < e_hi) en += fmaf(v[k].y, v[k].y, v[k].x * v[k].x);
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, m));
+        en += __shfl_xor_sync(0xffffffffu, en, m);
+    }
+    if (lane == 0) { sh.tc_wmax[warp] = mx; sh.tc_wsum[warp] = en; }
+    __syncthreads();
+    mx = 0.0f; en = 0.0f;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) { mx = fmaxf(mx, sh.tc_wmax[w]); en += sh.tc_wsum[w]; }
+    int ex = 0;
+    if (mx > 0.0f) ex = (int)((__float_as_uint(mx) >> 23) & 0xffu) - 127;
+    ex = max(-100, min(100, ex));
+    const float sc = __uint_as_float((uint32_t)(127 - ex) << 23);          // exact power of two
+    const float scale2 = __uint_as_float((uint32_t)(127 + 2 * ex) << 23);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int i = tid + kThreads * k;
+        if (i < n_samp) { xs[i] = __float2half_rn(v[k].x * sc); xs[432 + i] = __float2half_rn(v[k].y * sc); }
+    }
+    __syncthreads();
+    // ---- Z[c][8 m + e] = xs[c][m + e]
+    const int rows = 128 * n_t + 160;
+    for (int m = tid; m < rows; m += kThreads) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const __half *s = xs + 432 * c + m;
+            __half2 h0 = __halves2half2(s[0], s[1]), h1 = __halves2half2(s[2], s[3]);
+            __half2 h2 = __halves2half2(s[4], s[5]), h3 = __halves2half2(s[6], s[7]);
+            uint4 w;
+            w.x = *reinterpret_cast<uint32_t *>(&h0); w.y = *reinterpret_cast<uint32_t *>(&h1);
+            w.z = *reinterpret_cast<uint32_t *>(&h2); w.w = *reinterpret_cast<uint32_t *>(&h3);
+            *reinterpret_cast<uint4 *>(Z + c * kTcZBytes + 16 * m) = w;
+        }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    // ---- 20 MMAs (M=128, N=112, K=16) per tile, issued by one thread
+    const uint32_t tmem = sh.tmem_base;
+    if (tid == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t idesc = (1u << 4) | ((uint32_t)(kN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t b_addr = smem_u32(Bsm);
+        for (int t = 0; t < n_t; ++t) {
+            uint32_t acc = 0;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const uint32_t za = smem_u32(Z + c * kTcZBytes) + 2048u * t;
+#pragma unroll
+                for (int j = 0; j < 10; ++j) {
+                    mma_f16(tmem + 128u * t, make_desc(za + 256u * j, 128u, 128u),
+                            make_desc(b_addr + (uint32_t)((c * 10 + j) * 2) * kBChunkBytes, kBChunkBytes, 128u), idesc, acc);
+                    acc = 1;
+                }
+            }
+        }
+        mma_commit(&sh.tc_bar);
+    }
+    mbar_wait(&sh.tc_bar, phase);
+    phase ^= 1u;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // ---- epilogue: thread = lag row; max over the 49 bins of re^2 + im^2
+    for (int t = 0; t < n_t; ++t) {
+        const uint32_t taddr = tmem + 128u * t + ((uint32_t)(warp * 32) << 16);
+        float best = 0.0f;
+#pragma unroll
+        for (int q = 0; q < 7; ++q) {
+            uint32_t r[16];
+            tmem_ld16(taddr + 16u * q, r);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int k = 0; k < 16; k += 2) {
+                if (16 * q + k < 2 * kNBins) {
+                    const float re = __uint_as_float(r[k]), im = __uint_as_float(r[k + 1]);
+                    best = fmaxf(best, fmaf(im, im, re * re));
+                }
+            }
+        }
+        rowmax[128 * t + tid] = best * scale2;
+    }
+    if (tid == 0) sh.tc_energy = en;
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+}
+
+// max of rowmax[lo .. hi) over the CTA -> every thread
+__device__ float tc_rowmax(SeekShared &sh, int lo, int hi, int tid)
+{
+    const float *rowmax = reinterpret_cast<const float *>(reinterpret_cast<unsigned char *>(sh.scr) + 2 * kTcZBytes + 2 * 432 * sizeof(__half));
+    const int warp = tid >> 5, lane = tid & 31;
+    float m = 0.0f;
+    for (int i = lo + tid; i < hi; i += kThreads) m = fmaxf(m, rowmax[i]);
+#pragma unroll
+    for (int k = 16; k >= 1; k >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, k));
+    __syncthreads();
+    if (lane == 0) sh.tc_red[warp] = m;
+    __syncthreads();
+    m = 0.0f;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) m = fmaxf(m, sh.tc_red[w]);
+    return m;
 }
 
 // Pre-filter test for the window starting r0 samples after the carry base: true when the tensor-core
@@ -409,15 +549,37 @@ k_seek(SeekParams P)
     const DevTables *T = P.tables;
     const StreamIO io = P.io[blockIdx.x];
 
+    extern __shared__ unsigned char dyn_smem[];
+    unsigned char *Bsm = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(dyn_smem) + 127) & ~uintptr_t(127));
+    const bool fused = (P.coarse == 2);
+    unsigned tc_phase = 0;
+    if (fused) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(P.bmat);
+        uint4 *dst = reinterpret_cast<uint4 *>(Bsm);
+        for (int i = tid; i < tc::kBBytes / 16; i += kThreads) dst[i] = src[i];
+        if (tid == 0) tc::mbar_init(reinterpret_cast<uint64_t *>(&sh.tc_bar), 1);
+        if (tid < 32) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tc::smem_u32(&sh.tmem_base)), "r"(256));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
     for (int i = tid; i < 512; i += kThreads) sh.Sc[i] = T->Sc[i];
     for (int i = tid; i < 256; i += kThreads) sh.W[i] = T->W512[i];
     if (tid == 0) st = P.states[io.stream];
     __syncthreads();
     fft512_fill_compact(sh.Wc, sh.W, tid, kThreads);
     __syncthreads();
+    if (fused) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // pre-filter carry-over between consecutive windows of one hop grid (uniform across the CTA)
+    bool c_valid = false;
+    long long c_w = 0;
+    float c_tail = 0.0f, c_half = 0.0f;
 
     unsigned n_windows = 0, n_aligns = 0, n_exact = 0;      // work counters (uniform across the CTA)
-    const unsigned long long coff = P.coarse ? (unsigned long long)P.tile_prefix[blockIdx.x] * 16ull : 0ull;
+    const unsigned long long coff = P.coarse == 1 ? (unsigned long long)P.tile_prefix[blockIdx.x] * 16ull : 0ull;
     StreamView sv;
     sv.carry = P.carry[st.carry_sel] + (size_t)io.stream * P.carry_cap;
     sv.in = io.in;
@@ -431,7 +593,33 @@ k_seek(SeekParams P)
         if (st.mode == 0) {
             if (st.wstart + 512 > sv.end) break;
             ++n_windows;
-            if (P.coarse && st.wstart >= st.G && coarse_rules_out(sh, P, T, coff, st.wstart - sv.base, tid)) {
+            if (fused && st.wstart >= st.G) {
+                const long long w = st.wstart;
+                if (!(c_valid && c_w == w)) {
+                    // cold start of a hop grid: lags [w-28, w+100), first-half energy [w, w+256)
+                    tc_block(sh, Bsm, sv, w - 28, 1, w, w + 256, tc_phase, tid);
+                    c_tail = tc_rowmax(sh, 28, 128, tid);
+                    c_half = sh.tc_energy;
+                }
+                // lags [w+100, w+356) and the second-half energy [w+256, w+512)
+                tc_block(sh, Bsm, sv, w + 100, 2, w + 256, w + 512, tc_phase, tid);
+                const float m_new = tc_rowmax(sh, 0, 256, tid);
+                const float m_tail = tc_rowmax(sh, 156, 256, tid);
+                const float e2 = sh.tc_energy;
+                const float mm = fmaxf(c_tail, m_new), E = c_half + e2;
+                bool skip = false;
+                if (E > 0.0f) {
+                    const float ub = sqrtf(mm) / (sqrtf(E) * sqrtf(156.0f / 512.0f) * sqrtf(T->s2_sum));
+                    skip = ub < T->threshold - 0.008f;
+                }
+                c_tail = m_tail; c_half = e2; c_w = w + 256; c_valid = true;
+                __syncthreads();
+                if (skip) {
+                    if (tid == 0) st.wstart += 256;
+                    __syncthreads();
+                    continue;
+                }
+            } else if (P.coarse == 1 && st.wstart >= st.G && coarse_rules_out(sh, P, T, coff, st.wstart - sv.base, tid)) {
                 if (tid == 0) st.wstart += 256;
                 __syncthreads();
                 continue;
@@ -454,7 +642,8 @@ k_seek(SeekParams P)
             }
             __syncthreads();
         }
-        // ---------------- PENDING: frame start known
+        // ---------------- PENDING: frame start known (the hop grid restarts afterwards)
+        c_valid = false;
         if (sv.end < st.need_until) break;
         const long long F = st.F;
         load_window(sh, sv, F, tid);
@@ -557,6 +746,11 @@ k_seek(SeekParams P)
         sv.G = st.G;
     }
 
+    if (fused) {
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(sh.tmem_base), "r"(256));
+    }
     if (tid == 0) {
         long long r = (st.mode == 0) ? st.wstart : st.F;
         if (r < st.G) r = st.G;
@@ -596,7 +790,13 @@ __global__ void k_carry(SeekParams P)
     }
 }
 
-void launch_seek(const SeekParams &P, unsigned n_io, cudaStream_t s) { k_seek<<<n_io, kThreads, 0, s>>>(P); }
+void launch_seek(const SeekParams &P, unsigned n_io, cudaStream_t s)
+{
+    static bool attr_set = false;
+    const int dyn = tc::kBBytes + 256;
+    if (!attr_set) { cudaFuncSetAttribute(k_seek, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn); attr_set = true; }
+    k_seek<<<n_io, kThreads, P.coarse == 2 ? dyn : 0, s>>>(P);
+}
 void launch_carry(const SeekParams &P, unsigned n_io, cudaStream_t s) { k_carry<<<n_io, 256, 0, s>>>(P); }
 
 }  // namespace lqb

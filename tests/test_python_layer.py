@@ -1,0 +1,102 @@
+"""Python layer: policy stand-in (numbering contract), channel sharding + host-side gather over a
+world-size-2 gloo group on CPU, and -- on the GPU -- the Python block mirrors in a closed loop."""
+import os
+
+import numpy as np
+import pytest
+
+import lqo_py as o
+import util
+from liquiddsp import policy, sharding
+
+
+def test_policy_numbering_matches_cognitive_engine():
+    assert policy.N_CONFIGS == 616
+    assert policy.config_id(0, 0, 0) == 1 and policy.config_id(10, 6, 7) == 616
+    m, i, oo = policy.from_config_id(np.arange(1, 617))
+    assert np.array_equal(policy.config_id(m, i, oo), np.arange(1, 617))
+    p = policy.EpsilonGreedy(3, epsilon=0.0, seed=1)
+    p.trials[:] = 1                                   # everything tried once with zero reward ...
+    p.update([0, 1, 2], [{"modulation": 8, "inner_code": 0, "outer_code": 0, "payload_valid": 1, "header_valid": 1}] * 3)
+    assert p.choose() == [{"modulation": 8, "inner_code": 0, "outer_code": 0}] * 3   # ... so the rewarded one wins
+    p.update([0], [{"modulation": -1, "inner_code": 0, "outer_code": 0, "payload_valid": 1, "header_valid": 1}])   # ignored
+
+
+def test_channel_partition_is_exact():
+    for world in (1, 2, 4, 8):
+        got = np.sort(np.concatenate([sharding.channels_of_rank(4096, r, world) for r in range(world)]))
+        assert np.array_equal(got, np.arange(4096))
+        for r in range(world):
+            ch = sharding.channels_of_rank(4096, r, world)
+            assert np.array_equal(sharding.local_stream_of(ch, world), np.arange(len(ch)))
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n_channels = 10
+    mine = sharding.channels_of_rank(n_channels, rank, world)
+    frames = []
+    for s, ch in enumerate(mine):                     # two fake frames per local stream, as Rx.poll() would return them
+        for seq in range(2):
+            frames.append(dict(stream=s, seq=seq, sample_index=1000 * seq + ch, header_valid=1, payload_valid=seq,
+                               mod_scheme=2, fec0=11, fec1=27, payload_len=1500, evm=-20.0 - ch, rssi=0.0, cfo=0.001 * ch))
+    rec = sharding.records_from_frames(frames, rank, world)
+    allrec = sharding.gather_records(rec, dst=0)
+    if rank == 0:
+        q.put(allrec)
+    else:
+        assert allrec is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_host_side_gather_world_size_2_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + os.getpid() % 300
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    rec = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert len(rec) == 20
+    assert rec["channel"].tolist() == [c for c in range(10) for _ in range(2)]
+    assert rec["seq"].tolist() == [0, 1] * 10
+    assert np.allclose(rec["evm"][::2], -20.0 - np.arange(10))
+    assert rec["payload_valid"].sum() == 10
+
+
+@pytest.mark.gpu
+def test_python_blocks_closed_loop_with_policy(gpu_required):
+    import liquiddsp
+    rng = np.random.default_rng(6)
+    tx, rx, det = liquiddsp.flex_tx(1, 0, 0), liquiddsp.flex_rx(), liquiddsp.frame_detector_cc()
+    frames, infos, payloads = liquiddsp.blocks.sink(), liquiddsp.blocks.sink(), liquiddsp.blocks.sink()
+    tx.msg_connect("pdus", frames, "in")
+    rx.msg_connect("packet_info", infos, "in")
+    rx.msg_connect("payload_data", payloads, "in")
+    assert tx.message_ports_in() == ["pdus", "configuration"] and rx.message_ports_out() == ["constellation", "payload_data", "packet_info"]
+    with pytest.raises(RuntimeError, match="This is not a stream block."):
+        tx.work()
+    pol = policy.EpsilonGreedy(1, epsilon=1.0, seed=3)
+    sent = []
+    for k in range(6):
+        pl = rng.integers(0, 256, 256, dtype=np.uint8)
+        sent.append(pl.tobytes())
+        tx.post("pdus", (None, pl))
+        cap = util.impair(frames.msgs[-1][1], rng, snr_db=35.0, pre=512, post=1024)
+        cap = np.concatenate([cap, np.zeros((-len(cap)) % 256, np.complex64)])
+        assert np.array_equal(det.work(cap), cap)
+        rx.work(cap)
+        pol.update([0], [infos.msgs[-1]])
+        tx.post("configuration", pol.choose()[0])            # cognitive_engine -> flex_tx contract
+    assert [p[1] for p in payloads.msgs] == sent
+    assert all(i["header_valid"] == 1 and i["payload_valid"] == 1 for i in infos.msgs)
+    assert len({(i["modulation"], i["inner_code"], i["outer_code"]) for i in infos.msgs}) > 1   # the loop really reconfigured
+    assert det.num_frames >= 6

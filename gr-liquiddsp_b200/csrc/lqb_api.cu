@@ -146,8 +146,8 @@ struct Front {
         CU(cudaMemcpy(d_tables, &T, sizeof(DevTables), cudaMemcpyHostToDevice));
         CU(cudaMalloc(&d_states, (size_t)ns * sizeof(StreamState)));
         for (int k = 0; k < 2; ++k) CU(cudaMalloc(&d_carry[k], (size_t)ns * cap * sizeof(float2)));
-        CU(cudaMalloc(&d_count, 4 * sizeof(unsigned)));
-        CU(cudaMallocHost(&h_count, 4 * sizeof(unsigned)));
+        CU(cudaMalloc(&d_count, 8 * sizeof(unsigned)));
+        CU(cudaMallocHost(&h_count, 8 * sizeof(unsigned)));
         CU(cudaMallocHost(&h_states, (size_t)ns * sizeof(StreamState)));
         CU(cudaEventCreate(&cev[0])); CU(cudaEventCreate(&cev[1]));
         fed.assign(ns, 0);
@@ -385,13 +385,13 @@ int lqb_rx_execute(lqb_rx h, uint32_t n, const uint32_t *ids, const float *const
 
     CU(cudaEventRecord(h->ev[0], st));
     if (int e = f.run_coarse(n, ns, sp)) return e;
-    CU(cudaMemsetAsync(f.d_count, 0, 4 * sizeof(unsigned), st));
+    CU(cudaMemsetAsync(f.d_count, 0, 8 * sizeof(unsigned), st));
     launch_seek(sp, n, st); f.launches++;
     CU(cudaEventRecord(h->ev[1], st));
-    CU(cudaMemcpyAsync(f.h_count, f.d_count, 4 * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(f.h_count, f.d_count, 8 * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     unsigned nf = std::min<unsigned>(f.h_count[0], (unsigned)max_frames);
-    h->work[0] = f.h_count[1]; h->work[1] = f.h_count[2]; h->work[2] = 0; h->work[3] = total; h->work[4] = f.h_count[3]; h->work[5] = f.coarse_ok ? (uint64_t)f.h_tpre.p[n] : 0;
+    h->work[0] = f.h_count[1]; h->work[1] = f.h_count[2]; h->work[2] = 0; h->work[3] = total; h->work[4] = f.h_count[3]; h->work[5] = sp.coarse == 2 ? (uint64_t)f.h_count[4] : (sp.coarse == 1 ? (uint64_t)f.h_tpre.p[n] : 0);
     FrameDesc *fr = h->h_frames.p;
     if (nf) {
         CU(cudaMemcpyAsync(fr, h->d_frames.p, nf * sizeof(FrameDesc), cudaMemcpyDeviceToHost, st));
@@ -649,7 +649,7 @@ int lqb_det_execute(lqb_det h, uint32_t n, const uint32_t *ids, const float *con
     sp.n_out = f.d_count; sp.max_out = (unsigned)max_det;
     CU(cudaEventRecord(h->ev[0], st));
     if (int e = f.run_coarse(n, ns, sp)) return e;
-    CU(cudaMemsetAsync(f.d_count, 0, 4 * sizeof(unsigned), st));
+    CU(cudaMemsetAsync(f.d_count, 0, 8 * sizeof(unsigned), st));
     launch_seek(sp, n, st); f.launches++;
     launch_carry(sp, n, st); f.launches++;
     if (int e = f.mirror_states()) return e;

@@ -163,8 +163,11 @@ constexpr int kTcRows = 2 * 128 + 160;          // 416 rows of 16 bytes per comp
 constexpr int kTcZBytes = kTcRows * 16;         // 6656
 constexpr int kTcSamp = kTcRows + 8;            // 424 staged samples
 
+// pre[] / pre_a0: samples already fetched for the block starting at pre_a0 (by the previous call, while its
+// MMAs were running); next_a0: where the caller expects the following block to start.
 __device__ void tc_block(SeekShared &sh, const unsigned char *Bsm, const StreamView &sv, long long a0, int n_t,
-                         long long e_lo, long long e_hi, unsigned &phase, int tid)
+                         long long e_lo, long long e_hi, unsigned &phase, int tid,
+                         float2 (&pre)[4], long long &pre_a0, long long next_a0)
 {
     using namespace tc;
     const int warp = tid >> 5, lane = tid & 31;
@@ -179,7 +182,8 @@ __device__ void tc_block(SeekShared &sh, const unsigned char *Bsm, const StreamV
     for (int k = 0; k < 4; ++k) {
         const int i = tid + kThreads * k;
         const long long n = a0 + i;
-        v[k] = (i < n_samp) ? sv.at(n) : make_float2(0.0f, 0.0f);
+        v[k] = (pre_a0 == a0) ? pre[k] : ((i < 424) ? sv.at(n) : make_float2(0.0f, 0.0f));
+        if (i >= n_samp) v[k] = make_float2(0.0f, 0.0f);
         mx = fmaxf(mx, fmaxf(fabsf(v[k].x), fabsf(v[k].y)));
         if (i < n_samp && n >= e_lo && n < e_hi) en += fmaf(v[k].y, v[k].y, v[k].x * v[k].x);
     }
@@ -241,6 +245,13 @@ __device__ void tc_block(SeekShared &sh, const unsigned char *Bsm, const StreamV
         }
         mma_commit(&sh.tc_bar);
     }
+    // while the tensor core works: fetch the samples of the block the caller will ask for next
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int i = tid + kThreads * k;
+        pre[k] = (i < 424) ? sv.at(next_a0 + i) : make_float2(0.0f, 0.0f);
+    }
+    pre_a0 = next_a0;
     mbar_wait(&sh.tc_bar, phase);
     phase ^= 1u;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -249,15 +260,21 @@ __device__ void tc_block(SeekShared &sh, const unsigned char *Bsm, const StreamV
         const uint32_t taddr = tmem + 128u * t + ((uint32_t)(warp * 32) << 16);
         float best = 0.0f;
 #pragma unroll
-        for (int q = 0; q < 7; ++q) {
-            uint32_t r[16];
-            tmem_ld16(taddr + 16u * q, r);
+        for (int half = 0; half < 2; ++half) {
+            uint32_t r[4][16];
+            const int q0 = half * 4, nq = half ? 3 : 4;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) if (q < nq) tmem_ld16(taddr + 16u * (q0 + q), r[q]);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-            for (int k = 0; k < 16; k += 2) {
-                if (16 * q + k < 2 * kNBins) {
-                    const float re = __uint_as_float(r[k]), im = __uint_as_float(r[k + 1]);
-                    best = fmaxf(best, fmaf(im, im, re * re));
+            for (int q = 0; q < 4; ++q) {
+                if (q >= nq) continue;
+#pragma unroll
+                for (int k = 0; k < 16; k += 2) {
+                    if (16 * (q0 + q) + k < 2 * kNBins) {
+                        const float re = __uint_as_float(r[q][k]), im = __uint_as_float(r[q][k + 1]);
+                        best = fmaxf(best, fmaf(im, im, re * re));
+                    }
                 }
             }
         }
@@ -265,6 +282,31 @@ __device__ void tc_block(SeekShared &sh, const unsigned char *Bsm, const StreamV
     }
     if (tid == 0) sh.tc_energy = en;
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+}
+
+// max of rowmax[lo .. hi) and of rowmax[lo2 .. hi) over the CTA -> every thread (one pass, two results)
+__device__ void tc_rowmax2(SeekShared &sh, int lo, int lo2, int hi, int tid, float &m_all, float &m_tail)
+{
+    const float *rowmax = reinterpret_cast<const float *>(reinterpret_cast<unsigned char *>(sh.scr) + 2 * kTcZBytes + 2 * 432 * sizeof(__half));
+    const int warp = tid >> 5, lane = tid & 31;
+    float a = 0.0f, b = 0.0f;
+    for (int i = lo + tid; i < hi; i += kThreads) {
+        const float v = rowmax[i];
+        a = fmaxf(a, v);
+        if (i >= lo2) b = fmaxf(b, v);
+    }
+#pragma unroll
+    for (int k = 16; k >= 1; k >>= 1) {
+        a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, k));
+        b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, k));
+    }
+    if (lane == 0) { sh.tc_red[warp] = a; sh.tc_red[kWarps + warp] = b; }
+    __syncthreads();
+    a = 0.0f; b = 0.0f;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) { a = fmaxf(a, sh.tc_red[w]); b = fmaxf(b, sh.tc_red[kWarps + w]); }
+    m_all = a; m_tail = b;
     __syncthreads();
 }
 
@@ -577,8 +619,12 @@ k_seek(SeekParams P)
     bool c_valid = false;
     long long c_w = 0;
     float c_tail = 0.0f, c_half = 0.0f;
+    float2 tc_pre[4];
+    long long tc_pre_a0 = -(1ll << 62);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) tc_pre[k] = make_float2(0.0f, 0.0f);
 
-    unsigned n_windows = 0, n_aligns = 0, n_exact = 0;      // work counters (uniform across the CTA)
+    unsigned n_windows = 0, n_aligns = 0, n_exact = 0, n_tc_tiles = 0;      // work counters (uniform across the CTA)
     const unsigned long long coff = P.coarse == 1 ? (unsigned long long)P.tile_prefix[blockIdx.x] * 16ull : 0ull;
     StreamView sv;
     sv.carry = P.carry[st.carry_sel] + (size_t)io.stream * P.carry_cap;
@@ -597,14 +643,16 @@ k_seek(SeekParams P)
                 const long long w = st.wstart;
                 if (!(c_valid && c_w == w)) {
                     // cold start of a hop grid: lags [w-28, w+100), first-half energy [w, w+256)
-                    tc_block(sh, Bsm, sv, w - 28, 1, w, w + 256, tc_phase, tid);
+                    tc_block(sh, Bsm, sv, w - 28, 1, w, w + 256, tc_phase, tid, tc_pre, tc_pre_a0, w + 100);
+                    n_tc_tiles += 1;
                     c_tail = tc_rowmax(sh, 28, 128, tid);
                     c_half = sh.tc_energy;
                 }
                 // lags [w+100, w+356) and the second-half energy [w+256, w+512)
-                tc_block(sh, Bsm, sv, w + 100, 2, w + 256, w + 512, tc_phase, tid);
-                const float m_new = tc_rowmax(sh, 0, 256, tid);
-                const float m_tail = tc_rowmax(sh, 156, 256, tid);
+                tc_block(sh, Bsm, sv, w + 100, 2, w + 256, w + 512, tc_phase, tid, tc_pre, tc_pre_a0, w + 356);
+                n_tc_tiles += 2;
+                float m_new, m_tail;
+                tc_rowmax2(sh, 0, 156, 256, tid, m_new, m_tail);
                 const float e2 = sh.tc_energy;
                 const float mm = fmaxf(c_tail, m_new), E = c_half + e2;
                 bool skip = false;
@@ -644,6 +692,7 @@ k_seek(SeekParams P)
         }
         // ---------------- PENDING: frame start known (the hop grid restarts afterwards)
         c_valid = false;
+        tc_pre_a0 = -(1ll << 62);          // prefetched samples were taken under the old zero boundary
         if (sv.end < st.need_until) break;
         const long long F = st.F;
         load_window(sh, sv, F, tid);
@@ -761,6 +810,7 @@ k_seek(SeekParams P)
         atomicAdd(P.n_out + 1, n_windows);
         atomicAdd(P.n_out + 2, n_aligns);
         atomicAdd(P.n_out + 3, n_exact);
+        atomicAdd(P.n_out + 4, n_tc_tiles);
     }
 }
 

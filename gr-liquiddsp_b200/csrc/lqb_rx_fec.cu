@@ -28,14 +28,27 @@ __device__ __forceinline__ StageIO stage_io(const PayloadParams &P, const FrameD
 }
 
 // ------------------------------------------------------------------ interleaver
+// The frame's bytes are brought into shared memory once (16 KB window; longer buffers take the
+// global-memory route), the four involutive passes run there, and the result is written back.
+constexpr unsigned kIlvSmem = 16384;
+
 __global__ void __launch_bounds__(256)
 k_deinterleave(PayloadParams P, const unsigned *__restrict__ list, int stage)
 {
+    __shared__ __align__(16) unsigned char buf[kIlvSmem];
     const FrameDesc &d = P.frames[list[blockIdx.x]];
-    unsigned char *x = (stage == 1) ? (P.bufA + d.buf_off) : (P.bufB + d.buf_off);
+    unsigned char *g = (stage == 1) ? (P.bufA + d.buf_off) : (P.bufB + d.buf_off);
     const unsigned n = (stage == 1) ? d.n1 : d.n0, n2 = n / 2;
     const unsigned *maps = P.ilv_maps + ((stage == 1) ? d.ilv1_off : d.ilv0_off);
     const unsigned masks[4] = { 0xffu, 0x0fu, 0x55u, 0x33u };
+    const bool in_smem = n <= kIlvSmem;
+    unsigned char *x = in_smem ? buf : g;
+    if (in_smem) {
+        const unsigned n16 = (n + 15) / 16;                     // buffers are 16-byte aligned and padded
+        for (unsigned i = threadIdx.x; i < n16; i += blockDim.x)
+            reinterpret_cast<uint4 *>(buf)[i] = reinterpret_cast<const uint4 *>(g)[i];
+        __syncthreads();
+    }
     for (int pass = 3; pass >= 0; --pass) {
         const unsigned *map = maps + (size_t)pass * n2;
         const unsigned mask = masks[pass];
@@ -46,6 +59,11 @@ k_deinterleave(PayloadParams P, const unsigned *__restrict__ list, int stage)
             x[2 * i] = (unsigned char)((a & mask) | (b & ~mask));
         }
         __syncthreads();
+    }
+    if (in_smem) {
+        const unsigned n16 = (n + 15) / 16;
+        for (unsigned i = threadIdx.x; i < n16; i += blockDim.x)
+            reinterpret_cast<uint4 *>(g)[i] = reinterpret_cast<const uint4 *>(buf)[i];
     }
 }
 
@@ -377,7 +395,7 @@ k_rs(PayloadParams P, const unsigned *__restrict__ blocks, unsigned n_blocks, in
 {
     __shared__ unsigned char gexp[512], glog[256];
     __shared__ unsigned char data[kRsWarps][256];
-    __shared__ unsigned char synd[kRsWarps][32], lam[kRsWarps][36], bb[kRsWarps][36], tt[kRsWarps][36], omg[kRsWarps][32];
+    __shared__ unsigned char synd[kRsWarps][32], lam[kRsWarps][36], omg[kRsWarps][32];
     __shared__ int deg_s[kRsWarps];
     for (int i = threadIdx.x; i < 512; i += blockDim.x) gexp[i] = P.tables->gf_exp[i];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) glog[i] = P.tables->gf_log[i];
@@ -403,38 +421,57 @@ k_rs(PayloadParams P, const unsigned *__restrict__ blocks, unsigned n_blocks, in
     const unsigned any = __ballot_sync(0xffffffffu, s != 0);
     __syncwarp();
     if (any) {
-        unsigned char *S = synd[warp], *L = lam[warp], *B = bb[warp], *Tm = tt[warp], *O = omg[warp];
-        if (lane == 0) {
-            for (int i = 0; i < 33; ++i) { L[i] = 0; B[i] = 0; }
-            L[0] = 1; B[0] = 1;
+        unsigned char *S = synd[warp], *L = lam[warp], *O = omg[warp];
+        // Berlekamp-Massey with one locator coefficient per lane (lane i holds lambda[i], b[i]; coefficient 32 is
+        // carried by lane 31 in a second register).  Same recurrence as the serial specification: every
+        // quantity is a GF(256) value, so the result is identical.
+        {
+            unsigned lam_i = (lane == 0) ? 1u : 0u, b_i = (lane == 0) ? 1u : 0u;     // coefficients 0..31
+            unsigned lam32 = 0u, b32 = 0u;                                            // coefficient 32 (meaningful on lane 31)
             unsigned el = 0;
             for (unsigned r = 1; r <= 32; ++r) {
-                unsigned dsc = 0;
-                for (unsigned i = 0; i < r; ++i) if (L[i] && S[r - i - 1]) dsc ^= gexp[glog[L[i]] + glog[S[r - i - 1]]];
+                // discrepancy = sum_{i<r} lambda[i] * s[r-i-1]
+                unsigned term = 0;
+                if ((unsigned)lane < r) {
+                    const unsigned sv_ = S[r - lane - 1];
+                    if (lam_i && sv_) term = gexp[glog[lam_i] + glog[sv_]];
+                }
+#pragma unroll
+                for (int k = 16; k >= 1; k >>= 1) term ^= __shfl_xor_sync(0xffffffffu, term, k);
+                const unsigned dsc = term;
+                // x * b(x): coefficient i takes b[i-1]
+                unsigned b_shift = __shfl_up_sync(0xffffffffu, b_i, 1);
+                if (lane == 0) b_shift = 0;
+                const unsigned b31 = __shfl_sync(0xffffffffu, b_i, 31);               // becomes coefficient 32
                 if (dsc == 0) {
-                    for (int i = 32; i > 0; --i) B[i] = B[i - 1];
-                    B[0] = 0;
+                    b_i = b_shift; b32 = b31;
                 } else {
-                    Tm[0] = L[0];
-                    for (int i = 0; i < 32; ++i) Tm[i + 1] = L[i + 1] ^ (B[i] ? gexp[glog[dsc] + glog[B[i]]] : 0);
+                    const unsigned ld = glog[dsc];
+                    const unsigned t_i = lam_i ^ (b_shift ? gexp[ld + glog[b_shift]] : 0u);
+                    const unsigned t32 = lam32 ^ (b31 ? gexp[ld + glog[b31]] : 0u);
                     if (2 * el <= r - 1) {
                         el = r - el;
-                        const unsigned dinv = 255 - glog[dsc];
-                        for (int i = 0; i <= 32; ++i) B[i] = L[i] ? gexp[glog[L[i]] + dinv] : 0;
+                        const unsigned dinv = 255 - ld;
+                        b_i = lam_i ? gexp[glog[lam_i] + dinv] : 0u;
+                        b32 = lam32 ? gexp[glog[lam32] + dinv] : 0u;
                     } else {
-                        for (int i = 32; i > 0; --i) B[i] = B[i - 1];
-                        B[0] = 0;
+                        b_i = b_shift; b32 = b31;
                     }
-                    for (int i = 0; i <= 32; ++i) L[i] = Tm[i];
+                    lam_i = t_i; lam32 = t32;
                 }
             }
-            int deg = 0;
-            for (int i = 0; i <= 32; ++i) if (L[i]) deg = i;
-            deg_s[warp] = deg;
-            for (int i = 0; i < deg; ++i) {
+            L[lane] = (unsigned char)lam_i;
+            if (lane == 31) L[32] = (unsigned char)lam32;
+            __syncwarp();
+            // degree and omega = (S * lambda) mod x^deg, one coefficient per lane
+            unsigned nzmask = __ballot_sync(0xffffffffu, lam_i != 0);
+            int deg = nzmask ? 31 - __clz(nzmask) : 0;
+            if (L[32]) deg = 32;
+            if (lane == 0) deg_s[warp] = deg;
+            if (lane < deg) {
                 unsigned acc = 0;
-                for (int j = 0; j <= i; ++j) if (S[i - j] && L[j]) acc ^= gexp[glog[S[i - j]] + glog[L[j]]];
-                O[i] = (unsigned char)acc;
+                for (int j = 0; j <= lane; ++j) if (S[lane - j] && L[j]) acc ^= gexp[glog[S[lane - j]] + glog[L[j]]];
+                O[lane] = (unsigned char)acc;
             }
         }
         __syncwarp();

@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--e2e-samples", type=int, default=1 << 18, help="samples per channel per e2e step")
     ap.add_argument("--workload", default="flex_rx", choices=["flex_rx", "detector"],
                     help="flex_rx = configs[2] (default, the headline metric); detector = configs[1] bulk frame_detector_cc")
+    ap.add_argument("--lanes", type=int, default=0, help="pipeline lanes per receiver handle (0 = library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -402,7 +403,8 @@ def main():
     cap, sent = make_capture(torch, frames, S, N, 1, dev, stream_offset=rank * S)
     torch.cuda.synchronize(dev)
     cs = torch.cuda.current_stream(dev)
-    rx = capi.Rx(S, device=local, max_frame_samples=65536, flags=capi.RX_NO_FRAMESYMS, cuda_stream=cs.cuda_stream)
+    rx = capi.Rx(S, device=local, max_frame_samples=65536, flags=capi.RX_NO_FRAMESYMS, cuda_stream=cs.cuda_stream, lanes=args.lanes)
+    lanes = rx.lanes()
 
     def step():
         rx.execute_dense_ptr(cap.data_ptr(), N, N, capi.MEM_DEVICE)
@@ -447,13 +449,36 @@ def main():
     secs = ms / 1e3
     value = world * S * N * args.steps / secs / 1e6
 
+    # ---- per-kernel breakdown: in the timed region the lanes' kernels overlap on the GPU, so the kernel times
+    # used for the roofline come from the same K steps repeated with one lane (kernels back to back on one stream)
+    serial_ms = None
+    if lanes > 1:
+        rx.close()
+        rx = capi.Rx(S, device=local, max_frame_samples=65536, flags=capi.RX_NO_FRAMESYMS, cuda_stream=cs.cuda_stream, lanes=1)
+        step()
+        torch.cuda.synchronize(dev)
+        kt = [0.0] * 6
+        work = {k: 0 for k in work}
+        e0.record(cs)
+        for _ in range(args.steps):
+            step()
+            t = rx.timing()
+            kt = [a + b for a, b in zip(kt, t)]
+            w = rx.work()
+            for k in work:
+                work[k] += w[k]
+        e1.record(cs)
+        torch.cuda.synchronize(dev)
+        serial_ms = e0.elapsed_time(e1) / args.steps
+    rx.close()
+
     # ---- e2e: host buffers through the same C-ABI call (H2D + all results D2H inside the timed region)
     e2e = None
     if not args.no_e2e:
         Ne = min(args.e2e_samples, N)
         host = torch.empty((S, Ne), dtype=torch.complex64).pin_memory()
         host.copy_(cap[:, :Ne])
-        rx2 = capi.Rx(S, device=local, max_frame_samples=65536, flags=0, cuda_stream=cs.cuda_stream)
+        rx2 = capi.Rx(S, device=local, max_frame_samples=65536, flags=0, cuda_stream=cs.cuda_stream, lanes=args.lanes)
         for _ in range(max(1, args.warmup)):
             rx2.execute_dense_ptr(host.data_ptr(), Ne, Ne, capi.MEM_HOST)
         torch.cuda.synchronize(dev)
@@ -566,7 +591,10 @@ def main():
                    "snr_db": "-2..+12 per stream", "l2": "inputs (%.1f GB per step) larger than L2" % (S * N * 8 / 1e9)},
         "decoded_frames_per_s": va_all / secs, "frames_per_s": fr_all / secs,
         "frames_sent_per_step": sent_all, "frames_found_per_step": fr_all / args.steps, "frames_valid_per_step": va_all / args.steps,
-        "gpu_launches": int(launches_all),
+        "gpu_launches": int(launches_all), "lanes": lanes,
+        "kernel_times": ("CUDA events around each kernel on its launching stream, same K steps repeated with lanes=1 right after the "
+                         "timed region (%.2f ms/step serialized; in the timed region the lanes overlap)" % serial_ms) if serial_ms else
+                        "CUDA events around each kernel on its launching stream inside the timed region",
         "clocks": clk, "e2e": e2e, "roofline": roof, "kernels": kernels, "cpu_baseline": cpu,
     }
     print(json.dumps(out))

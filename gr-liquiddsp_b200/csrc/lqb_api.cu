@@ -130,7 +130,7 @@ struct Front {
     float coarse_ms = 0.0f;
     cudaEvent_t cev[2] = { nullptr, nullptr };
 
-    int init(int dev, unsigned ns, unsigned cap, void *user_stream, const DevTables &T)
+    int init(int dev, unsigned ns, unsigned cap, void *user_stream, const DevTables &T, bool low_priority = false)
     {
         int ndev = 0;
         if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return fail(LQB_ENODEV, "no CUDA device available (no CPU fallback exists)");
@@ -141,7 +141,12 @@ struct Front {
         device = dev; n_streams = ns; carry_cap = cap;
         CU(cudaSetDevice(dev));
         if (user_stream) stream = (cudaStream_t)user_stream;
-        else { CU(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking)); own_stream = true; }
+        else {
+            int lo = 0, hi = 0;
+            cudaDeviceGetStreamPriorityRange(&lo, &hi);
+            CU(cudaStreamCreateWithPriority(&stream, cudaStreamNonBlocking, low_priority ? lo : hi));
+            own_stream = true;
+        }
         CU(cudaMalloc(&d_tables, sizeof(DevTables)));
         CU(cudaMemcpy(d_tables, &T, sizeof(DevTables), cudaMemcpyHostToDevice));
         CU(cudaMalloc(&d_states, (size_t)ns * sizeof(StreamState)));
@@ -274,9 +279,21 @@ struct Front {
 }  // namespace
 
 // =================================================================== RX handle
-struct lqb_rx_s {
+// The receiver is split into independent LANES: lane l owns the streams s with s % L == l, its own
+// CUDA streams, stream states, carries and arenas.  One host thread drives all lanes as a software
+// pipeline -- seek(l) is queued for every lane, then for each lane in turn the host reads the frame
+// list, plans and queues the payload kernels -- so lane l's payload kernels, host planning and result
+// copies run while the tensor-core search of lanes l+1.. is still in flight, and with host inputs the
+// H2D copy of lane l+1 runs under lane l's search.  Results do not depend on the lane count
+// (tests/test_gpu_parity.py::test_lane_count_does_not_change_results).
+namespace {
+
+struct RxLane {
     Front f;
+    cudaStream_t pay = nullptr;           // payload + gather stream (higher priority than the search stream)
+    bool own_pay = false;
     unsigned flags = 0;
+    unsigned lane = 0, n_lanes = 1;
     DevBuf<FrameDesc> d_frames;
     PinBuf<FrameDesc> h_frames;
     DevBuf<float2> d_syms;
@@ -289,12 +306,242 @@ struct lqb_rx_s {
     DevBuf<unsigned long long> d_dec;
     DevBuf<unsigned> d_lists, d_tilemap;
     PinBuf<unsigned> h_lists;
-    std::vector<unsigned> order;
     unsigned n_frames = 0;
     uint64_t n_valid = 0;
     cudaEvent_t ev[7] = {};
     float ms[6] = {};
     uint64_t work[6] = {};
+    // per-call state carried between the phases
+    std::vector<uint32_t> ids;
+    std::vector<const float *> iq;
+    std::vector<uint64_t> ns;
+    SeekParams sp;
+    size_t max_frames = 0;
+    uint64_t total = 0;
+
+    void destroy()
+    {
+        cudaSetDevice(f.device);
+        if (f.stream) cudaStreamSynchronize(f.stream);
+        if (pay) cudaStreamSynchronize(pay);
+        d_frames.release(); h_frames.release(); d_syms.release(); h_syms.release();
+        d_bufA.release(); d_bufB.release(); d_payload.release(); h_payload.release();
+        d_ilv.release(); d_dec.release(); d_lists.release(); h_lists.release(); d_tilemap.release();
+        for (auto &e : ev) if (e) cudaEventDestroy(e);
+        if (own_pay && pay) cudaStreamDestroy(pay);
+        f.destroy();
+    }
+
+    size_t ilv_offset(unsigned n)
+    {
+        auto it = ilv_cache.find(n);
+        if (it != ilv_cache.end()) return it->second;
+        std::vector<uint32_t> maps = ilv_maps(n);
+        size_t off = ilv_used;
+        if (d_ilv.reserve(off + maps.size() + 4, true, pay)) return (size_t)-1;
+        if (!maps.empty())
+            cudaMemcpyAsync(d_ilv.p + off, maps.data(), maps.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, pay);
+        cudaStreamSynchronize(pay);         // maps is a local; finish the copy before it dies
+        ilv_used = off + maps.size();
+        ilv_cache.emplace(n, off);
+        return off;
+    }
+
+    // phase A: stage the inputs and queue the search on the lane's search stream
+    int phase_seek(int mem)
+    {
+        const uint32_t n = (uint32_t)ids.size();
+        n_frames = 0; n_valid = 0;
+        std::memset(ms, 0, sizeof ms);
+        std::memset(work, 0, sizeof work);
+        total = 0;
+        if (!n) return 0;
+        cudaStream_t st = f.stream;
+        uint64_t max_n = 0;
+        if (int e = f.feed(n, ids.data(), iq.data(), ns.data(), mem, &total, &max_n)) return e;
+        // upper bound on frames: a frame spans at least 618 samples
+        max_frames = 0;
+        for (uint32_t i = 0; i < n; ++i) max_frames += (size_t)((ns[i] + f.carry_cap) / 600 + 2);
+        if (int e = d_frames.reserve(max_frames)) return e;
+        if (int e = h_frames.reserve(max_frames)) return e;
+        sp.tables = f.d_tables; sp.states = f.d_states; sp.io = f.d_io.p;
+        sp.carry[0] = f.d_carry[0]; sp.carry[1] = f.d_carry[1]; sp.carry_cap = f.carry_cap;
+        sp.det_mode = 0; sp.frames = d_frames.p; sp.detections = nullptr;
+        sp.n_out = f.d_count; sp.max_out = (unsigned)max_frames;
+        CU(cudaEventRecord(ev[0], st));
+        if (int e = f.run_coarse(n, ns.data(), sp)) return e;
+        CU(cudaMemsetAsync(f.d_count, 0, 8 * sizeof(unsigned), st));
+        launch_seek(sp, n, st); f.launches++;
+        CU(cudaEventRecord(ev[1], st));
+        CU(cudaMemcpyAsync(f.h_count, f.d_count, 8 * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+        return 0;
+    }
+
+    // phase B: read the frame list, plan, queue payload kernels + carry + result copies on the payload stream
+    int phase_payload()
+    {
+        const uint32_t n = (uint32_t)ids.size();
+        if (!n) return 0;
+        cudaStream_t st = f.stream, ps = pay;
+        CU(cudaStreamSynchronize(st));
+        unsigned nf = std::min<unsigned>(f.h_count[0], (unsigned)max_frames);
+        work[0] = f.h_count[1]; work[1] = f.h_count[2]; work[2] = 0; work[3] = total; work[4] = f.h_count[3];
+        work[5] = sp.coarse == 2 ? (uint64_t)f.h_count[4] : (sp.coarse == 1 ? (uint64_t)f.h_tpre.p[n] : 0);
+        FrameDesc *fr = h_frames.p;
+        if (nf) {
+            CU(cudaMemcpyAsync(fr, d_frames.p, nf * sizeof(FrameDesc), cudaMemcpyDeviceToHost, ps));
+            CU(cudaStreamSynchronize(ps));
+        }
+
+        // ---------------- plan
+        size_t sym_total = 0, buf_total = 0, pay_total = 0, dec_total = 0, n_tiles = 0;
+        std::vector<unsigned> tile_start(nf + 1, 0), valid, deint[2], blk[2], vit[2], vit9[2], rsb[2];
+        size_t tmax7[2] = { 0, 0 };
+        for (unsigned i = 0; i < nf; ++i) {
+            FrameDesc &d = fr[i];
+            tile_start[i] = (unsigned)n_tiles;
+            if (!d.header_valid) continue;
+            valid.push_back(i);
+            d.sym_off = sym_total; sym_total += (d.n_sym + 1u) & ~1u;      // even: 16-byte aligned symbol rows
+            unsigned bl = std::max(std::max(d.n1, d.n0), d.k0) + 16;
+            bl = (bl + 15u) & ~15u;
+            d.buf_len = bl; d.buf_off = buf_total; buf_total += bl;
+            d.pay_off = pay_total; pay_total += (d.payload_len + 3u) & ~3u;
+            n_tiles += (d.n_sym + 255) / 256;
+            const unsigned fs[2] = { d.fec0, d.fec1 }, enc[2] = { d.n0, d.n1 }, dl[2] = { d.k0, d.n0 };
+            size_t need_dec = 0;
+            for (int stg = 1; stg >= 0; --stg) {
+                if (fs[stg] != FEC_NONE) {
+                    size_t off = ilv_offset(enc[stg]);
+                    if (off == (size_t)-1) return LQB_ENOMEM;
+                    (stg ? d.ilv1_off : d.ilv0_off) = (unsigned)off;
+                    deint[stg].push_back(i);
+                }
+                if (is_conv(fs[stg])) {
+                    size_t T = (size_t)8 * dl[stg] + conv_K(fs[stg]) - 1;
+                    if (conv_K(fs[stg]) == 7) { vit[stg].push_back(i); tmax7[stg] = std::max(tmax7[stg], T); }   // [step][thread] arena
+                    else { vit9[stg].push_back(i); need_dec = std::max(need_dec, T * 4); }                      // 8 words per step
+                } else if (fs[stg] == FEC_RS_M8) {
+                    unsigned blocks = (dl[stg] + 222) / 223;
+                    for (unsigned b = 0; b < blocks; ++b) { rsb[stg].push_back(i); rsb[stg].push_back(b); }
+                } else {
+                    blk[stg].push_back(i);
+                }
+            }
+            d.dec_off = dec_total; dec_total += need_dec;
+        }
+        tile_start[nf] = (unsigned)n_tiles;
+        // K=7 frames share one [step][thread] decision arena at the front; K=9 frames follow with private slices
+        const size_t dec7 = std::max(tmax7[0] * vit[0].size(), tmax7[1] * vit[1].size());
+        for (unsigned i = 0; i < nf; ++i) fr[i].dec_off += dec7;
+        dec_total += dec7;
+        work[2] = sym_total;
+        // group the PLL work list by modulation so warps diverge less
+        std::vector<unsigned> pll = valid;
+        std::stable_sort(pll.begin(), pll.end(), [&](unsigned a, unsigned b) { return fr[a].ms < fr[b].ms; });
+
+        if (nf && !valid.empty()) {
+            if (int e = d_syms.reserve(sym_total + 1)) return e;
+            if (int e = d_bufA.reserve(buf_total + 16)) return e;
+            if (int e = d_bufB.reserve(buf_total + 16)) return e;
+            if (int e = d_payload.reserve(pay_total + 16)) return e;
+            if (int e = d_dec.reserve(dec_total + 1)) return e;
+            if (int e = d_tilemap.reserve(n_tiles + 1)) return e;
+            // one list arena: tile_start | pll | valid | deint1 | blk1 | vit1 | rs1 | deint0 | blk0 | vit0 | rs0
+            std::vector<const std::vector<unsigned> *> parts = { &tile_start, &pll, &valid, &deint[1], &blk[1], &vit[1], &rsb[1],
+                                                                 &deint[0], &blk[0], &vit[0], &rsb[0], &vit9[1], &vit9[0] };
+            size_t ltot = 0;
+            std::vector<size_t> loff;
+            for (auto p : parts) { loff.push_back(ltot); ltot += p->size(); }
+            if (int e = h_lists.reserve(ltot + 1)) return e;
+            if (int e = d_lists.reserve(ltot + 1)) return e;
+            for (size_t k = 0; k < parts.size(); ++k)
+                if (!parts[k]->empty()) std::memcpy(h_lists.p + loff[k], parts[k]->data(), parts[k]->size() * sizeof(unsigned));
+            CU(cudaMemcpyAsync(d_lists.p, h_lists.p, ltot * sizeof(unsigned), cudaMemcpyHostToDevice, ps));
+            CU(cudaMemcpyAsync(d_frames.p, fr, nf * sizeof(FrameDesc), cudaMemcpyHostToDevice, ps));
+
+            PayloadParams pp;
+            pp.tables = f.d_tables; pp.states = f.d_states; pp.io = f.d_io.p;
+            pp.carry[0] = f.d_carry[0]; pp.carry[1] = f.d_carry[1]; pp.carry_cap = f.carry_cap;
+            pp.frames = d_frames.p; pp.n_frames = nf;
+            pp.tile_start = d_lists.p + loff[0]; pp.n_tiles = (unsigned)n_tiles; pp.tile_frame = d_tilemap.p;
+            pp.syms = d_syms.p; pp.bufA = d_bufA.p; pp.bufB = d_bufB.p; pp.payload = d_payload.p;
+            pp.ilv_maps = d_ilv.p; pp.decisions = d_dec.p;
+
+            CU(cudaEventRecord(ev[2], ps));
+            launch_mf(pp, ps); f.launches += n_tiles ? 2 : 0;
+            CU(cudaEventRecord(ev[3], ps));
+            launch_pll(pp, d_lists.p + loff[1], (unsigned)pll.size(), ps); f.launches++;
+            CU(cudaEventRecord(ev[4], ps));
+            for (int stg = 1; stg >= 0; --stg) {
+                const size_t base = stg ? 3 : 7;
+                if (!deint[stg].empty()) { launch_deinterleave(pp, d_lists.p + loff[base], (unsigned)deint[stg].size(), stg, ps); f.launches++; }
+                if (!blk[stg].empty()) { launch_blockfec(pp, d_lists.p + loff[base + 1], (unsigned)blk[stg].size(), stg, ps); f.launches++; }
+                if (!vit[stg].empty()) { launch_viterbi(pp, d_lists.p + loff[base + 2], (unsigned)vit[stg].size(), stg, 7, ps); f.launches++; }
+                if (!vit9[stg].empty()) { launch_viterbi(pp, d_lists.p + loff[stg ? 11 : 12], (unsigned)vit9[stg].size(), stg, 9, ps); f.launches++; }
+                if (!rsb[stg].empty()) { launch_rs(pp, d_lists.p + loff[base + 3], (unsigned)(rsb[stg].size() / 2), stg, ps); f.launches++; }
+            }
+            launch_crc(pp, d_lists.p + loff[2], (unsigned)valid.size(), ps); f.launches++;
+            CU(cudaEventRecord(ev[5], ps));
+        } else {
+            for (int k = 2; k <= 5; ++k) CU(cudaEventRecord(ev[k], ps));
+        }
+        launch_carry(sp, n, ps); f.launches++;
+        CU(cudaMemcpyAsync(f.h_states, f.d_states, (size_t)f.n_streams * sizeof(StreamState), cudaMemcpyDeviceToHost, ps));
+        CU(cudaEventRecord(ev[6], ps));
+
+        // ---------------- gather
+        if (nf && !valid.empty()) {
+            CU(cudaMemcpyAsync(fr, d_frames.p, nf * sizeof(FrameDesc), cudaMemcpyDeviceToHost, ps));
+            if (!(flags & LQB_RX_DEVICE_RESULTS)) {
+                if (int e = h_payload.reserve(pay_total + 16)) return e;
+                if (pay_total) CU(cudaMemcpyAsync(h_payload.p, d_payload.p, pay_total, cudaMemcpyDeviceToHost, ps));
+                if (!(flags & LQB_RX_NO_FRAMESYMS)) {
+                    if (int e = h_syms.reserve(sym_total + 1)) return e;
+                    if (sym_total) CU(cudaMemcpyAsync(h_syms.p, d_syms.p, sym_total * sizeof(float2), cudaMemcpyDeviceToHost, ps));
+                }
+            }
+        }
+        n_frames = nf;
+        return 0;
+    }
+
+    // phase C: wait for the lane, read the event times
+    int phase_finish()
+    {
+        if (ids.empty()) return 0;
+        CU(cudaStreamSynchronize(pay));
+        CU(cudaGetLastError());
+        cudaEventElapsedTime(&ms[0], ev[0], ev[1]);
+        for (int k = 1; k < 4; ++k) cudaEventElapsedTime(&ms[k], ev[k + 1], ev[k + 2]);
+        cudaEventElapsedTime(&ms[4], ev[0], ev[6]);
+        ms[5] = 0.0f;
+        if (sp.coarse == 1) cudaEventElapsedTime(&ms[5], f.cev[0], f.cev[1]);
+        const FrameDesc *fr = h_frames.p;
+        for (unsigned i = 0; i < n_frames; ++i) n_valid += fr[i].payload_valid ? 1 : 0;
+        return 0;
+    }
+};
+
+}  // namespace
+
+struct lqb_rx_s {
+    int device = 0;
+    unsigned n_streams = 0, flags = 0;
+    std::vector<RxLane *> lanes;
+    cudaStream_t user_stream = nullptr;
+    cudaEvent_t ev_in = nullptr;
+    std::vector<cudaEvent_t> ev_out;
+    std::vector<std::pair<unsigned, unsigned>> order;    // (lane, frame index) sorted by (stream, seq)
+    unsigned n_frames = 0;
+    uint64_t n_valid = 0;
+    float ms[6] = {};
+    uint64_t work[6] = {};
+    unsigned global_stream(unsigned lane, unsigned local) const { return local * (unsigned)lanes.size() + lane; }
+    void sync_all()
+    {
+        for (auto *l : lanes) { if (l->f.stream) cudaStreamSynchronize(l->f.stream); if (l->pay) cudaStreamSynchronize(l->pay); }
+    }
 };
 
 extern "C" {
@@ -309,226 +556,125 @@ int lqb_device_count(void)
     return n;
 }
 
+void lqb_rx_destroy(lqb_rx h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    for (auto *l : h->lanes) { l->destroy(); delete l; }
+    if (h->ev_in) cudaEventDestroy(h->ev_in);
+    for (auto &e : h->ev_out) if (e) cudaEventDestroy(e);
+    delete h;
+}
+
 lqb_rx lqb_rx_create(const lqb_rx_opts *o)
 {
     if (!o || !o->n_streams) { fail(LQB_EINVAL, "bad options"); return nullptr; }
     DevTables *T = new DevTables;
     build_tables(*T, kRxBeta, 0.5f, 0.3f);
     lqb_rx h = new lqb_rx_s;
+    h->device = o->device; h->n_streams = o->n_streams; h->flags = o->flags;
+    h->user_stream = (cudaStream_t)o->cuda_stream;
     unsigned cap = o->max_frame_samples ? o->max_frame_samples : 65536u;
     if (cap < 2048) cap = 2048;
-    int e = h->f.init(o->device, o->n_streams, cap, o->cuda_stream, *T);
+    // lane count: explicit option, else LQB_RX_LANES, else one lane per 128 streams up to 8
+    unsigned L = o->n_lanes;
+    if (!L) { const char *e = getenv("LQB_RX_LANES"); if (e) L = (unsigned)atoi(e); }
+    if (!L) L = std::min(8u, std::max(1u, o->n_streams / 128u));
+    L = std::max(1u, std::min(L, std::min(o->n_streams, 64u)));
+    int lo = 0, hi = 0;
+    bool ok = true;
+    for (unsigned l = 0; l < L && ok; ++l) {
+        RxLane *ln = new RxLane;
+        h->lanes.push_back(ln);
+        ln->lane = l; ln->n_lanes = L; ln->flags = o->flags;
+        const unsigned ns = (o->n_streams - l + L - 1) / L;
+        // a single lane on a caller's stream keeps everything on that stream; otherwise the lane owns a
+        // low-priority search stream and a high-priority payload stream
+        const bool on_user = (L == 1 && o->cuda_stream);
+        if (ln->f.init(o->device, ns, cap, on_user ? o->cuda_stream : nullptr, *T, /*low_priority=*/!on_user)) { ok = false; break; }
+        if (on_user) ln->pay = ln->f.stream;
+        else {
+            cudaDeviceGetStreamPriorityRange(&lo, &hi);
+            if (cudaStreamCreateWithPriority(&ln->pay, cudaStreamNonBlocking, hi) != cudaSuccess) { fail(LQB_ECUDA, "cudaStreamCreate failed"); ok = false; break; }
+            ln->own_pay = true;
+        }
+        for (auto &ev : ln->ev) cudaEventCreate(&ev);
+    }
     delete T;
-    if (e) { h->f.destroy(); delete h; return nullptr; }
-    h->flags = o->flags;
-    for (auto &ev : h->ev) cudaEventCreate(&ev);
+    if (ok && h->user_stream && !(L == 1)) {
+        ok = cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming) == cudaSuccess;
+        h->ev_out.assign(L, nullptr);
+        for (auto &e : h->ev_out) ok = ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
+    }
+    if (!ok) { lqb_rx_destroy(h); return nullptr; }
     return h;
-}
-
-void lqb_rx_destroy(lqb_rx h)
-{
-    if (!h) return;
-    cudaSetDevice(h->f.device);
-    if (h->f.stream) cudaStreamSynchronize(h->f.stream);
-    h->d_frames.release(); h->h_frames.release(); h->d_syms.release(); h->h_syms.release();
-    h->d_bufA.release(); h->d_bufB.release(); h->d_payload.release(); h->h_payload.release();
-    h->d_ilv.release(); h->d_dec.release(); h->d_lists.release(); h->h_lists.release(); h->d_tilemap.release();
-    for (auto &ev : h->ev) if (ev) cudaEventDestroy(ev);
-    h->f.destroy();
-    delete h;
 }
 
 int lqb_rx_reset(lqb_rx h, int stream)
 {
     if (!h) return fail(LQB_EINVAL, "null handle");
-    return h->f.reset(stream);
-}
-
-static size_t ilv_offset(lqb_rx h, unsigned n)
-{
-    auto it = h->ilv_cache.find(n);
-    if (it != h->ilv_cache.end()) return it->second;
-    std::vector<uint32_t> maps = ilv_maps(n);
-    size_t off = h->ilv_used;
-    if (h->d_ilv.reserve(off + maps.size() + 4, true, h->f.stream)) return (size_t)-1;
-    if (!maps.empty())
-        cudaMemcpyAsync(h->d_ilv.p + off, maps.data(), maps.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, h->f.stream);
-    cudaStreamSynchronize(h->f.stream);     // maps is a local; finish the copy before it dies
-    h->ilv_used = off + maps.size();
-    h->ilv_cache.emplace(n, off);
-    return off;
+    const unsigned L = (unsigned)h->lanes.size();
+    if (stream < 0) {
+        for (auto *l : h->lanes) if (int e = l->f.reset(-1)) return e;
+        return 0;
+    }
+    if ((unsigned)stream >= h->n_streams) return fail(LQB_EINVAL, "stream index out of range");
+    return h->lanes[(unsigned)stream % L]->f.reset((int)((unsigned)stream / L));
 }
 
 int lqb_rx_execute(lqb_rx h, uint32_t n, const uint32_t *ids, const float *const *iq, const uint64_t *ns, int mem)
 {
     if (!h) return fail(LQB_EINVAL, "null handle");
-    Front &f = h->f;
-    CU(cudaSetDevice(f.device));
-    cudaStream_t st = f.stream;
+    CU(cudaSetDevice(h->device));
+    const unsigned L = (unsigned)h->lanes.size();
     h->n_frames = 0; h->n_valid = 0; h->order.clear();
     std::memset(h->ms, 0, sizeof h->ms);
-    uint64_t total = 0, max_n = 0;
-    if (int e = f.feed(n, ids, iq, ns, mem, &total, &max_n)) return e;
+    std::memset(h->work, 0, sizeof h->work);
+    if (n > h->n_streams) return fail(LQB_EINVAL, "more entries than streams");
+    for (auto *l : h->lanes) { l->ids.clear(); l->iq.clear(); l->ns.clear(); l->n_frames = 0; l->n_valid = 0; }
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint32_t s = ids ? ids[i] : i;
+        if (s >= h->n_streams) return fail(LQB_EINVAL, "stream index out of range");
+        RxLane *l = h->lanes[s % L];
+        l->ids.push_back(s / L); l->iq.push_back(iq[i]); l->ns.push_back(ns[i]);
+    }
     if (!n) return 0;
-
-    // upper bound on frames: a frame spans at least 618 samples
-    size_t max_frames = 0;
-    for (uint32_t i = 0; i < n; ++i) max_frames += (size_t)((ns[i] + f.carry_cap) / 600 + 2);
-    if (int e = h->d_frames.reserve(max_frames)) return e;
-    if (int e = h->h_frames.reserve(max_frames)) return e;
-
-    SeekParams sp;
-    sp.tables = f.d_tables; sp.states = f.d_states; sp.io = f.d_io.p;
-    sp.carry[0] = f.d_carry[0]; sp.carry[1] = f.d_carry[1]; sp.carry_cap = f.carry_cap;
-    sp.det_mode = 0; sp.frames = h->d_frames.p; sp.detections = nullptr;
-    sp.n_out = f.d_count; sp.max_out = (unsigned)max_frames;
-
-    CU(cudaEventRecord(h->ev[0], st));
-    if (int e = f.run_coarse(n, ns, sp)) return e;
-    CU(cudaMemsetAsync(f.d_count, 0, 8 * sizeof(unsigned), st));
-    launch_seek(sp, n, st); f.launches++;
-    CU(cudaEventRecord(h->ev[1], st));
-    CU(cudaMemcpyAsync(f.h_count, f.d_count, 8 * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    unsigned nf = std::min<unsigned>(f.h_count[0], (unsigned)max_frames);
-    h->work[0] = f.h_count[1]; h->work[1] = f.h_count[2]; h->work[2] = 0; h->work[3] = total; h->work[4] = f.h_count[3]; h->work[5] = sp.coarse == 2 ? (uint64_t)f.h_count[4] : (sp.coarse == 1 ? (uint64_t)f.h_tpre.p[n] : 0);
-    FrameDesc *fr = h->h_frames.p;
-    if (nf) {
-        CU(cudaMemcpyAsync(fr, h->d_frames.p, nf * sizeof(FrameDesc), cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
+    // inputs produced on the caller's stream must be complete before any lane reads them
+    if (h->ev_in) {
+        CU(cudaEventRecord(h->ev_in, h->user_stream));
+        for (auto *l : h->lanes) CU(cudaStreamWaitEvent(l->f.stream, h->ev_in, 0));
     }
-
-    // ---------------- plan
-    size_t sym_total = 0, buf_total = 0, pay_total = 0, dec_total = 0, n_tiles = 0;
-    std::vector<unsigned> tile_start(nf + 1, 0), valid, deint[2], blk[2], vit[2], vit9[2], rsb[2];
-    size_t tmax7[2] = { 0, 0 };
-    for (unsigned i = 0; i < nf; ++i) {
-        FrameDesc &d = fr[i];
-        tile_start[i] = (unsigned)n_tiles;
-        if (!d.header_valid) continue;
-        valid.push_back(i);
-        d.sym_off = sym_total; sym_total += (d.n_sym + 1u) & ~1u;      // even: 16-byte aligned symbol rows
-        unsigned bl = std::max(std::max(d.n1, d.n0), d.k0) + 16;
-        bl = (bl + 15u) & ~15u;
-        d.buf_len = bl; d.buf_off = buf_total; buf_total += bl;
-        d.pay_off = pay_total; pay_total += (d.payload_len + 3u) & ~3u;
-        n_tiles += (d.n_sym + 255) / 256;
-        const unsigned fs[2] = { d.fec0, d.fec1 }, enc[2] = { d.n0, d.n1 }, dl[2] = { d.k0, d.n0 };
-        size_t need_dec = 0;
-        for (int stg = 1; stg >= 0; --stg) {
-            if (fs[stg] != FEC_NONE) {
-                size_t off = ilv_offset(h, enc[stg]);
-                if (off == (size_t)-1) return LQB_ENOMEM;
-                (stg ? d.ilv1_off : d.ilv0_off) = (unsigned)off;
-                deint[stg].push_back(i);
-            }
-            if (is_conv(fs[stg])) {
-                size_t T = (size_t)8 * dl[stg] + conv_K(fs[stg]) - 1;
-                if (conv_K(fs[stg]) == 7) { vit[stg].push_back(i); tmax7[stg] = std::max(tmax7[stg], T); }   // [step][thread] arena
-                else { vit9[stg].push_back(i); need_dec = std::max(need_dec, T * 4); }                      // 8 words per step
-            } else if (fs[stg] == FEC_RS_M8) {
-                unsigned blocks = (dl[stg] + 222) / 223;
-                for (unsigned b = 0; b < blocks; ++b) { rsb[stg].push_back(i); rsb[stg].push_back(b); }
-            } else {
-                blk[stg].push_back(i);
-            }
-        }
-        d.dec_off = dec_total; dec_total += need_dec;
-    }
-    tile_start[nf] = (unsigned)n_tiles;
-    // K=7 frames share one [step][thread] decision arena at the front; K=9 frames follow with private slices
-    const size_t dec7 = std::max(tmax7[0] * vit[0].size(), tmax7[1] * vit[1].size());
-    for (unsigned i = 0; i < nf; ++i) fr[i].dec_off += dec7;
-    dec_total += dec7;
-    h->work[2] = sym_total;
-    // group the PLL work list by modulation so warps diverge less
-    std::vector<unsigned> pll = valid;
-    std::stable_sort(pll.begin(), pll.end(), [&](unsigned a, unsigned b) { return fr[a].ms < fr[b].ms; });
-
-    if (nf && !valid.empty()) {
-        if (int e = h->d_syms.reserve(sym_total + 1)) return e;
-        if (int e = h->d_bufA.reserve(buf_total + 16)) return e;
-        if (int e = h->d_bufB.reserve(buf_total + 16)) return e;
-        if (int e = h->d_payload.reserve(pay_total + 16)) return e;
-        if (int e = h->d_dec.reserve(dec_total + 1)) return e;
-        if (int e = h->d_tilemap.reserve(n_tiles + 1)) return e;
-        // one list arena: tile_start | pll | valid | deint1 | blk1 | vit1 | rs1 | deint0 | blk0 | vit0 | rs0
-        std::vector<const std::vector<unsigned> *> parts = { &tile_start, &pll, &valid, &deint[1], &blk[1], &vit[1], &rsb[1],
-                                                             &deint[0], &blk[0], &vit[0], &rsb[0], &vit9[1], &vit9[0] };
-        size_t ltot = 0;
-        std::vector<size_t> loff;
-        for (auto p : parts) { loff.push_back(ltot); ltot += p->size(); }
-        if (int e = h->h_lists.reserve(ltot + 1)) return e;
-        if (int e = h->d_lists.reserve(ltot + 1)) return e;
-        for (size_t k = 0; k < parts.size(); ++k)
-            if (!parts[k]->empty()) std::memcpy(h->h_lists.p + loff[k], parts[k]->data(), parts[k]->size() * sizeof(unsigned));
-        CU(cudaMemcpyAsync(h->d_lists.p, h->h_lists.p, ltot * sizeof(unsigned), cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(h->d_frames.p, fr, nf * sizeof(FrameDesc), cudaMemcpyHostToDevice, st));
-
-        PayloadParams pp;
-        pp.tables = f.d_tables; pp.states = f.d_states; pp.io = f.d_io.p;
-        pp.carry[0] = f.d_carry[0]; pp.carry[1] = f.d_carry[1]; pp.carry_cap = f.carry_cap;
-        pp.frames = h->d_frames.p; pp.n_frames = nf;
-        pp.tile_start = h->d_lists.p + loff[0]; pp.n_tiles = (unsigned)n_tiles; pp.tile_frame = h->d_tilemap.p;
-        pp.syms = h->d_syms.p; pp.bufA = h->d_bufA.p; pp.bufB = h->d_bufB.p; pp.payload = h->d_payload.p;
-        pp.ilv_maps = h->d_ilv.p; pp.decisions = h->d_dec.p;
-
-        CU(cudaEventRecord(h->ev[2], st));
-        launch_mf(pp, st); f.launches += n_tiles ? 2 : 0;
-        CU(cudaEventRecord(h->ev[3], st));
-        launch_pll(pp, h->d_lists.p + loff[1], (unsigned)pll.size(), st); f.launches++;
-        CU(cudaEventRecord(h->ev[4], st));
-        for (int stg = 1; stg >= 0; --stg) {
-            const size_t base = stg ? 3 : 7;
-            if (!deint[stg].empty()) { launch_deinterleave(pp, h->d_lists.p + loff[base], (unsigned)deint[stg].size(), stg, st); f.launches++; }
-            if (!blk[stg].empty()) { launch_blockfec(pp, h->d_lists.p + loff[base + 1], (unsigned)blk[stg].size(), stg, st); f.launches++; }
-            if (!vit[stg].empty()) { launch_viterbi(pp, h->d_lists.p + loff[base + 2], (unsigned)vit[stg].size(), stg, 7, st); f.launches++; }
-            if (!vit9[stg].empty()) { launch_viterbi(pp, h->d_lists.p + loff[stg ? 11 : 12], (unsigned)vit9[stg].size(), stg, 9, st); f.launches++; }
-            if (!rsb[stg].empty()) { launch_rs(pp, h->d_lists.p + loff[base + 3], (unsigned)(rsb[stg].size() / 2), stg, st); f.launches++; }
-        }
-        launch_crc(pp, h->d_lists.p + loff[2], (unsigned)valid.size(), st); f.launches++;
-        CU(cudaEventRecord(h->ev[5], st));
-    } else {
-        for (int k = 2; k <= 5; ++k) CU(cudaEventRecord(h->ev[k], st));
-    }
-    launch_carry(sp, n, st); f.launches++;
-    if (int e = f.mirror_states()) return e;
-    CU(cudaEventRecord(h->ev[6], st));
-
-    // ---------------- gather
-    if (nf && !valid.empty()) {
-        CU(cudaMemcpyAsync(fr, h->d_frames.p, nf * sizeof(FrameDesc), cudaMemcpyDeviceToHost, st));
-        if (!(h->flags & LQB_RX_DEVICE_RESULTS)) {
-            if (int e = h->h_payload.reserve(pay_total + 16)) return e;
-            if (pay_total) CU(cudaMemcpyAsync(h->h_payload.p, h->d_payload.p, pay_total, cudaMemcpyDeviceToHost, st));
-            if (!(h->flags & LQB_RX_NO_FRAMESYMS)) {
-                if (int e = h->h_syms.reserve(sym_total + 1)) return e;
-                if (sym_total) CU(cudaMemcpyAsync(h->h_syms.p, h->d_syms.p, sym_total * sizeof(float2), cudaMemcpyDeviceToHost, st));
-            }
+    int rc = 0;
+    for (auto *l : h->lanes) if ((rc = l->phase_seek(mem))) break;
+    if (!rc) for (auto *l : h->lanes) if ((rc = l->phase_payload())) break;
+    if (!rc) for (auto *l : h->lanes) if ((rc = l->phase_finish())) break;
+    if (rc) { const std::string keep = g_err; h->sync_all(); cudaGetLastError(); g_err = keep; return rc; }
+    if (h->ev_in) {
+        for (unsigned l = 0; l < L; ++l) {
+            CU(cudaEventRecord(h->ev_out[l], h->lanes[l]->pay));
+            CU(cudaStreamWaitEvent(h->user_stream, h->ev_out[l], 0));
         }
     }
-    CU(cudaStreamSynchronize(st));
-    CU(cudaGetLastError());
-    cudaEventElapsedTime(&h->ms[0], h->ev[0], h->ev[1]);
-    for (int k = 1; k < 4; ++k) cudaEventElapsedTime(&h->ms[k], h->ev[k + 1], h->ev[k + 2]);
-    cudaEventElapsedTime(&h->ms[4], h->ev[0], h->ev[6]);
-    h->ms[5] = 0.0f;
-    if (sp.coarse == 1) cudaEventElapsedTime(&h->ms[5], f.cev[0], f.cev[1]);
-
-    h->n_frames = nf;
-    h->order.resize(nf);
-    for (unsigned i = 0; i < nf; ++i) h->order[i] = i;
-    std::sort(h->order.begin(), h->order.end(), [&](unsigned a, unsigned b) {
-        return fr[a].stream != fr[b].stream ? fr[a].stream < fr[b].stream : fr[a].seq < fr[b].seq;
+    for (unsigned l = 0; l < L; ++l) {
+        RxLane *ln = h->lanes[l];
+        for (int k = 0; k < 6; ++k) h->work[k] += ln->work[k];
+        for (int k = 0; k < 6; ++k) if (k != 4) h->ms[k] += ln->ms[k];
+        h->ms[4] = std::max(h->ms[4], ln->ms[4]);
+        h->n_frames += ln->n_frames; h->n_valid += ln->n_valid;
+        for (unsigned i = 0; i < ln->n_frames; ++i) h->order.emplace_back(l, i);
+    }
+    std::sort(h->order.begin(), h->order.end(), [&](const std::pair<unsigned, unsigned> &a, const std::pair<unsigned, unsigned> &b) {
+        const FrameDesc &x = h->lanes[a.first]->h_frames.p[a.second], &y = h->lanes[b.first]->h_frames.p[b.second];
+        const unsigned sx = h->global_stream(a.first, x.stream), sy = h->global_stream(b.first, y.stream);
+        return sx != sy ? sx < sy : x.seq < y.seq;
     });
-    for (unsigned i = 0; i < nf; ++i) h->n_valid += fr[i].payload_valid ? 1 : 0;
     return 0;
 }
 
 int lqb_rx_execute_dense(lqb_rx h, const float *iq, uint64_t stride, uint64_t ns, int mem)
 {
     if (!h) return fail(LQB_EINVAL, "null handle");
-    unsigned n = h->f.n_streams;
+    unsigned n = h->n_streams;
     std::vector<const float *> ptr(n);
     std::vector<uint64_t> len(n, ns);
     for (unsigned s = 0; s < n; ++s) ptr[s] = iq + 2 * (size_t)s * stride;
@@ -541,16 +687,17 @@ int lqb_rx_poll(lqb_rx h, lqb_frame_result *out, uint32_t max_out, uint32_t *n_o
     unsigned n = std::min<unsigned>(h->n_frames, max_out);
     const bool host_res = !(h->flags & LQB_RX_DEVICE_RESULTS);
     for (unsigned k = 0; k < n && out; ++k) {
-        const FrameDesc &d = h->h_frames.p[h->order[k]];
+        const RxLane *ln = h->lanes[h->order[k].first];
+        const FrameDesc &d = ln->h_frames.p[h->order[k].second];
         lqb_frame_result &r = out[k];
         std::memset(&r, 0, sizeof r);
-        r.stream = d.stream; r.seq = d.seq; r.sample_index = d.F;
+        r.stream = h->global_stream(ln->lane, d.stream); r.seq = d.seq; r.sample_index = d.F;
         std::memcpy(r.header, d.header, 20);
         r.header_valid = d.header_valid; r.payload_valid = d.payload_valid; r.payload_len = d.payload_len;
         if (d.header_valid) {
-            r.payload = host_res ? h->h_payload.p + d.pay_off : h->d_payload.p + d.pay_off;
-            if (h->flags & LQB_RX_DEVICE_RESULTS) r.framesyms = reinterpret_cast<const float *>(h->d_syms.p + d.sym_off);
-            else if (!(h->flags & LQB_RX_NO_FRAMESYMS)) r.framesyms = reinterpret_cast<const float *>(h->h_syms.p + d.sym_off);
+            r.payload = host_res ? ln->h_payload.p + d.pay_off : ln->d_payload.p + d.pay_off;
+            if (h->flags & LQB_RX_DEVICE_RESULTS) r.framesyms = reinterpret_cast<const float *>(ln->d_syms.p + d.sym_off);
+            else if (!(h->flags & LQB_RX_NO_FRAMESYMS)) r.framesyms = reinterpret_cast<const float *>(ln->h_syms.p + d.sym_off);
             r.num_framesyms = d.n_sym;
         }
         r.mod_scheme = d.ms; r.mod_bps = d.bps; r.check = d.check; r.fec0 = d.fec0; r.fec1 = d.fec1;
@@ -584,9 +731,12 @@ int lqb_rx_last_work(lqb_rx h, uint64_t w[6])
 int lqb_rx_launch_count(lqb_rx h, uint64_t *l)
 {
     if (!h) return fail(LQB_EINVAL, "null handle");
-    *l = h->f.launches;
+    uint64_t t = 0;
+    for (auto *ln : h->lanes) t += ln->f.launches;
+    *l = t;
     return 0;
 }
+int lqb_rx_lane_count(lqb_rx h) { return h ? (int)h->lanes.size() : fail(LQB_EINVAL, "null handle"); }
 
 }  // extern "C"
 

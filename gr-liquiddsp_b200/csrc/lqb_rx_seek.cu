@@ -17,23 +17,47 @@ namespace lqb {
 
 namespace {
 
-#ifndef LQB_SEEK_WARPS
-#define LQB_SEEK_WARPS 4
-#endif
-#ifndef LQB_SEEK_MINB
-#define LQB_SEEK_MINB 2
-#endif
-constexpr int kWarps = LQB_SEEK_WARPS;
-constexpr int kThreads = 32 * kWarps;
+constexpr int kWarps = 4;                 // worker warps (TMEM lane quarters: warp w reads accumulator rows 32w .. 32w+31)
+constexpr int kThreads = 32 * kWarps;     // worker threads
+constexpr int kCtaThreads = kThreads + 32; // + one warp that only issues tcgen05.mma
 constexpr float kPiF = 3.14159274f;     // (float)M_PI
 
+#ifdef LQB_SEEK_PROF
+// per-phase cycle accounting (thread 0 of every CTA), debug builds only: see lqb_dbg_seek_prof()
+__device__ unsigned long long g_seek_prof[16];
+#define PROF_DECL long long prof_last = clock64(); long long prof_acc[12] = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 }
+#define PROF_MARK(i) do { if (threadIdx.x == 0) { long long now_ = clock64(); prof_acc[i] += now_ - prof_last; prof_last = now_; } } while (0)
+#define PROF_ARGS , long long &prof_last, long long (&prof_acc)[12]
+#define PROF_PASS , prof_last, prof_acc
+#else
+#define PROF_DECL
+#define PROF_MARK(i)
+#define PROF_ARGS
+#define PROF_PASS
+#endif
+
+// barrier over the worker warps only (the MMA warp never joins it)
+__device__ __forceinline__ void wsync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// fused tensor-core pre-filter geometry: a block correlates n_t * 128 consecutive lags
+constexpr int kTcRows = 2 * 128 + 160;          // 416 rows of 16 bytes per component
+constexpr int kTcZBytes = kTcRows * 16;         // 6656
+
 struct SeekShared {
-    float2 Xw[512];           // time-domain window / aligned buffer
-    float2 Xf[512];           // its spectrum (also reused for the CFO spectrum)
-    float2 Sc[512];           // conj(S)
-    float2 W[256];            // twiddles
+    // The exact-evaluation buffers and the second Z strip never live at the same time (the pre-filter
+    // pipeline is drained before a window is evaluated exactly), so they share storage; Sc and W are
+    // reloaded from the constant tables when the strip has overwritten them (tables_dirty).
+    union {
+        struct {
+            float2 Xw[512];           // time-domain window / aligned buffer
+            float2 Xf[512];           // its spectrum (also reused for the CFO spectrum)
+            float2 Sc[512];           // conj(S)
+            float2 W[256];            // twiddles
+        };
+        unsigned char Z1[2 * kTcZBytes];
+    };
     float2 Wc[240];           // per-stage compact twiddles (stages 5-8)
-    float2 scr[(kWarps * 544 > 1824) ? kWarps * 544 : 1824]; // per-warp FFT transpose scratch; reused flat by the header stage
+    float2 scr[2176];         // per-warp FFT transpose scratch (4 x 544); flat header-stage scratch; Z strip 0 + staged halfs
     unsigned long long best[kWarps];
     float  energy[2];
     float2 y3[3];             // align: y[511], y[0], y[1]
@@ -41,11 +65,16 @@ struct SeekShared {
     int    trig, idx, off, stop, hv;
     float  rxy, tau, gamma, dphi, phi, mf_scale;
     unsigned theta0, dtheta, pfb, tau_neg;
-    // fused tensor-core pre-filter
-    uint64_t tc_bar;
+    // fused tensor-core pre-filter pipeline
+    uint64_t z_full[2];       // workers -> MMA warp: strip b is staged (count = 128)
+    uint64_t acc_full;        // tcgen05.commit -> workers: accumulators hold the block
+    uint64_t acc_empty;       // workers -> MMA warp: accumulators have been read out (count = 128)
     unsigned tmem_base;
-    float tc_wmax[kWarps], tc_wsum[kWarps], tc_red[2 * kWarps];
-    float tc_scale2, tc_energy, tc_m0, tc_m1;
+    int    tc_cmd[2];         // tiles in strip b (0 = the MMA warp exits)
+    int    tables_dirty;
+    float  part_max[2][kWarps], part_en[2][kWarps];
+    float  red[kWarps][4];
+    float  tc_red[2 * kWarps];
     unsigned char hbytes[64]; // header: 54 demodulated bytes
     unsigned char hdec[32];   // decoded header (24 bytes incl. CRC)
 };
@@ -109,7 +138,7 @@ __device__ void eval_window(SeekShared &sh, const DevTables *T, int tid)
         if (lane == 0) sh.energy[warp] = e;
     }
     if (warp == 0) forward_fft_to(sh, sh.Xw, sh.Xf, lane);
-    __syncthreads();
+    wsync();
     const float g0 = __fmul_rn(__fsqrt_rn(__fadd_rn(sh.energy[0], sh.energy[1])), __fsqrt_rn(156.0f / 512.0f));
     unsigned long long best = 0ull;
     if (g0 >= 1e-10f) {
@@ -133,7 +162,7 @@ __device__ void eval_window(SeekShared &sh, const DevTables *T, int tid)
         best = warp_max_u64(best);
     }
     if (lane == 0) sh.best[warp] = best;
-    __syncthreads();
+    wsync();
     if (tid == 0) {
         unsigned long long b = sh.best[0];
         for (int w = 1; w < kWarps; ++w) b = sh.best[w] > b ? sh.best[w] : b;
@@ -149,183 +178,302 @@ __device__ void eval_window(SeekShared &sh, const DevTables *T, int tid)
         }
         sh.trig = trig; sh.idx = idx; sh.off = off; sh.rxy = rxy;
     }
-    __syncthreads();
+    wsync();
 }
 
 
-// ------------------------------------------------------------------ fused tensor-core correlation block
-// Correlates n_t * 128 consecutive lags starting at absolute sample a0 against the template at all
-// 49 CFO bins on the tensor cores (fp16 operands, fp32 accumulation in TMEM; same implicit-Hankel
-// operand trick as lqb_rx_coarse.cu) and leaves max_b |C|^2 per lag in rowmax[]; also returns the
-// exact-input energy of the staged samples with absolute index in [e_lo, e_hi).
-// scr layout while this runs: Z[2][416*16] | xs[2][432] halfs | rowmax[256] floats.
-constexpr int kTcRows = 2 * 128 + 160;          // 416 rows of 16 bytes per component
-constexpr int kTcZBytes = kTcRows * 16;         // 6656
-constexpr int kTcSamp = kTcRows + 8;            // 424 staged samples
+// ------------------------------------------------------------------ fused tensor-core pre-filter (pipelined)
+// A block correlates n_t * 128 consecutive lags starting at absolute sample a0 against the template at
+// all 49 CFO bins on the tensor cores (fp16 operands, fp32 accumulation in TMEM; same implicit-Hankel
+// operand as lqb_rx_coarse.cu).  Work is split three ways so that the tensor pipe never waits for the
+// CUDA cores of its own CTA:
+//   tc_issue  (workers)  : stage the samples of block k+2 as fp16, build its Z strip, hand it to the MMA warp
+//   mma_warp  (warp 4)   : wait for strip + free accumulators, issue the 20 n_t MMAs of block k+1, commit
+//   tc_retire (workers)  : read the accumulators of block k (max_b |C|^2 per lag), release them, reduce
+// Strip layout: Z[c][8 m + e] = fp16(x_c[a0 + m + e] * 2^-ex), two components, 416 rows of 16 bytes.
+struct TcBlk {
+    long long a0, e_lo, e_hi, w;    // first lag; energy range; window this block belongs to
+    int n_t, cold, ex, buf;         // tiles; cold-start block of a hop grid; scale exponent; strip buffer
+};
+struct TcRes { float m0_all, m0_ge28, m1_all, m1_ge28, mx, en; };
 
-// pre[] / pre_a0: samples already fetched for the block starting at pre_a0 (by the previous call, while its
-// MMAs were running); next_a0: where the caller expects the following block to start.
-__device__ void tc_block(SeekShared &sh, const unsigned char *Bsm, const StreamView &sv, long long a0, int n_t,
-                         long long e_lo, long long e_hi, unsigned &phase, int tid,
+__device__ __forceinline__ unsigned char *tc_strip(SeekShared &sh, int buf)
+{
+    return buf ? sh.Z1 : reinterpret_cast<unsigned char *>(sh.scr);
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(tc::smem_u32(bar)) : "memory");
+}
+
+// pre[] / pre_a0: samples already fetched for the block starting at pre_a0 (by the previous call);
+// next_a0: where the following block will start (its samples are requested before returning).
+__device__ void tc_issue(SeekShared &sh, const StreamView &sv, const TcBlk &b, int tid,
                          float2 (&pre)[4], long long &pre_a0, long long next_a0)
 {
     using namespace tc;
     const int warp = tid >> 5, lane = tid & 31;
-    unsigned char *Z = reinterpret_cast<unsigned char *>(sh.scr);
-    __half *xs = reinterpret_cast<__half *>(Z + 2 * kTcZBytes);
-    float *rowmax = reinterpret_cast<float *>(Z + 2 * kTcZBytes + 2 * 432 * sizeof(__half));
-    const int n_samp = 128 * n_t + 168;
-    // ---- stage samples: magnitude max (tile scale) and window-half energy from the exact inputs
-    float2 v[4];
+    unsigned char *Z = tc_strip(sh, b.buf);
+    uint32_t *xs = reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(sh.scr) + 2 * kTcZBytes);   // [2][216] half pairs
+    const int n_samp = 128 * b.n_t + 168;
+    const float sc = __uint_as_float((uint32_t)(127 - b.ex) << 23);          // exact power of two
+    wsync();                                   // the previous strip build has finished reading xs
     float mx = 0.0f, en = 0.0f;
+    __half *xh = reinterpret_cast<__half *>(xs);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int i = tid + kThreads * k;
-        const long long n = a0 + i;
-        v[k] = (pre_a0 == a0) ? pre[k] : ((i < 424) ? sv.at(n) : make_float2(0.0f, 0.0f));
-        if (i >= n_samp) v[k] = make_float2(0.0f, 0.0f);
-        mx = fmaxf(mx, fmaxf(fabsf(v[k].x), fabsf(v[k].y)));
-        if (i < n_samp && n >= e_lo && n < e_hi) en += fmaf(v[k].y, v[k].y, v[k].x * v[k].x);
+        const long long n = b.a0 + i;
+        float2 v = (pre_a0 == b.a0) ? pre[k] : ((i < 424) ? sv.at(n) : make_float2(0.0f, 0.0f));
+        if (i >= n_samp) v = make_float2(0.0f, 0.0f);
+        mx = fmaxf(mx, fmaxf(fabsf(v.x), fabsf(v.y)));
+        if (i < n_samp && n >= b.e_lo && n < b.e_hi) en += fmaf(v.y, v.y, v.x * v.x);
+        if (i < 432) { xh[i] = __float2half_rn(v.x * sc); xh[432 + i] = __float2half_rn(v.y * sc); }
     }
 #pragma unroll
     for (int m = 16; m >= 1; m >>= 1) {
         mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, m));
         en += __shfl_xor_sync(0xffffffffu, en, m);
     }
-    if (lane == 0) { sh.tc_wmax[warp] = mx; sh.tc_wsum[warp] = en; }
-    __syncthreads();
-    mx = 0.0f; en = 0.0f;
-#pragma unroll
-    for (int w = 0; w < kWarps; ++w) { mx = fmaxf(mx, sh.tc_wmax[w]); en += sh.tc_wsum[w]; }
-    int ex = 0;
-    if (mx > 0.0f) ex = (int)((__float_as_uint(mx) >> 23) & 0xffu) - 127;
-    ex = max(-100, min(100, ex));
-    const float sc = __uint_as_float((uint32_t)(127 - ex) << 23);          // exact power of two
-    const float scale2 = __uint_as_float((uint32_t)(127 + 2 * ex) << 23);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int i = tid + kThreads * k;
-        if (i < n_samp) { xs[i] = __float2half_rn(v[k].x * sc); xs[432 + i] = __float2half_rn(v[k].y * sc); }
-    }
-    __syncthreads();
-    // ---- Z[c][8 m + e] = xs[c][m + e]
-    const int rows = 128 * n_t + 160;
+    if (lane == 0) { sh.part_max[b.buf][warp] = mx; sh.part_en[b.buf][warp] = en; }
+    wsync();
+    // ---- Z[c][8 m + e] = xs[c][m + e]: row m is the 16 bytes at half offset m (word aligned for even m)
+    const int rows = 128 * b.n_t + 160;
     for (int m = tid; m < rows; m += kThreads) {
+        const int w0 = m >> 1;
+        const unsigned sh16 = (m & 1) ? 16u : 0u;
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
-            const __half *s = xs + 432 * c + m;
-            __half2 h0 = __halves2half2(s[0], s[1]), h1 = __halves2half2(s[2], s[3]);
-            __half2 h2 = __halves2half2(s[4], s[5]), h3 = __halves2half2(s[6], s[7]);
-            uint4 w;
-            w.x = *reinterpret_cast<uint32_t *>(&h0); w.y = *reinterpret_cast<uint32_t *>(&h1);
-            w.z = *reinterpret_cast<uint32_t *>(&h2); w.w = *reinterpret_cast<uint32_t *>(&h3);
-            *reinterpret_cast<uint4 *>(Z + c * kTcZBytes + 16 * m) = w;
+            const uint32_t *s = xs + 216 * c + w0;
+            const uint32_t q0 = s[0], q1 = s[1], q2 = s[2], q3 = s[3], q4 = s[4];
+            uint4 o;
+            o.x = __funnelshift_r(q0, q1, sh16); o.y = __funnelshift_r(q1, q2, sh16);
+            o.z = __funnelshift_r(q2, q3, sh16); o.w = __funnelshift_r(q3, q4, sh16);
+            *reinterpret_cast<uint4 *>(Z + c * kTcZBytes + 16 * m) = o;
         }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncthreads();
-    // ---- 20 MMAs (M=128, N=112, K=16) per tile, issued by one thread
-    const uint32_t tmem = sh.tmem_base;
-    if (tid == 0) {
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t idesc = (1u << 4) | ((uint32_t)(kN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-        const uint32_t b_addr = smem_u32(Bsm);
-        for (int t = 0; t < n_t; ++t) {
-            uint32_t acc = 0;
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                const uint32_t za = smem_u32(Z + c * kTcZBytes) + 2048u * t;
-#pragma unroll
-                for (int j = 0; j < 10; ++j) {
-                    mma_f16(tmem + 128u * t, make_desc(za + 256u * j, 128u, 128u),
-                            make_desc(b_addr + (uint32_t)((c * 10 + j) * 2) * kBChunkBytes, kBChunkBytes, 128u), idesc, acc);
-                    acc = 1;
-                }
-            }
-        }
-        mma_commit(&sh.tc_bar);
-    }
-    // while the tensor core works: fetch the samples of the block the caller will ask for next
+    if (tid == 0) sh.tc_cmd[b.buf] = b.n_t;
+    mbar_arrive(&sh.z_full[b.buf]);
+    // the samples of the block that will be staged next travel while this one is multiplied
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int i = tid + kThreads * k;
         pre[k] = (i < 424) ? sv.at(next_a0 + i) : make_float2(0.0f, 0.0f);
     }
     pre_a0 = next_a0;
-    mbar_wait(&sh.tc_bar, phase);
-    phase ^= 1u;
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    // ---- epilogue: thread = lag row; max over the 49 bins of re^2 + im^2
-    for (int t = 0; t < n_t; ++t) {
-        const uint32_t taddr = tmem + 128u * t + ((uint32_t)(warp * 32) << 16);
-        float best = 0.0f;
+}
+
+// the MMA warp: one lane issues, the warp only ever waits on mbarriers
+__device__ void mma_warp(SeekShared &sh, const unsigned char *Bsm, int lane)
+{
+    using namespace tc;
+    unsigned pz[2] = { 0u, 0u }, pe = 1u;      // parity 1 on a fresh barrier: "the accumulators start out free"
+    int buf = 0;
+    const uint32_t tmem = sh.tmem_base;
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(kN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t b_addr = smem_u32(Bsm);
+    while (true) {
+        mbar_wait(&sh.z_full[buf], pz[buf]);
+        pz[buf] ^= 1u;
+        const int n_t = *reinterpret_cast<volatile int *>(&sh.tc_cmd[buf]);
+        if (n_t == 0) break;
+        mbar_wait(&sh.acc_empty, pe);
+        pe ^= 1u;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (lane == 0) {
+            const unsigned char *Z = tc_strip(sh, buf);
+            for (int t = 0; t < n_t; ++t) {
+                uint32_t acc = 0;
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            uint32_t r[4][16];
-            const int q0 = half * 4, nq = half ? 3 : 4;
+                for (int c = 0; c < 2; ++c) {
+                    const uint32_t za = smem_u32(Z + c * kTcZBytes) + 2048u * t;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) if (q < nq) tmem_ld16(taddr + 16u * (q0 + q), r[q]);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                if (q >= nq) continue;
-#pragma unroll
-                for (int k = 0; k < 16; k += 2) {
-                    if (16 * (q0 + q) + k < 2 * kNBins) {
-                        const float re = __uint_as_float(r[q][k]), im = __uint_as_float(r[q][k + 1]);
-                        best = fmaxf(best, fmaf(im, im, re * re));
+                    for (int j = 0; j < 10; ++j) {
+                        mma_f16(tmem + 128u * t, make_desc(za + 256u * j, 128u, 128u),
+                                make_desc(b_addr + (uint32_t)((c * 10 + j) * 2) * kBChunkBytes, kBChunkBytes, 128u), idesc, acc);
+                        acc = 1;
                     }
                 }
             }
+            mma_commit(&sh.acc_full);
         }
-        rowmax[128 * t + tid] = best * scale2;
+        __syncwarp();
+        buf ^= 1;
     }
-    if (tid == 0) sh.tc_energy = en;
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
 }
 
-// max of rowmax[lo .. hi) and of rowmax[lo2 .. hi) over the CTA -> every thread (one pass, two results)
-__device__ void tc_rowmax2(SeekShared &sh, int lo, int lo2, int hi, int tid, float &m_all, float &m_tail)
+// wait for block b, reduce max_b |C|^2 per lag to the four range maxima the decisions need
+__device__ void tc_retire(SeekShared &sh, const TcBlk &b, unsigned &ph_full, int tid, TcRes &r, bool discard PROF_ARGS)
 {
-    const float *rowmax = reinterpret_cast<const float *>(reinterpret_cast<unsigned char *>(sh.scr) + 2 * kTcZBytes + 2 * 432 * sizeof(__half));
+    using namespace tc;
     const int warp = tid >> 5, lane = tid & 31;
-    float a = 0.0f, b = 0.0f;
-    for (int i = lo + tid; i < hi; i += kThreads) {
-        const float v = rowmax[i];
-        a = fmaxf(a, v);
-        if (i >= lo2) b = fmaxf(b, v);
+    PROF_MARK(0);
+    mbar_wait(&sh.acc_full, ph_full);
+    ph_full ^= 1u;
+    PROF_MARK(4);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    float best[2] = { 0.0f, 0.0f };
+    if (!discard) {
+        const uint32_t tmem = sh.tmem_base;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            if (t >= b.n_t) break;
+            const uint32_t taddr = tmem + 128u * t + ((uint32_t)(warp * 32) << 16);
+            float bt = 0.0f;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                uint32_t q[4][16];
+                const int q0 = half * 4, nq = half ? 3 : 4;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) if (u < nq) tmem_ld16(taddr + 16u * (q0 + u), q[u]);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (u >= nq) continue;
+#pragma unroll
+                    for (int k = 0; k < 16; k += 2) {
+                        if (16 * (q0 + u) + k < 2 * kNBins) {
+                            const float re = __uint_as_float(q[u][k]), im = __uint_as_float(q[u][k + 1]);
+                            bt = fmaxf(bt, fmaf(im, im, re * re));
+                        }
+                    }
+                }
+            }
+            best[t] = bt;
+        }
     }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    mbar_arrive(&sh.acc_empty);
+    PROF_MARK(5);
+    if (discard) return;
+    float a = best[0], bb = tid >= 28 ? best[0] : 0.0f, c = best[1], d = tid >= 28 ? best[1] : 0.0f;
 #pragma unroll
     for (int k = 16; k >= 1; k >>= 1) {
         a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, k));
-        b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, k));
+        bb = fmaxf(bb, __shfl_xor_sync(0xffffffffu, bb, k));
+        c = fmaxf(c, __shfl_xor_sync(0xffffffffu, c, k));
+        d = fmaxf(d, __shfl_xor_sync(0xffffffffu, d, k));
     }
-    if (lane == 0) { sh.tc_red[warp] = a; sh.tc_red[kWarps + warp] = b; }
-    __syncthreads();
-    a = 0.0f; b = 0.0f;
+    if (lane == 0) { sh.red[warp][0] = a; sh.red[warp][1] = bb; sh.red[warp][2] = c; sh.red[warp][3] = d; }
+    wsync();
+    r.m0_all = 0.0f; r.m0_ge28 = 0.0f; r.m1_all = 0.0f; r.m1_ge28 = 0.0f; r.mx = 0.0f; r.en = 0.0f;
 #pragma unroll
-    for (int w = 0; w < kWarps; ++w) { a = fmaxf(a, sh.tc_red[w]); b = fmaxf(b, sh.tc_red[kWarps + w]); }
-    m_all = a; m_tail = b;
-    __syncthreads();
+    for (int w = 0; w < kWarps; ++w) {
+        r.m0_all = fmaxf(r.m0_all, sh.red[w][0]); r.m0_ge28 = fmaxf(r.m0_ge28, sh.red[w][1]);
+        r.m1_all = fmaxf(r.m1_all, sh.red[w][2]); r.m1_ge28 = fmaxf(r.m1_ge28, sh.red[w][3]);
+        r.mx = fmaxf(r.mx, sh.part_max[b.buf][w]); r.en += sh.part_en[b.buf][w];
+    }
+    wsync();
+    PROF_MARK(6);
 }
 
-// max of rowmax[lo .. hi) over the CTA -> every thread
-__device__ float tc_rowmax(SeekShared &sh, int lo, int hi, int tid)
+// carry between consecutive windows of one hop grid (uniform across the workers)
+struct ScanCarry {
+    bool valid, unsafe, ex_valid;
+    long long w;            // window the carried tail / half-energy belong to
+    float tail, half;       // max |C|^2 over its first 100 lags; energy of its first 256 samples
+    int ex;                 // scale exponent for the next strips
+};
+
+__device__ __forceinline__ int exponent_of(float mx)
 {
-    const float *rowmax = reinterpret_cast<const float *>(reinterpret_cast<unsigned char *>(sh.scr) + 2 * kTcZBytes + 2 * 432 * sizeof(__half));
-    const int warp = tid >> 5, lane = tid & 31;
-    float m = 0.0f;
-    for (int i = lo + tid; i < hi; i += kThreads) m = fmaxf(m, rowmax[i]);
+    int ex = 0;
+    if (mx > 0.0f) ex = (int)((__float_as_uint(mx) >> 23) & 0xffu) - 127;
+    return max(-100, min(100, ex));
+}
+
+// Walk the hop grid from st.wstart with the pre-filter while windows can be ruled out.
+// Returns 1 when window st.wstart (updated) needs the exact evaluation, 0 when the input is exhausted.
+// The pipeline is empty on return.
+__device__ int fused_scan(SeekShared &sh, const StreamView &sv, const DevTables *T, StreamState &st, int tid,
+                          ScanCarry &c, float2 (&pre)[4], long long &pre_a0, unsigned &ph_full, int &buf_w,
+                          unsigned &n_windows, unsigned &n_tiles PROF_ARGS)
+{
+    long long g_w = st.wstart;                         // block generator: next window to stage
+    bool g_cold = !(c.valid && c.w == g_w);
+    long long w_done = g_w;                            // first window not yet decided
+    if (g_w + 512 > sv.end) return 0;
+    sh.tables_dirty = 1;                               // (every worker writes the same value)
+    if (!c.ex_valid) {
+        // first strip of this launch: take the scale from the samples themselves
+        float mx = 0.0f;
+        const long long a0 = g_cold ? g_w - 28 : g_w + 100;
 #pragma unroll
-    for (int k = 16; k >= 1; k >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, k));
-    __syncthreads();
-    if (lane == 0) sh.tc_red[warp] = m;
-    __syncthreads();
-    m = 0.0f;
+        for (int k = 0; k < 4; ++k) {
+            const int i = tid + kThreads * k;
+            const float2 v = (i < 424) ? sv.at(a0 + i) : make_float2(0.0f, 0.0f);
+            mx = fmaxf(mx, fmaxf(fabsf(v.x), fabsf(v.y)));
+        }
 #pragma unroll
-    for (int w = 0; w < kWarps; ++w) m = fmaxf(m, sh.tc_red[w]);
-    return m;
+        for (int m = 16; m >= 1; m >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, m));
+        wsync();
+        if ((tid & 31) == 0) sh.tc_red[tid >> 5] = mx;
+        wsync();
+        mx = fmaxf(fmaxf(sh.tc_red[0], sh.tc_red[1]), fmaxf(sh.tc_red[2], sh.tc_red[3]));
+        c.ex = exponent_of(mx);
+        c.ex_valid = true;
+    }
+    TcBlk q0, q1;                                       // in flight, q0 the older
+    int inflight = 0, result = 0;
+    auto gen = [&](TcBlk &b, long long &next_a0) {
+        b.w = g_w; b.ex = c.ex; b.buf = buf_w; buf_w ^= 1;
+        if (g_cold) { b.a0 = g_w - 28; b.n_t = 1; b.e_lo = g_w; b.e_hi = g_w + 256; b.cold = 1; next_a0 = g_w + 100; g_cold = false; }
+        else { b.a0 = g_w + 100; b.n_t = 2; b.e_lo = g_w + 256; b.e_hi = g_w + 512; b.cold = 0; next_a0 = g_w + 356; g_w += 256; }
+        n_tiles += (unsigned)b.n_t;
+    };
+    auto more = [&]() { return g_w + 512 <= sv.end; };
+    while (inflight < 2 && more()) {
+        TcBlk &b = inflight ? q1 : q0;
+        long long na;
+        gen(b, na);
+        tc_issue(sh, sv, b, tid, pre, pre_a0, na);
+        ++inflight;
+    }
+    PROF_MARK(1);
+    while (inflight) {
+        TcRes r;
+        tc_retire(sh, q0, ph_full, tid, r, false PROF_PASS);
+        const TcBlk d = q0;
+        q0 = q1; --inflight;
+        const float s2 = __uint_as_float((uint32_t)(127 + 2 * d.ex) << 23);
+        const float scaled_mx = r.mx * __uint_as_float((uint32_t)(127 - d.ex) << 23);
+        // outside this range fp16 staging loses the error bound (overflow / everything subnormal): do not trust the block
+        const bool unsafe_blk = !(scaled_mx < 32768.0f) || (r.mx > 0.0f && scaled_mx < 0.001953125f);
+        c.ex = exponent_of(r.mx);
+        if (d.cold) {
+            c.tail = r.m0_ge28 * s2; c.half = r.en; c.unsafe = unsafe_blk; c.w = d.w; c.valid = true;
+        } else {
+            ++n_windows;
+            const float mm = fmaxf(c.tail, fmaxf(r.m0_all, r.m1_all) * s2), E = c.half + r.en;
+            bool skip = false;
+            if (E > 0.0f && !c.unsafe && !unsafe_blk) {
+                const float ub = sqrtf(mm) / (sqrtf(E) * sqrtf(156.0f / 512.0f) * sqrtf(T->s2_sum));
+                skip = ub < T->threshold - 0.008f;
+            }
+            c.tail = r.m1_ge28 * s2; c.half = r.en; c.unsafe = unsafe_blk; c.w = d.w + 256; c.valid = true;
+            if (!skip) {
+                // speculative blocks behind this one are dropped (their accumulators are released unread)
+                while (inflight) { TcRes dummy; tc_retire(sh, q0, ph_full, tid, dummy, true PROF_PASS); q0 = q1; --inflight; }
+                w_done = d.w;
+                result = 1;
+                break;
+            }
+            w_done = d.w + 256;
+        }
+        if (more()) {
+            TcBlk &b = inflight ? q1 : q0;
+            long long na;
+            gen(b, na);
+            PROF_MARK(0);
+            tc_issue(sh, sv, b, tid, pre, pre_a0, na);
+            PROF_MARK(2);
+            ++inflight;
+        }
+    }
+    if (tid == 0) st.wstart = w_done;
+    wsync();
+    return result;
 }
 
 // Pre-filter test for the window starting r0 samples after the carry base: true when the tensor-core
@@ -352,12 +500,12 @@ __device__ bool coarse_rules_out(SeekShared &sh, const SeekParams &P, const DevT
         el += __shfl_xor_sync(0xffffffffu, el, k);
         eu += __shfl_xor_sync(0xffffffffu, eu, k);
     }
-    __syncthreads();                       // protect the reduction scratch against the previous use
+    wsync();                       // protect the reduction scratch against the previous use
     float *red = reinterpret_cast<float *>(sh.best);
     if (lane == 0) red[warp] = m;
     __shared__ float red_el[kWarps], red_eu[kWarps];
     if (lane == 0) { red_el[warp] = el; red_eu[warp] = eu; }
-    __syncthreads();
+    wsync();
     if (tid == 0) {
         float mm = 0.0f, l = 0.0f, u = 0.0f;
         for (int w = 0; w < kWarps; ++w) { mm = fmaxf(mm, red[w]); l += red_el[w]; u += red_eu[w]; }
@@ -368,9 +516,9 @@ __device__ bool coarse_rules_out(SeekShared &sh, const SeekParams &P, const DevT
         }
         sh.trig = skip;
     }
-    __syncthreads();
+    wsync();
     const bool r = sh.trig != 0;
-    __syncthreads();
+    wsync();
     return r;
 }
 
@@ -383,7 +531,7 @@ __device__ void align_frame(SeekShared &sh, const DevTables *T, int tid)
     // CFO product (other warps start while warp 0 transforms; zbuf does not alias warp 0's scratch)
     for (int i = tid; i < 512; i += kThreads)
         zbuf[i] = (i < 156) ? cmulf(sh.Xw[i], T->sconj[i]) : make_float2(0.0f, 0.0f);
-    __syncthreads();
+    wsync();
     if (warp == 0) {
         float2 v[16];
         cross_ifft(sh, sh.off, v, sh.scr, lane);
@@ -406,7 +554,7 @@ __device__ void align_frame(SeekShared &sh, const DevTables *T, int tid)
         best = warp_max_u64(best);
         if (lane == 0) sh.best[0] = best;
     }
-    __syncthreads();
+    wsync();
     if (tid == 0) {
         float yneg = __fsqrt_rn(cabsf_(sh.y3[0])), y0 = __fsqrt_rn(cabsf_(sh.y3[1])), ypos = __fsqrt_rn(cabsf_(sh.y3[2]));
         float a = __fsub_rn(__fmul_rn(0.5f, __fadd_rn(ypos, yneg)), y0);
@@ -428,7 +576,7 @@ __device__ void align_frame(SeekShared &sh, const DevTables *T, int tid)
         float base = (i0 > 256u) ? __fsub_rn(index, 512.0f) : index;
         sh.dphi = __fdiv_rn(__fmul_rn(__fmul_rn(base, 2.0f), kPiF), 512.0f);
     }
-    __syncthreads();
+    wsync();
     const float dphi = sh.dphi;
     for (int i = tid; i < 156; i += kThreads) {
         float ang = __fmul_rn(-dphi, (float)i);
@@ -436,7 +584,7 @@ __device__ void align_frame(SeekShared &sh, const DevTables *T, int tid)
         sincosf(ang, &sn, &cs);
         vsum[i] = cmulf(zbuf[i], make_float2(cs, sn));
     }
-    __syncthreads();
+    wsync();
     if (tid == 0) {
         float mr = 0.0f, mi = 0.0f;
         for (int i = 0; i < 156; ++i) { mr = __fadd_rn(mr, vsum[i].x); mi = __fadd_rn(mi, vsum[i].y); }
@@ -452,7 +600,7 @@ __device__ void align_frame(SeekShared &sh, const DevTables *T, int tid)
         }
         sh.mf_scale = __fdiv_rn(0.5f, sh.gamma);
     }
-    __syncthreads();
+    wsync();
 }
 
 // in-place interleaver pass on a small byte buffer (serial; header only)
@@ -477,7 +625,7 @@ __device__ void decode_header(SeekShared &sh, const DevTables *T, const StreamVi
         unsigned n = 128u + (unsigned)m;
         vbuf[m] = nco_mix_down(T->sintab, theta0 + n * dtheta, sv.at(F + n));
     }
-    __syncthreads();
+    wsync();
     const float *h = T->banks + sh.pfb * 28;
     for (int k = tid; k < 231; k += kThreads) {
         int nt = 2 * (78 + k) - (int)tau_neg;           // sample index of symbol t = 78 + k
@@ -487,7 +635,7 @@ __device__ void decode_header(SeekShared &sh, const DevTables *T, const StreamVi
         for (int j = 0; j < 28; ++j) { ar = __fmaf_rn(h[j], w[j].x, ar); ai = __fmaf_rn(h[j], w[j].y, ai); }
         hsym[k] = make_float2(__fmul_rn(ar, sh.mf_scale), __fmul_rn(ai, sh.mf_scale));
     }
-    __syncthreads();
+    wsync();
     // ---- pilot sync (thread 0): 15 pilots -> FFT-32 -> residual dphi / phi / gain
     if (tid == 0) {
         float2 *bt = pil, *bf = pil + 32;
@@ -522,7 +670,7 @@ __device__ void decode_header(SeekShared &sh, const DevTables *T, const StreamVi
         *pll_dtheta = nco_constrain_dev(dphi);
         *pll_theta0 = nco_constrain_dev(__fadd_rn(phi, __fmul_rn(dphi, 231.0f)));
     }
-    __syncthreads();
+    wsync();
     // ---- derotate the 216 data symbols and slice QPSK: 4 symbols -> one byte
     {
         const float dphi = pil[0].x, phi = pil[0].y, g = pil[1].x;
@@ -542,7 +690,7 @@ __device__ void decode_header(SeekShared &sh, const DevTables *T, const StreamVi
             sh.hbytes[byte] = (unsigned char)out;
         }
     }
-    __syncthreads();
+    wsync();
     // ---- decode (thread 0): deinterleave(54) -> Hamming(8,4) -> deinterleave(27) -> SECDED(72,64) -> unscramble -> CRC-32
     if (tid == 0) {
         unsigned char *e = sh.hbytes, d27[28], *d = sh.hdec;
@@ -575,31 +723,37 @@ __device__ void decode_header(SeekShared &sh, const DevTables *T, const StreamVi
         unsigned rx = ((unsigned)d[20] << 24) | ((unsigned)d[21] << 16) | ((unsigned)d[22] << 8) | d[23];
         sh.hv = (key == rx);
     }
-    __syncthreads();
+    wsync();
 }
 
 }  // namespace
 
 // ------------------------------------------------------------------ the kernel
-__global__ void __launch_bounds__(kThreads, LQB_SEEK_MINB)
+// 4 worker warps walk the stream's state machine; a fifth warp only issues tcgen05.mma for the
+// pre-filter pipeline (fused mode) and otherwise idles until the end of the CTA.
+__global__ void __launch_bounds__(kCtaThreads, 2)
 k_seek(SeekParams P)
 {
     __shared__ SeekShared sh;
     __shared__ StreamState st;
     __shared__ unsigned pll_theta0, pll_dtheta;
     const int tid = threadIdx.x;
+    PROF_DECL;
     const DevTables *T = P.tables;
     const StreamIO io = P.io[blockIdx.x];
 
     extern __shared__ unsigned char dyn_smem[];
     unsigned char *Bsm = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(dyn_smem) + 127) & ~uintptr_t(127));
     const bool fused = (P.coarse == 2);
-    unsigned tc_phase = 0;
     if (fused) {
         const uint4 *src = reinterpret_cast<const uint4 *>(P.bmat);
         uint4 *dst = reinterpret_cast<uint4 *>(Bsm);
-        for (int i = tid; i < tc::kBBytes / 16; i += kThreads) dst[i] = src[i];
-        if (tid == 0) tc::mbar_init(reinterpret_cast<uint64_t *>(&sh.tc_bar), 1);
+        for (int i = tid; i < tc::kBBytes / 16; i += kCtaThreads) dst[i] = src[i];
+        if (tid == 0) {
+            tc::mbar_init(&sh.z_full[0], kThreads); tc::mbar_init(&sh.z_full[1], kThreads);
+            tc::mbar_init(&sh.acc_full, 1); tc::mbar_init(&sh.acc_empty, kThreads);
+            sh.tc_cmd[0] = 0; sh.tc_cmd[1] = 0;
+        }
         if (tid < 32) {
             asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tc::smem_u32(&sh.tmem_base)), "r"(256));
             asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -608,23 +762,32 @@ k_seek(SeekParams P)
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
-    for (int i = tid; i < 512; i += kThreads) sh.Sc[i] = T->Sc[i];
-    for (int i = tid; i < 256; i += kThreads) sh.W[i] = T->W512[i];
-    if (tid == 0) st = P.states[io.stream];
-    __syncthreads();
-    fft512_fill_compact(sh.Wc, sh.W, tid, kThreads);
+    if (tid == 0) { st = P.states[io.stream]; sh.tables_dirty = 1; }
     __syncthreads();
     if (fused) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    // pre-filter carry-over between consecutive windows of one hop grid (uniform across the CTA)
-    bool c_valid = false;
-    long long c_w = 0;
-    float c_tail = 0.0f, c_half = 0.0f;
+
+    if (tid >= kThreads) {
+        if (fused) mma_warp(sh, Bsm, tid & 31);
+    } else {
+    // ======================================================== worker warps
+    // compact twiddles survive the strips; W itself is (re)loaded together with Sc on demand
+    for (int i = tid; i < 240; i += kThreads) {
+        int sidx = (i >= 112) ? 3 : (i >= 48) ? 2 : (i >= 16) ? 1 : 0;
+        int j = i - 16 * ((1 << sidx) - 1);
+        sh.Wc[i] = T->W512[j * (16 >> sidx)];
+    }
+    wsync();
+    ScanCarry sc_;
+    sc_.valid = false; sc_.unsafe = false; sc_.ex_valid = false; sc_.w = 0; sc_.tail = 0.0f; sc_.half = 0.0f; sc_.ex = 0;
     float2 tc_pre[4];
     long long tc_pre_a0 = -(1ll << 62);
 #pragma unroll
     for (int k = 0; k < 4; ++k) tc_pre[k] = make_float2(0.0f, 0.0f);
+    unsigned ph_full = 0u;
+    int buf_w = 0;
 
-    unsigned n_windows = 0, n_aligns = 0, n_exact = 0, n_tc_tiles = 0;      // work counters (uniform across the CTA)
+    unsigned n_windows = 0, n_aligns = 0, n_exact = 0, n_tc_tiles = 0;      // work counters (uniform across the workers)
+    PROF_MARK(10);
     const unsigned long long coff = P.coarse == 1 ? (unsigned long long)P.tile_prefix[blockIdx.x] * 16ull : 0ull;
     StreamView sv;
     sv.carry = P.carry[st.carry_sel] + (size_t)io.stream * P.carry_cap;
@@ -634,51 +797,41 @@ k_seek(SeekParams P)
     sv.end = st.base + (long long)st.carry_len + (long long)io.n_in;
     sv.G = st.G;
 
+    // make Sc / W valid again after a strip overwrote them
+    auto restore_tables = [&]() {
+        if (sh.tables_dirty) {
+            wsync();
+            for (int i = tid; i < 512; i += kThreads) sh.Sc[i] = T->Sc[i];
+            for (int i = tid; i < 256; i += kThreads) sh.W[i] = T->W512[i];
+            if (tid == 0) sh.tables_dirty = 0;
+            wsync();
+        }
+    };
+
     while (true) {
         // ---------------- SEEK
         if (st.mode == 0) {
             if (st.wstart + 512 > sv.end) break;
-            ++n_windows;
-            if (fused && st.wstart >= st.G) {
-                const long long w = st.wstart;
-                if (!(c_valid && c_w == w)) {
-                    // cold start of a hop grid: lags [w-28, w+100), first-half energy [w, w+256)
-                    tc_block(sh, Bsm, sv, w - 28, 1, w, w + 256, tc_phase, tid, tc_pre, tc_pre_a0, w + 100);
-                    n_tc_tiles += 1;
-                    c_tail = tc_rowmax(sh, 28, 128, tid);
-                    c_half = sh.tc_energy;
-                }
-                // lags [w+100, w+356) and the second-half energy [w+256, w+512)
-                tc_block(sh, Bsm, sv, w + 100, 2, w + 256, w + 512, tc_phase, tid, tc_pre, tc_pre_a0, w + 356);
-                n_tc_tiles += 2;
-                float m_new, m_tail;
-                tc_rowmax2(sh, 0, 156, 256, tid, m_new, m_tail);
-                const float e2 = sh.tc_energy;
-                const float mm = fmaxf(c_tail, m_new), E = c_half + e2;
-                bool skip = false;
-                if (E > 0.0f) {
-                    const float ub = sqrtf(mm) / (sqrtf(E) * sqrtf(156.0f / 512.0f) * sqrtf(T->s2_sum));
-                    skip = ub < T->threshold - 0.008f;
-                }
-                c_tail = m_tail; c_half = e2; c_w = w + 256; c_valid = true;
-                __syncthreads();
-                if (skip) {
+            if (fused) {
+                if (!fused_scan(sh, sv, T, st, tid, sc_, tc_pre, tc_pre_a0, ph_full, buf_w, n_windows, n_tc_tiles PROF_PASS)) break;
+            } else {
+                ++n_windows;
+                if (P.coarse == 1 && st.wstart >= st.G && coarse_rules_out(sh, P, T, coff, st.wstart - sv.base, tid)) {
                     if (tid == 0) st.wstart += 256;
-                    __syncthreads();
+                    wsync();
                     continue;
                 }
-            } else if (P.coarse == 1 && st.wstart >= st.G && coarse_rules_out(sh, P, T, coff, st.wstart - sv.base, tid)) {
-                if (tid == 0) st.wstart += 256;
-                __syncthreads();
-                continue;
             }
             ++n_exact;
+            PROF_MARK(7);
+            restore_tables();
             load_window(sh, sv, st.wstart, tid);
-            __syncthreads();
+            wsync();
             eval_window(sh, T, tid);
+            PROF_MARK(8);
             if (!sh.trig) {
                 if (tid == 0) st.wstart += 256;
-                __syncthreads();
+                wsync();
                 continue;
             }
             if (tid == 0) {
@@ -688,16 +841,18 @@ k_seek(SeekParams P)
                 st.rxy = sh.rxy;
                 st.need_until = st.F + 512;
             }
-            __syncthreads();
+            wsync();
         }
         // ---------------- PENDING: frame start known (the hop grid restarts afterwards)
-        c_valid = false;
+        sc_.valid = false;
         tc_pre_a0 = -(1ll << 62);          // prefetched samples were taken under the old zero boundary
         if (sv.end < st.need_until) break;
+        PROF_MARK(7);
+        restore_tables();
         const long long F = st.F;
         load_window(sh, sv, F, tid);
         if (tid == 0) sh.off = st.offset;
-        __syncthreads();
+        wsync();
         align_frame(sh, T, tid);
         ++n_aligns;
 
@@ -715,14 +870,15 @@ k_seek(SeekParams P)
                 st.mode = 0;
                 st.wstart = F + 256;
             }
-            __syncthreads();
+            wsync();
+            PROF_MARK(9);
             continue;
         }
 
         const long long hdr_last = F + 616 - (long long)sh.tau_neg;    // sample that completes header symbol 308
         if (hdr_last + 1 > sv.end) {
             if (tid == 0) st.need_until = hdr_last + 1;
-            __syncthreads();
+            wsync();
             break;
         }
         decode_header(sh, T, sv, F, tid, &pll_theta0, &pll_dtheta);
@@ -755,12 +911,12 @@ k_seek(SeekParams P)
                         st.dropped++;
                         st.mode = 0; st.G = F + 512; st.wstart = st.G - 256;
                     }
-                    __syncthreads();
+                    wsync();
                     sv.G = st.G;
                     continue;
                 }
                 if (tid == 0) st.need_until = last + 1;
-                __syncthreads();
+                wsync();
                 break;
             }
         }
@@ -791,14 +947,16 @@ k_seek(SeekParams P)
             st.G = last + 1;
             st.wstart = st.G - 256;
         }
-        __syncthreads();
+        wsync();
         sv.G = st.G;
+        PROF_MARK(9);
     }
+    PROF_MARK(7);
 
     if (fused) {
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();
-        if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(sh.tmem_base), "r"(256));
+        // tell the MMA warp to leave (the pipeline is empty here)
+        if (tid == 0) sh.tc_cmd[buf_w] = 0;
+        mbar_arrive(&sh.z_full[buf_w]);
     }
     if (tid == 0) {
         long long r = (st.mode == 0) ? st.wstart : st.F;
@@ -811,6 +969,16 @@ k_seek(SeekParams P)
         atomicAdd(P.n_out + 2, n_aligns);
         atomicAdd(P.n_out + 3, n_exact);
         atomicAdd(P.n_out + 4, n_tc_tiles);
+#ifdef LQB_SEEK_PROF
+        for (int i = 0; i < 12; ++i) atomicAdd(&g_seek_prof[i], (unsigned long long)prof_acc[i]);
+#endif
+    }
+    }   // workers
+
+    if (fused) {
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(sh.tmem_base), "r"(256));
     }
 }
 
@@ -845,8 +1013,18 @@ void launch_seek(const SeekParams &P, unsigned n_io, cudaStream_t s)
     static bool attr_set = false;
     const int dyn = tc::kBBytes + 256;
     if (!attr_set) { cudaFuncSetAttribute(k_seek, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn); attr_set = true; }
-    k_seek<<<n_io, kThreads, P.coarse == 2 ? dyn : 0, s>>>(P);
+    k_seek<<<n_io, kCtaThreads, P.coarse == 2 ? dyn : 0, s>>>(P);
 }
 void launch_carry(const SeekParams &P, unsigned n_io, cudaStream_t s) { k_carry<<<n_io, 256, 0, s>>>(P); }
+
+#ifdef LQB_SEEK_PROF
+extern "C" int lqb_dbg_seek_prof(unsigned long long *out16, int reset)
+{
+    cudaDeviceSynchronize();
+    if (cudaMemcpyFromSymbol(out16, g_seek_prof, sizeof(unsigned long long) * 16) != cudaSuccess) return -5;
+    if (reset) { unsigned long long z[16] = {}; cudaMemcpyToSymbol(g_seek_prof, z, sizeof z); }
+    return 0;
+}
+#endif
 
 }  // namespace lqb

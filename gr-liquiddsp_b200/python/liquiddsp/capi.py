@@ -19,7 +19,7 @@ RX_NO_FRAMESYMS, RX_DEVICE_RESULTS = 1, 2
 DECLARED_SYMBOLS = [
     "lqb_last_error", "lqb_device_count", "lqb_version",
     "lqb_rx_create", "lqb_rx_destroy", "lqb_rx_reset", "lqb_rx_execute", "lqb_rx_execute_dense",
-    "lqb_rx_poll", "lqb_rx_counts", "lqb_rx_last_timing", "lqb_rx_launch_count", "lqb_rx_last_work",
+    "lqb_rx_poll", "lqb_rx_counts", "lqb_rx_last_timing", "lqb_rx_launch_count", "lqb_rx_last_work", "lqb_rx_lane_count",
     "lqb_tx_create", "lqb_tx_destroy", "lqb_tx_props_init_default", "lqb_tx_frame_len", "lqb_tx_assemble",
     "lqb_det_create", "lqb_det_destroy", "lqb_det_reset", "lqb_det_execute", "lqb_det_execute_dense",
     "lqb_det_poll", "lqb_det_last_timing", "lqb_det_last_work",
@@ -30,7 +30,7 @@ DECLARED_SYMBOLS = [
 
 class RxOpts(C.Structure):
     _fields_ = [("device", C.c_int), ("n_streams", C.c_uint32), ("max_frame_samples", C.c_uint32),
-                ("flags", C.c_uint32), ("cuda_stream", C.c_void_p)]
+                ("flags", C.c_uint32), ("cuda_stream", C.c_void_p), ("n_lanes", C.c_uint32)]
 
 
 class FrameResult(C.Structure):
@@ -86,6 +86,7 @@ def lib():
     L.lqb_rx_last_timing.argtypes = [vp, C.POINTER(C.c_float)]
     L.lqb_rx_launch_count.argtypes = [vp, C.POINTER(u64)]
     L.lqb_rx_last_work.argtypes = [vp, C.POINTER(u64)]
+    L.lqb_rx_lane_count.argtypes = [vp]
     L.lqb_det_last_work.argtypes = [vp, C.POINTER(u64)]
     if hasattr(L, "lqb_tx_create"):
         L.lqb_tx_create.restype = vp
@@ -138,8 +139,8 @@ def _frame_to_dict(r, host_results=True):
 class Rx:
     """Batch flexframesync: n_streams independent channels on one GPU."""
 
-    def __init__(self, n_streams=1, device=0, max_frame_samples=0, flags=0, cuda_stream=None):
-        o = RxOpts(device, n_streams, max_frame_samples, flags, cuda_stream)
+    def __init__(self, n_streams=1, device=0, max_frame_samples=0, flags=0, cuda_stream=None, lanes=0):
+        o = RxOpts(device, n_streams, max_frame_samples, flags, cuda_stream, lanes)
         self._L = lib()
         self._h = self._L.lqb_rx_create(C.byref(o))
         if not self._h:
@@ -193,6 +194,9 @@ class Rx:
         ms = (C.c_float * 6)()
         _check(self._L.lqb_rx_last_timing(self._h, ms))
         return list(ms)
+
+    def lanes(self):
+        return int(self._L.lqb_rx_lane_count(self._h))
 
     def launches(self):
         v = C.c_uint64(0)

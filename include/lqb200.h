@@ -112,7 +112,12 @@ typedef struct {
     uint32_t n_streams;          /* independent channel streams in this batch */
     uint32_t max_frame_samples;  /* per-stream carry capacity; 0 = 65536. Frames longer than this are dropped */
     uint32_t flags;              /* LQB_RX_* */
-    void    *cuda_stream;        /* cudaStream_t to enqueue on; NULL = library-owned stream */
+    void    *cuda_stream;        /* cudaStream_t the caller works on (inputs are ordered after it, it is ordered
+                                    after the results); NULL = library-owned streams only */
+    uint32_t n_lanes;            /* streams are split over this many independent pipeline lanes (stream s -> lane
+                                    s % n_lanes) whose search, payload kernels and copies overlap; 0 = automatic
+                                    (env LQB_RX_LANES, else one per 128 streams, at most 8).  Results do not
+                                    depend on it. */
 } lqb_rx_opts;
 
 /* mirrors framesync_callback's arguments + framesyncstats_s (lib/flex_rx_impl.cc:182-201),
@@ -150,11 +155,14 @@ int    lqb_rx_execute_dense(lqb_rx h, const float *iq, uint64_t stride_samples, 
 int    lqb_rx_poll(lqb_rx h, lqb_frame_result *out, uint32_t max_out, uint32_t *n_out);
 /* number of frames completed by the last execute / payloads with a passing check */
 int    lqb_rx_counts(lqb_rx h, uint64_t *frames, uint64_t *valid_payloads);
-/* per-kernel device times (ms) of the last execute, measured with CUDA events on the handle's
- * stream: [0]=pre-filter+seek/align/header [1]=matched filter [2]=PLL+demod [3]=FEC+CRC [4]=total
- * [5]=tensor-core pre-filter alone (included in [0]) */
+/* per-kernel device times (ms) of the last execute, measured with CUDA events on the streams the
+ * kernels are launched on: [0]=pre-filter+seek/align/header [1]=matched filter [2]=PLL+demod
+ * [3]=FEC+CRC [4]=total [5]=tensor-core pre-filter alone (included in [0]).  With more than one lane
+ * [0..3],[5] are sums over lanes of intervals that overlap each other on the GPU (use n_lanes = 1
+ * for an undisturbed per-kernel breakdown) and [4] is the longest lane. */
 int    lqb_rx_last_timing(lqb_rx h, float ms[6]);
 int    lqb_rx_launch_count(lqb_rx h, uint64_t *launches);   /* kernels launched since create */
+int    lqb_rx_lane_count(lqb_rx h);                         /* pipeline lanes of this handle */
 /* work done by the last execute: [0] 512-sample detector windows visited, [1] frame alignments,
  * [2] payload symbols matched-filtered/demodulated, [3] input samples consumed,
  * [4] windows that needed the exact 50-FFT evaluation, [5] 128-lag pre-filter tiles */

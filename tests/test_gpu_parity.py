@@ -170,6 +170,42 @@ def test_many_ragged_streams_and_streaming_chunks():
         assert [g["seq"] for g in acc[s]] == list(range(len(acc[s])))
 
 
+@pytest.mark.parametrize("lanes", [1, 2, 5, 12])
+def test_lane_count_does_not_change_results(lanes):
+    """Streams are split over independent pipeline lanes (stream s -> lane s % L); the frames reported,
+    their order and every byte/estimate must not depend on L (host and device inputs, chunked feeding)."""
+    rng = np.random.default_rng(77)
+    n_streams = 12
+    caps, refs = [], []
+    for s in range(n_streams):
+        ms = util.MODS[(2 * s + 1) % len(util.MODS)]
+        f0 = util.INNER[(s + 1) % len(util.INNER)]
+        f1 = util.OUTER[(5 * s) % len(util.OUTER)]
+        frames = [o.tx_frame(ms, util.CRC24, f0, f1, rng.integers(0, 256, 60 + 29 * k + s, dtype=np.uint8)) for k in range(3)]
+        cap = util.build_capture(frames, rng, [400 + 101 * k for k in range(3)], snr_db=27.0,
+                                 cfo=0.02 * (s / n_streams - 0.5), tau=0.4 * (s % 3 - 1), gain=0.6 + 0.1 * s,
+                                 lead=64 + 131 * s, tail=900)
+        caps.append(cap)
+        refs.append(o.rx_capture(cap))
+    rx = capi.Rx(n_streams, lanes=lanes)
+    assert rx.lanes() == lanes
+    # first half of every capture, then the rest for a shuffled subset order
+    half = [len(c) // 2 for c in caps]
+    rx.execute([c[:h] for c, h in zip(caps, half)])
+    got = rx.poll()
+    ids = [7, 0, 11, 3, 4, 1, 2, 10, 9, 8, 6, 5]
+    rx.execute([caps[s][half[s]:] for s in ids], ids)
+    second = rx.poll()
+    assert [(g["stream"], g["seq"]) for g in second] == sorted((g["stream"], g["seq"]) for g in second)
+    got += second
+    for s in range(n_streams):
+        assert_frames_match(refs[s], [g for g in got if g["stream"] == s])
+    rx.reset(3)
+    rx.execute([caps[3]], [3])
+    assert_frames_match(refs[3], rx.poll())
+    rx.close()
+
+
 def test_gr_block_chunking_256_multiples():
     rng = np.random.default_rng(32)
     frames = [o.tx_frame(util.PSK4, util.CRC24, 1, 1, rng.integers(0, 256, 256, dtype=np.uint8)) for _ in range(3)]

@@ -7,6 +7,7 @@
 #include "lqb_tables.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -19,6 +20,20 @@ using namespace lqb;
 namespace {
 
 thread_local std::string g_err;
+
+// LQB_TRACE=1: host-side timeline of every execute on stderr (ms since the call started)
+struct Trace {
+    bool on = getenv("LQB_TRACE") != nullptr;
+    std::chrono::steady_clock::time_point t0;
+    void start() { if (on) t0 = std::chrono::steady_clock::now(); }
+    void mark(const char *what, unsigned lane) const
+    {
+        if (!on) return;
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        fprintf(stderr, "[lqb %8.3f ms] lane %u %s\n", ms, lane, what);
+    }
+};
+Trace g_trace;
 int fail(int code, const char *fmt, const char *a = "")
 {
     char buf[512];
@@ -279,7 +294,7 @@ struct Front {
 }  // namespace
 
 // =================================================================== RX handle
-// The receiver is split into independent LANES: lane l owns the streams s with s % L == l, its own
+// The receiver is split into independent LANES: every lane owns a fixed subset of the streams, its own
 // CUDA streams, stream states, carries and arenas.  One host thread drives all lanes as a software
 // pipeline -- seek(l) is queued for every lane, then for each lane in turn the host reads the frame
 // list, plans and queues the payload kernels -- so lane l's payload kernels, host planning and result
@@ -304,6 +319,7 @@ struct RxLane {
     size_t ilv_used = 0;
     std::unordered_map<unsigned, size_t> ilv_cache;
     DevBuf<unsigned long long> d_dec;
+    DevBuf<uint4> d_ckpt;
     DevBuf<unsigned> d_lists, d_tilemap;
     PinBuf<unsigned> h_lists;
     unsigned n_frames = 0;
@@ -326,7 +342,7 @@ struct RxLane {
         if (pay) cudaStreamSynchronize(pay);
         d_frames.release(); h_frames.release(); d_syms.release(); h_syms.release();
         d_bufA.release(); d_bufB.release(); d_payload.release(); h_payload.release();
-        d_ilv.release(); d_dec.release(); d_lists.release(); h_lists.release(); d_tilemap.release();
+        d_ilv.release(); d_dec.release(); d_ckpt.release(); d_lists.release(); h_lists.release(); d_tilemap.release();
         for (auto &e : ev) if (e) cudaEventDestroy(e);
         if (own_pay && pay) cudaStreamDestroy(pay);
         f.destroy();
@@ -383,7 +399,9 @@ struct RxLane {
         const uint32_t n = (uint32_t)ids.size();
         if (!n) return 0;
         cudaStream_t st = f.stream, ps = pay;
+        g_trace.mark("wait seek", lane);
         CU(cudaStreamSynchronize(st));
+        g_trace.mark("seek done", lane);
         unsigned nf = std::min<unsigned>(f.h_count[0], (unsigned)max_frames);
         work[0] = f.h_count[1]; work[1] = f.h_count[2]; work[2] = 0; work[3] = total; work[4] = f.h_count[3];
         work[5] = sp.coarse == 2 ? (uint64_t)f.h_count[4] : (sp.coarse == 1 ? (uint64_t)f.h_tpre.p[n] : 0);
@@ -393,10 +411,12 @@ struct RxLane {
             CU(cudaStreamSynchronize(ps));
         }
 
+        g_trace.mark("frame list on host", lane);
         // ---------------- plan
-        size_t sym_total = 0, buf_total = 0, pay_total = 0, dec_total = 0, n_tiles = 0;
+        size_t sym_total = 0, buf_total = 0, pay_total = 0, dec_total = 0, n_tiles = 0, ck_total = 0;
         std::vector<unsigned> tile_start(nf + 1, 0), valid, deint[2], blk[2], vit[2], vit9[2], rsb[2];
         size_t tmax7[2] = { 0, 0 };
+        bool punct7[2] = { false, false };
         for (unsigned i = 0; i < nf; ++i) {
             FrameDesc &d = fr[i];
             tile_start[i] = (unsigned)n_tiles;
@@ -407,7 +427,8 @@ struct RxLane {
             bl = (bl + 15u) & ~15u;
             d.buf_len = bl; d.buf_off = buf_total; buf_total += bl;
             d.pay_off = pay_total; pay_total += (d.payload_len + 3u) & ~3u;
-            n_tiles += (d.n_sym + 255) / 256;
+            n_tiles += (d.n_sym + kMfTileSyms - 1) / kMfTileSyms;
+            d.ck_off = (unsigned)ck_total; ck_total += (d.n_sym + 31) / 32;
             const unsigned fs[2] = { d.fec0, d.fec1 }, enc[2] = { d.n0, d.n1 }, dl[2] = { d.k0, d.n0 };
             size_t need_dec = 0;
             for (int stg = 1; stg >= 0; --stg) {
@@ -419,7 +440,7 @@ struct RxLane {
                 }
                 if (is_conv(fs[stg])) {
                     size_t T = (size_t)8 * dl[stg] + conv_K(fs[stg]) - 1;
-                    if (conv_K(fs[stg]) == 7) { vit[stg].push_back(i); tmax7[stg] = std::max(tmax7[stg], T); }   // [step][thread] arena
+                    if (conv_K(fs[stg]) == 7) { vit[stg].push_back(i); tmax7[stg] = std::max(tmax7[stg], T); punct7[stg] = punct7[stg] || fs[stg] != FEC_CONV_V27; }   // [step][thread] arena
                     else { vit9[stg].push_back(i); need_dec = std::max(need_dec, T * 4); }                      // 8 words per step
                 } else if (fs[stg] == FEC_RS_M8) {
                     unsigned blocks = (dl[stg] + 222) / 223;
@@ -439,7 +460,10 @@ struct RxLane {
         // group the PLL work list by modulation so warps diverge less
         std::vector<unsigned> pll = valid;
         std::stable_sort(pll.begin(), pll.end(), [&](unsigned a, unsigned b) { return fr[a].ms < fr[b].ms; });
+        std::vector<unsigned> span_start(pll.size() + 1, 0);          // 4096-symbol spans of the emit pass, over the pll order
+        for (size_t k = 0; k < pll.size(); ++k) span_start[k + 1] = span_start[k] + (fr[pll[k]].n_sym + 4095) / 4096;
 
+        g_trace.mark("planned", lane);
         if (nf && !valid.empty()) {
             if (int e = d_syms.reserve(sym_total + 1)) return e;
             if (int e = d_bufA.reserve(buf_total + 16)) return e;
@@ -447,9 +471,10 @@ struct RxLane {
             if (int e = d_payload.reserve(pay_total + 16)) return e;
             if (int e = d_dec.reserve(dec_total + 1)) return e;
             if (int e = d_tilemap.reserve(n_tiles + 1)) return e;
+            if (int e = d_ckpt.reserve(ck_total + 1)) return e;
             // one list arena: tile_start | pll | valid | deint1 | blk1 | vit1 | rs1 | deint0 | blk0 | vit0 | rs0
             std::vector<const std::vector<unsigned> *> parts = { &tile_start, &pll, &valid, &deint[1], &blk[1], &vit[1], &rsb[1],
-                                                                 &deint[0], &blk[0], &vit[0], &rsb[0], &vit9[1], &vit9[0] };
+                                                                 &deint[0], &blk[0], &vit[0], &rsb[0], &vit9[1], &vit9[0], &span_start };
             size_t ltot = 0;
             std::vector<size_t> loff;
             for (auto p : parts) { loff.push_back(ltot); ltot += p->size(); }
@@ -466,19 +491,19 @@ struct RxLane {
             pp.frames = d_frames.p; pp.n_frames = nf;
             pp.tile_start = d_lists.p + loff[0]; pp.n_tiles = (unsigned)n_tiles; pp.tile_frame = d_tilemap.p;
             pp.syms = d_syms.p; pp.bufA = d_bufA.p; pp.bufB = d_bufB.p; pp.payload = d_payload.p;
-            pp.ilv_maps = d_ilv.p; pp.decisions = d_dec.p;
+            pp.ilv_maps = d_ilv.p; pp.decisions = d_dec.p; pp.pll_ckpt = d_ckpt.p;
 
             CU(cudaEventRecord(ev[2], ps));
             launch_mf(pp, ps); f.launches += n_tiles ? 2 : 0;
             CU(cudaEventRecord(ev[3], ps));
-            launch_pll(pp, d_lists.p + loff[1], (unsigned)pll.size(), ps); f.launches++;
+            launch_pll(pp, d_lists.p + loff[1], d_lists.p + loff[13], (unsigned)pll.size(), span_start.back(), ps); f.launches += 2;
             CU(cudaEventRecord(ev[4], ps));
             for (int stg = 1; stg >= 0; --stg) {
                 const size_t base = stg ? 3 : 7;
                 if (!deint[stg].empty()) { launch_deinterleave(pp, d_lists.p + loff[base], (unsigned)deint[stg].size(), stg, ps); f.launches++; }
                 if (!blk[stg].empty()) { launch_blockfec(pp, d_lists.p + loff[base + 1], (unsigned)blk[stg].size(), stg, ps); f.launches++; }
-                if (!vit[stg].empty()) { launch_viterbi(pp, d_lists.p + loff[base + 2], (unsigned)vit[stg].size(), stg, 7, ps); f.launches++; }
-                if (!vit9[stg].empty()) { launch_viterbi(pp, d_lists.p + loff[stg ? 11 : 12], (unsigned)vit9[stg].size(), stg, 9, ps); f.launches++; }
+                if (!vit[stg].empty()) { launch_viterbi(pp, d_lists.p + loff[base + 2], (unsigned)vit[stg].size(), stg, 7, punct7[stg], ps); f.launches++; }
+                if (!vit9[stg].empty()) { launch_viterbi(pp, d_lists.p + loff[stg ? 11 : 12], (unsigned)vit9[stg].size(), stg, 9, false, ps); f.launches++; }
                 if (!rsb[stg].empty()) { launch_rs(pp, d_lists.p + loff[base + 3], (unsigned)(rsb[stg].size() / 2), stg, ps); f.launches++; }
             }
             launch_crc(pp, d_lists.p + loff[2], (unsigned)valid.size(), ps); f.launches++;
@@ -503,6 +528,7 @@ struct RxLane {
             }
         }
         n_frames = nf;
+        g_trace.mark("payload queued", lane);
         return 0;
     }
 
@@ -511,6 +537,7 @@ struct RxLane {
     {
         if (ids.empty()) return 0;
         CU(cudaStreamSynchronize(pay));
+        g_trace.mark("lane complete", lane);
         CU(cudaGetLastError());
         cudaEventElapsedTime(&ms[0], ev[0], ev[1]);
         for (int k = 1; k < 4; ++k) cudaEventElapsedTime(&ms[k], ev[k + 1], ev[k + 2]);
@@ -533,11 +560,15 @@ struct lqb_rx_s {
     cudaEvent_t ev_in = nullptr;
     std::vector<cudaEvent_t> ev_out;
     std::vector<std::pair<unsigned, unsigned>> order;    // (lane, frame index) sorted by (stream, seq)
+    std::vector<unsigned> stream_count;
     unsigned n_frames = 0;
     uint64_t n_valid = 0;
     float ms[6] = {};
     uint64_t work[6] = {};
-    unsigned global_stream(unsigned lane, unsigned local) const { return local * (unsigned)lanes.size() + lane; }
+    // stream -> (lane, index inside the lane) and back (a fixed interleaved partition)
+    std::vector<unsigned> lane_of, local_of;
+    std::vector<std::vector<unsigned>> global_of;
+    unsigned global_stream(unsigned lane, unsigned local) const { return global_of[lane][local]; }
     void sync_all()
     {
         for (auto *l : lanes) { if (l->f.stream) cudaStreamSynchronize(l->f.stream); if (l->pay) cudaStreamSynchronize(l->pay); }
@@ -576,18 +607,43 @@ lqb_rx lqb_rx_create(const lqb_rx_opts *o)
     h->user_stream = (cudaStream_t)o->cuda_stream;
     unsigned cap = o->max_frame_samples ? o->max_frame_samples : 65536u;
     if (cap < 2048) cap = 2048;
-    // lane count: explicit option, else LQB_RX_LANES, else one lane per 128 streams up to 8
+    // lane count: explicit option, else LQB_RX_LANES, else one lane per 128 streams up to 4
     unsigned L = o->n_lanes;
     if (!L) { const char *e = getenv("LQB_RX_LANES"); if (e) L = (unsigned)atoi(e); }
-    if (!L) L = std::min(8u, std::max(1u, o->n_streams / 128u));
+    if (!L) L = std::min(4u, std::max(1u, o->n_streams / 128u));
     L = std::max(1u, std::min(L, std::min(o->n_streams, 64u)));
+    {
+        // equal lanes by default; LQB_LANE_WEIGHTS="40,30,20,10" makes them unequal (measured: no gain on B200)
+        std::vector<double> w(L, 1.0);
+        const char *we = getenv("LQB_LANE_WEIGHTS");
+        if (we) { unsigned l = 0; for (const char *p = we; *p && l < L; ++l) { w[l] = std::max(1e-3, atof(p)); while (*p && *p != ',') ++p; if (*p) ++p; } }
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            double wsum = 0.0;
+            for (double x : w) wsum += x;
+            h->lane_of.assign(o->n_streams, 0); h->local_of.assign(o->n_streams, 0); h->global_of.assign(L, {});
+            // largest-deficit assignment: deterministic, interleaves the lanes over the stream index
+            for (unsigned s2 = 0; s2 < o->n_streams; ++s2) {
+                unsigned best = 0; double bd = -1e300;
+                for (unsigned l = 0; l < L; ++l) {
+                    const double dfc = w[l] / wsum * (double)(s2 + 1) - (double)h->global_of[l].size();
+                    if (dfc > bd) { bd = dfc; best = l; }
+                }
+                h->lane_of[s2] = best; h->local_of[s2] = (unsigned)h->global_of[best].size();
+                h->global_of[best].push_back(s2);
+            }
+            bool empty = false;
+            for (unsigned l = 0; l < L; ++l) empty = empty || h->global_of[l].empty();
+            if (!empty) break;
+            std::fill(w.begin(), w.end(), 1.0);         // weights left a lane without streams: fall back to equal lanes
+        }
+    }
     int lo = 0, hi = 0;
     bool ok = true;
     for (unsigned l = 0; l < L && ok; ++l) {
         RxLane *ln = new RxLane;
         h->lanes.push_back(ln);
         ln->lane = l; ln->n_lanes = L; ln->flags = o->flags;
-        const unsigned ns = (o->n_streams - l + L - 1) / L;
+        const unsigned ns = (unsigned)h->global_of[l].size();
         // a single lane on a caller's stream keeps everything on that stream; otherwise the lane owns a
         // low-priority search stream and a high-priority payload stream
         const bool on_user = (L == 1 && o->cuda_stream);
@@ -613,13 +669,12 @@ lqb_rx lqb_rx_create(const lqb_rx_opts *o)
 int lqb_rx_reset(lqb_rx h, int stream)
 {
     if (!h) return fail(LQB_EINVAL, "null handle");
-    const unsigned L = (unsigned)h->lanes.size();
     if (stream < 0) {
         for (auto *l : h->lanes) if (int e = l->f.reset(-1)) return e;
         return 0;
     }
     if ((unsigned)stream >= h->n_streams) return fail(LQB_EINVAL, "stream index out of range");
-    return h->lanes[(unsigned)stream % L]->f.reset((int)((unsigned)stream / L));
+    return h->lanes[h->lane_of[(unsigned)stream]]->f.reset((int)h->local_of[(unsigned)stream]);
 }
 
 int lqb_rx_execute(lqb_rx h, uint32_t n, const uint32_t *ids, const float *const *iq, const uint64_t *ns, int mem)
@@ -635,8 +690,8 @@ int lqb_rx_execute(lqb_rx h, uint32_t n, const uint32_t *ids, const float *const
     for (uint32_t i = 0; i < n; ++i) {
         const uint32_t s = ids ? ids[i] : i;
         if (s >= h->n_streams) return fail(LQB_EINVAL, "stream index out of range");
-        RxLane *l = h->lanes[s % L];
-        l->ids.push_back(s / L); l->iq.push_back(iq[i]); l->ns.push_back(ns[i]);
+        RxLane *l = h->lanes[h->lane_of[s]];
+        l->ids.push_back(h->local_of[s]); l->iq.push_back(iq[i]); l->ns.push_back(ns[i]);
     }
     if (!n) return 0;
     // inputs produced on the caller's stream must be complete before any lane reads them
@@ -645,7 +700,9 @@ int lqb_rx_execute(lqb_rx h, uint32_t n, const uint32_t *ids, const float *const
         for (auto *l : h->lanes) CU(cudaStreamWaitEvent(l->f.stream, h->ev_in, 0));
     }
     int rc = 0;
+    g_trace.start();
     for (auto *l : h->lanes) if ((rc = l->phase_seek(mem))) break;
+    g_trace.mark("seek queued (all lanes)", 0);
     if (!rc) for (auto *l : h->lanes) if ((rc = l->phase_payload())) break;
     if (!rc) for (auto *l : h->lanes) if ((rc = l->phase_finish())) break;
     if (rc) { const std::string keep = g_err; h->sync_all(); cudaGetLastError(); g_err = keep; return rc; }
@@ -655,19 +712,27 @@ int lqb_rx_execute(lqb_rx h, uint32_t n, const uint32_t *ids, const float *const
             CU(cudaStreamWaitEvent(h->user_stream, h->ev_out[l], 0));
         }
     }
+    std::vector<unsigned> &cnt = h->stream_count;        // frames per global stream, then running offsets
+    cnt.assign(h->n_streams + 1, 0);
     for (unsigned l = 0; l < L; ++l) {
         RxLane *ln = h->lanes[l];
         for (int k = 0; k < 6; ++k) h->work[k] += ln->work[k];
         for (int k = 0; k < 6; ++k) if (k != 4) h->ms[k] += ln->ms[k];
         h->ms[4] = std::max(h->ms[4], ln->ms[4]);
         h->n_frames += ln->n_frames; h->n_valid += ln->n_valid;
-        for (unsigned i = 0; i < ln->n_frames; ++i) h->order.emplace_back(l, i);
+        const FrameDesc *fr = ln->h_frames.p;
+        for (unsigned i = 0; i < ln->n_frames; ++i) cnt[h->global_stream(l, fr[i].stream) + 1]++;
     }
-    std::sort(h->order.begin(), h->order.end(), [&](const std::pair<unsigned, unsigned> &a, const std::pair<unsigned, unsigned> &b) {
-        const FrameDesc &x = h->lanes[a.first]->h_frames.p[a.second], &y = h->lanes[b.first]->h_frames.p[b.second];
-        const unsigned sx = h->global_stream(a.first, x.stream), sy = h->global_stream(b.first, y.stream);
-        return sx != sy ? sx < sy : x.seq < y.seq;
-    });
+    // Order by (stream, seq).  A stream is walked by one CTA that emits its frames in time order, so within a
+    // lane's list the frames of a stream already appear by increasing seq: a counting sort on the stream is enough.
+    for (unsigned s2 = 0; s2 < h->n_streams; ++s2) cnt[s2 + 1] += cnt[s2];
+    h->order.resize(h->n_frames);
+    for (unsigned l = 0; l < L; ++l) {
+        const RxLane *ln = h->lanes[l];
+        const FrameDesc *fr = ln->h_frames.p;
+        for (unsigned i = 0; i < ln->n_frames; ++i) h->order[cnt[h->global_stream(l, fr[i].stream)]++] = std::make_pair(l, i);
+    }
+    g_trace.mark("results ordered", 0);
     return 0;
 }
 

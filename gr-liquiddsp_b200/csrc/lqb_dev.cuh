@@ -76,7 +76,8 @@ struct FrameDesc {
     unsigned ilv1_off, ilv0_off;     // offsets (in uint32 entries) of this frame's interleaver maps
     float    evm, rssi, cfo, evm_acc;
     unsigned char header[20];
-    unsigned pad[3];
+    unsigned ck_off;                 // first PLL checkpoint of this frame (16-byte entries)
+    unsigned pad[2];
 };
 
 struct Detection {

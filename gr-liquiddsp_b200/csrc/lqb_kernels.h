@@ -35,6 +35,8 @@ struct CoarseParams {
     float             *m8, *e8;     // [n_tiles * 16]
 };
 
+constexpr unsigned kMfTileSyms = 512;   // payload symbols per matched-filter tile (host plan and k_mf agree on it)
+
 // work list entry for kernels that run per FEC stage
 struct StageItem { unsigned frame; unsigned pad; };
 
@@ -55,6 +57,7 @@ struct PayloadParams {
     unsigned char     *payload;     // payload output pool
     const unsigned    *ilv_maps;    // interleaver map arena
     unsigned long long *decisions;  // Viterbi decision arena
+    void              *pll_ckpt;    // PLL checkpoints, 16 bytes per 32 payload symbols (FrameDesc::ck_off)
 };
 
 void launch_seek(const SeekParams &P, unsigned n_io, cudaStream_t s);
@@ -63,11 +66,13 @@ void build_coarse_bmat(const float *s_re, const float *s_im, int range, std::vec
 void launch_carry(const SeekParams &P, unsigned n_io, cudaStream_t s);
 
 void launch_mf(const PayloadParams &P, cudaStream_t s);
-void launch_pll(const PayloadParams &P, const unsigned *list, unsigned n, cudaStream_t s);
+// list: frames grouped by modulation; span_start: exclusive prefix (n + 1) of 4096-symbol spans over that list
+void launch_pll(const PayloadParams &P, const unsigned *list, const unsigned *span_start, unsigned n, unsigned n_spans, cudaStream_t s);
 // stage = 1: bufA(n1) -> bufB(n0) with fec1;  stage = 0: bufB(n0) -> bufA(k0) with fec0
 void launch_deinterleave(const PayloadParams &P, const unsigned *list, unsigned n, int stage, cudaStream_t s);
 void launch_blockfec(const PayloadParams &P, const unsigned *list, unsigned n, int stage, cudaStream_t s);
-void launch_viterbi(const PayloadParams &P, const unsigned *list, unsigned n, int stage, unsigned K, cudaStream_t s);
+// punct: some frame in the list uses a punctured code (K = 7 only: selects the generic symbol fetch)
+void launch_viterbi(const PayloadParams &P, const unsigned *list, unsigned n, int stage, unsigned K, bool punct, cudaStream_t s);
 void launch_rs(const PayloadParams &P, const unsigned *blocks /* pairs (frame, block) */, unsigned n_blocks, int stage, cudaStream_t s);
 void launch_crc(const PayloadParams &P, const unsigned *list, unsigned n, cudaStream_t s);
 

@@ -387,6 +387,177 @@ k_viterbi27(PayloadParams P, const unsigned *__restrict__ list, unsigned n_list,
     }
 }
 
+// ------------------------------------------------------------------ Viterbi K=7, four lanes per codeword
+// The thread-per-codeword kernel above is limited by how many codewords there are (a warp issues about
+// every fourth cycle; 31 k codewords are 1.6 warps per scheduler).  Here the 64 path metrics of a codeword
+// are spread over 4 lanes x 16 registers in a CONSTANT-GEOMETRY layout: the metric of state s at step t
+// lives at position p = rotr6(s, t mod 6) (lane = p >> 4, register = p & 15).  The two predecessors of a
+// butterfly then always sit at positions that differ in bit k = 5 - (t mod 6) and its two successors are
+// written back in place, so four steps out of six are register-only and two exchange with one other lane
+// through one shuffle per metric.  Branch labels are parities of position bits: the register part is a
+// compile-time constant, the lane part a per-thread mask XORed into the received symbols once per step.
+// Decisions are stored per position ([step][codeword] 64-bit, lane l owns bits 16 l .. 16 l + 15); the
+// traceback undoes the rotation.  Same integer metrics, comparisons and tie-breaks as the specification.
+constexpr int kV4Lanes = 4, kV4Pos = 16, kV4PosBits = 4;
+
+__host__ __device__ constexpr unsigned v4_par6(unsigned x) { x ^= x >> 4; x ^= x >> 2; x ^= x >> 1; return x & 1u; }
+// position bits that enter the branch label of polynomial `poly` in phase r (label = parity(2 i & poly), 2 i = rotl6(p, r + 1) & ~1)
+__host__ __device__ constexpr unsigned v4_phase_mask(unsigned poly, int r)
+{
+    unsigned m = 0;
+    for (int q = 0; q < 6; ++q) {
+        const int tpos = (q + r + 1) % 6;
+        if (tpos != 0 && ((poly >> tpos) & 1u)) m |= 1u << q;
+    }
+    return m;
+}
+__host__ __device__ constexpr unsigned v4_label(int r, unsigned pos_bits)
+{
+    return v4_par6(pos_bits & v4_phase_mask(0x6d, r)) | (v4_par6(pos_bits & v4_phase_mask(0x4f, r)) << 1);
+}
+
+template <int R>
+__device__ __forceinline__ void v4_step(unsigned (&M)[kV4Pos], unsigned s0, unsigned s1, unsigned lane_l, unsigned mask, unsigned &dec)
+{
+    constexpr int k = 5 - R;                       // position bit that separates the two predecessors
+    unsigned A[4];
+    A[0] = s0 + s1; A[1] = (s0 ^ 255u) + s1; A[2] = s0 + (s1 ^ 255u); A[3] = 510u - A[0];
+    dec = 0;
+    if constexpr (k < kV4PosBits) {
+#pragma unroll
+        for (int j = 0; j < kV4Pos; ++j) {
+            if (j & (1 << k)) continue;
+            const int j1 = j | (1 << k);
+            const unsigned lab = v4_label(R, (unsigned)j);
+            const unsigned a = A[lab], b = A[3 - lab];
+            unsigned m0 = M[j] + a, m1 = M[j1] + b;
+            const unsigned d0 = m0 > m1 ? 1u : 0u;
+            const unsigned n0 = m0 > m1 ? m1 : m0;
+            m0 = M[j] + b; m1 = M[j1] + a;
+            const unsigned d1 = m0 > m1 ? 1u : 0u;
+            const unsigned n1 = m0 > m1 ? m1 : m0;
+            M[j] = n0; M[j1] = n1;
+            dec |= (d0 << j) | (d1 << j1);
+        }
+    } else {
+        constexpr int lb = k - kV4PosBits;         // lane bit exchanged in this phase
+        const bool upper = (lane_l >> lb) & 1u;    // this lane holds the state-bit-5 = 1 predecessors
+#pragma unroll
+        for (int j = 0; j < kV4Pos; ++j) {
+            const unsigned lab = v4_label(R, (unsigned)j);
+            const unsigned a = A[lab], b = A[3 - lab];
+            const unsigned other = __shfl_xor_sync(mask, M[j], 1 << lb);
+            const unsigned c_own = M[j] + a, c_oth = other + b;
+            // lower lane: successor 2i = min(own + a, other + b), decision = own + a > other + b
+            // upper lane: successor 2i+1 = min(other + b, own + a), decision = other + b > own + a
+            const bool d = upper ? (c_oth > c_own) : (c_own > c_oth);
+            M[j] = c_own < c_oth ? c_own : c_oth;
+            dec |= (d ? 1u : 0u) << j;
+        }
+    }
+}
+
+constexpr int kV4Threads = 64;
+
+template <bool PUNCT>
+__global__ void __launch_bounds__(kV4Threads)
+k_viterbi27x4(PayloadParams P, const unsigned *__restrict__ list, unsigned n_list, int stage, unsigned short *__restrict__ dec)
+{
+    const unsigned gt = blockIdx.x * kV4Threads + threadIdx.x;
+    const unsigned gi = gt / kV4Lanes, l = gt % kV4Lanes;
+    // a whole group is either inside the list or outside (kV4Lanes divides the warp), shuffles stay inside a group
+    if (gi >= n_list) return;
+    // codewords in one warp have different lengths: only the four lanes of a group ever shuffle together
+    const unsigned mask = 0xfu << ((threadIdx.x & 31u) & ~3u);
+    const FrameDesc &d = P.frames[list[gi]];
+    const StageIO io = stage_io(P, d, stage);
+    const ConvSpec cs = conv_spec(io.fs);
+    const unsigned nbits = 8 * io.dec_len, T = nbits + 6;
+    unsigned per = 0, pre[8];
+    for (unsigned c = 0; c < cs.P; ++c) { pre[c] = per; per += ((cs.keep0 >> c) & 1u) + ((cs.keep1 >> c) & 1u); }
+    const unsigned char *enc = io.src;
+
+    // lane part of the branch labels, as XOR masks on the received symbols, per phase
+    unsigned mk0[6], mk1[6];
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+        const unsigned lb = l << kV4PosBits;
+        mk0[r] = (__popc(lb & v4_phase_mask(0x6d, r)) & 1) ? 255u : 0u;
+        mk1[r] = (__popc(lb & v4_phase_mask(0x4f, r)) & 1) ? 255u : 0u;
+    }
+    unsigned M[kV4Pos];
+#pragma unroll
+    for (int j = 0; j < kV4Pos; ++j) M[j] = 63u;
+    if (l == 0) M[0] = 0u;                          // state 0 sits at position 0 at t = 0
+
+    unsigned col = 0, q = 0;                        // punctured: t = q * P + col
+    unsigned word = 0, have = 0;                    // unpunctured: 32 encoded bits, MSB first
+    const unsigned *enc32 = reinterpret_cast<const unsigned *>(enc);     // byte arenas are 16-byte aligned per frame
+    auto symbols = [&](unsigned &s0, unsigned &s1) {
+        if (PUNCT) {
+            unsigned ib = q * per + pre[col];
+            s0 = 127u; s1 = 127u;
+            if ((cs.keep0 >> col) & 1u) { s0 = soft_bit(enc, ib); ++ib; }
+            if ((cs.keep1 >> col) & 1u) { s1 = soft_bit(enc, ib); }
+            if (++col == cs.P) { col = 0; ++q; }
+        } else {
+            if (have == 0) { word = __byte_perm(__ldg(enc32++), 0, 0x0123); have = 16; }
+            s0 = (unsigned)((int)word >> 31) & 255u;
+            s1 = (unsigned)((int)(word << 1) >> 31) & 255u;
+            word <<= 2; --have;
+        }
+    };
+    unsigned short *out_dec = dec + (size_t)gi * kV4Lanes + l;
+    const size_t dstride = (size_t)n_list * kV4Lanes;
+    unsigned t = 0;
+#define LQB_V4_STEP(R)                                                            \
+    {                                                                             \
+        unsigned s0, s1, dd;                                                      \
+        symbols(s0, s1);                                                          \
+        v4_step<R>(M, s0 ^ mk0[R], s1 ^ mk1[R], l, mask, dd);                           \
+        out_dec[(size_t)(t + R) * dstride] = (unsigned short)dd;                  \
+    }
+    for (; t + 6 <= T; t += 6) {
+        LQB_V4_STEP(0) LQB_V4_STEP(1) LQB_V4_STEP(2) LQB_V4_STEP(3) LQB_V4_STEP(4) LQB_V4_STEP(5)
+    }
+    if (t + 0 < T) LQB_V4_STEP(0)
+    if (t + 1 < T) LQB_V4_STEP(1)
+    if (t + 2 < T) LQB_V4_STEP(2)
+    if (t + 3 < T) LQB_V4_STEP(3)
+    if (t + 4 < T) LQB_V4_STEP(4)
+#undef LQB_V4_STEP
+    __syncwarp(mask);
+    if (l != 0) return;
+    // traceback from state 0 (lane 0 of the group); the decision of successor state s at step ts is bit
+    // rotr6(s, (ts + 1) mod 6) of that step's word; the bit shifted out at step ts entered at ts - 6
+    const uint2 *dec64 = reinterpret_cast<const uint2 *>(dec) + gi;
+    unsigned char *out = io.dst;
+    unsigned state = 0, byte_acc = 0;
+    long long tt = (long long)T - 1;
+    unsigned ph = (unsigned)((tt + 1) % 6);         // rotation of step tt
+    while (tt >= 0) {
+        uint2 w[8];
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) w[kk] = (tt - kk >= 0) ? dec64[(size_t)(tt - kk) * n_list] : make_uint2(0u, 0u);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+            const long long ts = tt - kk;
+            if (ts < 0) break;
+            const unsigned pos = ((state >> ph) | (state << (6u - ph))) & 63u;
+            const unsigned wsel = (pos & 32u) ? w[kk].y : w[kk].x;
+            const unsigned bit = (wsel >> (pos & 31u)) & 1u;
+            if (ts >= 6) {
+                const unsigned bi = (unsigned)ts - 6u;
+                byte_acc |= bit << (7 - (bi & 7u));
+                if ((bi & 7u) == 0) { out[bi >> 3] = (unsigned char)byte_acc; byte_acc = 0; }
+            }
+            state = (state >> 1) | (bit << 5);
+            ph = ph ? ph - 1u : 5u;
+        }
+        tt -= 8;
+    }
+}
+
 // ------------------------------------------------------------------ Reed-Solomon (warp per 255-byte block)
 constexpr int kRsWarps = 4;
 
@@ -551,10 +722,16 @@ void launch_blockfec(const PayloadParams &P, const unsigned *list, unsigned n, i
 {
     if (n) k_blockfec<<<n, 256, 0, s>>>(P, list, stage);
 }
-void launch_viterbi(const PayloadParams &P, const unsigned *list, unsigned n, int stage, unsigned K, cudaStream_t s)
+void launch_viterbi(const PayloadParams &P, const unsigned *list, unsigned n, int stage, unsigned K, bool punct, cudaStream_t s)
 {
     if (!n) return;
-    if (K == 7) k_viterbi27<<<(n + 63) / 64, 64, 0, s>>>(P, list, n, stage, reinterpret_cast<uint2 *>(P.decisions));
+    if (K == 7) {
+        // all frames of one launch share the stage's scheme class only loosely: punctured and plain rate-1/2 codes may be
+        // mixed in one list, so the generic symbol fetch is used unless the caller's list is known to be plain (punct == 0)
+        const unsigned threads = n * kV4Lanes;
+        if (punct) k_viterbi27x4<true><<<(threads + kV4Threads - 1) / kV4Threads, kV4Threads, 0, s>>>(P, list, n, stage, reinterpret_cast<unsigned short *>(P.decisions));
+        else k_viterbi27x4<false><<<(threads + kV4Threads - 1) / kV4Threads, kV4Threads, 0, s>>>(P, list, n, stage, reinterpret_cast<unsigned short *>(P.decisions));
+    }
     else k_viterbi<<<(n + kVitWarps - 1) / kVitWarps, 32 * kVitWarps, 0, s>>>(P, list, n, stage);
 }
 void launch_rs(const PayloadParams &P, const unsigned *blocks, unsigned n_blocks, int stage, cudaStream_t s)

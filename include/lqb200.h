@@ -114,10 +114,10 @@ typedef struct {
     uint32_t flags;              /* LQB_RX_* */
     void    *cuda_stream;        /* cudaStream_t the caller works on (inputs are ordered after it, it is ordered
                                     after the results); NULL = library-owned streams only */
-    uint32_t n_lanes;            /* streams are split over this many independent pipeline lanes (stream s -> lane
-                                    s % n_lanes) whose search, payload kernels and copies overlap; 0 = automatic
-                                    (env LQB_RX_LANES, else one per 128 streams, at most 8).  Results do not
-                                    depend on it. */
+    uint32_t n_lanes;            /* streams are split over this many independent pipeline lanes (a fixed, interleaved
+                                    partition) whose search, payload kernels and copies overlap;
+                                    0 = automatic (env LQB_RX_LANES, else one per 128 streams, at most 4).  Results
+                                    do not depend on it. */
 } lqb_rx_opts;
 
 /* mirrors framesync_callback's arguments + framesyncstats_s (lib/flex_rx_impl.cc:182-201),

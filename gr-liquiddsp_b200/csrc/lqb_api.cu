@@ -50,7 +50,7 @@ template <typename T> struct DevBuf {
     int reserve(size_t n, bool keep = false, cudaStream_t s = 0)
     {
         if (n <= cap) return 0;
-        size_t ncap = std::max(n, cap + cap / 2);
+        size_t ncap = std::max(n + n / 4, cap + cap / 2);      // headroom: call-to-call variation must not reallocate
         T *q = nullptr;
         if (cudaMalloc(&q, ncap * sizeof(T)) != cudaSuccess) return fail(LQB_ENOMEM, "cudaMalloc failed");
         if (keep && p && cap) { cudaMemcpyAsync(q, p, cap * sizeof(T), cudaMemcpyDeviceToDevice, s); cudaStreamSynchronize(s); }
@@ -65,7 +65,7 @@ template <typename T> struct PinBuf {
     int reserve(size_t n)
     {
         if (n <= cap) return 0;
-        size_t ncap = std::max(n, cap + cap / 2);
+        size_t ncap = std::max(n + n / 4, cap + cap / 2);      // pinned allocations are slow (0.4 s per GB): leave headroom
         T *q = nullptr;
         if (cudaMallocHost(&q, ncap * sizeof(T)) != cudaSuccess) return fail(LQB_ENOMEM, "cudaMallocHost failed");
         if (p) cudaFreeHost(p);
@@ -128,11 +128,16 @@ struct Front {
     DevTables *d_tables = nullptr;
     StreamState *d_states = nullptr;
     float2 *d_carry[2] = { nullptr, nullptr };
-    DevBuf<StreamIO> d_io;
-    PinBuf<StreamIO> h_io;
-    DevBuf<float2> d_stage;
-    unsigned *d_count = nullptr;
-    unsigned *h_count = nullptr;
+    // per-call I/O state exists twice so that a call can be staged while the previous one is still being
+    // finished on the GPU (pipelined receiver); the detector only ever uses set 0
+    struct IoSet {
+        DevBuf<StreamIO> d_io;
+        PinBuf<StreamIO> h_io;
+        DevBuf<float2> d_stage;
+        unsigned *d_count = nullptr;
+        unsigned *h_count = nullptr;
+    } io[2];
+    unsigned cur = 0;
     std::vector<uint8_t> fed;
     uint64_t launches = 0;
     // tensor-core pre-filter (lqb_rx_coarse.cu)
@@ -166,8 +171,10 @@ struct Front {
         CU(cudaMemcpy(d_tables, &T, sizeof(DevTables), cudaMemcpyHostToDevice));
         CU(cudaMalloc(&d_states, (size_t)ns * sizeof(StreamState)));
         for (int k = 0; k < 2; ++k) CU(cudaMalloc(&d_carry[k], (size_t)ns * cap * sizeof(float2)));
-        CU(cudaMalloc(&d_count, 8 * sizeof(unsigned)));
-        CU(cudaMallocHost(&h_count, 8 * sizeof(unsigned)));
+        for (auto &x : io) {
+            CU(cudaMalloc(&x.d_count, 8 * sizeof(unsigned)));
+            CU(cudaMallocHost(&x.h_count, 8 * sizeof(unsigned)));
+        }
         CU(cudaMallocHost(&h_states, (size_t)ns * sizeof(StreamState)));
         CU(cudaEventCreate(&cev[0])); CU(cudaEventCreate(&cev[1]));
         fed.assign(ns, 0);
@@ -205,6 +212,9 @@ struct Front {
     {
         if (!n) { *total = 0; *max_n = 0; return 0; }
         if (n > n_streams) return fail(LQB_EINVAL, "more entries than streams");
+        DevBuf<StreamIO> &d_io = io[cur].d_io;
+        PinBuf<StreamIO> &h_io = io[cur].h_io;
+        DevBuf<float2> &d_stage = io[cur].d_stage;
         if (int e = h_io.reserve(n)) return e;
         if (int e = d_io.reserve(n)) return e;
         std::fill(fed.begin(), fed.end(), 0);
@@ -247,6 +257,8 @@ struct Front {
         sp.coarse = 0; sp.tile_prefix = nullptr; sp.m8 = nullptr; sp.e8 = nullptr; sp.bmat = d_bmat;
         coarse_ms = 0.0f;
         if (!coarse_ok || !n) return 0;
+        DevBuf<StreamIO> &d_io = io[cur].d_io;
+        PinBuf<StreamIO> &h_io = io[cur].h_io;
         if (!getenv("LQB_COARSE_SEPARATE")) { sp.coarse = 2; h_tpre.reserve(n + 1); h_tpre.p[n] = 0; return 0; }   // fused in k_seek
         if (int e = h_tpre.reserve(n + 1)) return e;
         if (int e = d_tpre.reserve(n + 1)) return e;
@@ -280,13 +292,15 @@ struct Front {
         if (d_tables) cudaFree(d_tables);
         if (d_states) cudaFree(d_states);
         for (int k = 0; k < 2; ++k) if (d_carry[k]) cudaFree(d_carry[k]);
-        d_io.release(); h_io.release(); d_stage.release();
+        for (auto &x : io) {
+            x.d_io.release(); x.h_io.release(); x.d_stage.release();
+            if (x.d_count) cudaFree(x.d_count);
+            if (x.h_count) cudaFreeHost(x.h_count);
+        }
         d_m8.release(); d_e8.release(); d_tpre.release(); h_tpre.release();
         if (d_bmat) cudaFree(d_bmat);
         if (h_states) cudaFreeHost(h_states);
         for (auto &e : cev) if (e) cudaEventDestroy(e);
-        if (d_count) cudaFree(d_count);
-        if (h_count) cudaFreeHost(h_count);
         if (own_stream && stream) cudaStreamDestroy(stream);
     }
 };
@@ -303,47 +317,64 @@ struct Front {
 // (tests/test_gpu_parity.py::test_lane_count_does_not_change_results).
 namespace {
 
-struct RxLane {
-    Front f;
-    cudaStream_t pay = nullptr;           // payload + gather stream (higher priority than the search stream)
-    bool own_pay = false;
-    unsigned flags = 0;
-    unsigned lane = 0, n_lanes = 1;
+// everything one execute call produces; two generations alternate so that the payload chain of call k runs
+// while call k+1 is being searched
+struct RxGen {
     DevBuf<FrameDesc> d_frames;
     PinBuf<FrameDesc> h_frames;
     DevBuf<float2> d_syms;
     PinBuf<float2> h_syms;
     DevBuf<unsigned char> d_bufA, d_bufB, d_payload;
     PinBuf<unsigned char> h_payload;
-    DevBuf<unsigned> d_ilv;
-    size_t ilv_used = 0;
-    std::unordered_map<unsigned, size_t> ilv_cache;
     DevBuf<unsigned long long> d_dec;
     DevBuf<uint4> d_ckpt;
     DevBuf<unsigned> d_lists, d_tilemap;
     PinBuf<unsigned> h_lists;
-    unsigned n_frames = 0;
+    DevBuf<StreamView> d_views;
+    unsigned n_frames = 0, n_fed = 0;
     uint64_t n_valid = 0;
     cudaEvent_t ev[7] = {};
+    cudaEvent_t mf_done = nullptr;        // the matched filter (the only payload kernel that reads input / carry) has run
+    cudaEvent_t done = nullptr;           // results are on the host
+    bool mf_pending = false;
     float ms[6] = {};
     uint64_t work[6] = {};
-    // per-call state carried between the phases
-    std::vector<uint32_t> ids;
-    std::vector<const float *> iq;
-    std::vector<uint64_t> ns;
     SeekParams sp;
     size_t max_frames = 0;
     uint64_t total = 0;
+    void release()
+    {
+        d_frames.release(); h_frames.release(); d_syms.release(); h_syms.release();
+        d_bufA.release(); d_bufB.release(); d_payload.release(); h_payload.release();
+        d_dec.release(); d_ckpt.release(); d_lists.release(); h_lists.release(); d_tilemap.release(); d_views.release();
+        for (auto &e : ev) if (e) cudaEventDestroy(e);
+        if (mf_done) cudaEventDestroy(mf_done);
+        if (done) cudaEventDestroy(done);
+    }
+};
+
+struct RxLane {
+    Front f;
+    cudaStream_t pay = nullptr;           // payload + gather stream (higher priority than the search stream)
+    bool own_pay = false;
+    unsigned flags = 0;
+    unsigned lane = 0, n_lanes = 1;
+    RxGen g[2];
+    DevBuf<unsigned> d_ilv;
+    size_t ilv_used = 0;
+    std::unordered_map<unsigned, size_t> ilv_cache;
+    // per-call input lists (lane-local stream ids)
+    std::vector<uint32_t> ids;
+    std::vector<const float *> iq;
+    std::vector<uint64_t> ns;
 
     void destroy()
     {
         cudaSetDevice(f.device);
         if (f.stream) cudaStreamSynchronize(f.stream);
         if (pay) cudaStreamSynchronize(pay);
-        d_frames.release(); h_frames.release(); d_syms.release(); h_syms.release();
-        d_bufA.release(); d_bufB.release(); d_payload.release(); h_payload.release();
-        d_ilv.release(); d_dec.release(); d_ckpt.release(); d_lists.release(); h_lists.release(); d_tilemap.release();
-        for (auto &e : ev) if (e) cudaEventDestroy(e);
+        for (auto &x : g) x.release();
+        d_ilv.release();
         if (own_pay && pay) cudaStreamDestroy(pay);
         f.destroy();
     }
@@ -354,6 +385,7 @@ struct RxLane {
         if (it != ilv_cache.end()) return it->second;
         std::vector<uint32_t> maps = ilv_maps(n);
         size_t off = ilv_used;
+        if (off + maps.size() + 4 > d_ilv.cap) cudaStreamSynchronize(pay);   // growing frees the old arena: no chain may still read it
         if (d_ilv.reserve(off + maps.size() + 4, true, pay)) return (size_t)-1;
         if (!maps.empty())
             cudaMemcpyAsync(d_ilv.p + off, maps.data(), maps.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, pay);
@@ -364,51 +396,64 @@ struct RxLane {
     }
 
     // phase A: stage the inputs and queue the search on the lane's search stream
-    int phase_seek(int mem)
+    int phase_seek(int mem, unsigned gen)
     {
+        RxGen &G = g[gen];
+        f.cur = gen;
         const uint32_t n = (uint32_t)ids.size();
-        n_frames = 0; n_valid = 0;
-        std::memset(ms, 0, sizeof ms);
-        std::memset(work, 0, sizeof work);
-        total = 0;
+        G.n_fed = n;
+        G.n_frames = 0; G.n_valid = 0;
+        std::memset(G.ms, 0, sizeof G.ms);
+        std::memset(G.work, 0, sizeof G.work);
+        G.total = 0;
         if (!n) return 0;
         cudaStream_t st = f.stream;
         uint64_t max_n = 0;
-        if (int e = f.feed(n, ids.data(), iq.data(), ns.data(), mem, &total, &max_n)) return e;
+        if (int e = f.feed(n, ids.data(), iq.data(), ns.data(), mem, &G.total, &max_n)) return e;
         // upper bound on frames: a frame spans at least 618 samples
-        max_frames = 0;
-        for (uint32_t i = 0; i < n; ++i) max_frames += (size_t)((ns[i] + f.carry_cap) / 600 + 2);
-        if (int e = d_frames.reserve(max_frames)) return e;
-        if (int e = h_frames.reserve(max_frames)) return e;
-        sp.tables = f.d_tables; sp.states = f.d_states; sp.io = f.d_io.p;
-        sp.carry[0] = f.d_carry[0]; sp.carry[1] = f.d_carry[1]; sp.carry_cap = f.carry_cap;
-        sp.det_mode = 0; sp.frames = d_frames.p; sp.detections = nullptr;
-        sp.n_out = f.d_count; sp.max_out = (unsigned)max_frames;
-        CU(cudaEventRecord(ev[0], st));
-        if (int e = f.run_coarse(n, ns.data(), sp)) return e;
-        CU(cudaMemsetAsync(f.d_count, 0, 8 * sizeof(unsigned), st));
-        launch_seek(sp, n, st); f.launches++;
-        CU(cudaEventRecord(ev[1], st));
-        CU(cudaMemcpyAsync(f.h_count, f.d_count, 8 * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+        G.max_frames = 0;
+        for (uint32_t i = 0; i < n; ++i) G.max_frames += (size_t)((ns[i] + f.carry_cap) / 600 + 2);
+        if (int e = G.d_frames.reserve(G.max_frames)) return e;
+        if (int e = G.h_frames.reserve(G.max_frames)) return e;
+        if (int e = G.d_views.reserve(n)) return e;
+        G.sp.views = G.d_views.p;
+        G.sp.tables = f.d_tables; G.sp.states = f.d_states; G.sp.io = f.io[f.cur].d_io.p;
+        G.sp.carry[0] = f.d_carry[0]; G.sp.carry[1] = f.d_carry[1]; G.sp.carry_cap = f.carry_cap;
+        G.sp.det_mode = 0; G.sp.frames = G.d_frames.p; G.sp.detections = nullptr;
+        G.sp.n_out = f.io[f.cur].d_count; G.sp.max_out = (unsigned)G.max_frames;
+        CU(cudaEventRecord(G.ev[0], st));
+        if (int e = f.run_coarse(n, ns.data(), G.sp)) return e;
+        CU(cudaMemsetAsync(f.io[f.cur].d_count, 0, 8 * sizeof(unsigned), st));
+        launch_seek(G.sp, n, st); f.launches++;
+        CU(cudaEventRecord(G.ev[1], st));
+        CU(cudaMemcpyAsync(f.io[f.cur].h_count, f.io[f.cur].d_count, 8 * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+        // The unconsumed tails move to the other carry buffer right away, so that the next call can be searched while this
+        // call's payload chain is still running.  That buffer is the one the PREVIOUS call's matched filter reads: wait for it.
+        RxGen &prev = g[gen ^ 1u];
+        if (prev.mf_pending) { CU(cudaStreamWaitEvent(st, prev.mf_done, 0)); prev.mf_pending = false; }
+        launch_carry(G.sp, n, st); f.launches++;
+        CU(cudaMemcpyAsync(f.h_states, f.d_states, (size_t)f.n_streams * sizeof(StreamState), cudaMemcpyDeviceToHost, st));
         return 0;
     }
 
     // phase B: read the frame list, plan, queue payload kernels + carry + result copies on the payload stream
-    int phase_payload()
+    int phase_payload(unsigned gen)
     {
-        const uint32_t n = (uint32_t)ids.size();
+        RxGen &G = g[gen];
+        const uint32_t n = G.n_fed;
         if (!n) return 0;
+        f.cur = gen;
         cudaStream_t st = f.stream, ps = pay;
         g_trace.mark("wait seek", lane);
         CU(cudaStreamSynchronize(st));
         g_trace.mark("seek done", lane);
-        unsigned nf = std::min<unsigned>(f.h_count[0], (unsigned)max_frames);
-        work[0] = f.h_count[1]; work[1] = f.h_count[2]; work[2] = 0; work[3] = total; work[4] = f.h_count[3];
-        work[5] = sp.coarse == 2 ? (uint64_t)f.h_count[4] : (sp.coarse == 1 ? (uint64_t)f.h_tpre.p[n] : 0);
-        FrameDesc *fr = h_frames.p;
+        unsigned nf = std::min<unsigned>(f.io[f.cur].h_count[0], (unsigned)G.max_frames);
+        G.work[0] = f.io[f.cur].h_count[1]; G.work[1] = f.io[f.cur].h_count[2]; G.work[2] = 0; G.work[3] = G.total; G.work[4] = f.io[f.cur].h_count[3];
+        G.work[5] = G.sp.coarse == 2 ? (uint64_t)f.io[f.cur].h_count[4] : (G.sp.coarse == 1 ? (uint64_t)f.h_tpre.p[n] : 0);
+        FrameDesc *fr = G.h_frames.p;
         if (nf) {
-            CU(cudaMemcpyAsync(fr, d_frames.p, nf * sizeof(FrameDesc), cudaMemcpyDeviceToHost, ps));
-            CU(cudaStreamSynchronize(ps));
+            CU(cudaMemcpyAsync(fr, G.d_frames.p, nf * sizeof(FrameDesc), cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
         }
 
         g_trace.mark("frame list on host", lane);
@@ -456,7 +501,7 @@ struct RxLane {
         const size_t dec7 = std::max(tmax7[0] * vit[0].size(), tmax7[1] * vit[1].size());
         for (unsigned i = 0; i < nf; ++i) fr[i].dec_off += dec7;
         dec_total += dec7;
-        work[2] = sym_total;
+        G.work[2] = sym_total;
         // group the PLL work list by modulation so warps diverge less
         std::vector<unsigned> pll = valid;
         std::stable_sort(pll.begin(), pll.end(), [&](unsigned a, unsigned b) { return fr[a].ms < fr[b].ms; });
@@ -465,87 +510,88 @@ struct RxLane {
 
         g_trace.mark("planned", lane);
         if (nf && !valid.empty()) {
-            if (int e = d_syms.reserve(sym_total + 1)) return e;
-            if (int e = d_bufA.reserve(buf_total + 16)) return e;
-            if (int e = d_bufB.reserve(buf_total + 16)) return e;
-            if (int e = d_payload.reserve(pay_total + 16)) return e;
-            if (int e = d_dec.reserve(dec_total + 1)) return e;
-            if (int e = d_tilemap.reserve(n_tiles + 1)) return e;
-            if (int e = d_ckpt.reserve(ck_total + 1)) return e;
+            if (int e = G.d_syms.reserve(sym_total + 1)) return e;
+            if (int e = G.d_bufA.reserve(buf_total + 16)) return e;
+            if (int e = G.d_bufB.reserve(buf_total + 16)) return e;
+            if (int e = G.d_payload.reserve(pay_total + 16)) return e;
+            if (int e = G.d_dec.reserve(dec_total + 1)) return e;
+            if (int e = G.d_tilemap.reserve(n_tiles + 1)) return e;
+            if (int e = G.d_ckpt.reserve(ck_total + 1)) return e;
             // one list arena: tile_start | pll | valid | deint1 | blk1 | vit1 | rs1 | deint0 | blk0 | vit0 | rs0
             std::vector<const std::vector<unsigned> *> parts = { &tile_start, &pll, &valid, &deint[1], &blk[1], &vit[1], &rsb[1],
                                                                  &deint[0], &blk[0], &vit[0], &rsb[0], &vit9[1], &vit9[0], &span_start };
             size_t ltot = 0;
             std::vector<size_t> loff;
             for (auto p : parts) { loff.push_back(ltot); ltot += p->size(); }
-            if (int e = h_lists.reserve(ltot + 1)) return e;
-            if (int e = d_lists.reserve(ltot + 1)) return e;
+            if (int e = G.h_lists.reserve(ltot + 1)) return e;
+            if (int e = G.d_lists.reserve(ltot + 1)) return e;
             for (size_t k = 0; k < parts.size(); ++k)
-                if (!parts[k]->empty()) std::memcpy(h_lists.p + loff[k], parts[k]->data(), parts[k]->size() * sizeof(unsigned));
-            CU(cudaMemcpyAsync(d_lists.p, h_lists.p, ltot * sizeof(unsigned), cudaMemcpyHostToDevice, ps));
-            CU(cudaMemcpyAsync(d_frames.p, fr, nf * sizeof(FrameDesc), cudaMemcpyHostToDevice, ps));
+                if (!parts[k]->empty()) std::memcpy(G.h_lists.p + loff[k], parts[k]->data(), parts[k]->size() * sizeof(unsigned));
+            CU(cudaMemcpyAsync(G.d_lists.p, G.h_lists.p, ltot * sizeof(unsigned), cudaMemcpyHostToDevice, ps));
+            CU(cudaMemcpyAsync(G.d_frames.p, fr, nf * sizeof(FrameDesc), cudaMemcpyHostToDevice, ps));
 
             PayloadParams pp;
-            pp.tables = f.d_tables; pp.states = f.d_states; pp.io = f.d_io.p;
-            pp.carry[0] = f.d_carry[0]; pp.carry[1] = f.d_carry[1]; pp.carry_cap = f.carry_cap;
-            pp.frames = d_frames.p; pp.n_frames = nf;
-            pp.tile_start = d_lists.p + loff[0]; pp.n_tiles = (unsigned)n_tiles; pp.tile_frame = d_tilemap.p;
-            pp.syms = d_syms.p; pp.bufA = d_bufA.p; pp.bufB = d_bufB.p; pp.payload = d_payload.p;
-            pp.ilv_maps = d_ilv.p; pp.decisions = d_dec.p; pp.pll_ckpt = d_ckpt.p;
+            pp.tables = f.d_tables; pp.views = G.d_views.p;
+            pp.frames = G.d_frames.p; pp.n_frames = nf;
+            pp.tile_start = G.d_lists.p + loff[0]; pp.n_tiles = (unsigned)n_tiles; pp.tile_frame = G.d_tilemap.p;
+            pp.syms = G.d_syms.p; pp.bufA = G.d_bufA.p; pp.bufB = G.d_bufB.p; pp.payload = G.d_payload.p;
+            pp.ilv_maps = d_ilv.p; pp.decisions = G.d_dec.p; pp.pll_ckpt = G.d_ckpt.p;
 
-            CU(cudaEventRecord(ev[2], ps));
+            CU(cudaEventRecord(G.ev[2], ps));
             launch_mf(pp, ps); f.launches += n_tiles ? 2 : 0;
-            CU(cudaEventRecord(ev[3], ps));
-            launch_pll(pp, d_lists.p + loff[1], d_lists.p + loff[13], (unsigned)pll.size(), span_start.back(), ps); f.launches += 2;
-            CU(cudaEventRecord(ev[4], ps));
+            CU(cudaEventRecord(G.mf_done, ps));
+            G.mf_pending = true;
+            CU(cudaEventRecord(G.ev[3], ps));
+            launch_pll(pp, G.d_lists.p + loff[1], G.d_lists.p + loff[13], (unsigned)pll.size(), span_start.back(), ps); f.launches += 2;
+            CU(cudaEventRecord(G.ev[4], ps));
             for (int stg = 1; stg >= 0; --stg) {
                 const size_t base = stg ? 3 : 7;
-                if (!deint[stg].empty()) { launch_deinterleave(pp, d_lists.p + loff[base], (unsigned)deint[stg].size(), stg, ps); f.launches++; }
-                if (!blk[stg].empty()) { launch_blockfec(pp, d_lists.p + loff[base + 1], (unsigned)blk[stg].size(), stg, ps); f.launches++; }
-                if (!vit[stg].empty()) { launch_viterbi(pp, d_lists.p + loff[base + 2], (unsigned)vit[stg].size(), stg, 7, punct7[stg], ps); f.launches++; }
-                if (!vit9[stg].empty()) { launch_viterbi(pp, d_lists.p + loff[stg ? 11 : 12], (unsigned)vit9[stg].size(), stg, 9, false, ps); f.launches++; }
-                if (!rsb[stg].empty()) { launch_rs(pp, d_lists.p + loff[base + 3], (unsigned)(rsb[stg].size() / 2), stg, ps); f.launches++; }
+                if (!deint[stg].empty()) { launch_deinterleave(pp, G.d_lists.p + loff[base], (unsigned)deint[stg].size(), stg, ps); f.launches++; }
+                if (!blk[stg].empty()) { launch_blockfec(pp, G.d_lists.p + loff[base + 1], (unsigned)blk[stg].size(), stg, ps); f.launches++; }
+                if (!vit[stg].empty()) { launch_viterbi(pp, G.d_lists.p + loff[base + 2], (unsigned)vit[stg].size(), stg, 7, punct7[stg], ps); f.launches++; }
+                if (!vit9[stg].empty()) { launch_viterbi(pp, G.d_lists.p + loff[stg ? 11 : 12], (unsigned)vit9[stg].size(), stg, 9, false, ps); f.launches++; }
+                if (!rsb[stg].empty()) { launch_rs(pp, G.d_lists.p + loff[base + 3], (unsigned)(rsb[stg].size() / 2), stg, ps); f.launches++; }
             }
-            launch_crc(pp, d_lists.p + loff[2], (unsigned)valid.size(), ps); f.launches++;
-            CU(cudaEventRecord(ev[5], ps));
+            launch_crc(pp, G.d_lists.p + loff[2], (unsigned)valid.size(), ps); f.launches++;
+            CU(cudaEventRecord(G.ev[5], ps));
         } else {
-            for (int k = 2; k <= 5; ++k) CU(cudaEventRecord(ev[k], ps));
+            for (int k = 2; k <= 5; ++k) CU(cudaEventRecord(G.ev[k], ps));
         }
-        launch_carry(sp, n, ps); f.launches++;
-        CU(cudaMemcpyAsync(f.h_states, f.d_states, (size_t)f.n_streams * sizeof(StreamState), cudaMemcpyDeviceToHost, ps));
-        CU(cudaEventRecord(ev[6], ps));
+        CU(cudaEventRecord(G.ev[6], ps));
 
         // ---------------- gather
         if (nf && !valid.empty()) {
-            CU(cudaMemcpyAsync(fr, d_frames.p, nf * sizeof(FrameDesc), cudaMemcpyDeviceToHost, ps));
+            CU(cudaMemcpyAsync(fr, G.d_frames.p, nf * sizeof(FrameDesc), cudaMemcpyDeviceToHost, ps));
             if (!(flags & LQB_RX_DEVICE_RESULTS)) {
-                if (int e = h_payload.reserve(pay_total + 16)) return e;
-                if (pay_total) CU(cudaMemcpyAsync(h_payload.p, d_payload.p, pay_total, cudaMemcpyDeviceToHost, ps));
+                if (int e = G.h_payload.reserve(pay_total + 16)) return e;
+                if (pay_total) CU(cudaMemcpyAsync(G.h_payload.p, G.d_payload.p, pay_total, cudaMemcpyDeviceToHost, ps));
                 if (!(flags & LQB_RX_NO_FRAMESYMS)) {
-                    if (int e = h_syms.reserve(sym_total + 1)) return e;
-                    if (sym_total) CU(cudaMemcpyAsync(h_syms.p, d_syms.p, sym_total * sizeof(float2), cudaMemcpyDeviceToHost, ps));
+                    if (int e = G.h_syms.reserve(sym_total + 1)) return e;
+                    if (sym_total) CU(cudaMemcpyAsync(G.h_syms.p, G.d_syms.p, sym_total * sizeof(float2), cudaMemcpyDeviceToHost, ps));
                 }
             }
         }
-        n_frames = nf;
+        CU(cudaEventRecord(G.done, ps));
+        G.n_frames = nf;
         g_trace.mark("payload queued", lane);
         return 0;
     }
 
     // phase C: wait for the lane, read the event times
-    int phase_finish()
+    int phase_finish(unsigned gen)
     {
-        if (ids.empty()) return 0;
-        CU(cudaStreamSynchronize(pay));
+        RxGen &G = g[gen];
+        if (!G.n_fed) return 0;
+        CU(cudaEventSynchronize(G.done));
         g_trace.mark("lane complete", lane);
         CU(cudaGetLastError());
-        cudaEventElapsedTime(&ms[0], ev[0], ev[1]);
-        for (int k = 1; k < 4; ++k) cudaEventElapsedTime(&ms[k], ev[k + 1], ev[k + 2]);
-        cudaEventElapsedTime(&ms[4], ev[0], ev[6]);
-        ms[5] = 0.0f;
-        if (sp.coarse == 1) cudaEventElapsedTime(&ms[5], f.cev[0], f.cev[1]);
-        const FrameDesc *fr = h_frames.p;
-        for (unsigned i = 0; i < n_frames; ++i) n_valid += fr[i].payload_valid ? 1 : 0;
+        cudaEventElapsedTime(&G.ms[0], G.ev[0], G.ev[1]);
+        for (int k = 1; k < 4; ++k) cudaEventElapsedTime(&G.ms[k], G.ev[k + 1], G.ev[k + 2]);
+        cudaEventElapsedTime(&G.ms[4], G.ev[0], G.ev[6]);
+        G.ms[5] = 0.0f;
+        if (G.sp.coarse == 1) cudaEventElapsedTime(&G.ms[5], f.cev[0], f.cev[1]);
+        const FrameDesc *fr = G.h_frames.p;
+        for (unsigned i = 0; i < G.n_frames; ++i) G.n_valid += fr[i].payload_valid ? 1 : 0;
         return 0;
     }
 };
@@ -559,6 +605,9 @@ struct lqb_rx_s {
     cudaStream_t user_stream = nullptr;
     cudaEvent_t ev_in = nullptr;
     std::vector<cudaEvent_t> ev_out;
+    // two calls may be in flight: `submit_gen` is the generation the next submit uses, `pending` how many
+    // submits have not been collected, `cur_gen` the generation whose results poll / counts / timing report
+    unsigned submit_gen = 0, pending = 0, cur_gen = 0;
     std::vector<std::pair<unsigned, unsigned>> order;    // (lane, frame index) sorted by (stream, seq)
     std::vector<unsigned> stream_count;
     unsigned n_frames = 0;
@@ -591,6 +640,7 @@ void lqb_rx_destroy(lqb_rx h)
 {
     if (!h) return;
     cudaSetDevice(h->device);
+    h->sync_all();
     for (auto *l : h->lanes) { l->destroy(); delete l; }
     if (h->ev_in) cudaEventDestroy(h->ev_in);
     for (auto &e : h->ev_out) if (e) cudaEventDestroy(e);
@@ -607,10 +657,10 @@ lqb_rx lqb_rx_create(const lqb_rx_opts *o)
     h->user_stream = (cudaStream_t)o->cuda_stream;
     unsigned cap = o->max_frame_samples ? o->max_frame_samples : 65536u;
     if (cap < 2048) cap = 2048;
-    // lane count: explicit option, else LQB_RX_LANES, else one lane per 128 streams up to 4
+    // lane count: explicit option, else LQB_RX_LANES, else one lane per 256 streams up to 2
     unsigned L = o->n_lanes;
     if (!L) { const char *e = getenv("LQB_RX_LANES"); if (e) L = (unsigned)atoi(e); }
-    if (!L) L = std::min(4u, std::max(1u, o->n_streams / 128u));
+    if (!L) L = std::min(2u, std::max(1u, o->n_streams / 256u));
     L = std::max(1u, std::min(L, std::min(o->n_streams, 64u)));
     {
         // equal lanes by default; LQB_LANE_WEIGHTS="40,30,20,10" makes them unequal (measured: no gain on B200)
@@ -644,20 +694,20 @@ lqb_rx lqb_rx_create(const lqb_rx_opts *o)
         h->lanes.push_back(ln);
         ln->lane = l; ln->n_lanes = L; ln->flags = o->flags;
         const unsigned ns = (unsigned)h->global_of[l].size();
-        // a single lane on a caller's stream keeps everything on that stream; otherwise the lane owns a
-        // low-priority search stream and a high-priority payload stream
-        const bool on_user = (L == 1 && o->cuda_stream);
-        if (ln->f.init(o->device, ns, cap, on_user ? o->cuda_stream : nullptr, *T, /*low_priority=*/!on_user)) { ok = false; break; }
-        if (on_user) ln->pay = ln->f.stream;
-        else {
-            cudaDeviceGetStreamPriorityRange(&lo, &hi);
-            if (cudaStreamCreateWithPriority(&ln->pay, cudaStreamNonBlocking, hi) != cudaSuccess) { fail(LQB_ECUDA, "cudaStreamCreate failed"); ok = false; break; }
-            ln->own_pay = true;
+        // every lane owns a low-priority search stream and a high-priority payload stream; a caller's stream is
+        // ordered against them with events (inputs before the search, the caller's later work after the results)
+        if (ln->f.init(o->device, ns, cap, nullptr, *T, /*low_priority=*/true)) { ok = false; break; }
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if (cudaStreamCreateWithPriority(&ln->pay, cudaStreamNonBlocking, hi) != cudaSuccess) { fail(LQB_ECUDA, "cudaStreamCreate failed"); ok = false; break; }
+        ln->own_pay = true;
+        for (auto &G : ln->g) {
+            for (auto &ev : G.ev) ok = ok && cudaEventCreate(&ev) == cudaSuccess;
+            ok = ok && cudaEventCreateWithFlags(&G.mf_done, cudaEventDisableTiming) == cudaSuccess;
+            ok = ok && cudaEventCreateWithFlags(&G.done, cudaEventDisableTiming) == cudaSuccess;
         }
-        for (auto &ev : ln->ev) cudaEventCreate(&ev);
     }
     delete T;
-    if (ok && h->user_stream && !(L == 1)) {
+    if (ok && h->user_stream) {
         ok = cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming) == cudaSuccess;
         h->ev_out.assign(L, nullptr);
         for (auto &e : h->ev_out) ok = ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
@@ -666,47 +716,24 @@ lqb_rx lqb_rx_create(const lqb_rx_opts *o)
     return h;
 }
 
-int lqb_rx_reset(lqb_rx h, int stream)
+// wait for the oldest submitted call and make its results current
+int lqb_rx_collect(lqb_rx h)
 {
     if (!h) return fail(LQB_EINVAL, "null handle");
-    if (stream < 0) {
-        for (auto *l : h->lanes) if (int e = l->f.reset(-1)) return e;
-        return 0;
-    }
-    if ((unsigned)stream >= h->n_streams) return fail(LQB_EINVAL, "stream index out of range");
-    return h->lanes[h->lane_of[(unsigned)stream]]->f.reset((int)h->local_of[(unsigned)stream]);
-}
-
-int lqb_rx_execute(lqb_rx h, uint32_t n, const uint32_t *ids, const float *const *iq, const uint64_t *ns, int mem)
-{
-    if (!h) return fail(LQB_EINVAL, "null handle");
+    if (!h->pending) return fail(LQB_EINVAL, "nothing submitted");
     CU(cudaSetDevice(h->device));
     const unsigned L = (unsigned)h->lanes.size();
+    const unsigned gen = (h->pending == 2) ? h->submit_gen : (h->submit_gen ^ 1u);
+    h->pending--;
+    h->cur_gen = gen;
     h->n_frames = 0; h->n_valid = 0; h->order.clear();
     std::memset(h->ms, 0, sizeof h->ms);
     std::memset(h->work, 0, sizeof h->work);
-    if (n > h->n_streams) return fail(LQB_EINVAL, "more entries than streams");
-    for (auto *l : h->lanes) { l->ids.clear(); l->iq.clear(); l->ns.clear(); l->n_frames = 0; l->n_valid = 0; }
-    for (uint32_t i = 0; i < n; ++i) {
-        const uint32_t s = ids ? ids[i] : i;
-        if (s >= h->n_streams) return fail(LQB_EINVAL, "stream index out of range");
-        RxLane *l = h->lanes[h->lane_of[s]];
-        l->ids.push_back(h->local_of[s]); l->iq.push_back(iq[i]); l->ns.push_back(ns[i]);
-    }
-    if (!n) return 0;
-    // inputs produced on the caller's stream must be complete before any lane reads them
-    if (h->ev_in) {
-        CU(cudaEventRecord(h->ev_in, h->user_stream));
-        for (auto *l : h->lanes) CU(cudaStreamWaitEvent(l->f.stream, h->ev_in, 0));
-    }
     int rc = 0;
-    g_trace.start();
-    for (auto *l : h->lanes) if ((rc = l->phase_seek(mem))) break;
-    g_trace.mark("seek queued (all lanes)", 0);
-    if (!rc) for (auto *l : h->lanes) if ((rc = l->phase_payload())) break;
-    if (!rc) for (auto *l : h->lanes) if ((rc = l->phase_finish())) break;
+    for (auto *l : h->lanes) if ((rc = l->phase_finish(gen))) break;
     if (rc) { const std::string keep = g_err; h->sync_all(); cudaGetLastError(); g_err = keep; return rc; }
     if (h->ev_in) {
+        // the caller's stream continues after everything this call queued
         for (unsigned l = 0; l < L; ++l) {
             CU(cudaEventRecord(h->ev_out[l], h->lanes[l]->pay));
             CU(cudaStreamWaitEvent(h->user_stream, h->ev_out[l], 0));
@@ -715,25 +742,85 @@ int lqb_rx_execute(lqb_rx h, uint32_t n, const uint32_t *ids, const float *const
     std::vector<unsigned> &cnt = h->stream_count;        // frames per global stream, then running offsets
     cnt.assign(h->n_streams + 1, 0);
     for (unsigned l = 0; l < L; ++l) {
-        RxLane *ln = h->lanes[l];
-        for (int k = 0; k < 6; ++k) h->work[k] += ln->work[k];
-        for (int k = 0; k < 6; ++k) if (k != 4) h->ms[k] += ln->ms[k];
-        h->ms[4] = std::max(h->ms[4], ln->ms[4]);
-        h->n_frames += ln->n_frames; h->n_valid += ln->n_valid;
-        const FrameDesc *fr = ln->h_frames.p;
-        for (unsigned i = 0; i < ln->n_frames; ++i) cnt[h->global_stream(l, fr[i].stream) + 1]++;
+        const RxGen &G = h->lanes[l]->g[gen];
+        for (int k = 0; k < 6; ++k) h->work[k] += G.work[k];
+        for (int k = 0; k < 6; ++k) if (k != 4) h->ms[k] += G.ms[k];
+        h->ms[4] = std::max(h->ms[4], G.ms[4]);
+        h->n_frames += G.n_frames; h->n_valid += G.n_valid;
+        const FrameDesc *fr = G.h_frames.p;
+        for (unsigned i = 0; i < G.n_frames; ++i) cnt[h->global_stream(l, fr[i].stream) + 1]++;
     }
     // Order by (stream, seq).  A stream is walked by one CTA that emits its frames in time order, so within a
     // lane's list the frames of a stream already appear by increasing seq: a counting sort on the stream is enough.
     for (unsigned s2 = 0; s2 < h->n_streams; ++s2) cnt[s2 + 1] += cnt[s2];
     h->order.resize(h->n_frames);
     for (unsigned l = 0; l < L; ++l) {
-        const RxLane *ln = h->lanes[l];
-        const FrameDesc *fr = ln->h_frames.p;
-        for (unsigned i = 0; i < ln->n_frames; ++i) h->order[cnt[h->global_stream(l, fr[i].stream)]++] = std::make_pair(l, i);
+        const RxGen &G = h->lanes[l]->g[gen];
+        const FrameDesc *fr = G.h_frames.p;
+        for (unsigned i = 0; i < G.n_frames; ++i) h->order[cnt[h->global_stream(l, fr[i].stream)]++] = std::make_pair(l, i);
     }
     g_trace.mark("results ordered", 0);
     return 0;
+}
+
+int lqb_rx_reset(lqb_rx h, int stream)
+{
+    if (!h) return fail(LQB_EINVAL, "null handle");
+    while (h->pending) if (int e = lqb_rx_collect(h)) return e;      // nothing may be in flight while states are rewritten
+    h->sync_all();
+    if (stream < 0) {
+        for (auto *l : h->lanes) if (int e = l->f.reset(-1)) return e;
+        return 0;
+    }
+    if ((unsigned)stream >= h->n_streams) return fail(LQB_EINVAL, "stream index out of range");
+    return h->lanes[h->lane_of[(unsigned)stream]]->f.reset((int)h->local_of[(unsigned)stream]);
+}
+
+// Search the new samples and queue the payload work; returns when the search has finished (the payload kernels,
+// result copies and CRC checks of this call keep running on the GPU until lqb_rx_collect).
+int lqb_rx_submit(lqb_rx h, uint32_t n, const uint32_t *ids, const float *const *iq, const uint64_t *ns, int mem)
+{
+    if (!h) return fail(LQB_EINVAL, "null handle");
+    if (h->pending >= 2) return fail(LQB_EBUSY, "two submitted calls are waiting for lqb_rx_collect");
+    CU(cudaSetDevice(h->device));
+    if (n > h->n_streams) return fail(LQB_EINVAL, "more entries than streams");
+    for (auto *l : h->lanes) { l->ids.clear(); l->iq.clear(); l->ns.clear(); }
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint32_t s = ids ? ids[i] : i;
+        if (s >= h->n_streams) return fail(LQB_EINVAL, "stream index out of range");
+        RxLane *l = h->lanes[h->lane_of[s]];
+        l->ids.push_back(h->local_of[s]); l->iq.push_back(iq[i]); l->ns.push_back(ns[i]);
+    }
+    const unsigned gen = h->submit_gen;
+    // inputs produced on the caller's stream must be complete before any lane reads them
+    if (h->ev_in && n) {
+        CU(cudaEventRecord(h->ev_in, h->user_stream));
+        for (auto *l : h->lanes) CU(cudaStreamWaitEvent(l->f.stream, h->ev_in, 0));
+    }
+    int rc = 0;
+    g_trace.start();
+    for (auto *l : h->lanes) if ((rc = l->phase_seek(mem, gen))) break;
+    g_trace.mark("seek queued (all lanes)", 0);
+    if (!rc) for (auto *l : h->lanes) if ((rc = l->phase_payload(gen))) break;
+    if (rc) {
+        const std::string keep = g_err;
+        h->sync_all(); cudaGetLastError();
+        for (auto *l : h->lanes) for (auto &G : l->g) { G.mf_pending = false; G.n_fed = 0; G.n_frames = 0; }
+        h->pending = 0;
+        g_err = keep;
+        return rc;
+    }
+    h->submit_gen ^= 1u;
+    h->pending++;
+    return 0;
+}
+
+int lqb_rx_execute(lqb_rx h, uint32_t n, const uint32_t *ids, const float *const *iq, const uint64_t *ns, int mem)
+{
+    if (!h) return fail(LQB_EINVAL, "null handle");
+    while (h->pending) if (int e = lqb_rx_collect(h)) return e;      // results of uncollected submits are dropped
+    if (int e = lqb_rx_submit(h, n, ids, iq, ns, mem)) return e;
+    return lqb_rx_collect(h);
 }
 
 int lqb_rx_execute_dense(lqb_rx h, const float *iq, uint64_t stride, uint64_t ns, int mem)
@@ -746,6 +833,16 @@ int lqb_rx_execute_dense(lqb_rx h, const float *iq, uint64_t stride, uint64_t ns
     return lqb_rx_execute(h, n, nullptr, ptr.data(), len.data(), mem);
 }
 
+int lqb_rx_submit_dense(lqb_rx h, const float *iq, uint64_t stride, uint64_t ns, int mem)
+{
+    if (!h) return fail(LQB_EINVAL, "null handle");
+    unsigned n = h->n_streams;
+    std::vector<const float *> ptr(n);
+    std::vector<uint64_t> len(n, ns);
+    for (unsigned s = 0; s < n; ++s) ptr[s] = iq + 2 * (size_t)s * stride;
+    return lqb_rx_submit(h, n, nullptr, ptr.data(), len.data(), mem);
+}
+
 int lqb_rx_poll(lqb_rx h, lqb_frame_result *out, uint32_t max_out, uint32_t *n_out)
 {
     if (!h) return fail(LQB_EINVAL, "null handle");
@@ -753,16 +850,17 @@ int lqb_rx_poll(lqb_rx h, lqb_frame_result *out, uint32_t max_out, uint32_t *n_o
     const bool host_res = !(h->flags & LQB_RX_DEVICE_RESULTS);
     for (unsigned k = 0; k < n && out; ++k) {
         const RxLane *ln = h->lanes[h->order[k].first];
-        const FrameDesc &d = ln->h_frames.p[h->order[k].second];
+        const RxGen &G = ln->g[h->cur_gen];
+        const FrameDesc &d = G.h_frames.p[h->order[k].second];
         lqb_frame_result &r = out[k];
         std::memset(&r, 0, sizeof r);
         r.stream = h->global_stream(ln->lane, d.stream); r.seq = d.seq; r.sample_index = d.F;
         std::memcpy(r.header, d.header, 20);
         r.header_valid = d.header_valid; r.payload_valid = d.payload_valid; r.payload_len = d.payload_len;
         if (d.header_valid) {
-            r.payload = host_res ? ln->h_payload.p + d.pay_off : ln->d_payload.p + d.pay_off;
-            if (h->flags & LQB_RX_DEVICE_RESULTS) r.framesyms = reinterpret_cast<const float *>(ln->d_syms.p + d.sym_off);
-            else if (!(h->flags & LQB_RX_NO_FRAMESYMS)) r.framesyms = reinterpret_cast<const float *>(ln->h_syms.p + d.sym_off);
+            r.payload = host_res ? G.h_payload.p + d.pay_off : G.d_payload.p + d.pay_off;
+            if (h->flags & LQB_RX_DEVICE_RESULTS) r.framesyms = reinterpret_cast<const float *>(G.d_syms.p + d.sym_off);
+            else if (!(h->flags & LQB_RX_NO_FRAMESYMS)) r.framesyms = reinterpret_cast<const float *>(G.h_syms.p + d.sym_off);
             r.num_framesyms = d.n_sym;
         }
         r.mod_scheme = d.ms; r.mod_bps = d.bps; r.check = d.check; r.fec0 = d.fec0; r.fec1 = d.fec1;
@@ -858,21 +956,21 @@ int lqb_det_execute(lqb_det h, uint32_t n, const uint32_t *ids, const float *con
     if (int e = h->d_det.reserve(max_det)) return e;
     if (int e = h->h_det.reserve(max_det)) return e;
     SeekParams sp;
-    sp.tables = f.d_tables; sp.states = f.d_states; sp.io = f.d_io.p;
+    sp.tables = f.d_tables; sp.states = f.d_states; sp.io = f.io[0].d_io.p;
     sp.carry[0] = f.d_carry[0]; sp.carry[1] = f.d_carry[1]; sp.carry_cap = f.carry_cap;
-    sp.det_mode = 1; sp.frames = nullptr; sp.detections = h->d_det.p;
-    sp.n_out = f.d_count; sp.max_out = (unsigned)max_det;
+    sp.det_mode = 1; sp.frames = nullptr; sp.detections = h->d_det.p; sp.views = nullptr;
+    sp.n_out = f.io[0].d_count; sp.max_out = (unsigned)max_det;
     CU(cudaEventRecord(h->ev[0], st));
     if (int e = f.run_coarse(n, ns, sp)) return e;
-    CU(cudaMemsetAsync(f.d_count, 0, 8 * sizeof(unsigned), st));
+    CU(cudaMemsetAsync(f.io[0].d_count, 0, 8 * sizeof(unsigned), st));
     launch_seek(sp, n, st); f.launches++;
     launch_carry(sp, n, st); f.launches++;
     if (int e = f.mirror_states()) return e;
     CU(cudaEventRecord(h->ev[1], st));
-    CU(cudaMemcpyAsync(f.h_count, f.d_count, 4 * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(f.io[0].h_count, f.io[0].d_count, 4 * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    h->windows = f.h_count[1];
-    unsigned nd = std::min<unsigned>(f.h_count[0], (unsigned)max_det);
+    h->windows = f.io[0].h_count[1];
+    unsigned nd = std::min<unsigned>(f.io[0].h_count[0], (unsigned)max_det);
     if (nd) {
         CU(cudaMemcpyAsync(h->h_det.p, h->d_det.p, nd * sizeof(Detection), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));

@@ -16,6 +16,7 @@ struct SeekParams {
     Detection       *detections;    // det_mode 1
     unsigned        *n_out;
     unsigned         max_out;
+    StreamView      *views;         // [n_io] out: the sample view every fed stream was searched under (payload kernels read through it)
     // tensor-core pre-filter results (lqb_rx_coarse.cu); coarse == 0 disables the shortcut
     int              coarse;        // 0: off, 1: separate pre-filter kernel results in m8/e8, 2: fused in k_seek
     const void      *bmat;          // fp16 B operand (coarse == 2)
@@ -42,10 +43,7 @@ struct StageItem { unsigned frame; unsigned pad; };
 
 struct PayloadParams {
     const DevTables   *tables;
-    const StreamState *states;
-    const StreamIO    *io;
-    const float2      *carry[2];
-    unsigned           carry_cap;
+    const StreamView  *views;       // [n_io] written by k_seek: carry / input pointers and bounds as of this call
     FrameDesc         *frames;
     unsigned           n_frames;
     // matched filter tiling: tile_start[f] = first tile of frame f (exclusive prefix), n_tiles total

@@ -796,6 +796,7 @@ k_seek(SeekParams P)
     sv.carry_len = st.carry_len;
     sv.end = st.base + (long long)st.carry_len + (long long)io.n_in;
     sv.G = st.G;
+    if (tid == 0 && P.views) P.views[blockIdx.x] = sv;
 
     // make Sc / W valid again after a strip overwrote them
     auto restore_tables = [&]() {

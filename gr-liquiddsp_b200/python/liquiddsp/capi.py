@@ -19,6 +19,7 @@ RX_NO_FRAMESYMS, RX_DEVICE_RESULTS = 1, 2
 DECLARED_SYMBOLS = [
     "lqb_last_error", "lqb_device_count", "lqb_version",
     "lqb_rx_create", "lqb_rx_destroy", "lqb_rx_reset", "lqb_rx_execute", "lqb_rx_execute_dense",
+    "lqb_rx_submit", "lqb_rx_submit_dense", "lqb_rx_collect",
     "lqb_rx_poll", "lqb_rx_counts", "lqb_rx_last_timing", "lqb_rx_launch_count", "lqb_rx_last_work", "lqb_rx_lane_count",
     "lqb_tx_create", "lqb_tx_destroy", "lqb_tx_props_init_default", "lqb_tx_frame_len", "lqb_tx_assemble",
     "lqb_det_create", "lqb_det_destroy", "lqb_det_reset", "lqb_det_execute", "lqb_det_execute_dense",
@@ -81,6 +82,9 @@ def lib():
     L.lqb_rx_reset.argtypes = [vp, C.c_int]
     L.lqb_rx_execute.argtypes = [vp, u32, vp, vp, vp, C.c_int]
     L.lqb_rx_execute_dense.argtypes = [vp, vp, u64, u64, C.c_int]
+    L.lqb_rx_submit.argtypes = [vp, u32, vp, vp, vp, C.c_int]
+    L.lqb_rx_submit_dense.argtypes = [vp, vp, u64, u64, C.c_int]
+    L.lqb_rx_collect.argtypes = [vp]
     L.lqb_rx_poll.argtypes = [vp, vp, u32, C.POINTER(u32)]
     L.lqb_rx_counts.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
     L.lqb_rx_last_timing.argtypes = [vp, C.POINTER(C.c_float)]
@@ -169,6 +173,21 @@ class Rx:
 
     def execute_dense_ptr(self, ptr, stride, n_samples, mem):
         _check(self._L.lqb_rx_execute_dense(self._h, C.c_void_p(ptr), stride, n_samples, mem))
+
+    # pipelined form: submit() returns when the search is done, collect() makes the oldest submitted call current
+    def submit(self, chunks, stream_ids=None):
+        n = len(chunks)
+        arrs = [np.ascontiguousarray(c, dtype=np.complex64) for c in chunks]
+        ptrs = (C.c_void_p * n)(*[a.ctypes.data for a in arrs])
+        lens = (C.c_uint64 * n)(*[len(a) for a in arrs])
+        ids = None if stream_ids is None else (C.c_uint32 * n)(*stream_ids)
+        _check(self._L.lqb_rx_submit(self._h, n, ids, ptrs, lens, MEM_HOST))
+
+    def submit_dense_ptr(self, ptr, stride, n_samples, mem):
+        _check(self._L.lqb_rx_submit_dense(self._h, C.c_void_p(ptr), stride, n_samples, mem))
+
+    def collect(self):
+        _check(self._L.lqb_rx_collect(self._h))
 
     def execute_dense(self, x2d):
         x2d = np.ascontiguousarray(x2d, dtype=np.complex64)

@@ -51,6 +51,7 @@ extern "C" {
 #define LQB_ENODEV   (-19)
 #define LQB_ECUDA    (-5)
 #define LQB_ERANGE   (-34)
+#define LQB_EBUSY    (-16)
 
 #define LQB_MEM_HOST   0
 #define LQB_MEM_DEVICE 1
@@ -151,7 +152,19 @@ int    lqb_rx_execute(lqb_rx h, uint32_t n, const uint32_t *stream_ids,
                       const float *const *iq, const uint64_t *n_samples, int mem);
 /* Dense form: all n_streams streams, stream s at iq + 2*s*stride_samples floats, n_samples each */
 int    lqb_rx_execute_dense(lqb_rx h, const float *iq, uint64_t stride_samples, uint64_t n_samples, int mem);
-/* Frames completed by the last execute, ordered by (stream, seq). */
+/* Pipelined form of execute for callers that stream batch after batch: submit() searches the new samples and
+ * queues the payload work (matched filter, PLL, FEC, CRC, result copies) but returns as soon as the search is done;
+ * collect() waits for the oldest submitted call and makes its frames current for poll / counts / timing / work.
+ * Up to two calls may be in flight, so the payload work of call k runs under the search of call k+1:
+ *     submit(k); submit(k+1); collect() -> k; poll...; submit(k+2); collect() -> k+1; ...
+ * execute() == submit() + collect().  Results are identical to execute()'s.  Device input buffers of a call must
+ * stay valid until its collect() returns (host inputs are staged by submit and may be reused at once); result
+ * buffers of a collected call stay valid until the next-but-one submit.  A third submit returns LQB_EBUSY. */
+int    lqb_rx_submit(lqb_rx h, uint32_t n, const uint32_t *stream_ids,
+                     const float *const *iq, const uint64_t *n_samples, int mem);
+int    lqb_rx_submit_dense(lqb_rx h, const float *iq, uint64_t stride_samples, uint64_t n_samples, int mem);
+int    lqb_rx_collect(lqb_rx h);
+/* Frames completed by the last execute / collect, ordered by (stream, seq). */
 int    lqb_rx_poll(lqb_rx h, lqb_frame_result *out, uint32_t max_out, uint32_t *n_out);
 /* number of frames completed by the last execute / payloads with a passing check */
 int    lqb_rx_counts(lqb_rx h, uint64_t *frames, uint64_t *valid_payloads);

@@ -206,6 +206,60 @@ def test_lane_count_does_not_change_results(lanes):
     rx.close()
 
 
+@pytest.mark.parametrize("lanes", [1, 3])
+def test_pipelined_submit_collect_equals_execute(lanes):
+    """submit()/collect() keep two calls in flight (the payload work of call k runs under the search of call
+    k+1); the frames must be exactly those execute() reports, chunk by chunk, including frames that straddle
+    chunk boundaries (carried samples) and a reset in between."""
+    rng = np.random.default_rng(91)
+    n_streams = 6
+    caps, refs = [], []
+    for s in range(n_streams):
+        ms = util.MODS[(3 * s + 2) % len(util.MODS)]
+        f0 = util.INNER[(2 * s + 1) % len(util.INNER)]
+        f1 = util.OUTER[(3 * s + 1) % len(util.OUTER)]
+        frames = [o.tx_frame(ms, util.CRC24, f0, f1, rng.integers(0, 256, 90 + 41 * k + 3 * s, dtype=np.uint8)) for k in range(5)]
+        cap = util.build_capture(frames, rng, [350 + 77 * k for k in range(5)], snr_db=26.0,
+                                 cfo=0.015 * (s / n_streams - 0.5), tau=0.3 * (s % 3 - 1), gain=0.7 + 0.1 * s,
+                                 lead=200 + 53 * s, tail=1200)
+        caps.append(cap)
+        refs.append(o.rx_capture(cap))
+    n_chunks = 7
+    edges = [[(len(c) * k) // n_chunks for k in range(n_chunks + 1)] for c in caps]
+    rx = capi.Rx(n_streams, lanes=lanes)
+    acc = [[] for _ in range(n_streams)]
+
+    def take():
+        rx.collect()
+        got = rx.poll()
+        assert [(g["stream"], g["seq"]) for g in got] == sorted((g["stream"], g["seq"]) for g in got)
+        for g in got:
+            acc[g["stream"]].append(g)
+
+    for k in range(n_chunks):
+        rx.submit([caps[s][edges[s][k]:edges[s][k + 1]] for s in range(n_streams)])
+        if k >= 1:
+            take()                       # results of chunk k-1 while chunk k is still being finished
+    take()
+    with pytest.raises(capi.LqbError):
+        rx.collect()                     # nothing left
+    for s in range(n_streams):
+        assert_frames_match(refs[s], acc[s])
+    # three submits without a collect: the third is refused, nothing is lost
+    rx.reset()
+    rx.submit([c[:1000] for c in caps])
+    rx.submit([c[1000:2000] for c in caps])
+    with pytest.raises(capi.LqbError):
+        rx.submit([c[2000:3000] for c in caps])
+    rx.collect(); first = rx.poll()
+    rx.collect(); second = rx.poll()
+    rx.execute([c[2000:] for c in caps])
+    third = rx.poll()
+    for s in range(n_streams):
+        assert_frames_match(refs[s], [g for g in first + second + third if g["stream"] == s])
+    rx.close()
+
+
 def test_gr_block_chunking_256_multiples():
     rng = np.random.default_rng(32)
     frames = [o.tx_frame(util.PSK4, util.CRC24, 1, 1, rng.integers(0, 256, 256, dtype=np.uint8)) for _ in range(3)]

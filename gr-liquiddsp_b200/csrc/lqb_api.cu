@@ -108,6 +108,22 @@ int build_tables(DevTables &T, float beta, float threshold, float dphi_max)
         for (unsigned i = 0; i < 27; ++i) T.ilv54[p][i] = (uint16_t)m54[p * 27 + i];
         for (unsigned i = 0; i < 13; ++i) T.ilv27[p][i] = (uint16_t)m27[p * 13 + i];
     }
+    // the header's deinterleaver (passes 3, 2, 1, 0 of masked swaps between byte pairs) moves bits without changing
+    // them: run it once on bit labels and keep the resulting permutation, so the device can gather every byte at once
+    auto compose = [](const std::vector<uint32_t> &maps, unsigned n, uint16_t *perm) {
+        const unsigned n2 = n / 2, masks[4] = { 0xffu, 0x0fu, 0x55u, 0x33u };
+        std::vector<uint16_t> lab(8 * n);
+        for (unsigned i = 0; i < 8 * n; ++i) lab[i] = (uint16_t)i;
+        for (int pass = 3; pass >= 0; --pass)
+            for (unsigned i = 0; i < n2; ++i) {
+                const unsigned j = maps[(size_t)pass * n2 + i];
+                for (unsigned b = 0; b < 8; ++b)
+                    if ((masks[pass] >> b) & 1u) std::swap(lab[8 * (2 * j + 1) + b], lab[8 * (2 * i) + b]);
+            }
+        for (unsigned i = 0; i < 8 * n; ++i) perm[i] = lab[i];
+    };
+    compose(m54, 54, T.hperm54);
+    compose(m27, 27, T.hperm27);
     hamming_dec_tables(T.h84_dec, T.h74_dec);
     secded_cols(T.secded_col);
     uint8_t gen[33];

@@ -25,6 +25,8 @@ struct DevTables {
     uint32_t crc_tab[8][256];  // by liquid crc enum (3..6 used)
     uint16_t ilv54[4][28];     // header interleaver maps, n = 54 (27 pairs)
     uint16_t ilv27[4][16];     // n = 27 (13 pairs)
+    uint16_t hperm54[432];     // the four deinterleaver passes over 54 bytes as one bit permutation: out bit -> in bit
+    uint16_t hperm27[216];     // (bit b of byte i has index 8 i + b, b = 0 the least significant bit)
     uint8_t  h84_dec[256];
     uint8_t  h74_dec[128];
     uint8_t  secded_col[64];

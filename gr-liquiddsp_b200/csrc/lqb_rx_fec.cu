@@ -1,9 +1,10 @@
 // lqb_rx_fec.cu -- packetizer_decode on the GPU, frame-parallel:
 //   k_deinterleave : the four interleaver passes (CTA per frame, precomputed swap maps)
 //   k_blockfec     : NONE / REP3 / REP5 / Hamming(7,4)(8,4)(12,8) / Golay(24,12) / SECDED
-//   k_viterbi      : K=7 / K=9 rate-1/2 (optionally punctured) hard-input Viterbi, warp per
-//                    codeword: add-compare-select with metrics in shared memory, decisions by
-//                    ballot to HBM, then a shuffle-fed traceback from state 0
+//   k_viterbi27x4  : K=7 rate-1/2 (optionally punctured) hard-input Viterbi, four lanes per codeword,
+//                    constant-geometry register layout, sign-bit decisions, prefetched traceback
+//   k_viterbi      : K=9 variant, warp per codeword: add-compare-select with metrics in shared
+//                    memory, decisions by ballot to HBM, then a shuffle-fed traceback from state 0
 //   k_rs           : RS(255,223) over GF(256)/0x11d, warp per block: 32 syndromes in parallel
 //                    (one per lane), Berlekamp-Massey on lane 0, parallel Chien + Forney
 //   k_crc          : unscramble + CRC/checksum + payload copy-out, warp per frame
@@ -293,104 +294,11 @@ k_viterbi(PayloadParams P, const unsigned *__restrict__ list, unsigned n_list, i
 }
 
 
-// ------------------------------------------------------------------ Viterbi K=7, one thread per codeword
-// All 64 path metrics live in registers (two banks, ping-pong over an unrolled pair of trellis
-// steps), so a step is 32 fully unrolled butterflies of plain integer add / min / compare with
-// compile-time branch labels and no inter-thread traffic.  The 64 decision bits of a step go to
-// HBM as one 8-byte word laid out [step][thread] (coalesced across the warp); the traceback reads
-// them back the same way, so its loads do not depend on the state being traced.
-__device__ __forceinline__ void acs27(const unsigned (&mo)[64], unsigned (&mn)[64], unsigned sym0, unsigned sym1, unsigned &d0, unsigned &d1)
-{
-    unsigned A[4];
-#pragma unroll
-    for (int l = 0; l < 4; ++l) A[l] = (((l & 1) ? 255u : 0u) ^ sym0) + (((l & 2) ? 255u : 0u) ^ sym1);
-    unsigned lo = 0, hi = 0;
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-        const int lab = (__popc((2 * i) & 0x6d) & 1) | ((__popc((2 * i) & 0x4f) & 1) << 1);
-        const unsigned a = A[lab], b = A[3 - lab];
-        unsigned m0 = mo[i] + a, m1 = mo[i + 32] + b;
-        unsigned dcs = m0 > m1 ? 1u : 0u;
-        mn[2 * i] = m0 > m1 ? m1 : m0;
-        if (2 * i < 32) lo |= dcs << (2 * i); else hi |= dcs << (2 * i - 32);
-        m0 = mo[i] + b; m1 = mo[i + 32] + a;
-        dcs = m0 > m1 ? 1u : 0u;
-        mn[2 * i + 1] = m0 > m1 ? m1 : m0;
-        if (2 * i + 1 < 32) lo |= dcs << (2 * i + 1); else hi |= dcs << (2 * i + 1 - 32);
-    }
-    d0 = lo; d1 = hi;
-}
-
-__global__ void __launch_bounds__(64)
-k_viterbi27(PayloadParams P, const unsigned *__restrict__ list, unsigned n_list, int stage, uint2 *__restrict__ dec)
-{
-    const unsigned gi = blockIdx.x * blockDim.x + threadIdx.x;
-    if (gi >= n_list) return;
-    const FrameDesc &d = P.frames[list[gi]];
-    const StageIO io = stage_io(P, d, stage);
-    const ConvSpec cs = conv_spec(io.fs);
-    const unsigned nbits = 8 * io.dec_len, T = nbits + 6;
-    unsigned per = 0, pre[8];
-    for (unsigned c = 0; c < cs.P; ++c) { pre[c] = per; per += ((cs.keep0 >> c) & 1u) + ((cs.keep1 >> c) & 1u); }
-    const unsigned char *enc = io.src;
-
-    unsigned ma[64], mb[64];
-#pragma unroll
-    for (int i = 0; i < 64; ++i) ma[i] = 63u;
-    ma[0] = 0u;
-    unsigned col = 0, q = 0;                       // t = q * P + col
-    auto symbols = [&](unsigned &s0, unsigned &s1) {
-        unsigned ib = q * per + pre[col];
-        s0 = 127u; s1 = 127u;
-        if ((cs.keep0 >> col) & 1u) { s0 = soft_bit(enc, ib); ++ib; }
-        if ((cs.keep1 >> col) & 1u) { s1 = soft_bit(enc, ib); }
-        if (++col == cs.P) { col = 0; ++q; }
-    };
-    unsigned t = 0;
-    for (; t + 1 < T; t += 2) {
-        unsigned s0, s1, d0, d1;
-        symbols(s0, s1);
-        acs27(ma, mb, s0, s1, d0, d1);
-        dec[(size_t)t * n_list + gi] = make_uint2(d0, d1);
-        symbols(s0, s1);
-        acs27(mb, ma, s0, s1, d0, d1);
-        dec[(size_t)(t + 1) * n_list + gi] = make_uint2(d0, d1);
-    }
-    if (t < T) {
-        unsigned s0, s1, d0, d1;
-        symbols(s0, s1);
-        acs27(ma, mb, s0, s1, d0, d1);
-        dec[(size_t)t * n_list + gi] = make_uint2(d0, d1);
-    }
-    // traceback from state 0; bit shifted out at step t entered at t - 6
-    unsigned char *out = io.dst;
-    unsigned state = 0, byte_acc = 0;
-    long long tt = (long long)T - 1;
-    while (tt >= 0) {
-        uint2 w[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) w[k] = (tt - k >= 0) ? dec[(size_t)(tt - k) * n_list + gi] : make_uint2(0u, 0u);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const long long ts = tt - k;
-            if (ts < 0) break;
-            const unsigned word = (state & 32u) ? w[k].y : w[k].x;
-            const unsigned bit = (word >> (state & 31u)) & 1u;
-            if (ts >= 6) {
-                const unsigned bi = (unsigned)ts - 6u;
-                byte_acc |= bit << (7 - (bi & 7u));
-                if ((bi & 7u) == 0) { out[bi >> 3] = (unsigned char)byte_acc; byte_acc = 0; }
-            }
-            state = (state >> 1) | (bit << 5);
-        }
-        tt -= 8;
-    }
-}
-
 // ------------------------------------------------------------------ Viterbi K=7, four lanes per codeword
-// The thread-per-codeword kernel above is limited by how many codewords there are (a warp issues about
-// every fourth cycle; 31 k codewords are 1.6 warps per scheduler).  Here the 64 path metrics of a codeword
-// are spread over 4 lanes x 16 registers in a CONSTANT-GEOMETRY layout: the metric of state s at step t
+// A thread-per-codeword kernel (all 64 metrics in one thread's registers, 281 instructions per step) is limited
+// by how many codewords there are: a warp issues about every fourth cycle and 31 k codewords are 1.6 warps per
+// scheduler (8.9 ms, profiles/r01_notes.md).  Here the 64 path metrics of a codeword are spread over
+// 4 lanes x 16 registers in a CONSTANT-GEOMETRY layout: the metric of state s at step t
 // lives at position p = rotr6(s, t mod 6) (lane = p >> 4, register = p & 15).  The two predecessors of a
 // butterfly then always sit at positions that differ in bit k = 5 - (t mod 6) and its two successors are
 // written back in place, so four steps out of six are register-only and two exchange with one other lane
@@ -416,13 +324,16 @@ __host__ __device__ constexpr unsigned v4_label(int r, unsigned pos_bits)
     return v4_par6(pos_bits & v4_phase_mask(0x6d, r)) | (v4_par6(pos_bits & v4_phase_mask(0x4f, r)) << 1);
 }
 
+// One trellis step.  Decisions are collected as sign bits: for every position the candidate difference is formed so
+// that it is negative exactly when the specification's comparison m0 > m1 holds, and its top bit is funnel-shifted
+// into the decision word, positions 15 down to 0 (so bit j of the word is the decision of position j).
 template <int R>
-__device__ __forceinline__ void v4_step(unsigned (&M)[kV4Pos], unsigned s0, unsigned s1, unsigned lane_l, unsigned mask, unsigned &dec)
+__device__ __forceinline__ void v4_step(unsigned (&M)[kV4Pos], unsigned s0, unsigned s1, int upper_sign, unsigned &dec)
 {
     constexpr int k = 5 - R;                       // position bit that separates the two predecessors
     unsigned A[4];
     A[0] = s0 + s1; A[1] = (s0 ^ 255u) + s1; A[2] = s0 + (s1 ^ 255u); A[3] = 510u - A[0];
-    dec = 0;
+    unsigned diff[kV4Pos];
     if constexpr (k < kV4PosBits) {
 #pragma unroll
         for (int j = 0; j < kV4Pos; ++j) {
@@ -430,31 +341,31 @@ __device__ __forceinline__ void v4_step(unsigned (&M)[kV4Pos], unsigned s0, unsi
             const int j1 = j | (1 << k);
             const unsigned lab = v4_label(R, (unsigned)j);
             const unsigned a = A[lab], b = A[3 - lab];
-            unsigned m0 = M[j] + a, m1 = M[j1] + b;
-            const unsigned d0 = m0 > m1 ? 1u : 0u;
-            const unsigned n0 = m0 > m1 ? m1 : m0;
-            m0 = M[j] + b; m1 = M[j1] + a;
-            const unsigned d1 = m0 > m1 ? 1u : 0u;
-            const unsigned n1 = m0 > m1 ? m1 : m0;
-            M[j] = n0; M[j1] = n1;
-            dec |= (d0 << j) | (d1 << j1);
+            const unsigned m0 = M[j] + a, m1 = M[j1] + b;         // into successor 2i   (kept at position j)
+            const unsigned q0 = M[j] + b, q1 = M[j1] + a;         // into successor 2i+1 (kept at position j1)
+            diff[j] = m1 - m0;                                     // negative <=> m0 > m1
+            diff[j1] = q1 - q0;
+            M[j] = min(m0, m1);
+            M[j1] = min(q0, q1);
         }
     } else {
         constexpr int lb = k - kV4PosBits;         // lane bit exchanged in this phase
-        const bool upper = (lane_l >> lb) & 1u;    // this lane holds the state-bit-5 = 1 predecessors
 #pragma unroll
         for (int j = 0; j < kV4Pos; ++j) {
             const unsigned lab = v4_label(R, (unsigned)j);
             const unsigned a = A[lab], b = A[3 - lab];
-            const unsigned other = __shfl_xor_sync(mask, M[j], 1 << lb);
+            const unsigned other = __shfl_xor_sync(0xffffffffu, M[j], 1 << lb);
             const unsigned c_own = M[j] + a, c_oth = other + b;
-            // lower lane: successor 2i = min(own + a, other + b), decision = own + a > other + b
-            // upper lane: successor 2i+1 = min(other + b, own + a), decision = other + b > own + a
-            const bool d = upper ? (c_oth > c_own) : (c_own > c_oth);
-            M[j] = c_own < c_oth ? c_own : c_oth;
-            dec |= (d ? 1u : 0u) << j;
+            // lower lane keeps successor 2i:   decision = own + a > other + b  <=>  (other + b) - (own + a) < 0
+            // upper lane keeps successor 2i+1: decision = other + b > own + a  <=>  (own + a) - (other + b) < 0
+            diff[j] = (unsigned)((int)(c_oth - c_own) * upper_sign);
+            M[j] = min(c_own, c_oth);
         }
     }
+    unsigned d = 0;
+#pragma unroll
+    for (int j = kV4Pos - 1; j >= 0; --j) d = __funnelshift_l(diff[j], d, 1);
+    dec = d;
 }
 
 constexpr int kV4Threads = 64;
@@ -464,26 +375,34 @@ __global__ void __launch_bounds__(kV4Threads)
 k_viterbi27x4(PayloadParams P, const unsigned *__restrict__ list, unsigned n_list, int stage, unsigned short *__restrict__ dec)
 {
     const unsigned gt = blockIdx.x * kV4Threads + threadIdx.x;
-    const unsigned gi = gt / kV4Lanes, l = gt % kV4Lanes;
-    // a whole group is either inside the list or outside (kV4Lanes divides the warp), shuffles stay inside a group
-    if (gi >= n_list) return;
-    // codewords in one warp have different lengths: only the four lanes of a group ever shuffle together
-    const unsigned mask = 0xfu << ((threadIdx.x & 31u) & ~3u);
+    const unsigned l = gt % kV4Lanes;
+    unsigned gi = gt / kV4Lanes;
+    // groups past the end of the list shadow the last codeword without storing anything, so that every lane of a
+    // warp runs the same number of steps and the shuffles can use the full mask
+    const bool active = gi < n_list;
+    if (!active) gi = n_list - 1;
     const FrameDesc &d = P.frames[list[gi]];
     const StageIO io = stage_io(P, d, stage);
     const ConvSpec cs = conv_spec(io.fs);
     const unsigned nbits = 8 * io.dec_len, T = nbits + 6;
+    unsigned Tw = T;                                  // longest codeword in this warp
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) Tw = max(Tw, __shfl_xor_sync(0xffffffffu, Tw, m));
     unsigned per = 0, pre[8];
     for (unsigned c = 0; c < cs.P; ++c) { pre[c] = per; per += ((cs.keep0 >> c) & 1u) + ((cs.keep1 >> c) & 1u); }
     const unsigned char *enc = io.src;
+    const unsigned enc_words = (io.enc_len + 3u) / 4u;
 
     // lane part of the branch labels, as XOR masks on the received symbols, per phase
     unsigned mk0[6], mk1[6];
+    int up[6];                                       // -1 when this lane holds the state-bit-5 = 1 predecessors in phase r
 #pragma unroll
     for (int r = 0; r < 6; ++r) {
         const unsigned lb = l << kV4PosBits;
         mk0[r] = (__popc(lb & v4_phase_mask(0x6d, r)) & 1) ? 255u : 0u;
         mk1[r] = (__popc(lb & v4_phase_mask(0x4f, r)) & 1) ? 255u : 0u;
+        const int k = 5 - r;
+        up[r] = (k >= kV4PosBits && ((l >> (k - kV4PosBits)) & 1u)) ? -1 : 1;
     }
     unsigned M[kV4Pos];
 #pragma unroll
@@ -491,17 +410,17 @@ k_viterbi27x4(PayloadParams P, const unsigned *__restrict__ list, unsigned n_lis
     if (l == 0) M[0] = 0u;                          // state 0 sits at position 0 at t = 0
 
     unsigned col = 0, q = 0;                        // punctured: t = q * P + col
-    unsigned word = 0, have = 0;                    // unpunctured: 32 encoded bits, MSB first
+    unsigned word = 0, have = 0, wi = 0;            // unpunctured: 32 encoded bits, MSB first
     const unsigned *enc32 = reinterpret_cast<const unsigned *>(enc);     // byte arenas are 16-byte aligned per frame
     auto symbols = [&](unsigned &s0, unsigned &s1) {
         if (PUNCT) {
             unsigned ib = q * per + pre[col];
             s0 = 127u; s1 = 127u;
-            if ((cs.keep0 >> col) & 1u) { s0 = soft_bit(enc, ib); ++ib; }
-            if ((cs.keep1 >> col) & 1u) { s1 = soft_bit(enc, ib); }
+            if ((cs.keep0 >> col) & 1u) { s0 = (ib >> 3) < io.enc_len ? soft_bit(enc, ib) : 0u; ++ib; }
+            if ((cs.keep1 >> col) & 1u) { s1 = (ib >> 3) < io.enc_len ? soft_bit(enc, ib) : 0u; }
             if (++col == cs.P) { col = 0; ++q; }
         } else {
-            if (have == 0) { word = __byte_perm(__ldg(enc32++), 0, 0x0123); have = 16; }
+            if (have == 0) { word = wi < enc_words ? __byte_perm(__ldg(enc32 + wi), 0, 0x0123) : 0u; ++wi; have = 16; }
             s0 = (unsigned)((int)word >> 31) & 255u;
             s1 = (unsigned)((int)(word << 1) >> 31) & 255u;
             word <<= 2; --have;
@@ -514,20 +433,16 @@ k_viterbi27x4(PayloadParams P, const unsigned *__restrict__ list, unsigned n_lis
     {                                                                             \
         unsigned s0, s1, dd;                                                      \
         symbols(s0, s1);                                                          \
-        v4_step<R>(M, s0 ^ mk0[R], s1 ^ mk1[R], l, mask, dd);                           \
-        out_dec[(size_t)(t + R) * dstride] = (unsigned short)dd;                  \
+        v4_step<R>(M, s0 ^ mk0[R], s1 ^ mk1[R], up[R], dd);                       \
+        if (active && t + R < T) out_dec[(size_t)(t + R) * dstride] = (unsigned short)dd; \
     }
-    for (; t + 6 <= T; t += 6) {
+    // whole groups of six phases; steps past a codeword's end run on zero symbols and store nothing
+    for (; t < Tw; t += 6) {
         LQB_V4_STEP(0) LQB_V4_STEP(1) LQB_V4_STEP(2) LQB_V4_STEP(3) LQB_V4_STEP(4) LQB_V4_STEP(5)
     }
-    if (t + 0 < T) LQB_V4_STEP(0)
-    if (t + 1 < T) LQB_V4_STEP(1)
-    if (t + 2 < T) LQB_V4_STEP(2)
-    if (t + 3 < T) LQB_V4_STEP(3)
-    if (t + 4 < T) LQB_V4_STEP(4)
 #undef LQB_V4_STEP
-    __syncwarp(mask);
-    if (l != 0) return;
+    __syncwarp();
+    if (l != 0 || !active) return;
     // traceback from state 0 (lane 0 of the group); the decision of successor state s at step ts is bit
     // rotr6(s, (ts + 1) mod 6) of that step's word; the bit shifted out at step ts entered at ts - 6
     const uint2 *dec64 = reinterpret_cast<const uint2 *>(dec) + gi;
@@ -535,10 +450,13 @@ k_viterbi27x4(PayloadParams P, const unsigned *__restrict__ list, unsigned n_lis
     unsigned state = 0, byte_acc = 0;
     long long tt = (long long)T - 1;
     unsigned ph = (unsigned)((tt + 1) % 6);         // rotation of step tt
-    while (tt >= 0) {
-        uint2 w[8];
+    // the addresses do not depend on the state: the next eight words are requested before the current eight are walked
+    uint2 w[8], wn[8];
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) w[kk] = (tt - kk >= 0) ? dec64[(size_t)(tt - kk) * n_list] : make_uint2(0u, 0u);
+    for (int kk = 0; kk < 8; ++kk) w[kk] = (tt - kk >= 0) ? dec64[(size_t)(tt - kk) * n_list] : make_uint2(0u, 0u);
+    while (tt >= 0) {
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) wn[kk] = (tt - 8 - kk >= 0) ? dec64[(size_t)(tt - 8 - kk) * n_list] : make_uint2(0u, 0u);
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
             const long long ts = tt - kk;
@@ -554,6 +472,8 @@ k_viterbi27x4(PayloadParams P, const unsigned *__restrict__ list, unsigned n_lis
             state = (state >> 1) | (bit << 5);
             ph = ph ? ph - 1u : 5u;
         }
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) w[kk] = wn[kk];
         tt -= 8;
     }
 }

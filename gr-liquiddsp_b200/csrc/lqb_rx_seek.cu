@@ -61,6 +61,7 @@ struct SeekShared {
     unsigned long long best[kWarps];
     float  energy[2];
     float2 y3[3];             // align: y[511], y[0], y[1]
+    float  cfo_nb[2];         // align: |CFO spectrum| left and right of its peak
     // control (written by thread 0)
     int    trig, idx, off, stop, hv;
     float  rxy, tau, gamma, dphi, phi, mf_scale;
@@ -538,20 +539,29 @@ __device__ void align_frame(SeekShared &sh, const DevTables *T, int tid)
         if (lane == 0) sh.y3[1] = v[0];
         if (lane == 1) sh.y3[2] = v[0];
         if (lane == 31) sh.y3[0] = v[15];
-        __syncwarp();
-        // CFO spectrum
+    } else if (warp == 1) {
+        // CFO spectrum, at the same time on its own warp: only the peak bin and its two neighbours are kept
+        float2 v[16];
 #pragma unroll
         for (int r = 0; r < 16; ++r) v[r] = zbuf[fft512_in_index(lane, r)];
-        fft512_warp<+1>(v, sh.W, sh.Wc, sh.scr, lane);
+        fft512_warp<+1>(v, sh.W, sh.Wc, sh.scr + 544, lane);
         unsigned long long best = 0ull;
 #pragma unroll
         for (int r = 0; r < 16; ++r) {
-            int p = fft512_out_index(lane, r);
-            sh.Xf[p] = v[r];
+            const int p = fft512_out_index(lane, r);
             unsigned long long key = ((unsigned long long)__float_as_uint(abs2f(v[r])) << 32) | (0xffffffffu - (unsigned)p);
             best = key > best ? key : best;
         }
         best = warp_max_u64(best);
+        const float v2 = __uint_as_float((unsigned)(best >> 32));
+        const unsigned i0 = (v2 > 0.0f) ? (0xffffffffu - (unsigned)(best & 0xffffffffu)) : 0u;
+        const unsigned pn = (i0 + 511u) & 511u, pp = (i0 + 1u) & 511u;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            const unsigned p = (unsigned)fft512_out_index(lane, r);
+            if (p == pn) sh.cfo_nb[0] = cabsf_(v[r]);
+            if (p == pp) sh.cfo_nb[1] = cabsf_(v[r]);
+        }
         if (lane == 0) sh.best[0] = best;
     }
     wsync();
@@ -568,7 +578,7 @@ __device__ void align_frame(SeekShared &sh, const DevTables *T, int tid)
         float v2 = __uint_as_float((unsigned)(bb >> 32));
         unsigned i0 = (v2 > 0.0f) ? (0xffffffffu - (unsigned)(bb & 0xffffffffu)) : 0u;
         float v0 = __fsqrt_rn(v2);
-        float vneg = cabsf_(sh.Xf[(i0 + 511u) & 511u]), vpos = cabsf_(sh.Xf[(i0 + 1u) & 511u]);
+        float vneg = sh.cfo_nb[0], vpos = sh.cfo_nb[1];
         a = __fsub_rn(__fmul_rn(0.5f, __fadd_rn(vpos, vneg)), v0);
         b = __fmul_rn(0.5f, __fsub_rn(vpos, vneg));
         float idx = __fdiv_rn(-b, __fmul_rn(2.0f, a));
@@ -586,8 +596,10 @@ __device__ void align_frame(SeekShared &sh, const DevTables *T, int tid)
     }
     wsync();
     if (tid == 0) {
+        // summed in sample order (the specification's order); unrolled so the shared-memory loads run ahead of the adds
         float mr = 0.0f, mi = 0.0f;
-        for (int i = 0; i < 156; ++i) { mr = __fadd_rn(mr, vsum[i].x); mi = __fadd_rn(mi, vsum[i].y); }
+#pragma unroll 12
+        for (int i = 0; i < 156; ++i) { const float2 q = vsum[i]; mr = __fadd_rn(mr, q.x); mi = __fadd_rn(mi, q.y); }
         sh.phi = atan2f(mi, mr);
         sh.theta0 = nco_constrain_dev(sh.phi);
         sh.dtheta = nco_constrain_dev(sh.dphi);
@@ -636,39 +648,61 @@ __device__ void decode_header(SeekShared &sh, const DevTables *T, const StreamVi
         hsym[k] = make_float2(__fmul_rn(ar, sh.mf_scale), __fmul_rn(ai, sh.mf_scale));
     }
     wsync();
-    // ---- pilot sync (thread 0): 15 pilots -> FFT-32 -> residual dphi / phi / gain
-    if (tid == 0) {
-        float2 *bt = pil, *bf = pil + 32;
-        for (int i = 0; i < 32; ++i) bt[i] = (i < 15) ? cmulf(hsym[16 * i], T->pilots_conj[i]) : make_float2(0.0f, 0.0f);
-        for (int i = 0; i < 32; ++i) bf[i] = bt[brev5((unsigned)i)];
+    // ---- pilot sync (warp 0): 15 pilots -> FFT-32 (one point per lane, the specification's radix-2 DIT butterflies
+    // exchanged by shuffle) -> residual dphi / phi / gain
+    if (tid < 32) {
+        const unsigned lane = (unsigned)tid;
+        const float2 bt = (lane < 15u) ? cmulf(hsym[16 * lane], T->pilots_conj[lane]) : make_float2(0.0f, 0.0f);
+        // lane i starts with bt[brev5(i)]
+        const unsigned srcl = brev5(lane);
+        float2 v = make_float2(__shfl_sync(0xffffffffu, bt.x, srcl), __shfl_sync(0xffffffffu, bt.y, srcl));
+#pragma unroll
         for (int half = 1; half < 32; half <<= 1) {
-            int step = 16 / half;
-            for (int k = 0; k < 32; k += 2 * half)
-                for (int j = 0; j < half; ++j) bfly<+1>(bf[k + j], bf[k + j + half], T->W32[j * step]);
+            const float2 w = T->W32[(lane & (half - 1)) * (16 / half)];
+            const float2 o = make_float2(__shfl_xor_sync(0xffffffffu, v.x, half), __shfl_xor_sync(0xffffffffu, v.y, half));
+            const bool hi_side = (lane & half) != 0;
+            float2 lo = hi_side ? o : v, hi = hi_side ? v : o;
+            bfly<+1>(lo, hi, w);
+            v = hi_side ? hi : lo;
         }
-        unsigned i0 = 0; float y0 = 0.0f;
-        for (unsigned i = 0; i < 32; ++i) { float a = cabsf_(bf[i]); if (i == 0 || a > y0) { i0 = i; y0 = a; } }
-        float ypos = cabsf_(bf[(i0 + 1) & 31]), yneg = cabsf_(bf[(i0 + 31) & 31]);
+        const float a_me = cabsf_(v);
+        // first maximum wins
+        float y0 = a_me; unsigned i0 = lane;
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) {
+            const float oy = __shfl_xor_sync(0xffffffffu, y0, m);
+            const unsigned oi = __shfl_xor_sync(0xffffffffu, i0, m);
+            if (oy > y0 || (oy == y0 && oi < i0)) { y0 = oy; i0 = oi; }
+        }
+        const float ypos = __shfl_sync(0xffffffffu, a_me, (i0 + 1) & 31), yneg = __shfl_sync(0xffffffffu, a_me, (i0 + 31) & 31);
         float a = __fsub_rn(__fmul_rn(0.5f, __fadd_rn(ypos, yneg)), y0);
         float b = __fmul_rn(0.5f, __fsub_rn(ypos, yneg));
         float idx = __fdiv_rn(-b, __fmul_rn(2.0f, a));
         float index = __fadd_rn((float)i0, idx);
         float base = (i0 > 16u) ? __fsub_rn(index, 32.0f) : index;
         float dphi = __fdiv_rn(__fmul_rn(__fmul_rn(base, 2.0f), kPiF), 512.0f);
-        float mr = 0.0f, mi = 0.0f;
-        for (int i = 0; i < 15; ++i) {
-            float ang = __fmul_rn(__fmul_rn(-dphi, (float)i), 16.0f);
+        // derotated pilots, one per lane, then summed in pilot order
+        float2 r = make_float2(0.0f, 0.0f);
+        if (lane < 15u) {
+            float ang = __fmul_rn(__fmul_rn(-dphi, (float)lane), 16.0f);
             float sn, cs;
             sincosf(ang, &sn, &cs);
-            float2 v = cmulf(bt[i], make_float2(cs, sn));
-            mr = __fadd_rn(mr, v.x); mi = __fadd_rn(mi, v.y);
+            r = cmulf(bt, make_float2(cs, sn));
         }
-        float phi = atan2f(mi, mr);
-        float g_hat = __fdiv_rn(cabsf_(make_float2(mr, mi)), 15.0f);
-        pil[0] = make_float2(dphi, phi);
-        pil[1] = make_float2(__fdiv_rn(1.0f, g_hat), 0.0f);
-        *pll_dtheta = nco_constrain_dev(dphi);
-        *pll_theta0 = nco_constrain_dev(__fadd_rn(phi, __fmul_rn(dphi, 231.0f)));
+        float mr = 0.0f, mi = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 15; ++i) {
+            mr = __fadd_rn(mr, __shfl_sync(0xffffffffu, r.x, i));
+            mi = __fadd_rn(mi, __shfl_sync(0xffffffffu, r.y, i));
+        }
+        if (lane == 0) {
+            float phi = atan2f(mi, mr);
+            float g_hat = __fdiv_rn(cabsf_(make_float2(mr, mi)), 15.0f);
+            pil[0] = make_float2(dphi, phi);
+            pil[1] = make_float2(__fdiv_rn(1.0f, g_hat), 0.0f);
+            *pll_dtheta = nco_constrain_dev(dphi);
+            *pll_theta0 = nco_constrain_dev(__fadd_rn(phi, __fmul_rn(dphi, 231.0f)));
+        }
     }
     wsync();
     // ---- derotate the 216 data symbols and slice QPSK: 4 symbols -> one byte
@@ -691,16 +725,38 @@ __device__ void decode_header(SeekShared &sh, const DevTables *T, const StreamVi
         }
     }
     wsync();
-    // ---- decode (thread 0): deinterleave(54) -> Hamming(8,4) -> deinterleave(27) -> SECDED(72,64) -> unscramble -> CRC-32
-    if (tid == 0) {
-        unsigned char *e = sh.hbytes, d27[28], *d = sh.hdec;
-        hdr_ilv_pass(e, T->ilv54[3], 27, 0x33); hdr_ilv_pass(e, T->ilv54[2], 27, 0x55);
-        hdr_ilv_pass(e, T->ilv54[1], 27, 0x0f); hdr_ilv_pass(e, T->ilv54[0], 27, 0xff);
-        for (int i = 0; i < 27; ++i) d27[i] = (unsigned char)((T->h84_dec[e[2 * i]] << 4) | T->h84_dec[e[2 * i + 1]]);
-        hdr_ilv_pass(d27, T->ilv27[3], 13, 0x33); hdr_ilv_pass(d27, T->ilv27[2], 13, 0x55);
-        hdr_ilv_pass(d27, T->ilv27[1], 13, 0x0f); hdr_ilv_pass(d27, T->ilv27[0], 13, 0xff);
-        for (int blk = 0; blk < 3; ++blk) {
-            const unsigned char *src = d27 + 9 * blk;
+    // ---- decode: deinterleave(54) -> Hamming(8,4) -> deinterleave(27) -> SECDED(72,64) -> unscramble -> CRC-32.
+    // Each deinterleaver is one gather through the precomputed bit permutation (thread per output byte); the three
+    // SECDED blocks decode on three threads; only the 20-byte CRC is serial.
+    {
+        unsigned char *e = sh.hbytes, *d = sh.hdec;
+        unsigned char *e2 = reinterpret_cast<unsigned char *>(pil + 8);         // 54 deinterleaved bytes (pil[0..1] stay live)
+        unsigned char *d27 = e2 + 64, *d27b = d27 + 32;
+        if (tid < 54) {
+            unsigned v = 0;
+#pragma unroll
+            for (int bit = 0; bit < 8; ++bit) {
+                const unsigned src = T->hperm54[8 * tid + bit];
+                v |= ((e[src >> 3] >> (src & 7u)) & 1u) << bit;
+            }
+            e2[tid] = (unsigned char)v;
+        }
+        wsync();
+        if (tid < 27) d27[tid] = (unsigned char)((T->h84_dec[e2[2 * tid]] << 4) | T->h84_dec[e2[2 * tid + 1]]);
+        wsync();
+        if (tid < 27) {
+            unsigned v = 0;
+#pragma unroll
+            for (int bit = 0; bit < 8; ++bit) {
+                const unsigned src = T->hperm27[8 * tid + bit];
+                v |= ((d27[src >> 3] >> (src & 7u)) & 1u) << bit;
+            }
+            d27b[tid] = (unsigned char)v;
+        }
+        wsync();
+        if (tid < 3) {
+            const int blk = tid;
+            const unsigned char *src = d27b + 9 * blk;
             unsigned rp = src[0], p = 0, all = 0, tot = 0;
             unsigned char b8[8];
             for (int q = 0; q < 8; ++q) { b8[q] = src[1 + q]; tot ^= (unsigned)__popc(b8[q]) & 1u; }
@@ -713,15 +769,17 @@ __device__ void decode_header(SeekShared &sh, const DevTables *T, const StreamVi
             if (tot && syn && (syn & (syn - 1)))
                 for (int bit = 0; bit < 64; ++bit)
                     if (T->secded_col[bit] == syn) { b8[bit >> 3] ^= (unsigned char)(0x80u >> (bit & 7)); break; }
-            for (int q = 0; q < 8; ++q) d[8 * blk + q] = b8[q];
+            const unsigned char mask[4] = { 0xb4, 0x6a, 0x8b, 0xc5 };
+            for (int q = 0; q < 8; ++q) d[8 * blk + q] = b8[q] ^ mask[q & 3];      // 8 blk is a multiple of 4: unscramble in place
         }
-        const unsigned char mask[4] = { 0xb4, 0x6a, 0x8b, 0xc5 };
-        for (int i = 0; i < 24; ++i) d[i] ^= mask[i & 3];
-        unsigned key = 0xffffffffu;
-        for (int i = 0; i < 20; ++i) key = (key >> 8) ^ T->crc_tab[6][(key ^ d[i]) & 0xffu];
-        key = ~key;
-        unsigned rx = ((unsigned)d[20] << 24) | ((unsigned)d[21] << 16) | ((unsigned)d[22] << 8) | d[23];
-        sh.hv = (key == rx);
+        wsync();
+        if (tid == 0) {
+            unsigned key = 0xffffffffu;
+            for (int i = 0; i < 20; ++i) key = (key >> 8) ^ T->crc_tab[6][(key ^ d[i]) & 0xffu];
+            key = ~key;
+            unsigned rx = ((unsigned)d[20] << 24) | ((unsigned)d[21] << 16) | ((unsigned)d[22] << 8) | d[23];
+            sh.hv = (key == rx);
+        }
     }
     wsync();
 }

@@ -221,21 +221,27 @@ __device__ void tc_issue(SeekShared &sh, const StreamView &sv, const TcBlk &b, i
     wsync();                                   // the previous strip build has finished reading xs
     float mx = 0.0f, en = 0.0f;
     __half *xh = reinterpret_cast<__half *>(xs);
+    if (pre_a0 != b.a0) {                      // (uniform) nothing usable was prefetched: fetch now
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int i = tid + kThreads * k;
+            pre[k] = (i < 424) ? sv.at(b.a0 + i) : make_float2(0.0f, 0.0f);
+        }
+    }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int i = tid + kThreads * k;
         const long long n = b.a0 + i;
-        float2 v = (pre_a0 == b.a0) ? pre[k] : ((i < 424) ? sv.at(n) : make_float2(0.0f, 0.0f));
+        float2 v = pre[k];
         if (i >= n_samp) v = make_float2(0.0f, 0.0f);
         mx = fmaxf(mx, fmaxf(fabsf(v.x), fabsf(v.y)));
         if (i < n_samp && n >= b.e_lo && n < b.e_hi) en += fmaf(v.y, v.y, v.x * v.x);
         if (i < 432) { xh[i] = __float2half_rn(v.x * sc); xh[432 + i] = __float2half_rn(v.y * sc); }
     }
+    // non-negative floats order like their bit patterns: one REDUX instead of five shuffle + max rounds
+    mx = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(mx)));
 #pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) {
-        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, m));
-        en += __shfl_xor_sync(0xffffffffu, en, m);
-    }
+    for (int m = 16; m >= 1; m >>= 1) en += __shfl_xor_sync(0xffffffffu, en, m);
     if (lane == 0) { sh.part_max[b.buf][warp] = mx; sh.part_en[b.buf][warp] = en; }
     wsync();
     // ---- Z[c][8 m + e] = xs[c][m + e]: row m is the 16 bytes at half offset m (word aligned for even m)
@@ -256,11 +262,24 @@ __device__ void tc_issue(SeekShared &sh, const StreamView &sv, const TcBlk &b, i
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     if (tid == 0) sh.tc_cmd[b.buf] = b.n_t;
     mbar_arrive(&sh.z_full[b.buf]);
-    // the samples of the block that will be staged next travel while this one is multiplied
+    // the samples of the block that will be staged next travel while this one is multiplied; a block that lies
+    // wholly inside the new input (the usual case) is read straight through the pointer
+    {
+        const long long i0 = next_a0 - sv.base - (long long)sv.carry_len;
+        if (i0 >= 0 && next_a0 >= sv.G && next_a0 + 424 <= sv.end) {
+            const float2 *src = sv.in + i0;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int i = tid + kThreads * k;
-        pre[k] = (i < 424) ? sv.at(next_a0 + i) : make_float2(0.0f, 0.0f);
+            for (int k = 0; k < 4; ++k) {
+                const int i = tid + kThreads * k;
+                pre[k] = (i < 424) ? __ldg(src + i) : make_float2(0.0f, 0.0f);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int i = tid + kThreads * k;
+                pre[k] = (i < 424) ? sv.at(next_a0 + i) : make_float2(0.0f, 0.0f);
+            }
+        }
     }
     pre_a0 = next_a0;
 }
@@ -348,14 +367,11 @@ __device__ void tc_retire(SeekShared &sh, const TcBlk &b, unsigned &ph_full, int
     mbar_arrive(&sh.acc_empty);
     PROF_MARK(5);
     if (discard) return;
-    float a = best[0], bb = tid >= 28 ? best[0] : 0.0f, c = best[1], d = tid >= 28 ? best[1] : 0.0f;
-#pragma unroll
-    for (int k = 16; k >= 1; k >>= 1) {
-        a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, k));
-        bb = fmaxf(bb, __shfl_xor_sync(0xffffffffu, bb, k));
-        c = fmaxf(c, __shfl_xor_sync(0xffffffffu, c, k));
-        d = fmaxf(d, __shfl_xor_sync(0xffffffffu, d, k));
-    }
+    // |C|^2 >= 0: the maxima are taken on the bit patterns with one REDUX each
+    const float a = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(best[0])));
+    const float bb = __uint_as_float(__reduce_max_sync(0xffffffffu, tid >= 28 ? __float_as_uint(best[0]) : 0u));
+    const float c = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(best[1])));
+    const float d = __uint_as_float(__reduce_max_sync(0xffffffffu, tid >= 28 ? __float_as_uint(best[1]) : 0u));
     if (lane == 0) { sh.red[warp][0] = a; sh.red[warp][1] = bb; sh.red[warp][2] = c; sh.red[warp][3] = d; }
     wsync();
     r.m0_all = 0.0f; r.m0_ge28 = 0.0f; r.m1_all = 0.0f; r.m1_ge28 = 0.0f; r.mx = 0.0f; r.en = 0.0f;

@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--workload", default="flex_rx", choices=["flex_rx", "detector"],
                     help="flex_rx = configs[2] (default, the headline metric); detector = configs[1] bulk frame_detector_cc")
     ap.add_argument("--lanes", type=int, default=0, help="pipeline lanes per receiver handle (0 = library default)")
+    ap.add_argument("--e2e-lanes", type=int, default=0, help="lanes of the host-buffer (e2e) receiver (0 = library default)")
     ap.add_argument("--no-pipeline", action="store_true", help="use lqb_rx_execute per step instead of submit/collect")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -495,7 +496,7 @@ def main():
         Ne = min(args.e2e_samples, N)
         host = torch.empty((S, Ne), dtype=torch.complex64).pin_memory()
         host.copy_(cap[:, :Ne])
-        rx2 = capi.Rx(S, device=local, max_frame_samples=65536, flags=0, cuda_stream=cs.cuda_stream, lanes=args.lanes)
+        rx2 = capi.Rx(S, device=local, max_frame_samples=65536, flags=0, cuda_stream=cs.cuda_stream, lanes=args.e2e_lanes or args.lanes)
         for _ in range(max(1, args.warmup)):
             rx2.execute_dense_ptr(host.data_ptr(), Ne, Ne, capi.MEM_HOST)
         torch.cuda.synchronize(dev)
@@ -528,7 +529,7 @@ def main():
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e = {"value": world * S * Ne * args.steps / (float(te[0]) / 1e3) / 1e6, "unit": "Msps",
                "h2d_bytes_per_step": S * Ne * 8, "d2h_bytes_per_step": d2h // max(args.steps, 1),
-               "samples_per_stream_per_step": Ne}
+               "samples_per_stream_per_step": Ne, "lanes": rx2.lanes()}
         rx2.close()
         del host
 
@@ -597,6 +598,19 @@ def main():
                         "not HBM-bound: see kernels[0].fp32_frac; whole-step HBM fraction in step_hbm_frac"}
     roof["step_hbm_gbs"] = step_bytes / secs / 1e9
     roof["step_hbm_frac"] = roof["step_hbm_gbs"] / hbm_peak
+    # measured DRAM traffic of the dominant kernel (one `ncu --set full` capture of this workload, committed under
+    # profiles/): reported next to the algorithmic bytes so that wasted re-reads would show
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+        if tj["config"]["streams"] == S and tj["config"]["samples"] == N:
+            kname = {0: "k_seek", 1: "k_mf"}.get(dom)
+            if kname in tj["kernels"]:
+                roof["traffic"] = tj["kernels"][kname]["dram_gb_per_launch"] * 1e9
+                roof["traffic_unit"] = "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu)"
+                roof["algorithmic_bytes"] = (win_bytes if dom == 0 else mf_bytes) / args.steps
+                roof["traffic_source"] = "profiles/roofline_traffic.json"
+    except Exception:
+        pass
 
     # ---- CPU baseline on a bounded sample of the same capture (rank 0, N = 1 only)
     cpu = None

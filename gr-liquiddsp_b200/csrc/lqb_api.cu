@@ -224,8 +224,9 @@ struct Front {
         return 0;
     }
     // stage inputs; fills d_io; returns total samples via *total
-    int feed(uint32_t n, const uint32_t *ids, const float *const *iq, const uint64_t *ns, int mem, uint64_t *total, uint64_t *max_n)
+    int feed(uint32_t n, const uint32_t *ids, const float *const *iq, const uint64_t *ns, int mem, uint64_t *total, uint64_t *max_n, cudaStream_t cs = nullptr)
     {
+        cudaStream_t stream = cs ? cs : this->stream;     // (shadows the member: copies go where the caller says)
         if (!n) { *total = 0; *max_n = 0; return 0; }
         if (n > n_streams) return fail(LQB_EINVAL, "more entries than streams");
         DevBuf<StreamIO> &d_io = io[cur].d_io;
@@ -245,17 +246,31 @@ struct Front {
         }
         if (mem == LQB_MEM_HOST) {
             if (int e = d_stage.reserve(tot + 1)) return e;
-            uint64_t off = 0;
-            uint32_t i = 0;
-            while (i < n) {                         // merge runs that are contiguous in host memory into one copy
-                uint32_t j = i; uint64_t run = ns[i];
-                while (j + 1 < n && iq[j + 1] == iq[j] + 2 * ns[j]) { ++j; run += ns[j]; }
-                if (run) CU(cudaMemcpyAsync(d_stage.p + off, iq[i], run * sizeof(float2), cudaMemcpyHostToDevice, stream));
-                for (uint32_t k = i; k <= j; ++k) {
-                    h_io.p[k].in = d_stage.p + off; h_io.p[k].n_in = ns[k]; h_io.p[k].stream = ids ? ids[k] : k; h_io.p[k].pad = 0;
-                    off += ns[k];
+            // equal-length streams at a constant pitch in host memory (the dense layout, also after the lane split):
+            // one strided 2-D copy instead of one call per stream
+            bool regular = n >= 2 && ns[0] > 0;
+            const ptrdiff_t pitch = regular ? (iq[1] - iq[0]) : 0;
+            for (uint32_t i = 1; i < n && regular; ++i) regular = ns[i] == ns[0] && (iq[i] - iq[i - 1]) == pitch;
+            regular = regular && pitch >= (ptrdiff_t)(2 * ns[0]);
+            if (regular) {
+                const size_t row = ns[0] * sizeof(float2);
+                CU(cudaMemcpy2DAsync(d_stage.p, row, iq[0], (size_t)pitch * sizeof(float), row, n, cudaMemcpyHostToDevice, stream));
+                for (uint32_t k = 0; k < n; ++k) {
+                    h_io.p[k].in = d_stage.p + (size_t)k * ns[0]; h_io.p[k].n_in = ns[k]; h_io.p[k].stream = ids ? ids[k] : k; h_io.p[k].pad = 0;
                 }
-                i = j + 1;
+            } else {
+                uint64_t off = 0;
+                uint32_t i = 0;
+                while (i < n) {                         // merge runs that are contiguous in host memory into one copy
+                    uint32_t j = i; uint64_t run = ns[i];
+                    while (j + 1 < n && iq[j + 1] == iq[j] + 2 * ns[j]) { ++j; run += ns[j]; }
+                    if (run) CU(cudaMemcpyAsync(d_stage.p + off, iq[i], run * sizeof(float2), cudaMemcpyHostToDevice, stream));
+                    for (uint32_t k = i; k <= j; ++k) {
+                        h_io.p[k].in = d_stage.p + off; h_io.p[k].n_in = ns[k]; h_io.p[k].stream = ids ? ids[k] : k; h_io.p[k].pad = 0;
+                        off += ns[k];
+                    }
+                    i = j + 1;
+                }
             }
         } else {
             for (uint32_t i = 0; i < n; ++i) {
@@ -352,12 +367,14 @@ struct RxGen {
     cudaEvent_t ev[7] = {};
     cudaEvent_t mf_done = nullptr;        // the matched filter (the only payload kernel that reads input / carry) has run
     cudaEvent_t done = nullptr;           // results are on the host
+    cudaEvent_t staged = nullptr;         // inputs and the I/O list are on the device
     bool mf_pending = false;
     float ms[6] = {};
     uint64_t work[6] = {};
     SeekParams sp;
     size_t max_frames = 0;
     uint64_t total = 0;
+    std::vector<uint64_t> ns_copy;        // sample counts of the fed streams (separate pre-filter kernel only)
     void release()
     {
         d_frames.release(); h_frames.release(); d_syms.release(); h_syms.release();
@@ -366,12 +383,14 @@ struct RxGen {
         for (auto &e : ev) if (e) cudaEventDestroy(e);
         if (mf_done) cudaEventDestroy(mf_done);
         if (done) cudaEventDestroy(done);
+        if (staged) cudaEventDestroy(staged);
     }
 };
 
 struct RxLane {
     Front f;
     cudaStream_t pay = nullptr;           // payload + gather stream (higher priority than the search stream)
+    cudaStream_t copy = nullptr;          // input staging (H2D) stream: the next call's samples arrive under this call's search
     bool own_pay = false;
     unsigned flags = 0;
     unsigned lane = 0, n_lanes = 1;
@@ -392,6 +411,7 @@ struct RxLane {
         for (auto &x : g) x.release();
         d_ilv.release();
         if (own_pay && pay) cudaStreamDestroy(pay);
+        if (copy) { cudaStreamSynchronize(copy); cudaStreamDestroy(copy); }
         f.destroy();
     }
 
@@ -411,8 +431,8 @@ struct RxLane {
         return off;
     }
 
-    // phase A: stage the inputs and queue the search on the lane's search stream
-    int phase_seek(int mem, unsigned gen)
+    // phase A1: stage the inputs (H2D on the copy stream, so they travel under the previous call's search)
+    int phase_stage(int mem, unsigned gen)
     {
         RxGen &G = g[gen];
         f.cur = gen;
@@ -423,32 +443,46 @@ struct RxLane {
         std::memset(G.work, 0, sizeof G.work);
         G.total = 0;
         if (!n) return 0;
-        cudaStream_t st = f.stream;
         uint64_t max_n = 0;
-        if (int e = f.feed(n, ids.data(), iq.data(), ns.data(), mem, &G.total, &max_n)) return e;
+        if (int e = f.feed(n, ids.data(), iq.data(), ns.data(), mem, &G.total, &max_n, copy)) return e;
+        CU(cudaEventRecord(G.staged, copy));
         // upper bound on frames: a frame spans at least 618 samples
         G.max_frames = 0;
         for (uint32_t i = 0; i < n; ++i) G.max_frames += (size_t)((ns[i] + f.carry_cap) / 600 + 2);
         if (int e = G.d_frames.reserve(G.max_frames)) return e;
         if (int e = G.h_frames.reserve(G.max_frames)) return e;
         if (int e = G.d_views.reserve(n)) return e;
+        G.ns_copy = ns;
+        return 0;
+    }
+
+    // phase A2: queue the search and the carry update on the lane's search stream
+    int phase_search(unsigned gen)
+    {
+        RxGen &G = g[gen];
+        f.cur = gen;
+        const uint32_t n = G.n_fed;
+        if (!n) return 0;
+        cudaStream_t st = f.stream;
+        CU(cudaStreamWaitEvent(st, G.staged, 0));
         G.sp.views = G.d_views.p;
         G.sp.tables = f.d_tables; G.sp.states = f.d_states; G.sp.io = f.io[f.cur].d_io.p;
         G.sp.carry[0] = f.d_carry[0]; G.sp.carry[1] = f.d_carry[1]; G.sp.carry_cap = f.carry_cap;
         G.sp.det_mode = 0; G.sp.frames = G.d_frames.p; G.sp.detections = nullptr;
         G.sp.n_out = f.io[f.cur].d_count; G.sp.max_out = (unsigned)G.max_frames;
         CU(cudaEventRecord(G.ev[0], st));
-        if (int e = f.run_coarse(n, ns.data(), G.sp)) return e;
+        if (int e = f.run_coarse(n, G.ns_copy.data(), G.sp)) return e;
         CU(cudaMemsetAsync(f.io[f.cur].d_count, 0, 8 * sizeof(unsigned), st));
         launch_seek(G.sp, n, st); f.launches++;
         CU(cudaEventRecord(G.ev[1], st));
-        CU(cudaMemcpyAsync(f.io[f.cur].h_count, f.io[f.cur].d_count, 8 * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+        launch_copy(f.io[f.cur].h_count, f.io[f.cur].d_count, 8 * sizeof(unsigned), st);
         // The unconsumed tails move to the other carry buffer right away, so that the next call can be searched while this
         // call's payload chain is still running.  That buffer is the one the PREVIOUS call's matched filter reads: wait for it.
         RxGen &prev = g[gen ^ 1u];
         if (prev.mf_pending) { CU(cudaStreamWaitEvent(st, prev.mf_done, 0)); prev.mf_pending = false; }
         launch_carry(G.sp, n, st); f.launches++;
-        CU(cudaMemcpyAsync(f.h_states, f.d_states, (size_t)f.n_streams * sizeof(StreamState), cudaMemcpyDeviceToHost, st));
+        if (G.sp.coarse == 1)       // only the separate pre-filter kernel plans from the host mirror of the stream states
+            CU(cudaMemcpyAsync(f.h_states, f.d_states, (size_t)f.n_streams * sizeof(StreamState), cudaMemcpyDeviceToHost, st));
         return 0;
     }
 
@@ -468,7 +502,7 @@ struct RxLane {
         G.work[5] = G.sp.coarse == 2 ? (uint64_t)f.io[f.cur].h_count[4] : (G.sp.coarse == 1 ? (uint64_t)f.h_tpre.p[n] : 0);
         FrameDesc *fr = G.h_frames.p;
         if (nf) {
-            CU(cudaMemcpyAsync(fr, G.d_frames.p, nf * sizeof(FrameDesc), cudaMemcpyDeviceToHost, st));
+            launch_copy(fr, G.d_frames.p, nf * sizeof(FrameDesc), st);
             CU(cudaStreamSynchronize(st));
         }
 
@@ -543,8 +577,8 @@ struct RxLane {
             if (int e = G.d_lists.reserve(ltot + 1)) return e;
             for (size_t k = 0; k < parts.size(); ++k)
                 if (!parts[k]->empty()) std::memcpy(G.h_lists.p + loff[k], parts[k]->data(), parts[k]->size() * sizeof(unsigned));
-            CU(cudaMemcpyAsync(G.d_lists.p, G.h_lists.p, ltot * sizeof(unsigned), cudaMemcpyHostToDevice, ps));
-            CU(cudaMemcpyAsync(G.d_frames.p, fr, nf * sizeof(FrameDesc), cudaMemcpyHostToDevice, ps));
+            launch_copy(G.d_lists.p, G.h_lists.p, ltot * sizeof(unsigned), ps);
+            launch_copy(G.d_frames.p, fr, nf * sizeof(FrameDesc), ps);
 
             PayloadParams pp;
             pp.tables = f.d_tables; pp.views = G.d_views.p;
@@ -624,6 +658,7 @@ struct lqb_rx_s {
     // two calls may be in flight: `submit_gen` is the generation the next submit uses, `pending` how many
     // submits have not been collected, `cur_gen` the generation whose results poll / counts / timing report
     unsigned submit_gen = 0, pending = 0, cur_gen = 0;
+    bool planned[2] = { false, false };      // the payload chain of that generation has been planned and queued
     std::vector<std::pair<unsigned, unsigned>> order;    // (lane, frame index) sorted by (stream, seq)
     std::vector<unsigned> stream_count;
     unsigned n_frames = 0;
@@ -636,7 +671,20 @@ struct lqb_rx_s {
     unsigned global_stream(unsigned lane, unsigned local) const { return global_of[lane][local]; }
     void sync_all()
     {
-        for (auto *l : lanes) { if (l->f.stream) cudaStreamSynchronize(l->f.stream); if (l->pay) cudaStreamSynchronize(l->pay); }
+        for (auto *l : lanes) {
+            if (l->copy) cudaStreamSynchronize(l->copy);
+            if (l->f.stream) cudaStreamSynchronize(l->f.stream);
+            if (l->pay) cudaStreamSynchronize(l->pay);
+        }
+    }
+    // wait for the search of generation `gen`, plan its payload work on the host and queue it
+    int plan(unsigned gen)
+    {
+        if (planned[gen]) return 0;
+        int rc = 0;
+        for (auto *l : lanes) if ((rc = l->phase_payload(gen))) break;
+        planned[gen] = true;
+        return rc;
     }
 };
 
@@ -716,10 +764,12 @@ lqb_rx lqb_rx_create(const lqb_rx_opts *o)
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
         if (cudaStreamCreateWithPriority(&ln->pay, cudaStreamNonBlocking, hi) != cudaSuccess) { fail(LQB_ECUDA, "cudaStreamCreate failed"); ok = false; break; }
         ln->own_pay = true;
+        if (cudaStreamCreateWithPriority(&ln->copy, cudaStreamNonBlocking, hi) != cudaSuccess) { fail(LQB_ECUDA, "cudaStreamCreate failed"); ok = false; break; }
         for (auto &G : ln->g) {
             for (auto &ev : G.ev) ok = ok && cudaEventCreate(&ev) == cudaSuccess;
             ok = ok && cudaEventCreateWithFlags(&G.mf_done, cudaEventDisableTiming) == cudaSuccess;
             ok = ok && cudaEventCreateWithFlags(&G.done, cudaEventDisableTiming) == cudaSuccess;
+            ok = ok && cudaEventCreateWithFlags(&G.staged, cudaEventDisableTiming) == cudaSuccess;
         }
     }
     delete T;
@@ -745,9 +795,16 @@ int lqb_rx_collect(lqb_rx h)
     h->n_frames = 0; h->n_valid = 0; h->order.clear();
     std::memset(h->ms, 0, sizeof h->ms);
     std::memset(h->work, 0, sizeof h->work);
-    int rc = 0;
-    for (auto *l : h->lanes) if ((rc = l->phase_finish(gen))) break;
-    if (rc) { const std::string keep = g_err; h->sync_all(); cudaGetLastError(); g_err = keep; return rc; }
+    int rc = h->plan(gen);
+    if (!rc) for (auto *l : h->lanes) if ((rc = l->phase_finish(gen))) break;
+    if (rc) {
+        const std::string keep = g_err;
+        h->sync_all(); cudaGetLastError();
+        for (auto *l : h->lanes) for (auto &G : l->g) { G.mf_pending = false; G.n_fed = 0; G.n_frames = 0; }
+        h->pending = 0;
+        g_err = keep;
+        return rc;
+    }
     if (h->ev_in) {
         // the caller's stream continues after everything this call queued
         for (unsigned l = 0; l < L; ++l) {
@@ -811,13 +868,18 @@ int lqb_rx_submit(lqb_rx h, uint32_t n, const uint32_t *ids, const float *const 
     // inputs produced on the caller's stream must be complete before any lane reads them
     if (h->ev_in && n) {
         CU(cudaEventRecord(h->ev_in, h->user_stream));
-        for (auto *l : h->lanes) CU(cudaStreamWaitEvent(l->f.stream, h->ev_in, 0));
+        for (auto *l : h->lanes) { CU(cudaStreamWaitEvent(l->copy, h->ev_in, 0)); CU(cudaStreamWaitEvent(l->f.stream, h->ev_in, 0)); }
     }
     int rc = 0;
     g_trace.start();
-    for (auto *l : h->lanes) if ((rc = l->phase_seek(mem, gen))) break;
-    g_trace.mark("seek queued (all lanes)", 0);
-    if (!rc) for (auto *l : h->lanes) if ((rc = l->phase_payload(gen))) break;
+    // 1. the new samples start travelling (copy streams) while the previous call is still being searched;
+    // 2. the previous call's search is awaited, its payload work planned and queued;
+    // 3. this call's search is queued behind its own copies.
+    for (auto *l : h->lanes) if ((rc = l->phase_stage(mem, gen))) break;
+    g_trace.mark("inputs queued (all lanes)", 0);
+    if (!rc && h->pending == 1) rc = h->plan(gen ^ 1u);
+    if (!rc) for (auto *l : h->lanes) if ((rc = l->phase_search(gen))) break;
+    g_trace.mark("search queued (all lanes)", 0);
     if (rc) {
         const std::string keep = g_err;
         h->sync_all(); cudaGetLastError();
@@ -826,6 +888,7 @@ int lqb_rx_submit(lqb_rx h, uint32_t n, const uint32_t *ids, const float *const 
         g_err = keep;
         return rc;
     }
+    h->planned[gen] = false;
     h->submit_gen ^= 1u;
     h->pending++;
     return 0;

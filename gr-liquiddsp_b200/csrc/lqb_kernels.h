@@ -63,6 +63,8 @@ void launch_coarse(const CoarseParams &P, cudaStream_t s);
 void build_coarse_bmat(const float *s_re, const float *s_im, int range, std::vector<unsigned short> &out);
 void launch_carry(const SeekParams &P, unsigned n_io, cudaStream_t s);
 
+// device <-> pinned-host copy of small control data by a kernel (never queues behind bulk DMA copies)
+void launch_copy(void *dst, const void *src, size_t bytes, cudaStream_t s);
 void launch_mf(const PayloadParams &P, cudaStream_t s);
 // list: frames grouped by modulation; span_start: exclusive prefix (n + 1) of 4096-symbol spans over that list
 void launch_pll(const PayloadParams &P, const unsigned *list, const unsigned *span_start, unsigned n, unsigned n_spans, cudaStream_t s);

@@ -152,14 +152,15 @@ int    lqb_rx_execute(lqb_rx h, uint32_t n, const uint32_t *stream_ids,
                       const float *const *iq, const uint64_t *n_samples, int mem);
 /* Dense form: all n_streams streams, stream s at iq + 2*s*stride_samples floats, n_samples each */
 int    lqb_rx_execute_dense(lqb_rx h, const float *iq, uint64_t stride_samples, uint64_t n_samples, int mem);
-/* Pipelined form of execute for callers that stream batch after batch: submit() searches the new samples and
- * queues the payload work (matched filter, PLL, FEC, CRC, result copies) but returns as soon as the search is done;
- * collect() waits for the oldest submitted call and makes its frames current for poll / counts / timing / work.
- * Up to two calls may be in flight, so the payload work of call k runs under the search of call k+1:
+/* Pipelined form of execute for callers that stream batch after batch.  submit() queues the input copies and the
+ * search of the new samples and returns without waiting for them; collect() waits for the oldest submitted call and
+ * makes its frames current for poll / counts / timing / work.  Up to two calls may be in flight:
  *     submit(k); submit(k+1); collect() -> k; poll...; submit(k+2); collect() -> k+1; ...
- * execute() == submit() + collect().  Results are identical to execute()'s.  Device input buffers of a call must
- * stay valid until its collect() returns (host inputs are staged by submit and may be reused at once); result
- * buffers of a collected call stay valid until the next-but-one submit.  A third submit returns LQB_EBUSY. */
+ * so the H2D copy of call k+1 runs under the search of call k, and the payload work of call k (matched filter, PLL,
+ * FEC, CRC, result copies) under the search of call k+1.  execute() == submit() + collect(); results are identical.
+ * Host input buffers may be reused as soon as submit returns only if they are pageable; pinned host buffers and
+ * device buffers must stay untouched until the matching collect() returns.  Result buffers of a collected call stay
+ * valid until the next-but-one submit.  A third submit without a collect returns LQB_EBUSY. */
 int    lqb_rx_submit(lqb_rx h, uint32_t n, const uint32_t *stream_ids,
                      const float *const *iq, const uint64_t *n_samples, int mem);
 int    lqb_rx_submit_dense(lqb_rx h, const float *iq, uint64_t stride_samples, uint64_t n_samples, int mem);

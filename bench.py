@@ -27,6 +27,7 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "gr-liquiddsp_b200", "python"))
+os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
 
 PSK4, CRC24, V27, RS8 = 2, 5, 11, 27
 PAYLOAD = 1500

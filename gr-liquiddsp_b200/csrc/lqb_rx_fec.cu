@@ -306,7 +306,7 @@ k_viterbi(PayloadParams P, const unsigned *__restrict__ list, unsigned n_list, i
 // compile-time constant, the lane part a per-thread mask XORed into the received symbols once per step.
 // Decisions are stored per position ([step][codeword] 64-bit, lane l owns bits 16 l .. 16 l + 15); the
 // traceback undoes the rotation.  Same integer metrics, comparisons and tie-breaks as the specification.
-constexpr int kV4Lanes = 4, kV4Pos = 16, kV4PosBits = 4;
+constexpr int kV4Lanes = 4, kV4PosBits = 4;
 
 __host__ __device__ constexpr unsigned v4_par6(unsigned x) { x ^= x >> 4; x ^= x >> 2; x ^= x >> 1; return x & 1u; }
 // position bits that enter the branch label of polynomial `poly` in phase r (label = parity(2 i & poly), 2 i = rotl6(p, r + 1) & ~1)
@@ -324,56 +324,113 @@ __host__ __device__ constexpr unsigned v4_label(int r, unsigned pos_bits)
     return v4_par6(pos_bits & v4_phase_mask(0x6d, r)) | (v4_par6(pos_bits & v4_phase_mask(0x4f, r)) << 1);
 }
 
-// One trellis step.  Decisions are collected as sign bits: for every position the candidate difference is formed so
-// that it is negative exactly when the specification's comparison m0 > m1 holds, and its top bit is funnel-shifted
-// into the decision word, positions 15 down to 0 (so bit j of the word is the decision of position j).
-template <int R>
-__device__ __forceinline__ void v4_step(unsigned (&M)[kV4Pos], unsigned s0, unsigned s1, int upper_sign, unsigned &dec)
+// Packed 16-bit path metrics (profiles/r01_notes.md v13).  A lane keeps its 16 positions in eight registers, position j
+// in the low half of word j & 7 when j < 8 and in the high half otherwise, so one VIADD.16x2 / VIMNMX.U16x2 serves two
+// positions.  16 bits are enough because the metric spread of a K = 7 trellis is at most 6 * 510 (every state is
+// reachable from the best state of six steps ago and metrics never decrease): the common minimum is subtracted every 96
+// steps, which leaves 3060 + 96 * 510 < 65536 and changes no comparison.  Same integer metrics relative to each other,
+// same comparisons and tie-breaks as the specification's 32-bit decoder.
+__device__ __forceinline__ unsigned v2_add(unsigned a, unsigned b) { return __vadd2(a, b); }
+__device__ __forceinline__ unsigned v2_min(unsigned a, unsigned b) { return __vminu2(a, b); }
+
+// packed branch metrics by label for one step: Ap[lab] = metric(lab) in the low half (positions 0..7 of the lane) and
+// metric(lab ^ delta) in the high half (positions 8..15, whose labels differ by the constant delta of the phase)
+__host__ __device__ inline uint4 v4_metrics(int r, unsigned s0, unsigned s1)
 {
-    constexpr int k = 5 - R;                       // position bit that separates the two predecessors
+    const unsigned delta = v4_label(r, 8u);
     unsigned A[4];
     A[0] = s0 + s1; A[1] = (s0 ^ 255u) + s1; A[2] = s0 + (s1 ^ 255u); A[3] = 510u - A[0];
-    unsigned diff[kV4Pos];
-    if constexpr (k < kV4PosBits) {
+    return make_uint4(A[0] | (A[0 ^ delta] << 16), A[1] | (A[1 ^ delta] << 16), A[2] | (A[2 ^ delta] << 16), A[3] | (A[3 ^ delta] << 16));
+}
+
+// One trellis step.  G[w] receives, in its two sign bits (15, 31), the RAW decision flags of positions w and w + 8:
+// a candidate difference minus one, whose sign is the complement of "first candidate > second" for the position that
+// keeps successor 2i and the condition itself for the position that keeps 2i + 1 in the exchange phases; the caller
+// undoes that with a constant XOR on the packed word.
+template <int R>
+__device__ __forceinline__ void v4_step(unsigned (&W)[8], const uint4 c, unsigned role, unsigned (&G)[8])
+{
+    constexpr int k = 5 - R;                       // position bit that separates the two predecessors
+    const unsigned Ap[4] = { c.x, c.y, c.z, c.w };
+    if constexpr (k < 3) {
 #pragma unroll
-        for (int j = 0; j < kV4Pos; ++j) {
-            if (j & (1 << k)) continue;
-            const int j1 = j | (1 << k);
-            const unsigned lab = v4_label(R, (unsigned)j);
-            const unsigned a = A[lab], b = A[3 - lab];
-            const unsigned m0 = M[j] + a, m1 = M[j1] + b;         // into successor 2i   (kept at position j)
-            const unsigned q0 = M[j] + b, q1 = M[j1] + a;         // into successor 2i+1 (kept at position j1)
-            diff[j] = m1 - m0;                                     // negative <=> m0 > m1
-            diff[j1] = q1 - q0;
-            M[j] = min(m0, m1);
-            M[j1] = min(q0, q1);
+        for (int w = 0; w < 8; ++w) {
+            if (w & (1 << k)) continue;
+            const int w1 = w | (1 << k);
+            const unsigned lab = v4_label(R, (unsigned)w);
+            const unsigned a = Ap[lab], b = Ap[3 - lab];
+            const unsigned m0 = v2_add(W[w], a), m1 = v2_add(W[w1], b);     // into successor 2i   (kept at w)
+            const unsigned q0 = v2_add(W[w], b), q1 = v2_add(W[w1], a);     // into successor 2i+1 (kept at w1)
+            G[w] = v2_add(m0, ~m1);                                          // m0 - m1 - 1: sign clear <=> m0 > m1
+            G[w1] = v2_add(q0, ~q1);
+            W[w] = v2_min(m0, m1);
+            W[w1] = v2_min(q0, q1);
         }
     } else {
-        constexpr int lb = k - kV4PosBits;         // lane bit exchanged in this phase
 #pragma unroll
-        for (int j = 0; j < kV4Pos; ++j) {
-            const unsigned lab = v4_label(R, (unsigned)j);
-            const unsigned a = A[lab], b = A[3 - lab];
-            const unsigned other = __shfl_xor_sync(0xffffffffu, M[j], 1 << lb);
-            const unsigned c_own = M[j] + a, c_oth = other + b;
-            // lower lane keeps successor 2i:   decision = own + a > other + b  <=>  (other + b) - (own + a) < 0
-            // upper lane keeps successor 2i+1: decision = other + b > own + a  <=>  (own + a) - (other + b) < 0
-            diff[j] = (unsigned)((int)(c_oth - c_own) * upper_sign);
-            M[j] = min(c_own, c_oth);
+        for (int w = 0; w < 8; ++w) {
+            const unsigned lab = v4_label(R, (unsigned)w);
+            const unsigned a = Ap[lab], b = Ap[3 - lab];
+            unsigned other;
+            if constexpr (k == 3) other = __byte_perm(W[w], 0u, 0x1032);
+            else other = __shfl_xor_sync(0xffffffffu, W[w], 1 << (k - kV4PosBits));
+            const unsigned c_own = v2_add(W[w], a), c_oth = v2_add(other, b);
+            // F = own - oth - 1.  Lower position (keeps 2i): decision own > oth <=> sign(F) clear.
+            // Upper position (keeps 2i+1): decision oth > own <=> F + 1 < 0 <=> sign(F + 1) set.
+            G[w] = v2_add(v2_add(c_own, ~c_oth), role);
+            W[w] = v2_min(c_own, c_oth);
         }
     }
-    unsigned d = 0;
-#pragma unroll
-    for (int j = kV4Pos - 1; j >= 0; --j) d = __funnelshift_l(diff[j], d, 1);
-    dec = d;
+}
+
+// sign bits of eight packed words -> the high nibble of each byte of one word: position p = w + 8 h lands in byte
+// 2 (w & 1) + h, bit 7 - (w >> 1); the low nibbles are garbage
+__device__ __forceinline__ unsigned v4_pack(const unsigned (&G)[8])
+{
+    const unsigned p0 = __byte_perm(G[0], G[1], 0x7531), p1 = __byte_perm(G[2], G[3], 0x7531);
+    const unsigned p2 = __byte_perm(G[4], G[5], 0x7531), p3 = __byte_perm(G[6], G[7], 0x7531);
+    unsigned r = (p0 & 0x80808080u) | ((p1 >> 1) & ~0x80808080u);
+    r = (r & 0xc0c0c0c0u) | ((p2 >> 2) & ~0xc0c0c0c0u);
+    r = (r & 0xe0e0e0e0u) | ((p3 >> 3) & ~0xe0e0e0e0u);
+    return r;
+}
+
+// Traceback coordinates.  The walk keeps u, a bit permutation of the POSITION of the current state (position =
+// rotr6(state, phase)): in position coordinates one traceback step replaces a single bit by the decision bit, and u is
+// laid out so that the decision can be fetched from the pair word with byte permutes:
+//   u5 u4 = lane that owns the position, u3 u2 = (p0, p3) = byte of that lane's word, u1 u0 = ~(p2 p1) = bit in the nibble.
+__host__ __device__ constexpr int v4_ubit(int pos_bit) { return pos_bit == 0 ? 3 : pos_bit == 1 ? 0 : pos_bit == 2 ? 1 : pos_bit == 3 ? 2 : pos_bit; }
+__host__ __device__ constexpr bool v4_uinv(int pos_bit) { return pos_bit == 1 || pos_bit == 2; }
+constexpr unsigned kV4UZero = 3u;                    // u of position 0
+
+// one traceback step at chunk offset J (step = 24 c + J): reads the decision of the current position from the pair
+// word, shifts it into the output accumulator and replaces the position bit that leaves the state
+template <int J>
+__device__ __forceinline__ void v4_back(unsigned &u, unsigned &acc, const uint4 &pw)
+{
+    constexpr int ph = (J + 1) % 6;                 // rotation of this step
+    constexpr int kb = (6 - ph) % 6;                // position bit replaced by the decision
+    constexpr int ub = v4_ubit(kb);
+    const unsigned sel = (u >> 2) & 7u;
+    const unsigned lo = __byte_perm(pw.x, pw.y, sel), hi = __byte_perm(pw.z, pw.w, sel);
+    const unsigned byte = __byte_perm(lo, hi, (u >> 3) & 4u);
+    // even steps sit in the high nibbles
+    const unsigned raw = byte >> ((J & 1) ? (u & 3u) : ((u & 3u) | 4u));       // decision in bit 0, garbage above
+    acc = __funnelshift_r(acc, raw, 1);
+    const unsigned t = raw << ub;
+    if (v4_uinv(kb)) u = (u & ~(1u << ub)) | (~t & (1u << ub));
+    else u = (u & ~(1u << ub)) | (t & (1u << ub));
 }
 
 constexpr int kV4Threads = 64;
+constexpr unsigned kV4Renorm = 96;                    // steps between metric renormalisations (multiple of 6)
+constexpr int kV4Warm = 96;                           // speculative traceback warm-up, steps
 
 template <bool PUNCT>
 __global__ void __launch_bounds__(kV4Threads)
-k_viterbi27x4(PayloadParams P, const unsigned *__restrict__ list, unsigned n_list, int stage, unsigned short *__restrict__ dec)
+k_viterbi27x4(PayloadParams P, const unsigned *__restrict__ list, unsigned n_list, int stage, unsigned *__restrict__ dec)
 {
+    __shared__ uint4 lut[kV4Lanes][6][4];           // [lane][phase][two received bits] -> v4_metrics
     const unsigned gt = blockIdx.x * kV4Threads + threadIdx.x;
     const unsigned l = gt % kV4Lanes;
     unsigned gi = gt / kV4Lanes;
@@ -384,97 +441,182 @@ k_viterbi27x4(PayloadParams P, const unsigned *__restrict__ list, unsigned n_lis
     const FrameDesc &d = P.frames[list[gi]];
     const StageIO io = stage_io(P, d, stage);
     const ConvSpec cs = conv_spec(io.fs);
-    const unsigned nbits = 8 * io.dec_len, T = nbits + 6;
+    const unsigned nbits = 8 * io.dec_len, T = nbits + 6;          // T is even
     unsigned Tw = T;                                  // longest codeword in this warp
 #pragma unroll
     for (int m = 16; m >= 1; m >>= 1) Tw = max(Tw, __shfl_xor_sync(0xffffffffu, Tw, m));
     unsigned per = 0, pre[8];
     for (unsigned c = 0; c < cs.P; ++c) { pre[c] = per; per += ((cs.keep0 >> c) & 1u) + ((cs.keep1 >> c) & 1u); }
     const unsigned char *enc = io.src;
-    const unsigned enc_words = (io.enc_len + 3u) / 4u;
+    const unsigned enc_words = max((io.enc_len + 3u) / 4u, 1u);
 
     // lane part of the branch labels, as XOR masks on the received symbols, per phase
-    unsigned mk0[6], mk1[6];
-    int up[6];                                       // -1 when this lane holds the state-bit-5 = 1 predecessors in phase r
-#pragma unroll
-    for (int r = 0; r < 6; ++r) {
-        const unsigned lb = l << kV4PosBits;
-        mk0[r] = (__popc(lb & v4_phase_mask(0x6d, r)) & 1) ? 255u : 0u;
-        mk1[r] = (__popc(lb & v4_phase_mask(0x4f, r)) & 1) ? 255u : 0u;
-        const int k = 5 - r;
-        up[r] = (k >= kV4PosBits && ((l >> (k - kV4PosBits)) & 1u)) ? -1 : 1;
+    auto lane_mask = [](unsigned lane, int r, unsigned poly) { return (__popc((lane << kV4PosBits) & v4_phase_mask(poly, r)) & 1) ? 255u : 0u; };
+    if (!PUNCT) {
+        for (unsigned i = threadIdx.x; i < kV4Lanes * 6 * 4; i += kV4Threads) {
+            const unsigned ll = i / 24u, v = i & 3u;
+            const int r = (int)((i >> 2) % 6u);
+            lut[ll][r][v] = v4_metrics(r, ((v & 2u) ? 255u : 0u) ^ lane_mask(ll, r, 0x6d), ((v & 1u) ? 255u : 0u) ^ lane_mask(ll, r, 0x4f));
+        }
+        __syncthreads();
     }
-    unsigned M[kV4Pos];
+    unsigned mk0[6], mk1[6];
 #pragma unroll
-    for (int j = 0; j < kV4Pos; ++j) M[j] = 63u;
-    if (l == 0) M[0] = 0u;                          // state 0 sits at position 0 at t = 0
+    for (int r = 0; r < 6; ++r) { mk0[r] = lane_mask(l, r, 0x6d); mk1[r] = lane_mask(l, r, 0x4f); }
+    // phases 0 and 1 exchange with the lane that differs in bit 1 / bit 0; the lane holding the upper predecessors
+    // adds one to the raw difference (see v4_step) and its flags are stored uninverted
+    const unsigned up5 = (l >> 1) & 1u, up4 = l & 1u;
+    const unsigned role0 = up5 ? 0x00010001u : 0u, role1 = up4 ? 0x00010001u : 0u;
+    const unsigned xm0 = (up5 ? 0u : 0xf0f0f0f0u) | (up4 ? 0u : 0x0f0f0f0fu);     // steps 6n, 6n+1
+    constexpr unsigned xm1 = 0x00f000f0u | 0x0f0f0f0fu;                           // steps 6n+2 (halves exchange), 6n+3
+    constexpr unsigned xm2 = 0xffffffffu;                                         // steps 6n+4, 6n+5
+    unsigned W[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) W[j] = 63u | (63u << 16);
+    if (l == 0) W[0] = 63u << 16;                   // state 0 sits at position 0 at t = 0
 
     unsigned col = 0, q = 0;                        // punctured: t = q * P + col
-    unsigned word = 0, have = 0, wi = 0;            // unpunctured: 32 encoded bits, MSB first
     const unsigned *enc32 = reinterpret_cast<const unsigned *>(enc);     // byte arenas are 16-byte aligned per frame
-    auto symbols = [&](unsigned &s0, unsigned &s1) {
+    // unpunctured: the 12 encoded bits of six steps (MSB first, in the top bits), fetched one group ahead
+    auto fetch12 = [&](unsigned t0) {
+        const unsigned o = 2u * t0, idx = o >> 5;
+        const unsigned a = __byte_perm(__ldg(enc32 + min(idx, enc_words - 1u)), 0u, 0x0123);
+        const unsigned b = __byte_perm(__ldg(enc32 + min(idx + 1u, enc_words - 1u)), 0u, 0x0123);
+        return __funnelshift_l(b, a, o & 31u);
+    };
+    unsigned bits = 0, bits_next = PUNCT ? 0u : fetch12(0u);
+    const char *lut_l = reinterpret_cast<const char *>(&lut[l][0][0]);
+    auto metrics = [&](const int r, const unsigned m0, const unsigned m1) -> uint4 {
         if (PUNCT) {
             unsigned ib = q * per + pre[col];
-            s0 = 127u; s1 = 127u;
+            unsigned s0 = 127u, s1 = 127u;
             if ((cs.keep0 >> col) & 1u) { s0 = (ib >> 3) < io.enc_len ? soft_bit(enc, ib) : 0u; ++ib; }
             if ((cs.keep1 >> col) & 1u) { s1 = (ib >> 3) < io.enc_len ? soft_bit(enc, ib) : 0u; }
             if (++col == cs.P) { col = 0; ++q; }
+            return v4_metrics(r, s0 ^ m0, s1 ^ m1);
         } else {
-            if (have == 0) { word = wi < enc_words ? __byte_perm(__ldg(enc32 + wi), 0, 0x0123) : 0u; ++wi; have = 16; }
-            s0 = (unsigned)((int)word >> 31) & 255u;
-            s1 = (unsigned)((int)(word << 1) >> 31) & 255u;
-            word <<= 2; --have;
+            const int sh = 26 - 2 * r;                 // the step's two bits -> byte offset 16 * v
+            const unsigned off = (sh >= 0 ? bits >> sh : bits << -sh) & 0x30u;
+            return *reinterpret_cast<const uint4 *>(lut_l + 64 * r + off);
         }
     };
-    unsigned short *out_dec = dec + (size_t)gi * kV4Lanes + l;
+    // decisions: [step pair][codeword][lane] 32-bit words, even step in the high nibbles, odd step in the low ones
+    unsigned *out_dec = dec + (size_t)gi * kV4Lanes + l;
     const size_t dstride = (size_t)n_list * kV4Lanes;
-    unsigned t = 0;
-#define LQB_V4_STEP(R)                                                            \
+    unsigned t = 0, since = 0;
+#define LQB_V4_PAIR(R, ROLE_E, ROLE_O, XM)                                        \
     {                                                                             \
-        unsigned s0, s1, dd;                                                      \
-        symbols(s0, s1);                                                          \
-        v4_step<R>(M, s0 ^ mk0[R], s1 ^ mk1[R], up[R], dd);                       \
-        if (active && t + R < T) out_dec[(size_t)(t + R) * dstride] = (unsigned short)dd; \
+        unsigned G[8];                                                            \
+        v4_step<R>(W, metrics(R, mk0[R], mk1[R]), ROLE_E, G);                     \
+        const unsigned re = v4_pack(G);                                           \
+        v4_step<R + 1>(W, metrics(R + 1, mk0[R + 1], mk1[R + 1]), ROLE_O, G);     \
+        const unsigned ro = v4_pack(G);                                           \
+        const unsigned dd = ((re & 0xf0f0f0f0u) | ((ro >> 4) & 0x0f0f0f0fu)) ^ (XM); \
+        if (active && t + R < T) out_dec[(size_t)((t + R) >> 1) * dstride] = dd;  \
     }
-    // whole groups of six phases; steps past a codeword's end run on zero symbols and store nothing
+    // whole groups of six phases; steps past a codeword's end run on arbitrary symbols and store nothing
     for (; t < Tw; t += 6) {
-        LQB_V4_STEP(0) LQB_V4_STEP(1) LQB_V4_STEP(2) LQB_V4_STEP(3) LQB_V4_STEP(4) LQB_V4_STEP(5)
-    }
-#undef LQB_V4_STEP
-    __syncwarp();
-    if (l != 0 || !active) return;
-    // traceback from state 0 (lane 0 of the group); the decision of successor state s at step ts is bit
-    // rotr6(s, (ts + 1) mod 6) of that step's word; the bit shifted out at step ts entered at ts - 6
-    const uint2 *dec64 = reinterpret_cast<const uint2 *>(dec) + gi;
-    unsigned char *out = io.dst;
-    unsigned state = 0, byte_acc = 0;
-    long long tt = (long long)T - 1;
-    unsigned ph = (unsigned)((tt + 1) % 6);         // rotation of step tt
-    // the addresses do not depend on the state: the next eight words are requested before the current eight are walked
-    uint2 w[8], wn[8];
+        if (!PUNCT) { bits = bits_next; bits_next = fetch12(t + 6u); }
+        LQB_V4_PAIR(0, role0, role1, xm0)
+        LQB_V4_PAIR(2, 0x00010000u, 0u, xm1)
+        LQB_V4_PAIR(4, 0u, 0u, xm2)
+        since += 6;
+        if (since == kV4Renorm) {
+            since = 0;
+            unsigned mn = v2_min(v2_min(v2_min(W[0], W[1]), v2_min(W[2], W[3])), v2_min(v2_min(W[4], W[5]), v2_min(W[6], W[7])));
+            mn = v2_min(mn, __byte_perm(mn, 0u, 0x1032));
+            mn = v2_min(mn, __shfl_xor_sync(0xffffffffu, mn, 1));
+            mn = v2_min(mn, __shfl_xor_sync(0xffffffffu, mn, 2));
+            const unsigned neg = __vsub2(0u, mn);
 #pragma unroll
-    for (int kk = 0; kk < 8; ++kk) w[kk] = (tt - kk >= 0) ? dec64[(size_t)(tt - kk) * n_list] : make_uint2(0u, 0u);
-    while (tt >= 0) {
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk) wn[kk] = (tt - 8 - kk >= 0) ? dec64[(size_t)(tt - 8 - kk) * n_list] : make_uint2(0u, 0u);
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
-            const long long ts = tt - kk;
-            if (ts < 0) break;
-            const unsigned pos = ((state >> ph) | (state << (6u - ph))) & 63u;
-            const unsigned wsel = (pos & 32u) ? w[kk].y : w[kk].x;
-            const unsigned bit = (wsel >> (pos & 31u)) & 1u;
-            if (ts >= 6) {
-                const unsigned bi = (unsigned)ts - 6u;
-                byte_acc |= bit << (7 - (bi & 7u));
-                if ((bi & 7u) == 0) { out[bi >> 3] = (unsigned char)byte_acc; byte_acc = 0; }
-            }
-            state = (state >> 1) | (bit << 5);
-            ph = ph ? ph - 1u : 5u;
+            for (int j = 0; j < 8; ++j) W[j] = v2_add(W[j], neg);
         }
+    }
+#undef LQB_V4_PAIR
+    __syncwarp();
+
+    // ---- traceback, four lanes per codeword.  Lane q owns output bytes [B_q, B_q+1), i.e. steps [lo, hi) with
+    // lo = 8 B_q + 6: it starts kV4Warm..kV4Warm+23 steps above hi from an arbitrary state (the top lane: at T - 1 from
+    // state 0) and walks down to lo.  Survivor paths merge within a few constraint lengths, so the state a lane has
+    // when it reaches hi nearly always equals the state the lane above ends with; that is CHECKED afterwards, top
+    // down, and a lane whose start was wrong walks its segment again from the proven state - the output is exactly
+    // the serial traceback's.  Steps are processed in chunks of 24 (phase, byte and pair alignment all repeat).
+    const int Ti = (int)T;
+    const int lo = 8 * (int)((io.dec_len * l) >> 2) + 6, hi = 8 * (int)((io.dec_len * (l + 1u)) >> 2) + 6;
+    const uint4 *dec128 = reinterpret_cast<const uint4 *>(dec) + gi;
+    unsigned char *out = io.dst;
+    unsigned ustart = kV4UZero, uend = kV4UZero;
+    auto load4 = [&](uint4 (&w)[4], int ts_top) {     // pair words of steps ts_top, ts_top - 2, .. (ts_top odd)
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) w[kk] = wn[kk];
-        tt -= 8;
+        for (int kk = 0; kk < 4; ++kk) {
+            const int ts = ts_top - 2 * kk;
+            w[kk] = (ts >= 0 && ts < Ti) ? dec128[(size_t)(ts >> 1) * n_list] : make_uint4(0u, 0u, 0u, 0u);
+        }
+    };
+    // walk chunks c_top .. lo / 24; when the walk reaches step force_ts - 1 its state is replaced by u_force
+    auto walk = [&](int c_top, int force_ts, unsigned u_force) {
+        unsigned u = kV4UZero, acc = 0;
+        uint4 w[4], wn[4];
+        load4(w, 24 * c_top + 23);
+        const int c_bot = lo / 24;
+        for (int c = c_top; c >= c_bot; --c) {
+            const int base = 24 * c;
+            // before step base + J (J = 21, 13, 5): segment boundaries hi / lo / force_ts all lie at base + J + 1
+#define LQB_V4_MARK(J)                                                             \
+            {                                                                      \
+                const int tb = base + (J) + 1;                                     \
+                if (tb == force_ts) u = u_force;                                   \
+                if (tb == hi) ustart = u;                                          \
+                if (tb == lo) uend = u;                                            \
+            }
+            // after step base + J (J = 22, 14, 6) the accumulator's top byte is output byte (base + J - 6) / 8
+#define LQB_V4_EMIT(J)                                                             \
+            {                                                                      \
+                const int ts = base + (J);                                         \
+                if (active && ts >= lo && ts < hi) out[(ts - 6) >> 3] = (unsigned char)(acc >> 24); \
+            }
+            load4(wn, base + 15);
+            v4_back<23>(u, acc, w[0]); v4_back<22>(u, acc, w[0]); LQB_V4_EMIT(22) LQB_V4_MARK(21)
+            v4_back<21>(u, acc, w[1]); v4_back<20>(u, acc, w[1]);
+            v4_back<19>(u, acc, w[2]); v4_back<18>(u, acc, w[2]);
+            v4_back<17>(u, acc, w[3]); v4_back<16>(u, acc, w[3]);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) w[kk] = wn[kk];
+            load4(wn, base + 7);
+            v4_back<15>(u, acc, w[0]); v4_back<14>(u, acc, w[0]); LQB_V4_EMIT(14) LQB_V4_MARK(13)
+            v4_back<13>(u, acc, w[1]); v4_back<12>(u, acc, w[1]);
+            v4_back<11>(u, acc, w[2]); v4_back<10>(u, acc, w[2]);
+            v4_back<9>(u, acc, w[3]); v4_back<8>(u, acc, w[3]);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) w[kk] = wn[kk];
+            load4(wn, base - 1);
+            v4_back<7>(u, acc, w[0]); v4_back<6>(u, acc, w[0]); LQB_V4_EMIT(6) LQB_V4_MARK(5)
+            v4_back<5>(u, acc, w[1]); v4_back<4>(u, acc, w[1]);
+            v4_back<3>(u, acc, w[2]); v4_back<2>(u, acc, w[2]);
+            v4_back<1>(u, acc, w[3]); v4_back<0>(u, acc, w[3]);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) w[kk] = wn[kk];
+#undef LQB_V4_MARK
+#undef LQB_V4_EMIT
+        }
+    };
+    const int c_last = (Ti - 1) / 24;                // chunk of the last step
+    const bool top = hi + kV4Warm >= Ti;             // this lane's walk starts at the codeword's end: exact
+    walk(top ? c_last : (hi + kV4Warm) / 24, top ? Ti : -1, kV4UZero);
+    // verify top down; `ok` = this lane's segment is proven equal to the serial traceback's
+    bool ok = top;
+#pragma unroll 1
+    for (int qq = kV4Lanes - 2; qq >= 0; --qq) {
+        const unsigned need = __shfl_down_sync(0xffffffffu, uend, 1);       // end state of the lane above (same codeword for l < 3)
+        const bool okup = __shfl_down_sync(0xffffffffu, (int)ok, 1) != 0;
+        if ((int)l == qq && !ok) {
+            // the lane above is proven by now (okup) - its end state is the true state at step hi
+            if (okup && ustart != need) {
+                if (hi > lo) walk((hi - 1) / 24, hi, need);
+                else uend = need;                    // empty segment: pass the proven state on
+            }
+            ok = true;
+        }
     }
 }
 
@@ -649,8 +791,8 @@ void launch_viterbi(const PayloadParams &P, const unsigned *list, unsigned n, in
         // all frames of one launch share the stage's scheme class only loosely: punctured and plain rate-1/2 codes may be
         // mixed in one list, so the generic symbol fetch is used unless the caller's list is known to be plain (punct == 0)
         const unsigned threads = n * kV4Lanes;
-        if (punct) k_viterbi27x4<true><<<(threads + kV4Threads - 1) / kV4Threads, kV4Threads, 0, s>>>(P, list, n, stage, reinterpret_cast<unsigned short *>(P.decisions));
-        else k_viterbi27x4<false><<<(threads + kV4Threads - 1) / kV4Threads, kV4Threads, 0, s>>>(P, list, n, stage, reinterpret_cast<unsigned short *>(P.decisions));
+        if (punct) k_viterbi27x4<true><<<(threads + kV4Threads - 1) / kV4Threads, kV4Threads, 0, s>>>(P, list, n, stage, reinterpret_cast<unsigned *>(P.decisions));
+        else k_viterbi27x4<false><<<(threads + kV4Threads - 1) / kV4Threads, kV4Threads, 0, s>>>(P, list, n, stage, reinterpret_cast<unsigned *>(P.decisions));
     }
     else k_viterbi<<<(n + kVitWarps - 1) / kVitWarps, 32 * kVitWarps, 0, s>>>(P, list, n, stage);
 }

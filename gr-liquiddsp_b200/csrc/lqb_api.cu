@@ -129,6 +129,13 @@ int build_tables(DevTables &T, float beta, float threshold, float dphi_max)
     uint8_t gen[33];
     gf256_tables(T.gf_exp, T.gf_log, gen);
     std::memcpy(T.rs_gen, gen, 33);
+    for (unsigned v = 0; v < 256; ++v)
+        for (unsigned i = 0; i < 32; ++i) {
+            uint32_t w = 0;
+            for (unsigned k = 1; k <= 4; ++k)
+                if (v) w |= (uint32_t)T.gf_exp[(T.gf_log[v] + k * (i + 1)) % 255] << (8 * (k - 1));
+            T.rs_syn[v][i] = w;
+        }
     return 0;
 }
 
@@ -565,7 +572,7 @@ struct RxLane {
             if (int e = G.d_bufB.reserve(buf_total + 16)) return e;
             if (int e = G.d_payload.reserve(pay_total + 16)) return e;
             if (int e = G.d_dec.reserve(dec_total + 1)) return e;
-            if (int e = G.d_tilemap.reserve(n_tiles + 1)) return e;
+            if (int e = G.d_tilemap.reserve(12 * (n_tiles + 1))) return e;      // 48-byte records
             if (int e = G.d_ckpt.reserve(ck_total + 1)) return e;
             // one list arena: tile_start | pll | valid | deint1 | blk1 | vit1 | rs1 | deint0 | blk0 | vit0 | rs0
             std::vector<const std::vector<unsigned> *> parts = { &tile_start, &pll, &valid, &deint[1], &blk[1], &vit[1], &rsb[1],
@@ -583,7 +590,7 @@ struct RxLane {
             PayloadParams pp;
             pp.tables = f.d_tables; pp.views = G.d_views.p;
             pp.frames = G.d_frames.p; pp.n_frames = nf;
-            pp.tile_start = G.d_lists.p + loff[0]; pp.n_tiles = (unsigned)n_tiles; pp.tile_frame = G.d_tilemap.p;
+            pp.tile_start = G.d_lists.p + loff[0]; pp.n_tiles = (unsigned)n_tiles; pp.tile_rec = reinterpret_cast<uint4 *>(G.d_tilemap.p);
             pp.syms = G.d_syms.p; pp.bufA = G.d_bufA.p; pp.bufB = G.d_bufB.p; pp.payload = G.d_payload.p;
             pp.ilv_maps = d_ilv.p; pp.decisions = G.d_dec.p; pp.pll_ckpt = G.d_ckpt.p;
 

@@ -33,6 +33,7 @@ struct DevTables {
     uint8_t  gf_exp[512];
     uint8_t  gf_log[256];
     uint8_t  rs_gen[64];       // 33 used
+    alignas(16) uint32_t rs_syn[256][32];  // syndrome products: entry [v][i] packs v*b, v*b^2, v*b^3, v*b^4 (byte 0..3), b = alpha^(i+1)
 };
 
 // ------------------------------------------------------------------ per-stream persistent state

@@ -36,7 +36,7 @@ struct CoarseParams {
     float             *m8, *e8;     // [n_tiles * 16]
 };
 
-constexpr unsigned kMfTileSyms = 512;   // payload symbols per matched-filter tile (host plan and k_mf agree on it)
+constexpr unsigned kMfTileSyms = 1024;   // payload symbols per matched-filter tile (host plan and k_mf agree on it)
 
 // work list entry for kernels that run per FEC stage
 struct StageItem { unsigned frame; unsigned pad; };
@@ -49,7 +49,7 @@ struct PayloadParams {
     // matched filter tiling: tile_start[f] = first tile of frame f (exclusive prefix), n_tiles total
     const unsigned    *tile_start;
     unsigned           n_tiles;
-    unsigned          *tile_frame;  // [n_tiles] tile -> frame index (filled on the device)
+    uint4             *tile_rec;    // [3 * n_tiles] per-tile matched-filter records (MfTileRec, filled on the device)
     float2            *syms;        // symbol arena
     unsigned char     *bufA, *bufB; // byte arenas
     unsigned char     *payload;     // payload output pool

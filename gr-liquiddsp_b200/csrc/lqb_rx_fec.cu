@@ -11,6 +11,8 @@
 // This is what liquid-dsp's qpacketmodem_decode/packetizer_decode (and libfec underneath)
 // do at the end of flexframesync_execute_rxpayload (reference call site
 // lib/flex_rx_impl.cc:213; schemes named at lib/flex_rx_impl.cc:75-136).
+#include <cstdlib>
+#include <algorithm>
 #include "lqb_dev.cuh"
 #include "lqb_kernels.h"
 
@@ -424,11 +426,11 @@ __device__ __forceinline__ void v4_back(unsigned &u, unsigned &acc, const uint4 
 
 constexpr int kV4Threads = 64;
 constexpr unsigned kV4Renorm = 96;                    // steps between metric renormalisations (multiple of 6)
-constexpr int kV4Warm = 96;                           // speculative traceback warm-up, steps
+constexpr int kV4Warm = 96;                           // speculative traceback warm-up, steps (debug override: LQB_V4_WARM)
 
 template <bool PUNCT>
 __global__ void __launch_bounds__(kV4Threads)
-k_viterbi27x4(PayloadParams P, const unsigned *__restrict__ list, unsigned n_list, int stage, unsigned *__restrict__ dec)
+k_viterbi27x4(PayloadParams P, const unsigned *__restrict__ list, unsigned n_list, int stage, unsigned *__restrict__ dec, int warm)
 {
     __shared__ uint4 lut[kV4Lanes][6][4];           // [lane][phase][two received bits] -> v4_metrics
     const unsigned gt = blockIdx.x * kV4Threads + threadIdx.x;
@@ -601,8 +603,8 @@ k_viterbi27x4(PayloadParams P, const unsigned *__restrict__ list, unsigned n_lis
         }
     };
     const int c_last = (Ti - 1) / 24;                // chunk of the last step
-    const bool top = hi + kV4Warm >= Ti;             // this lane's walk starts at the codeword's end: exact
-    walk(top ? c_last : (hi + kV4Warm) / 24, top ? Ti : -1, kV4UZero);
+    const bool top = hi + warm >= Ti;                // this lane's walk starts at the codeword's end: exact
+    walk(top ? c_last : (hi + warm) / 24, top ? Ti : -1, kV4UZero);
     // verify top down; `ok` = this lane's segment is proven equal to the serial traceback's
     bool ok = top;
 #pragma unroll 1
@@ -622,20 +624,28 @@ k_viterbi27x4(PayloadParams P, const unsigned *__restrict__ list, unsigned n_lis
 
 // ------------------------------------------------------------------ Reed-Solomon (warp per 255-byte block)
 constexpr int kRsWarps = 4;
+constexpr int kRsSynBytes = 256 * 32 * 4;
 
 __global__ void __launch_bounds__(32 * kRsWarps)
 k_rs(PayloadParams P, const unsigned *__restrict__ blocks, unsigned n_blocks, int stage)
 {
+    // syn[v][lane]: lane's bank is its own, so a lookup with a different v in every lane is one conflict-free wavefront
+    extern __shared__ uint4 rs_dyn[];
+    unsigned (*syn)[32] = reinterpret_cast<unsigned (*)[32]>(rs_dyn);
     __shared__ unsigned char gexp[512], glog[256];
-    __shared__ unsigned char data[kRsWarps][256];
+    __shared__ __align__(16) unsigned char data[kRsWarps][256];
     __shared__ unsigned char synd[kRsWarps][32], lam[kRsWarps][36], omg[kRsWarps][32];
     __shared__ int deg_s[kRsWarps];
     for (int i = threadIdx.x; i < 512; i += blockDim.x) gexp[i] = P.tables->gf_exp[i];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) glog[i] = P.tables->gf_log[i];
+    {
+        const uint4 *g = reinterpret_cast<const uint4 *>(&P.tables->rs_syn[0][0]);
+        for (int i = threadIdx.x; i < 256 * 32 / 4; i += blockDim.x) rs_dyn[i] = g[i];
+    }
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const unsigned gi = blockIdx.x * kRsWarps + warp;
-    if (gi >= n_blocks) return;
+    // warps stride over the block list so that the 32 KB table is loaded once per CTA, not once per four blocks
+    for (unsigned gi = blockIdx.x * kRsWarps + warp; gi < n_blocks; gi += gridDim.x * kRsWarps) {
     const FrameDesc &d = P.frames[blocks[2 * gi]];
     const unsigned blk = blocks[2 * gi + 1];
     const StageIO io = stage_io(P, d, stage);
@@ -644,12 +654,25 @@ k_rs(PayloadParams P, const unsigned *__restrict__ blocks, unsigned n_blocks, in
     const unsigned nn = 255 - pad;
     unsigned char *x = data[warp];
     const unsigned char *src = io.src + (size_t)blk * enc_block;
+    __syncwarp();
     for (unsigned i = lane; i < enc_block; i += 32) x[i] = src[i];
     __syncwarp();
 
-    // syndrome lane: S_lane = r(alpha^(lane+1)) by Horner from the highest-degree byte
-    unsigned s = x[0];
-    for (unsigned j = 1; j < nn; ++j) s = x[j] ^ (s ? gexp[glog[s] + lane + 1] : 0);
+    // syndrome lane: S_lane = r(b), b = alpha^(lane+1), by Horner from the highest-degree byte, four bytes per
+    // dependent lookup: S <- S b^4 + x0 b^3 + x1 b^2 + x2 b + x3.  The running value lives in the top byte of `r`.
+    unsigned r = 0;
+    const char *tl = reinterpret_cast<const char *>(&syn[0][lane]);          // + 128 v
+    auto T = [&](unsigned off) { return *reinterpret_cast<const unsigned *>(tl + off); };
+    const unsigned ng = nn >> 2;
+    const unsigned *xw = reinterpret_cast<const unsigned *>(x);
+    for (unsigned g = 0; g < ng; ++g) {
+        const unsigned w = xw[g];                                            // x0 | x1 << 8 | x2 << 16 | x3 << 24
+        const unsigned ts = T((r >> 17) & 0x7f80u);
+        const unsigned t0 = T((w << 7) & 0x7f80u), t1 = T((w >> 1) & 0x7f80u), t2 = T((w >> 9) & 0x7f80u);
+        r = ts ^ (t0 << 8) ^ (t1 << 16) ^ (t2 << 24) ^ w;                    // only the top byte is meaningful
+    }
+    unsigned s = r >> 24;
+    for (unsigned j = 4 * ng; j < nn; ++j) s = x[j] ^ (T(s << 7) & 0xffu);
     synd[warp][lane] = (unsigned char)s;
     const unsigned any = __ballot_sync(0xffffffffu, s != 0);
     __syncwarp();
@@ -736,6 +759,7 @@ k_rs(PayloadParams P, const unsigned *__restrict__ blocks, unsigned n_blocks, in
     const unsigned take = (n - n0 >= dec_block) ? dec_block : (n - n0);
     unsigned char *dst = io.dst + n0;
     for (unsigned i = lane; i < take; i += 32) dst[i] = x[i];
+    }
 }
 
 // ------------------------------------------------------------------ unscramble + CRC + copy-out (warp per frame)
@@ -791,14 +815,20 @@ void launch_viterbi(const PayloadParams &P, const unsigned *list, unsigned n, in
         // all frames of one launch share the stage's scheme class only loosely: punctured and plain rate-1/2 codes may be
         // mixed in one list, so the generic symbol fetch is used unless the caller's list is known to be plain (punct == 0)
         const unsigned threads = n * kV4Lanes;
-        if (punct) k_viterbi27x4<true><<<(threads + kV4Threads - 1) / kV4Threads, kV4Threads, 0, s>>>(P, list, n, stage, reinterpret_cast<unsigned *>(P.decisions));
-        else k_viterbi27x4<false><<<(threads + kV4Threads - 1) / kV4Threads, kV4Threads, 0, s>>>(P, list, n, stage, reinterpret_cast<unsigned *>(P.decisions));
+        // test hook: a short warm-up makes the speculative traceback start wrong often, which exercises the re-walk
+        const char *we = std::getenv("LQB_V4_WARM");
+        const int warm = we ? std::max(0, std::atoi(we)) : kV4Warm;
+        if (punct) k_viterbi27x4<true><<<(threads + kV4Threads - 1) / kV4Threads, kV4Threads, 0, s>>>(P, list, n, stage, reinterpret_cast<unsigned *>(P.decisions), warm);
+        else k_viterbi27x4<false><<<(threads + kV4Threads - 1) / kV4Threads, kV4Threads, 0, s>>>(P, list, n, stage, reinterpret_cast<unsigned *>(P.decisions), warm);
     }
     else k_viterbi<<<(n + kVitWarps - 1) / kVitWarps, 32 * kVitWarps, 0, s>>>(P, list, n, stage);
 }
 void launch_rs(const PayloadParams &P, const unsigned *blocks, unsigned n_blocks, int stage, cudaStream_t s)
 {
-    if (n_blocks) k_rs<<<(n_blocks + kRsWarps - 1) / kRsWarps, 32 * kRsWarps, 0, s>>>(P, blocks, n_blocks, stage);
+    if (!n_blocks) return;
+    static const int sms = [] { int dev = 0, v = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev); return v; }();
+    const unsigned want = (n_blocks + kRsWarps - 1) / kRsWarps, cap = (unsigned)sms * 6u;     // six 34 KB CTAs per SM
+    k_rs<<<std::min(want, cap), 32 * kRsWarps, kRsSynBytes, s>>>(P, blocks, n_blocks, stage);
 }
 void launch_crc(const PayloadParams &P, const unsigned *list, unsigned n, cudaStream_t s)
 {

@@ -335,6 +335,31 @@ def test_per_near_threshold_agrees_with_oracle():
     assert abs(len(got) - len(ref)) <= 2
 
 
+def test_viterbi_parallel_traceback_rewalk_is_exact(monkeypatch):
+    # k_viterbi27x4 traces a codeword back on four lanes that start speculatively and are verified top down.
+    # With the warm-up shortened to 0..23 steps and noisy codewords the speculation fails often, so the re-walk
+    # path runs; bytes must still equal the oracle's serial traceback (valid and CRC-failed frames alike).
+    rng = np.random.default_rng(38)
+    n = 24
+    pls = [rng.integers(0, 256, 400, dtype=np.uint8) for _ in range(n)]
+    caps = []
+    for i, (f0, f1) in enumerate([(11, 1), (11, 27), (17, 1)]):
+        frames = [o.tx_frame(util.PSK4, util.CRC24, f0, f1, p) for p in pls[8 * i:8 * i + 8]]
+        caps.append(util.build_capture(frames, rng, [800] * 8, snr_db=2.0 + 1.5 * i))
+    ref = [o.rx_capture(c) for c in caps]
+    assert any(not r["payload_valid"] for rr in ref for r in rr) and any(r["payload_valid"] for rr in ref for r in rr)
+    for warm in ("0", None):
+        if warm is None:
+            monkeypatch.delenv("LQB_V4_WARM", raising=False)
+        else:
+            monkeypatch.setenv("LQB_V4_WARM", warm)
+        rx = capi.Rx(len(caps))
+        rx.execute(caps)
+        got = rx.poll()
+        for s, rr in enumerate(ref):
+            assert_frames_match(rr, [g for g in got if g["stream"] == s], syms=False)
+
+
 def test_large_batch_roundtrip_property():
     # size-independent property at scale: every transmitted payload comes back, per stream, in order
     rng = np.random.default_rng(37)

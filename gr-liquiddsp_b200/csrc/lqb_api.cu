@@ -162,6 +162,12 @@ struct Front {
     } io[2];
     unsigned cur = 0;
     std::vector<uint8_t> fed;
+    // search work a stream is expected to cost, in sample equivalents (from the last planned call): k_seek runs one CTA
+    // per stream and streams differ several-fold (a stream full of decodable frames skips most of its samples, one
+    // below the header threshold searches all of them and aligns at every detection), so the longest are started
+    // first (profiles/r01_notes.md v19).  Only the ORDER of the io entries changes; results do not depend on it.
+    std::vector<int64_t> est_work;
+    bool lpt = getenv("LQB_NO_LPT") == nullptr && getenv("LQB_COARSE_SEPARATE") == nullptr;
     uint64_t launches = 0;
     // tensor-core pre-filter (lqb_rx_coarse.cu)
     bool coarse_ok = false;
@@ -201,6 +207,7 @@ struct Front {
         CU(cudaMallocHost(&h_states, (size_t)ns * sizeof(StreamState)));
         CU(cudaEventCreate(&cev[0])); CU(cudaEventCreate(&cev[1]));
         fed.assign(ns, 0);
+        est_work.assign(ns, 0);
         if (T.range == 24 && !getenv("LQB_NO_COARSE")) {
             std::vector<float> sre(kSLen), sim(kSLen);
             for (unsigned i = 0; i < kSLen; ++i) { sre[i] = T.sconj[i].x; sim[i] = -T.sconj[i].y; }
@@ -285,6 +292,8 @@ struct Front {
                 h_io.p[i].stream = ids ? ids[i] : i; h_io.p[i].pad = 0;
             }
         }
+        if (lpt && n > 1)
+            std::stable_sort(h_io.p, h_io.p + n, [&](const StreamIO &a, const StreamIO &b) { return est_work[a.stream] > est_work[b.stream]; });
         CU(cudaMemcpyAsync(d_io.p, h_io.p, n * sizeof(StreamIO), cudaMemcpyHostToDevice, stream));
         *total = tot; *max_n = mx;
         return 0;
@@ -375,6 +384,7 @@ struct RxGen {
     cudaEvent_t mf_done = nullptr;        // the matched filter (the only payload kernel that reads input / carry) has run
     cudaEvent_t done = nullptr;           // results are on the host
     cudaEvent_t staged = nullptr;         // inputs and the I/O list are on the device
+    cudaEvent_t seek_done = nullptr;      // the search has run and its counters are on the host
     bool mf_pending = false;
     float ms[6] = {};
     uint64_t work[6] = {};
@@ -391,6 +401,7 @@ struct RxGen {
         if (mf_done) cudaEventDestroy(mf_done);
         if (done) cudaEventDestroy(done);
         if (staged) cudaEventDestroy(staged);
+        if (seek_done) cudaEventDestroy(seek_done);
     }
 };
 
@@ -463,7 +474,9 @@ struct RxLane {
         return 0;
     }
 
-    // phase A2: queue the search and the carry update on the lane's search stream
+    // phase A2: queue the search on the lane's search stream.  This happens BEFORE the previous call's payload chain is
+    // planned, so that the GPU goes straight from one search into the next while the host plans (the old order left it
+    // idle for the 4 ms that the wait / frame list / plan / queue sequence of both lanes takes, profiles/r01_notes.md v20).
     int phase_search(unsigned gen)
     {
         RxGen &G = g[gen];
@@ -478,13 +491,25 @@ struct RxLane {
         G.sp.det_mode = 0; G.sp.frames = G.d_frames.p; G.sp.detections = nullptr;
         G.sp.n_out = f.io[f.cur].d_count; G.sp.max_out = (unsigned)G.max_frames;
         CU(cudaEventRecord(G.ev[0], st));
+        if (!f.lpt) CU(cudaStreamSynchronize(st));      // debug modes plan the separate pre-filter from the host mirror of the states
         if (int e = f.run_coarse(n, G.ns_copy.data(), G.sp)) return e;
         CU(cudaMemsetAsync(f.io[f.cur].d_count, 0, 8 * sizeof(unsigned), st));
         launch_seek(G.sp, n, st); f.launches++;
         CU(cudaEventRecord(G.ev[1], st));
         launch_copy(f.io[f.cur].h_count, f.io[f.cur].d_count, 8 * sizeof(unsigned), st);
-        // The unconsumed tails move to the other carry buffer right away, so that the next call can be searched while this
-        // call's payload chain is still running.  That buffer is the one the PREVIOUS call's matched filter reads: wait for it.
+        CU(cudaEventRecord(G.seek_done, st));
+        return 0;
+    }
+    // phase A3: the carry update, after the previous call's payload chain has been queued.
+    // The unconsumed tails move to the other carry buffer right away, so that the next call can be searched while this
+    // call's payload chain is still running.  That buffer is the one the PREVIOUS call's matched filter reads: wait for it.
+    int phase_carry(unsigned gen)
+    {
+        RxGen &G = g[gen];
+        f.cur = gen;
+        const uint32_t n = G.n_fed;
+        if (!n) return 0;
+        cudaStream_t st = f.stream;
         RxGen &prev = g[gen ^ 1u];
         if (prev.mf_pending) { CU(cudaStreamWaitEvent(st, prev.mf_done, 0)); prev.mf_pending = false; }
         launch_carry(G.sp, n, st); f.launches++;
@@ -500,17 +525,19 @@ struct RxLane {
         const uint32_t n = G.n_fed;
         if (!n) return 0;
         f.cur = gen;
-        cudaStream_t st = f.stream, ps = pay;
+        cudaStream_t ps = pay;
         g_trace.mark("wait seek", lane);
-        CU(cudaStreamSynchronize(st));
+        CU(cudaEventSynchronize(G.seek_done));          // not the stream: the next call's search may already be queued behind
         g_trace.mark("seek done", lane);
         unsigned nf = std::min<unsigned>(f.io[f.cur].h_count[0], (unsigned)G.max_frames);
         G.work[0] = f.io[f.cur].h_count[1]; G.work[1] = f.io[f.cur].h_count[2]; G.work[2] = 0; G.work[3] = G.total; G.work[4] = f.io[f.cur].h_count[3];
         G.work[5] = G.sp.coarse == 2 ? (uint64_t)f.io[f.cur].h_count[4] : (G.sp.coarse == 1 ? (uint64_t)f.h_tpre.p[n] : 0);
         FrameDesc *fr = G.h_frames.p;
         if (nf) {
-            launch_copy(fr, G.d_frames.p, nf * sizeof(FrameDesc), st);
-            CU(cudaStreamSynchronize(st));
+            // on the payload stream (idle: the chain of this generation's previous use has been collected), by kernel:
+            // it fits beside the resident search CTAs of the next call
+            launch_copy(fr, G.d_frames.p, nf * sizeof(FrameDesc), ps);
+            CU(cudaStreamSynchronize(ps));
         }
 
         g_trace.mark("frame list on host", lane);
@@ -519,9 +546,13 @@ struct RxLane {
         std::vector<unsigned> tile_start(nf + 1, 0), valid, deint[2], blk[2], vit[2], vit9[2], rsb[2];
         size_t tmax7[2] = { 0, 0 };
         bool punct7[2] = { false, false };
+        std::fill(f.est_work.begin(), f.est_work.end(), 0);
         for (unsigned i = 0; i < nf; ++i) {
             FrameDesc &d = fr[i];
             tile_start[i] = (unsigned)n_tiles;
+            // every detection costs an exact window and an alignment (about 3000 samples' worth of search); a frame with
+            // a valid header lets the search skip its payload
+            if (d.stream < f.est_work.size()) f.est_work[d.stream] += 3000 - (d.header_valid ? 2ll * d.n_sym : 0ll);
             if (!d.header_valid) continue;
             valid.push_back(i);
             d.sym_off = sym_total; sym_total += (d.n_sym + 1u) & ~1u;      // even: 16-byte aligned symbol rows
@@ -777,6 +808,7 @@ lqb_rx lqb_rx_create(const lqb_rx_opts *o)
             ok = ok && cudaEventCreateWithFlags(&G.mf_done, cudaEventDisableTiming) == cudaSuccess;
             ok = ok && cudaEventCreateWithFlags(&G.done, cudaEventDisableTiming) == cudaSuccess;
             ok = ok && cudaEventCreateWithFlags(&G.staged, cudaEventDisableTiming) == cudaSuccess;
+            ok = ok && cudaEventCreateWithFlags(&G.seek_done, cudaEventDisableTiming) == cudaSuccess;
         }
     }
     delete T;
@@ -880,13 +912,15 @@ int lqb_rx_submit(lqb_rx h, uint32_t n, const uint32_t *ids, const float *const 
     int rc = 0;
     g_trace.start();
     // 1. the new samples start travelling (copy streams) while the previous call is still being searched;
-    // 2. the previous call's search is awaited, its payload work planned and queued;
-    // 3. this call's search is queued behind its own copies.
+    // 2. this call's search is queued behind its own copies (and behind the previous search, same stream);
+    // 3. the previous call's search is awaited, its payload work planned and queued;
+    // 4. this call's carry update is queued behind the previous call's matched filter.
     for (auto *l : h->lanes) if ((rc = l->phase_stage(mem, gen))) break;
     g_trace.mark("inputs queued (all lanes)", 0);
-    if (!rc && h->pending == 1) rc = h->plan(gen ^ 1u);
     if (!rc) for (auto *l : h->lanes) if ((rc = l->phase_search(gen))) break;
     g_trace.mark("search queued (all lanes)", 0);
+    if (!rc && h->pending == 1) rc = h->plan(gen ^ 1u);
+    if (!rc) for (auto *l : h->lanes) if ((rc = l->phase_carry(gen))) break;
     if (rc) {
         const std::string keep = g_err;
         h->sync_all(); cudaGetLastError();

@@ -593,8 +593,8 @@ struct RxLane {
         // group the PLL work list by modulation so warps diverge less
         std::vector<unsigned> pll = valid;
         std::stable_sort(pll.begin(), pll.end(), [&](unsigned a, unsigned b) { return fr[a].ms < fr[b].ms; });
-        std::vector<unsigned> span_start(pll.size() + 1, 0);          // 4096-symbol spans of the emit pass, over the pll order
-        for (size_t k = 0; k < pll.size(); ++k) span_start[k + 1] = span_start[k] + (fr[pll[k]].n_sym + 4095) / 4096;
+        std::vector<unsigned> span_start(pll.size() + 1, 0);          // kEmitSpan-symbol spans of the emit pass, over the pll order
+        for (size_t k = 0; k < pll.size(); ++k) span_start[k + 1] = span_start[k] + (fr[pll[k]].n_sym + kEmitSpan - 1) / kEmitSpan;
 
         g_trace.mark("planned", lane);
         if (nf && !valid.empty()) {

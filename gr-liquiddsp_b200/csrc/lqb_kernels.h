@@ -36,7 +36,7 @@ struct CoarseParams {
     float             *m8, *e8;     // [n_tiles * 16]
 };
 
-constexpr unsigned kMfTileSyms = 1024;   // payload symbols per matched-filter tile (host plan and k_mf agree on it)
+constexpr unsigned kMfTileSyms = 512;   // payload symbols per matched-filter tile (host plan and k_mf agree on it)
 
 // work list entry for kernels that run per FEC stage
 struct StageItem { unsigned frame; unsigned pad; };
@@ -66,7 +66,8 @@ void launch_carry(const SeekParams &P, unsigned n_io, cudaStream_t s);
 // device <-> pinned-host copy of small control data by a kernel (never queues behind bulk DMA copies)
 void launch_copy(void *dst, const void *src, size_t bytes, cudaStream_t s);
 void launch_mf(const PayloadParams &P, cudaStream_t s);
-// list: frames grouped by modulation; span_start: exclusive prefix (n + 1) of 4096-symbol spans over that list
+constexpr unsigned kEmitSpan = 1024;     // payload symbols per CTA of the PLL emit pass (host plan and k_pll_emit agree on it)
+// list: frames grouped by modulation; span_start: exclusive prefix (n + 1) of kEmitSpan-symbol spans over that list
 void launch_pll(const PayloadParams &P, const unsigned *list, const unsigned *span_start, unsigned n, unsigned n_spans, cudaStream_t s);
 // stage = 1: bufA(n1) -> bufB(n0) with fec1;  stage = 0: bufB(n0) -> bufA(k0) with fec0
 void launch_deinterleave(const PayloadParams &P, const unsigned *list, unsigned n, int stage, cudaStream_t s);

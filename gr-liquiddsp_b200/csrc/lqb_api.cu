@@ -537,6 +537,7 @@ struct RxLane {
             // on the payload stream (idle: the chain of this generation's previous use has been collected), by kernel:
             // it fits beside the resident search CTAs of the next call
             launch_copy(fr, G.d_frames.p, nf * sizeof(FrameDesc), ps);
+            g_trace.mark("frame list copy queued", lane);
             CU(cudaStreamSynchronize(ps));
         }
 

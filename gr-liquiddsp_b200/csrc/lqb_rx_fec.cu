@@ -361,8 +361,10 @@ __device__ __forceinline__ void v4_step(unsigned (&W)[8], const uint4 c, unsigne
             const int w1 = w | (1 << k);
             const unsigned lab = v4_label(R, (unsigned)w);
             const unsigned a = Ap[lab], b = Ap[3 - lab];
-            const unsigned m0 = v2_add(W[w], a), m1 = v2_add(W[w1], b);     // into successor 2i   (kept at w)
-            const unsigned q0 = v2_add(W[w], b), q1 = v2_add(W[w1], a);     // into successor 2i+1 (kept at w1)
+            // candidate sums never overflow a half (renormalisation keeps them below 65536), so a plain 32-bit add is
+            // a packed add -- and may issue on the FMA pipe (IMAD.IADD), which the ALU-bound loop leaves idle
+            const unsigned m0 = W[w] + a, m1 = W[w1] + b;                    // into successor 2i   (kept at w)
+            const unsigned q0 = W[w] + b, q1 = W[w1] + a;                    // into successor 2i+1 (kept at w1)
             G[w] = v2_add(m0, ~m1);                                          // m0 - m1 - 1: sign clear <=> m0 > m1
             G[w1] = v2_add(q0, ~q1);
             W[w] = v2_min(m0, m1);
@@ -376,7 +378,7 @@ __device__ __forceinline__ void v4_step(unsigned (&W)[8], const uint4 c, unsigne
             unsigned other;
             if constexpr (k == 3) other = __byte_perm(W[w], 0u, 0x1032);
             else other = __shfl_xor_sync(0xffffffffu, W[w], 1 << (k - kV4PosBits));
-            const unsigned c_own = v2_add(W[w], a), c_oth = v2_add(other, b);
+            const unsigned c_own = W[w] + a, c_oth = other + b;
             // F = own - oth - 1.  Lower position (keeps 2i): decision own > oth <=> sign(F) clear.
             // Upper position (keeps 2i+1): decision oth > own <=> F + 1 < 0 <=> sign(F + 1) set.
             G[w] = v2_add(v2_add(c_own, ~c_oth), role);

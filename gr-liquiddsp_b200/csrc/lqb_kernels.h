@@ -36,7 +36,16 @@ struct CoarseParams {
     float             *m8, *e8;     // [n_tiles * 16]
 };
 
-constexpr unsigned kMfTileSyms = 512;   // payload symbols per matched-filter tile (host plan and k_mf agree on it)
+// CTA shapes of k_mf / k_pll_emit.  64-thread / 1024-symbol variants (14 KB / 13 KB of shared memory) were built to fit
+// beside resident search CTAs; measured A/B on the pipelined bench they are no faster (profiles/r01_notes.md v21), and
+// the larger shapes are a little faster on their own.
+#ifndef LQB_MF_THREADS
+#define LQB_MF_THREADS 128
+#endif
+#ifndef LQB_EMIT_SPAN
+#define LQB_EMIT_SPAN 4096
+#endif
+constexpr unsigned kMfTileSyms = 8 * LQB_MF_THREADS;   // payload symbols per matched-filter tile (host plan and k_mf agree on it)
 
 // work list entry for kernels that run per FEC stage
 struct StageItem { unsigned frame; unsigned pad; };
@@ -66,7 +75,7 @@ void launch_carry(const SeekParams &P, unsigned n_io, cudaStream_t s);
 // device <-> pinned-host copy of small control data by a kernel (never queues behind bulk DMA copies)
 void launch_copy(void *dst, const void *src, size_t bytes, cudaStream_t s);
 void launch_mf(const PayloadParams &P, cudaStream_t s);
-constexpr unsigned kEmitSpan = 1024;     // payload symbols per CTA of the PLL emit pass (host plan and k_pll_emit agree on it)
+constexpr unsigned kEmitSpan = LQB_EMIT_SPAN;     // payload symbols per CTA of the PLL emit pass (host plan and k_pll_emit agree on it)
 // list: frames grouped by modulation; span_start: exclusive prefix (n + 1) of kEmitSpan-symbol spans over that list
 void launch_pll(const PayloadParams &P, const unsigned *list, const unsigned *span_start, unsigned n, unsigned n_spans, cudaStream_t s);
 // stage = 1: bufA(n1) -> bufB(n0) with fec1;  stage = 0: bufB(n0) -> bufA(k0) with fec0

@@ -27,7 +27,29 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "gr-liquiddsp_b200", "python"))
-os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
+# keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line (NCCL carries no data here, only barriers).
+# NCCL prints the banner at the VERSION and at the WARN level; with the variable unset it prints nothing.
+if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+    del os.environ["NCCL_DEBUG"]
+
+
+def bind_near_gpu(local):
+    """Pin this rank's host threads to the CPUs NVML reports as local to its GPU, so that the pinned staging buffers of
+    the host-buffer (e2e) leg are first-touched on that NUMA node.  Returns the CPU count it bound to (0 = left alone)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        allowed = os.sched_getaffinity(0)
+        cpus = {64 * i + b for i, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1} & allowed
+        if cpus and cpus != allowed:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return 0
 
 PSK4, CRC24, V27, RS8 = 2, 5, 11, 27
 PAYLOAD = 1500
@@ -398,6 +420,7 @@ def main():
         return
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
+    near = bind_near_gpu(local) if world > 1 else 0
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -636,6 +659,7 @@ def main():
         "frames_sent_per_step": sent_all, "frames_found_per_step": fr_all / args.steps, "frames_valid_per_step": va_all / args.steps,
         "gpu_launches": int(launches_all), "lanes": lanes,
         "api": "lqb_rx_submit + lqb_rx_collect, two calls in flight" if pipelined else "lqb_rx_execute",
+        "host_cpus_bound_near_gpu": near,
         "kernel_times": ("CUDA events around each kernel on its launching stream, same K steps repeated with lanes=1 right after the "
                          "timed region (%.2f ms/step serialized; in the timed region the lanes overlap)" % serial_ms) if serial_ms else
                         "CUDA events around each kernel on its launching stream inside the timed region",

@@ -32,6 +32,8 @@ struct TxTables {
 };
 
 struct TxFrame {               // one frame's plan (host-built)
+    const unsigned char *pay;  // payload bytes (device: the caller's buffer in place, or the staging buffer)
+    float2 *out;               // where the frame's samples go (device: the caller's buffer in place, or the staging buffer)
     unsigned long long pay_off, buf_off, sym_off, out_off;
     unsigned payload_len, check, fec0, fec1, ms, bps;
     unsigned k0, n0, n1, n_sym, buf_len, ilv0_off, ilv1_off, n_samples;
@@ -248,8 +250,7 @@ __device__ float2 modulate(const TxTables *T, unsigned ms, unsigned bps, unsigne
 }
 
 __global__ void __launch_bounds__(kTxThreads)
-k_tx(const TxTables *T, const TxFrame *frames, const unsigned char *payloads, unsigned char *bufA, unsigned char *bufB,
-     const unsigned *ilv, float2 *syms, float2 *out)
+k_tx(const TxTables *T, const TxFrame *frames, unsigned char *bufA, unsigned char *bufB, const unsigned *ilv, float2 *syms)
 {
     __shared__ float2 hsym[232];
     __shared__ unsigned char hb[64];
@@ -292,7 +293,7 @@ k_tx(const TxTables *T, const TxFrame *frames, const unsigned char *payloads, un
 
     // ---------------- payload bytes: CRC, whitening
     const unsigned plen = f.payload_len, cl = f.k0 - plen;
-    const unsigned char *pay = payloads + f.pay_off;
+    const unsigned char *pay = f.pay;
     for (unsigned i = tid; i < plen; i += kTxThreads) A[i] = pay[i];
     __syncthreads();
     if (tid == 0) {
@@ -349,7 +350,7 @@ k_tx(const TxTables *T, const TxFrame *frames, const unsigned char *payloads, un
 
     // ---------------- 2x interpolation: out[2t+ph] = sum_n h[ph + 2n] sym[t-n], oldest symbol first
     const int total_syms = 64 + 231 + (int)f.n_sym + 14;
-    float2 *o = out + f.out_off;
+    float2 *o = f.out;
     for (int m = tid; m < 2 * total_syms; m += kTxThreads) {
         const int t = m >> 1, ph = m & 1;
         float ar = 0.0f, ai = 0.0f;
@@ -385,6 +386,10 @@ struct lqb_tx_s {
     unsigned char *d_pay = nullptr, *d_A = nullptr, *d_B = nullptr; size_t pay_cap = 0, buf_cap = 0, bufB_cap = 0;
     float2 *d_syms = nullptr, *d_out = nullptr; size_t sym_cap = 0, out_cap = 0;
     unsigned *d_ilv = nullptr; size_t ilv_cap = 0, ilv_used = 0;
+    // pinned staging: frame plans, host payloads packed back to back (one H2D instead of one copy per frame), host outputs
+    TxFrame *h_frames = nullptr; size_t h_frames_cap = 0;
+    unsigned char *h_pay = nullptr; size_t h_pay_cap = 0;
+    float2 *h_out = nullptr; size_t h_out_cap = 0;
     std::unordered_map<unsigned, size_t> ilv_cache;
     std::vector<unsigned> ilv_host;
     uint64_t launches = 0;
@@ -398,6 +403,16 @@ template <typename T> int grow(T *&p, size_t &cap, size_t need)
     T *q = nullptr;
     if (cudaMalloc(&q, ncap * sizeof(T)) != cudaSuccess) return LQB_ENOMEM;
     if (p) cudaFree(p);
+    p = q; cap = ncap;
+    return 0;
+}
+template <typename T> int grow_pinned(T *&p, size_t &cap, size_t need)
+{
+    if (need <= cap) return 0;
+    size_t ncap = std::max(need, cap + cap / 2);
+    T *q = nullptr;
+    if (cudaMallocHost(&q, ncap * sizeof(T)) != cudaSuccess) return LQB_ENOMEM;
+    if (p) cudaFreeHost(p);
     p = q; cap = ncap;
     return 0;
 }
@@ -467,6 +482,9 @@ void lqb_tx_destroy(lqb_tx h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->d_tables); cudaFree(h->d_frames); cudaFree(h->d_pay); cudaFree(h->d_A); cudaFree(h->d_B);
     cudaFree(h->d_syms); cudaFree(h->d_out); cudaFree(h->d_ilv);
+    if (h->h_frames) cudaFreeHost(h->h_frames);
+    if (h->h_pay) cudaFreeHost(h->h_pay);
+    if (h->h_out) cudaFreeHost(h->h_out);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -478,7 +496,8 @@ int lqb_tx_assemble(lqb_tx h, uint32_t n, const lqb_tx_props *props, const uint8
     if (!n) return 0;
     if (cudaSetDevice(h->device) != cudaSuccess) return LQB_ECUDA;
     cudaStream_t st = h->stream;
-    std::vector<TxFrame> fr(n);
+    if (grow_pinned(h->h_frames, h->h_frames_cap, n)) return tx_fail(LQB_ENOMEM, "cudaMallocHost failed");
+    TxFrame *fr = h->h_frames;
     size_t pay_tot = 0, buf_tot = 0, sym_tot = 0, out_tot = 0;
     bool new_maps = false;
     for (uint32_t i = 0; i < n; ++i) {
@@ -512,31 +531,37 @@ int lqb_tx_assemble(lqb_tx h, uint32_t n, const lqb_tx_props *props, const uint8
             (s ? f.ilv1_off : f.ilv0_off) = (unsigned)off;
         }
     }
-    if (grow(h->d_frames, h->frames_cap, n) || grow(h->d_pay, h->pay_cap, pay_tot + 16) || grow(h->d_A, h->buf_cap, buf_tot + 16)) return tx_fail(LQB_ENOMEM, "cudaMalloc failed");
+    const bool dev_io = (mem == LQB_MEM_DEVICE);
+    if (grow(h->d_frames, h->frames_cap, n) || grow(h->d_A, h->buf_cap, buf_tot + 16)) return tx_fail(LQB_ENOMEM, "cudaMalloc failed");
     if (grow(h->d_B, h->bufB_cap, buf_tot + 16)) return tx_fail(LQB_ENOMEM, "cudaMalloc failed");
     if (grow(h->d_syms, h->sym_cap, sym_tot + 1)) return tx_fail(LQB_ENOMEM, "cudaMalloc failed");
     if (new_maps || !h->d_ilv) {
         if (grow(h->d_ilv, h->ilv_cap, h->ilv_host.size() + 4)) return tx_fail(LQB_ENOMEM, "cudaMalloc failed");
         if (!h->ilv_host.empty()) cudaMemcpyAsync(h->d_ilv, h->ilv_host.data(), h->ilv_host.size() * sizeof(unsigned), cudaMemcpyHostToDevice, st);
     }
-    // outputs: write straight into caller memory when it is device memory and frames are contiguous there
-    bool direct = (mem == LQB_MEM_DEVICE);
-    if (direct) for (uint32_t i = 1; i < n; ++i) if (out[i] != out[i - 1] + 2 * (size_t)fr[i - 1].n_samples) { direct = false; break; }
-    float2 *d_out = nullptr;
-    if (direct) d_out = reinterpret_cast<float2 *>(out[0]);
-    else { if (grow(h->d_out, h->out_cap, out_tot + 1)) return tx_fail(LQB_ENOMEM, "cudaMalloc failed"); d_out = h->d_out; }
-    for (uint32_t i = 0; i < n; ++i)
-        if (lens[i]) cudaMemcpyAsync(h->d_pay + fr[i].pay_off, payloads[i], lens[i], mem == LQB_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st);
-    cudaMemcpyAsync(h->d_frames, fr.data(), n * sizeof(TxFrame), cudaMemcpyHostToDevice, st);
-    k_tx<<<n, kTxThreads, 0, st>>>(h->d_tables, h->d_frames, h->d_pay, h->d_A, h->d_B, h->d_ilv, h->d_syms, d_out);
+    // Device buffers are used in place: the kernel reads every payload and writes every frame through the caller's
+    // pointers.  Host buffers are packed into one pinned staging area each way: one H2D and one D2H per call instead of
+    // one copy per frame (8192 frames took 32 ms of copy calls, profiles/r01_notes.md v23).
+    if (dev_io) {
+        for (uint32_t i = 0; i < n; ++i) { fr[i].pay = payloads[i]; fr[i].out = reinterpret_cast<float2 *>(out[i]); }
+    } else {
+        if (grow(h->d_pay, h->pay_cap, pay_tot + 16) || grow(h->d_out, h->out_cap, out_tot + 1)) return tx_fail(LQB_ENOMEM, "cudaMalloc failed");
+        if (grow_pinned(h->h_pay, h->h_pay_cap, pay_tot + 16) || grow_pinned(h->h_out, h->h_out_cap, out_tot + 1)) return tx_fail(LQB_ENOMEM, "cudaMallocHost failed");
+        for (uint32_t i = 0; i < n; ++i) {
+            if (lens[i]) std::memcpy(h->h_pay + fr[i].pay_off, payloads[i], lens[i]);
+            fr[i].pay = h->d_pay + fr[i].pay_off; fr[i].out = h->d_out + fr[i].out_off;
+        }
+        if (pay_tot) cudaMemcpyAsync(h->d_pay, h->h_pay, pay_tot, cudaMemcpyHostToDevice, st);
+    }
+    cudaMemcpyAsync(h->d_frames, fr, n * sizeof(TxFrame), cudaMemcpyHostToDevice, st);
+    k_tx<<<n, kTxThreads, 0, st>>>(h->d_tables, h->d_frames, h->d_A, h->d_B, h->d_ilv, h->d_syms);
     h->launches++;
-    if (!direct)
-        for (uint32_t i = 0; i < n; ++i)
-            cudaMemcpyAsync(out[i], d_out + fr[i].out_off, (size_t)fr[i].n_samples * sizeof(float2),
-                            mem == LQB_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st);
+    if (!dev_io) cudaMemcpyAsync(h->h_out, h->d_out, out_tot * sizeof(float2), cudaMemcpyDeviceToHost, st);
     cudaError_t e = cudaStreamSynchronize(st);
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) return tx_fail(LQB_ECUDA, cudaGetErrorString(e));
+    if (!dev_io)
+        for (uint32_t i = 0; i < n; ++i) std::memcpy(out[i], h->h_out + fr[i].out_off, (size_t)fr[i].n_samples * sizeof(float2));
     return 0;
 }
 

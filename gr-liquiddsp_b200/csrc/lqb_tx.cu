@@ -252,12 +252,28 @@ __device__ float2 modulate(const TxTables *T, unsigned ms, unsigned bps, unsigne
 __global__ void __launch_bounds__(kTxThreads)
 k_tx(const TxTables *T, const TxFrame *frames, unsigned char *bufA, unsigned char *bufB, const unsigned *ilv, float2 *syms)
 {
-    __shared__ float2 hsym[232];
     __shared__ unsigned char hb[64];
+    __shared__ unsigned crc4[4][256];                 // slicing-by-4 tables of the frame's check
     const int tid = threadIdx.x;
     const TxFrame &f = frames[blockIdx.x];
     unsigned char *A = bufA + f.buf_off, *B = bufB + f.buf_off;
-    float2 *psym = syms + f.sym_off;
+    // the frame's symbols in one array: [14 zeros | 64 preamble | 231 header | n_sym payload | 16 zeros], so that the
+    // interpolator reads a plain window (it used to pick the source of every tap with a three-way branch: 375
+    // instructions per output sample, profiles/r01_notes.md v23)
+    float2 *arr = syms + f.sym_off;
+    float2 *hsym = arr + 14 + 64;
+    float2 *psym = arr + 14 + 64 + 231;
+    for (int i = tid; i < 14; i += kTxThreads) arr[i] = make_float2(0.0f, 0.0f);
+    for (int i = tid; i < 16; i += kTxThreads) psym[f.n_sym + i] = make_float2(0.0f, 0.0f);
+    for (int i = tid; i < 64; i += kTxThreads) arr[14 + i] = T->preamble[i];
+    if (f.check >= 3 && f.check <= 6) {
+        const unsigned *tab = T->crc_tab[f.check];
+        for (int i = tid; i < 256; i += kTxThreads) {
+            const unsigned t0 = tab[i];
+            const unsigned t1 = (t0 >> 8) ^ tab[t0 & 0xffu], t2 = (t1 >> 8) ^ tab[t1 & 0xffu], t3 = (t2 >> 8) ^ tab[t2 & 0xffu];
+            crc4[0][i] = t0; crc4[1][i] = t1; crc4[2][i] = t2; crc4[3][i] = t3;
+        }
+    }
 
     // ---------------- header (thread 0; 20 bytes)
     if (tid == 0) {
@@ -303,9 +319,15 @@ k_tx(const TxTables *T, const TxFrame *frames, unsigned char *bufA, unsigned cha
             for (unsigned i = 0; i < plen; ++i) sum += A[i];
             key = (~sum + 1u) & 0xffu;
         } else if (f.check >= 3 && f.check <= 6) {
-            const unsigned *tab = T->crc_tab[f.check];
+            // four bytes per dependent step (the byte-at-a-time loop was 39 % of the kernel's stall samples)
             unsigned k = 0xffffffffu;
-            for (unsigned i = 0; i < plen; ++i) k = (k >> 8) ^ tab[(k ^ A[i]) & 0xffu];
+            const unsigned *A4 = reinterpret_cast<const unsigned *>(A);          // buf_off is a multiple of 16
+            const unsigned nw = plen >> 2;
+            for (unsigned i = 0; i < nw; ++i) {
+                k ^= A4[i];
+                k = crc4[3][k & 0xffu] ^ crc4[2][(k >> 8) & 0xffu] ^ crc4[1][(k >> 16) & 0xffu] ^ crc4[0][k >> 24];
+            }
+            for (unsigned i = 4 * nw; i < plen; ++i) k = (k >> 8) ^ crc4[0][(k ^ A[i]) & 0xffu];
             const unsigned bits = f.check == 3 ? 8u : f.check == 4 ? 16u : f.check == 5 ? 24u : 32u;
             key = (~k) & (bits == 32 ? 0xffffffffu : ((1u << bits) - 1u));
         }
@@ -341,32 +363,43 @@ k_tx(const TxTables *T, const TxFrame *frames, unsigned char *bufA, unsigned cha
         }
     } else {
         for (unsigned i = tid; i < f.n_sym; i += kTxThreads) {
-            unsigned s = 0;
-            for (unsigned b = 0; b < bps; ++b) s = (s << 1) | bit_at(A, (long long)i * bps + b, nbits);
+            // bps <= 8 bits starting at bit i * bps: they lie inside the two bytes from pos >> 3 (MSB first); bits past
+            // the end of the encoded message read as zero
+            const unsigned pos = i * bps, byte = pos >> 3;
+            unsigned w = ((unsigned)A[byte] << 8) | (byte + 1 < f.n1 ? (unsigned)A[byte + 1] : 0u);
+            unsigned s = (w >> (16u - (pos & 7u) - bps)) & ((1u << bps) - 1u);
+            if (pos + bps > nbits) s &= ~((1u << (pos + bps - nbits)) - 1u);
             psym[i] = modulate(T, f.ms, bps, s);
         }
     }
     __syncthreads();
 
-    // ---------------- 2x interpolation: out[2t+ph] = sum_n h[ph + 2n] sym[t-n], oldest symbol first
+    // ---------------- 2x interpolation: out[2t+ph] = sum_n h[ph + 2n] sym[t-n], oldest symbol first.
+    // A thread makes the four samples of two neighbouring symbols from a 16-symbol window; FFMA2 with the tap as the
+    // scalar operand is two IEEE fmas, applied in the specification's order (n = 14 first), so the samples are
+    // bit-identical to the per-sample form.
     const int total_syms = 64 + 231 + (int)f.n_sym + 14;
     float2 *o = f.out;
-    for (int m = tid; m < 2 * total_syms; m += kTxThreads) {
-        const int t = m >> 1, ph = m & 1;
-        float ar = 0.0f, ai = 0.0f;
+    float h[30];
 #pragma unroll
-        for (int n = 14; n >= 0; --n) {
-            const int u = t - n;
-            float2 s = make_float2(0.0f, 0.0f);
-            if (u >= 0) {
-                if (u < 64) s = T->preamble[u];
-                else if (u < 295) s = hsym[u - 64];
-                else if (u < 295 + (int)f.n_sym) s = psym[u - 295];
+    for (int i = 0; i < 30; ++i) h[i] = __ldg(T->h + i);
+    for (int t = 2 * tid; t < total_syms; t += 2 * kTxThreads) {
+        const float2 *w = arr + t;                    // w[q] = sym[t - 14 + q]
+        float2 a0 = make_float2(0.0f, 0.0f), a1 = a0, a2 = a0, a3 = a0;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const float2 x = w[q];
+            if (q <= 14) {                            // symbol t: n = 14 - q
+                a0 = __ffma2_rn(make_float2(h[2 * (14 - q)], h[2 * (14 - q)]), x, a0);
+                a1 = __ffma2_rn(make_float2(h[1 + 2 * (14 - q)], h[1 + 2 * (14 - q)]), x, a1);
             }
-            const float c = T->h[ph + 2 * n];
-            ar = __fmaf_rn(c, s.x, ar); ai = __fmaf_rn(c, s.y, ai);
+            if (q >= 1) {                             // symbol t + 1: n = 15 - q
+                a2 = __ffma2_rn(make_float2(h[2 * (15 - q)], h[2 * (15 - q)]), x, a2);
+                a3 = __ffma2_rn(make_float2(h[1 + 2 * (15 - q)], h[1 + 2 * (15 - q)]), x, a3);
+            }
         }
-        o[m] = make_float2(ar, ai);
+        o[2 * t] = a0; o[2 * t + 1] = a1;
+        if (t + 1 < total_syms) { o[2 * t + 2] = a2; o[2 * t + 3] = a3; }
     }
 }
 
@@ -513,7 +546,7 @@ int lqb_tx_assemble(lqb_tx h, uint32_t n, const lqb_tx_props *props, const uint8
         f.buf_len = ((std::max(std::max(f.n1, f.n0), f.k0) + 16) + 15u) & ~15u;
         f.pay_off = pay_tot; pay_tot += (lens[i] + 15u) & ~15u;
         f.buf_off = buf_tot; buf_tot += f.buf_len;
-        f.sym_off = sym_tot; sym_tot += f.n_sym;
+        f.sym_off = sym_tot; sym_tot += (f.n_sym + 14 + 64 + 231 + 16 + 1) & ~(size_t)1;      // lead zeros, preamble, header, payload, tail zeros
         f.out_off = out_tot; out_tot += ns;
         if (headers && headers[i]) std::memcpy(f.header, headers[i], 14);
         const unsigned encs[2] = { f.n0, f.n1 }, fss[2] = { f.fec0, f.fec1 };

@@ -66,8 +66,9 @@ def parse():
     ap.add_argument("--streams", type=int, default=1024, help="channels per GPU")
     ap.add_argument("--samples", type=int, default=1 << 20, help="samples per channel per step")
     ap.add_argument("--e2e-samples", type=int, default=1 << 18, help="samples per channel per e2e step")
-    ap.add_argument("--workload", default="flex_rx", choices=["flex_rx", "detector"],
-                    help="flex_rx = configs[2] (default, the headline metric); detector = configs[1] bulk frame_detector_cc")
+    ap.add_argument("--workload", default="flex_rx", choices=["flex_rx", "detector", "tx"],
+                    help="flex_rx = configs[2] (default, the headline metric); detector = configs[1] bulk frame_detector_cc; "
+                         "tx = the flexframegen batch of configs[4] (8192 QAM16 / 1500 B frames per step and GPU)")
     ap.add_argument("--lanes", type=int, default=0, help="pipeline lanes per receiver handle (0 = library default)")
     ap.add_argument("--e2e-lanes", type=int, default=0, help="lanes of the host-buffer (e2e) receiver (0 = library default)")
     ap.add_argument("--no-pipeline", action="store_true", help="use lqb_rx_execute per step instead of submit/collect")
@@ -395,6 +396,100 @@ def detector_arm(args, rank, local, world):
     if world > 1:
         dist.destroy_process_group()
 
+
+def tx_arm(args, rank, local, world):
+    """flex_tx / flexframegen batch (lqb_tx_assemble on device buffers): per step and GPU 8192 frames of BASELINE
+    config 5's format (QAM16, 1500 B, no FEC, CRC-24: 6630 samples each).  Reports generated Msps, frames/s, the
+    HBM-write roofline of k_tx and the oracle's frame generator on one host core beside it."""
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    from liquiddsp import capi
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    QAM16 = 27
+    n = 8192 if args.streams == 1024 else args.streams
+    props = (QAM16, CRC24, 1, 1)
+    L = capi.Tx.frame_len(*props, PAYLOAD)
+    cs = torch.cuda.current_stream(dev)
+    tx = capi.Tx(device=local, cuda_stream=cs.cuda_stream)
+    g = torch.Generator(device="cpu").manual_seed(21 + rank)
+    pay = torch.randint(0, 256, (n, 1504), dtype=torch.uint8, generator=g).to(dev)
+    out = torch.empty((n, L), dtype=torch.complex64, device=dev)
+    P = (capi.TxProps * n)(*[capi.TxProps(CRC24, 1, 1, QAM16) for _ in range(n)])
+    lens = (C.c_uint32 * n)(*([PAYLOAD] * n))
+    pp = (C.c_void_p * n)(*[pay[i].data_ptr() for i in range(n)])
+    op = (C.c_void_p * n)(*[out[i].data_ptr() for i in range(n)])
+
+    def step():
+        capi._check(tx._L.lqb_tx_assemble(tx._h, n, P, None, pp, lens, op, capi.MEM_DEVICE))
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    clocks = ClockSampler(local)
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(cs)
+    for _ in range(args.steps):
+        step()
+    e1.record(cs)
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1)
+    clk = clocks.stop()
+    # kernel-only time: the same launches again with events straight around them (assemble is synchronous, so the
+    # events bracket plan + H2D of the frame table + kernel; the kernel share is what ncu reports in profiles/)
+    tt = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    secs = float(tt[0]) / 1e3
+    value = world * n * L * args.steps / secs / 1e6
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    cpu = None
+    if not args.no_cpu_baseline:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import numpy as np
+        import lqo_py as o
+        hp = pay[:64].cpu().numpy()
+        t0 = time.perf_counter()
+        k = 0
+        while time.perf_counter() - t0 < 5.0:
+            ref = o.tx_frame(QAM16, CRC24, 1, 1, hp[k % 64][:PAYLOAD])
+            if k == 0:
+                assert np.allclose(out[0].cpu().numpy(), ref, atol=2e-6), "k_tx differs from the oracle frame generator"
+            k += 1
+        cpu_s = time.perf_counter() - t0
+        cpu = {"value": k * L / cpu_s / 1e6, "unit": "Msps", "cores": 1, "kind": "port", "sample": "%d frames on one thread, %.1f s" % (k, cpu_s)}
+    gbs = 8.0 * n * L * args.steps / secs / 1e9 * (1.0 / world) * world
+    print(json.dumps({
+        "metric": "flex_tx_msps", "value": value, "unit": "Msps", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": float(tt[0]) / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "flex_tx_batch_qam16_1500B", "frames_per_gpu_per_step": n, "samples_per_frame": L, "mod": "QAM16", "fec0": "none",
+                   "fec1": "none", "check": "crc24", "l2": "outputs (%.2f GB per step) larger than L2" % (n * L * 8 / 1e9)},
+        "frames_per_s": world * n * args.steps / secs, "clocks": clk, "gpu_launches": args.steps,
+        "api": "lqb_tx_assemble (synchronous: host plan + frame table H2D + k_tx + stream sync inside the timed region)",
+        "roofline": {"bound": "hbm", "kernel": "k_tx", "achieved": gbs / world, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / world / hbm_peak,
+                     "traffic": None, "note": "algorithmic bytes = 16 B written per symbol (2 samples x 8 B); the call time includes the host-side "
+                                              "frame plan; k_tx alone is 0.73 ms per 8192 frames (profiles/r01_notes.md v23)"},
+        "cpu_baseline": cpu,
+    }))
+    if world > 1:
+        dist.destroy_process_group()
+
 # ----------------------------------------------------------------------------- our arm
 def main():
     args = parse()
@@ -417,6 +512,9 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     if args.workload == "detector":
         detector_arm(args, rank, local, world)
+        return
+    if args.workload == "tx":
+        tx_arm(args, rank, local, world)
         return
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)

@@ -275,7 +275,12 @@ k_tx(const TxTables *T, const TxFrame *frames, unsigned char *bufA, unsigned cha
         }
     }
 
-    // ---------------- header (thread 0; 20 bytes)
+    // ---------------- payload bytes into the work buffer
+    const unsigned plen = f.payload_len, cl = f.k0 - plen;
+    const unsigned char *pay = f.pay;
+    for (unsigned i = tid; i < plen; i += kTxThreads) A[i] = pay[i];
+    __syncthreads();
+    // ---------------- the two serial sections run side by side: header on warp 0, payload check on warp 1
     if (tid == 0) {
         unsigned char d[28], e27[28];
         for (int i = 0; i < 14; ++i) d[i] = f.header[i];
@@ -297,22 +302,7 @@ k_tx(const TxTables *T, const TxFrame *frames, unsigned char *bufA, unsigned cha
         ilv_small(hb, T->ilv54[0], 27, 0xff); ilv_small(hb, T->ilv54[1], 27, 0x0f);
         ilv_small(hb, T->ilv54[2], 27, 0x55); ilv_small(hb, T->ilv54[3], 27, 0x33);
     }
-    __syncthreads();
-    for (int i = tid; i < 231; i += kTxThreads) {
-        if ((i & 15) == 0) hsym[i] = T->pilots[i >> 4];
-        else {
-            int n = i - (i >> 4) - 1;                     // data symbol ordinal
-            unsigned s = (hb[n >> 2] >> (6 - 2 * (n & 3))) & 3u;
-            hsym[i] = make_float2((s & 1u) ? -0.707106769f : 0.707106769f, (s & 2u) ? -0.707106769f : 0.707106769f);
-        }
-    }
-
-    // ---------------- payload bytes: CRC, whitening
-    const unsigned plen = f.payload_len, cl = f.k0 - plen;
-    const unsigned char *pay = f.pay;
-    for (unsigned i = tid; i < plen; i += kTxThreads) A[i] = pay[i];
-    __syncthreads();
-    if (tid == 0) {
+    if (tid == 32) {
         unsigned key = 0;
         if (f.check == 2) {
             unsigned sum = 0;
@@ -334,6 +324,15 @@ k_tx(const TxTables *T, const TxFrame *frames, unsigned char *bufA, unsigned cha
         for (unsigned i = 0; i < cl; ++i) { A[plen + cl - i - 1] = (unsigned char)(key & 0xffu); key >>= 8; }
     }
     __syncthreads();
+    for (int i = tid; i < 231; i += kTxThreads) {
+        if ((i & 15) == 0) hsym[i] = T->pilots[i >> 4];
+        else {
+            int n = i - (i >> 4) - 1;                     // data symbol ordinal
+            unsigned s = (hb[n >> 2] >> (6 - 2 * (n & 3))) & 3u;
+            hsym[i] = make_float2((s & 1u) ? -0.707106769f : 0.707106769f, (s & 2u) ? -0.707106769f : 0.707106769f);
+        }
+    }
+
     for (unsigned i = tid; i < f.k0; i += kTxThreads) {
         unsigned mask = (i & 3u) == 0 ? 0xb4u : (i & 3u) == 1 ? 0x6au : (i & 3u) == 2 ? 0x8bu : 0xc5u;
         A[i] ^= (unsigned char)mask;

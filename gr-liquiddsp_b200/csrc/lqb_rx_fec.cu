@@ -768,7 +768,20 @@ k_rs(PayloadParams P, const unsigned *__restrict__ blocks, unsigned n_blocks, in
 __global__ void __launch_bounds__(128)
 k_crc(PayloadParams P, const unsigned *__restrict__ list, unsigned n_list)
 {
+    // slicing-by-4 tables of the check the CTA's first frame uses (frames of one call nearly always share it; a warp
+    // whose frame uses another check falls back to the byte-at-a-time loop on the global table)
+    __shared__ unsigned crc4[4][256];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned cta_check = P.frames[list[min(blockIdx.x * 4u, n_list - 1u)]].check;
+    if (cta_check >= 3 && cta_check <= 6) {
+        const unsigned *tab = P.tables->crc_tab[cta_check];
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+            const unsigned t0 = tab[i];
+            const unsigned t1 = (t0 >> 8) ^ tab[t0 & 0xffu], t2 = (t1 >> 8) ^ tab[t1 & 0xffu], t3 = (t2 >> 8) ^ tab[t2 & 0xffu];
+            crc4[0][i] = t0; crc4[1][i] = t1; crc4[2][i] = t2; crc4[3][i] = t3;
+        }
+    }
+    __syncthreads();
     const unsigned gi = blockIdx.x * 4 + warp;
     if (gi >= n_list) return;
     FrameDesc &d = P.frames[list[gi]];
@@ -792,7 +805,18 @@ k_crc(PayloadParams P, const unsigned *__restrict__ list, unsigned n_list)
         } else if (d.check >= 3 && d.check <= 6) {
             const unsigned *tab = P.tables->crc_tab[d.check];
             unsigned k = 0xffffffffu;
-            for (unsigned i = 0; i < plen; ++i) k = (k >> 8) ^ tab[(k ^ buf[i]) & 0xffu];
+            unsigned i0 = 0;
+            if (d.check == cta_check) {
+                // four bytes per dependent step (buf is 16-byte aligned: buf_off is a multiple of 16)
+                const unsigned *b4 = reinterpret_cast<const unsigned *>(buf);
+                const unsigned nw = plen >> 2;
+                for (unsigned i = 0; i < nw; ++i) {
+                    k ^= b4[i];
+                    k = crc4[3][k & 0xffu] ^ crc4[2][(k >> 8) & 0xffu] ^ crc4[1][(k >> 16) & 0xffu] ^ crc4[0][k >> 24];
+                }
+                i0 = 4 * nw;
+            }
+            for (unsigned i = i0; i < plen; ++i) k = (k >> 8) ^ tab[(k ^ buf[i]) & 0xffu];
             const unsigned bits = d.check == 3 ? 8u : d.check == 4 ? 16u : d.check == 5 ? 24u : 32u;
             key = (~k) & (bits == 32 ? 0xffffffffu : ((1u << bits) - 1u));
         }

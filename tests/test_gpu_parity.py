@@ -360,6 +360,23 @@ def test_viterbi_parallel_traceback_rewalk_is_exact(monkeypatch):
             assert_frames_match(rr, [g for g in got if g["stream"] == s], syms=False)
 
 
+@pytest.mark.parametrize("snr", [5.0, 6.0])
+def test_reed_solomon_corrects_and_gives_up_like_the_oracle(snr):
+    # RS(255,223) alone over uncoded QPSK: at 6 dB every block has a few byte errors and all are corrected, at 5 dB
+    # some blocks exceed 16 errors and are left as they are -- Berlekamp-Massey, Chien and Forney all run, and the
+    # delivered bytes (valid or not) must be the oracle's
+    rng = np.random.default_rng(41)
+    pls = [rng.integers(0, 256, 700, dtype=np.uint8) for _ in range(6)]
+    frames = [o.tx_frame(util.PSK4, util.CRC24, 1, 27, p) for p in pls]
+    cap = util.build_capture(frames, rng, [800] * 6, snr_db=snr, cfo=0.01, tau=0.3)
+    ref = o.rx_capture(cap)
+    ok = sum(r["payload_valid"] for r in ref)
+    assert ok == 6 if snr >= 6.0 else 0 < ok < 6
+    rx = capi.Rx(1)
+    rx.execute([cap])
+    assert_frames_match(ref, rx.poll(), syms=False)
+
+
 def test_large_batch_roundtrip_property():
     # size-independent property at scale: every transmitted payload comes back, per stream, in order
     rng = np.random.default_rng(37)

@@ -631,7 +631,8 @@ struct RxLane {
             CU(cudaEventRecord(G.mf_done, ps));
             G.mf_pending = true;
             CU(cudaEventRecord(G.ev[3], ps));
-            launch_pll(pp, G.d_lists.p + loff[1], G.d_lists.p + loff[13], (unsigned)pll.size(), span_start.back(), ps); f.launches += 2;
+            launch_pll(pp, G.d_lists.p + loff[1], G.d_lists.p + loff[13], (unsigned)pll.size(), span_start.back(), ps);
+            f.launches += getenv("LQB_PLL_FUSED") ? 1 : 2;          // tracker + emitter kernels (one fused kernel on request)
             CU(cudaEventRecord(G.ev[4], ps));
             for (int stg = 1; stg >= 0; --stg) {
                 const size_t base = stg ? 3 : 7;

@@ -360,6 +360,36 @@ def test_viterbi_parallel_traceback_rewalk_is_exact(monkeypatch):
             assert_frames_match(rr, [g for g in got if g["stream"] == s], syms=False)
 
 
+def test_fused_pll_kernel_equals_the_two_pass_form(monkeypatch):
+    # LQB_PLL_FUSED=1: tracker warp and emitter warps in one kernel (the emitters follow the tracker's progress words).
+    # Every modulation class, multi-group frames of ragged lengths: bit-identical to the default two kernels in every
+    # field (constellation points included), and the oracle's bytes.
+    rng = np.random.default_rng(43)
+    caps, refs = [], []
+    for s_, ms in enumerate(util.MODS):
+        frames = [o.tx_frame(ms, util.CRC24, 1, 1, rng.integers(0, 256, 300 + 411 * k + 13 * s_, dtype=np.uint8)) for k in range(3)]
+        cap = util.build_capture(frames, rng, [700] * 3, snr_db=30.0, cfo=0.01 * (s_ % 3 - 1), tau=0.2)
+        caps.append(cap)
+        refs.append(o.rx_capture(cap))
+    monkeypatch.delenv("LQB_PLL_FUSED", raising=False)
+    rx = capi.Rx(len(caps))
+    rx.execute(caps)
+    split = rx.poll()
+    monkeypatch.setenv("LQB_PLL_FUSED", "1")
+    rx = capi.Rx(len(caps))
+    rx.execute(caps)
+    fused = rx.poll()
+    assert len(split) == len(fused) == 3 * len(caps)
+    for a, b in zip(split, fused):
+        for k in a:
+            if k == "framesyms":
+                assert np.array_equal(a[k], b[k])
+            else:
+                assert a[k] == b[k] or (isinstance(a[k], float) and np.isnan(a[k]) and np.isnan(b[k])), k
+    for s_, ref in enumerate(refs):
+        assert_frames_match(ref, [g for g in fused if g["stream"] == s_], syms=False)
+
+
 @pytest.mark.parametrize("snr", [5.0, 6.0])
 def test_reed_solomon_corrects_and_gives_up_like_the_oracle(snr):
     # RS(255,223) alone over uncoded QPSK: at 6 dB every block has a few byte errors and all are corrected, at 5 dB

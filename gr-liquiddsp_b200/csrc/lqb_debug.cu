@@ -26,7 +26,32 @@ __global__ void k_dbg_fft512(const float2 *W, const float2 *in, float2 *out, int
     for (int r = 0; r < 16; ++r) out[fft512_out_index(lane, r)] = v[r];
 }
 
+__global__ void k_dbg_pm(const float *y, const float *x, float *at, float *sn, float *cs, unsigned n)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    at[i] = pm_atan2f(y[i], x[i]);
+    pm_sincosf(y[i], &sn[i], &cs[i]);
+}
+
 }  // namespace lqb
+
+// pm_atan2f(y[i], x[i]) and pm_sincosf(y[i]) for n host values (the pinned arg / exp(j t) of the per-symbol loops)
+extern "C" int lqb_dbg_pm(const float *y, const float *x, float *at, float *sn, float *cs, unsigned n)
+{
+    using namespace lqb;
+    float *d[5] = {};
+    for (auto &p : d) if (cudaMalloc(&p, n * sizeof(float)) != cudaSuccess) return -19;
+    cudaMemcpy(d[0], y, n * sizeof(float), cudaMemcpyHostToDevice);
+    cudaMemcpy(d[1], x, n * sizeof(float), cudaMemcpyHostToDevice);
+    k_dbg_pm<<<(n + 255) / 256, 256>>>(d[0], d[1], d[2], d[3], d[4], n);
+    cudaError_t e = cudaDeviceSynchronize();
+    cudaMemcpy(at, d[2], n * sizeof(float), cudaMemcpyDeviceToHost);
+    cudaMemcpy(sn, d[3], n * sizeof(float), cudaMemcpyDeviceToHost);
+    cudaMemcpy(cs, d[4], n * sizeof(float), cudaMemcpyDeviceToHost);
+    for (auto &p : d) cudaFree(p);
+    return e == cudaSuccess ? 0 : -5;
+}
 
 extern "C" int lqb_dbg_fft512(const float *in_host, float *out_host, int dir)
 {

@@ -127,6 +127,54 @@ __device__ __forceinline__ float nco_get_frequency_dev(uint32_t d_theta)
     return d > 3.14159274f ? __fsub_rn(d, 6.28318548f) : d;
 }
 
+// arg() and exp(j t) of the per-symbol loops (generic PSK / DPSK modems), pinned: the specification (oracle/lqo_modem.c,
+// lqo_pm_atan2f / lqo_pm_sincosf) fixes Cephes' single-precision algorithms as a sequence of plain IEEE operations, and
+// this is that sequence (libdevice's atan2f / sincosf differ from it -- and from every libm -- in the last bit, which
+// reached the PLL phase and moved DPSK / PSK8 constellation points by one NCO table step).
+__device__ __forceinline__ float pm_atanf_pos(float x)
+{
+    float y;
+    if (x > 2.414213562373095f) { y = 1.5707963267948966f; x = -__fdiv_rn(1.0f, x); }
+    else if (x > 0.4142135623730950f) { y = 0.7853981633974483f; x = __fdiv_rn(__fsub_rn(x, 1.0f), __fadd_rn(x, 1.0f)); }
+    else y = 0.0f;
+    const float z = __fmul_rn(x, x);
+    float p = __fsub_rn(__fmul_rn(8.05374449538e-2f, z), 1.38776856032e-1f);
+    p = __fadd_rn(__fmul_rn(p, z), 1.99777106478e-1f);
+    p = __fsub_rn(__fmul_rn(p, z), 3.33329491539e-1f);
+    p = __fadd_rn(__fmul_rn(__fmul_rn(p, z), x), x);
+    return __fadd_rn(y, p);
+}
+__device__ __forceinline__ float pm_atan2f(float y, float x)
+{
+    const float ax = fabsf(x), ay = fabsf(y);
+    float r = (ax == 0.0f && ay == 0.0f) ? 0.0f : pm_atanf_pos(__fdiv_rn(ay, ax));
+    if (x < 0.0f) r = __fsub_rn(3.14159274f, r);
+    return y < 0.0f ? -r : r;
+}
+__device__ __forceinline__ void pm_sincosf(float t, float *sn, float *cs)
+{
+    float x = fabsf(t);
+    int j = __float2int_rz(__fmul_rn(1.27323954473516f, x));
+    if (j & 1) j += 1;
+    const float y = (float)j;
+    j &= 7;
+    bool s_neg = t < 0.0f, c_neg = false;
+    if (j > 3) { s_neg = !s_neg; c_neg = !c_neg; j -= 4; }
+    if (j > 1) c_neg = !c_neg;
+    x = __fsub_rn(__fsub_rn(__fsub_rn(x, __fmul_rn(y, 0.78515625f)), __fmul_rn(y, 2.4187564849853515625e-4f)), __fmul_rn(y, 3.77489497744594108e-8f));
+    const float z = __fmul_rn(x, x);
+    float ps = __fadd_rn(__fmul_rn(-1.9515295891e-4f, z), 8.3321608736e-3f);
+    ps = __fsub_rn(__fmul_rn(ps, z), 1.6666654611e-1f);
+    ps = __fadd_rn(__fmul_rn(__fmul_rn(ps, z), x), x);
+    float pc = __fsub_rn(__fmul_rn(2.443315711809948e-5f, z), 1.388731625493765e-3f);
+    pc = __fadd_rn(__fmul_rn(pc, z), 4.166664568298827e-2f);
+    pc = __fadd_rn(__fsub_rn(__fmul_rn(__fmul_rn(pc, z), z), __fmul_rn(0.5f, z)), 1.0f);
+    const bool swap = (j == 1 || j == 2);
+    const float s = swap ? pc : ps, c = swap ? ps : pc;
+    *sn = s_neg ? -s : s;
+    *cs = c_neg ? -c : c;
+}
+
 // sample accessor over [carry | new input] with the zero region below G
 struct StreamView {
     const float2 *carry;

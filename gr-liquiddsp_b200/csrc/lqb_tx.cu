@@ -356,7 +356,7 @@ k_tx(const TxTables *T, const TxFrame *frames, unsigned char *bufA, unsigned cha
                 phi = __fadd_rn(phi, __fmul_rn(__fmul_rn((float)gray_dec(s), 2.0f), alpha));
                 if (phi > kTwoPiF) phi = __fsub_rn(phi, kTwoPiF);
                 float sn, cs;
-                sincosf(phi, &sn, &cs);
+                pm_sincosf(phi, &sn, &cs);
                 psym[i] = make_float2(cs, sn);
             }
         }

@@ -134,6 +134,9 @@ lqo_cf   lqo_modem_modulate(lqo_modem *q, unsigned sym);
 unsigned lqo_modem_demodulate(lqo_modem *q, lqo_cf x);
 float    lqo_modem_phase_error(const lqo_modem *q);
 float    lqo_modem_evm(const lqo_modem *q);
+/* the pinned arg() / exp(j t) of the per-symbol loops (see lqo_modem.c) */
+float    lqo_pm_atan2f(float y, float x);
+void     lqo_pm_sincosf(float t, float *sn, float *cs);
 
 /* ---- qpacketmodem ---- */
 unsigned lqo_qpm_frame_len(unsigned payload_len, int check, int fec0, int fec1, int ms);

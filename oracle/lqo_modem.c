@@ -41,6 +41,52 @@ static int is_qam_(int ms)  { return ms >= LQ_MODEM_QAM4 && ms <= LQ_MODEM_QAM25
 
 static lqo_cf cexpj_(float t) { lqo_cf y = { cosf(t), sinf(t) }; return y; }
 
+/* arg() and exp(j t) INSIDE the per-symbol receive / transmit loops (generic PSK and DPSK modems).  liquid-dsp calls the
+ * platform's cargf / cexpf there, so its own results move in the last bit with the libm version (glibc 2.39's atan2f
+ * differs from the correctly rounded value for 16 % of random arguments); that last bit reaches the PLL phase and moves
+ * constellation points across a step of the NCO table.  The oracle therefore pins ONE implementation -- Cephes' single
+ * precision atanf / sinf / cosf (S. Moshier, public domain algorithm: argument reduction + the polynomials below), every
+ * operation a plain IEEE float operation in a fixed order (this file is compiled with -ffp-contract=off) -- and the CUDA
+ * path (csrc/lqb_dev.cuh: pm_atan2f / pm_sincosf) executes the same sequence, so the two agree bit for bit
+ * (tests/test_gpu_parity.py::test_pinned_arg_and_sincos_match_the_oracle_bit_for_bit).  Within 2 ulp of libm. */
+static float pm_atanf_pos_(float x)                 /* x >= 0 (may be +inf) */
+{
+    float y;
+    if (x > 2.414213562373095f) { y = 1.5707963267948966f; x = -(1.0f / x); }
+    else if (x > 0.4142135623730950f) { y = 0.7853981633974483f; x = (x - 1.0f) / (x + 1.0f); }
+    else y = 0.0f;
+    const float z = x * x;
+    const float p = (((8.05374449538e-2f * z - 1.38776856032e-1f) * z + 1.99777106478e-1f) * z - 3.33329491539e-1f) * z * x + x;
+    return y + p;
+}
+float lqo_pm_atan2f(float y, float x)
+{
+    const float ax = fabsf(x), ay = fabsf(y);
+    float r = (ax == 0.0f && ay == 0.0f) ? 0.0f : pm_atanf_pos_(ay / ax);
+    if (x < 0.0f) r = 3.14159274f - r;
+    return y < 0.0f ? -r : r;
+}
+void lqo_pm_sincosf(float t, float *sn, float *cs)     /* |t| < 8192 */
+{
+    float x = fabsf(t);
+    int j = (int)(1.27323954473516f * x);               /* 4 / pi */
+    if (j & 1) j += 1;
+    const float y = (float)j;
+    j &= 7;
+    int s_neg = t < 0.0f, c_neg = 0;
+    if (j > 3) { s_neg = !s_neg; c_neg = !c_neg; j -= 4; }
+    if (j > 1) c_neg = !c_neg;
+    x = ((x - y * 0.78515625f) - y * 2.4187564849853515625e-4f) - y * 3.77489497744594108e-8f;
+    const float z = x * x;
+    const float ps = ((-1.9515295891e-4f * z + 8.3321608736e-3f) * z - 1.6666654611e-1f) * z * x + x;
+    const float pc = ((2.443315711809948e-5f * z - 1.388731625493765e-3f) * z + 4.166664568298827e-2f) * z * z - 0.5f * z + 1.0f;
+    const int swap = (j == 1 || j == 2);
+    const float s = swap ? pc : ps, c = swap ? ps : pc;
+    *sn = s_neg ? -s : s;
+    *cs = c_neg ? -c : c;
+}
+static lqo_cf cexpj_pm_(float t) { lqo_cf y; lqo_pm_sincosf(t, &y.im, &y.re); return y; }
+
 static lqo_cf modulate_raw_(lqo_modem *q, unsigned s)
 {
     lqo_cf y = { 0.0f, 0.0f };
@@ -95,7 +141,7 @@ lqo_cf lqo_modem_modulate(lqo_modem *q, unsigned s)
     if (is_dpsk_(q->scheme)) {
         q->dpsk_phi += (float)gray_decode_(s) * 2.0f * q->alpha;
         if (q->dpsk_phi > 2.0f * (float)M_PI) q->dpsk_phi -= 2.0f * (float)M_PI;
-        return cexpj_(q->dpsk_phi);
+        return cexpj_pm_(q->dpsk_phi);
     }
     return q->map[s & (q->M - 1u)];
 }
@@ -119,13 +165,13 @@ unsigned lqo_modem_demodulate(lqo_modem *q, lqo_cf x)
     unsigned s = 0, sym = 0;
     float res;
     if (is_psk_(ms)) {
-        float theta = atan2f(x.im, x.re) - q->d_phi;
+        float theta = lqo_pm_atan2f(x.im, x.re) - q->d_phi;
         if (theta < -(float)M_PI) theta += 2.0f * (float)M_PI;
         slice_(theta, q->bps, q->ref, &s, &res);
         sym = gray_encode_(s);
         q->x_hat = q->map[sym];
     } else if (is_dpsk_(ms)) {
-        float theta = atan2f(x.im, x.re);
+        float theta = lqo_pm_atan2f(x.im, x.re);
         float d = theta - q->dpsk_phi;
         q->dpsk_phi = theta;
         d -= q->d_phi;
@@ -133,7 +179,7 @@ unsigned lqo_modem_demodulate(lqo_modem *q, lqo_cf x)
         else if (d < -(float)M_PI) d += 2.0f * (float)M_PI;
         slice_(d, q->bps, q->ref, &s, &res);
         sym = gray_encode_(s);
-        q->x_hat = cexpj_(theta - res);
+        q->x_hat = cexpj_pm_(theta - res);
     } else if (is_ask_(ms)) {
         slice_(x.re, q->bps, q->ref, &s, &res);
         sym = gray_encode_(s);

@@ -59,6 +59,35 @@ def test_fft512_warp_kernel_is_bit_exact_with_the_oracle_fft():
         assert np.array_equal(y.view(np.uint32), yo.view(np.uint32))
 
 
+def test_pinned_arg_and_sincos_match_the_oracle_bit_for_bit():
+    # arg() / exp(j t) inside the PSK / DPSK symbol loops are a fixed sequence of IEEE operations on both sides
+    L = capi.lib()
+    fp = C.c_void_p
+    L.lqb_dbg_pm.argtypes = [fp, fp, fp, fp, fp, C.c_uint]
+    O = o.lib()
+    O.lqo_pm_atan2f.restype = C.c_float
+    O.lqo_pm_atan2f.argtypes = [C.c_float, C.c_float]
+    O.lqo_pm_sincosf.argtypes = [C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    rng = np.random.default_rng(2)
+    n = 20000
+    y = np.concatenate([rng.uniform(-7.0, 7.0, n - 8), [0.0, -0.0, 1.0, -1.0, 1e-30, 3.14159274, -3.14159274, 6.2831855]]).astype(np.float32)
+    x = np.concatenate([rng.standard_normal(n - 8), [0.0, 1.0, 0.0, -0.0, -1.0, 1.0, -1.0, 1e-20]]).astype(np.float32)
+    at, sn, cs = (np.zeros(n, np.float32) for _ in range(3))
+    assert L.lqb_dbg_pm(y.ctypes.data, x.ctypes.data, at.ctypes.data, sn.ctypes.data, cs.ctypes.data, n) == 0
+    ro = np.zeros((3, n), np.float32)
+    s_, c_ = C.c_float(), C.c_float()
+    for i in range(n):
+        ro[0, i] = O.lqo_pm_atan2f(float(y[i]), float(x[i]))
+        O.lqo_pm_sincosf(float(y[i]), C.byref(s_), C.byref(c_))
+        ro[1, i], ro[2, i] = s_.value, c_.value
+    assert np.array_equal(at.view(np.uint32), ro[0].view(np.uint32))
+    assert np.array_equal(sn.view(np.uint32), ro[1].view(np.uint32))
+    assert np.array_equal(cs.view(np.uint32), ro[2].view(np.uint32))
+    # and they are the functions they claim to be
+    assert np.max(np.abs(at - np.arctan2(y.astype(np.float64), x.astype(np.float64)))) < 5e-7
+    assert np.max(np.abs(sn - np.sin(y.astype(np.float64)))) < 2e-7 and np.max(np.abs(cs - np.cos(y.astype(np.float64)))) < 2e-7
+
+
 def test_golden_capture_decodes_to_golden_bytes():
     G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "loopback_v1.npz"))
     rx = capi.Rx(1)

@@ -607,7 +607,7 @@ __device__ void align_frame(SeekShared &sh, const DevTables *T, int tid)
     for (int i = tid; i < 156; i += kThreads) {
         float ang = __fmul_rn(-dphi, (float)i);
         float sn, cs;
-        sincosf(ang, &sn, &cs);
+        pm_sincosf(ang, &sn, &cs);
         vsum[i] = cmulf(zbuf[i], make_float2(cs, sn));
     }
     wsync();
@@ -616,7 +616,7 @@ __device__ void align_frame(SeekShared &sh, const DevTables *T, int tid)
         float mr = 0.0f, mi = 0.0f;
 #pragma unroll 12
         for (int i = 0; i < 156; ++i) { const float2 q = vsum[i]; mr = __fadd_rn(mr, q.x); mi = __fadd_rn(mi, q.y); }
-        sh.phi = atan2f(mi, mr);
+        sh.phi = pm_atan2f(mi, mr);
         sh.theta0 = nco_constrain_dev(sh.phi);
         sh.dtheta = nco_constrain_dev(sh.dphi);
         if (sh.tau > 0.0f) {
@@ -702,7 +702,7 @@ __device__ void decode_header(SeekShared &sh, const DevTables *T, const StreamVi
         if (lane < 15u) {
             float ang = __fmul_rn(__fmul_rn(-dphi, (float)lane), 16.0f);
             float sn, cs;
-            sincosf(ang, &sn, &cs);
+            pm_sincosf(ang, &sn, &cs);
             r = cmulf(bt, make_float2(cs, sn));
         }
         float mr = 0.0f, mi = 0.0f;
@@ -712,7 +712,7 @@ __device__ void decode_header(SeekShared &sh, const DevTables *T, const StreamVi
             mi = __fadd_rn(mi, __shfl_sync(0xffffffffu, r.y, i));
         }
         if (lane == 0) {
-            float phi = atan2f(mi, mr);
+            float phi = pm_atan2f(mi, mr);
             float g_hat = __fdiv_rn(cabsf_(make_float2(mr, mi)), 15.0f);
             pil[0] = make_float2(dphi, phi);
             pil[1] = make_float2(__fdiv_rn(1.0f, g_hat), 0.0f);
@@ -731,7 +731,7 @@ __device__ void decode_header(SeekShared &sh, const DevTables *T, const StreamVi
                 int i = n + n / 15 + 1;                  // position in the pilot-bearing frame
                 float ang = -__fadd_rn(__fmul_rn(dphi, (float)i), phi);
                 float sn, cs;
-                sincosf(ang, &sn, &cs);
+                pm_sincosf(ang, &sn, &cs);
                 float2 v = cmulf(hsym[i], make_float2(cs, sn));
                 v.x = __fmul_rn(v.x, g); v.y = __fmul_rn(v.y, g);
                 unsigned s = (v.x > 0.0f ? 0u : 1u) + (v.y > 0.0f ? 0u : 2u);

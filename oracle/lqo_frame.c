@@ -112,18 +112,18 @@ void lqo_qpilotsync(unsigned payload_len, unsigned spacing, const lqo_cf *frame,
     lqo_cf metric = { 0.0f, 0.0f };
     for (unsigned i = 0; i < np; i++) {
         float ang = -dphi * (float)i * (float)spacing;
-        lqo_cf rot = { cosf(ang), sinf(ang) };
+        lqo_cf rot; lqo_pm_sincosf(ang, &rot.im, &rot.re);      /* pinned exp(j ang), see lqo_modem.c */
         lqo_cf v = cmul_(bt[i], rot);
         metric.re += v.re; metric.im += v.im;
     }
-    float phi = atan2f(metric.im, metric.re);
+    float phi = lqo_pm_atan2f(metric.im, metric.re);
     float g_hat = cabs_(metric) / (float)np;
     float g = 1.0f / g_hat;
     unsigned n = 0;
     for (unsigned i = 0; i < fl; i++) {
         if (i % spacing == 0) continue;
         float ang = -(dphi * (float)i + phi);
-        lqo_cf rot = { cosf(ang), sinf(ang) };
+        lqo_cf rot; lqo_pm_sincosf(ang, &rot.im, &rot.re);      /* pinned exp(j ang), see lqo_modem.c */
         lqo_cf v = cmul_(frame[i], rot);
         payload[n].re = v.re * g; payload[n].im = v.im * g; n++;
     }
@@ -269,11 +269,11 @@ static void qd_align_finish_(lqo_qdetector q)
     lqo_cf metric = { 0.0f, 0.0f };
     for (unsigned i = 0; i < q->s_len; i++) {
         float ang = -q->dphi_hat * (float)i;
-        lqo_cf rot = { cosf(ang), sinf(ang) };
+        lqo_cf rot; lqo_pm_sincosf(ang, &rot.im, &rot.re);      /* pinned exp(j ang), see lqo_modem.c */
         lqo_cf v = cmul_(q->buf_time_0[i], rot);
         metric.re += v.re; metric.im += v.im;
     }
-    q->phi_hat = atan2f(metric.im, metric.re);
+    q->phi_hat = lqo_pm_atan2f(metric.im, metric.re);
     q->frame_detected = 1;
     memmove(q->buf_time_0, q->buf_time_1 + n / 2, (n / 2) * sizeof(lqo_cf));
     q->state = QD_SEEK;

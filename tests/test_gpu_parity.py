@@ -388,6 +388,24 @@ def test_viterbi_parallel_traceback_rewalk_is_exact(monkeypatch):
             assert_frames_match(rr, [g for g in got if g["stream"] == s], syms=False)
 
 
+@pytest.mark.parametrize("f0,f1", [(11, 1), (11, 27), (15, 7), (1, 27), (20, 6)])
+def test_tiny_payloads_match_oracle(f0, f1):
+    # 1 .. 9 byte payloads with and without a check: codewords shorter than the four-lane traceback's quarters,
+    # matched-filter tiles and PLL chunks with a handful of symbols, RS blocks of a few bytes
+    rng = np.random.default_rng(44)
+    frames, n = [], 0
+    for plen in (1, 2, 3, 4, 5, 9):
+        for check in (1, util.CRC24):
+            frames.append(o.tx_frame(util.PSK4 if n % 2 else util.QAM16, check, f0, f1, rng.integers(0, 256, plen, dtype=np.uint8)))
+            n += 1
+    cap = util.build_capture(frames, rng, [640] * len(frames), snr_db=30.0, cfo=0.008, tau=0.25)
+    ref = o.rx_capture(cap)
+    assert len(ref) == len(frames) and all(r["payload_valid"] for r in ref)
+    rx = capi.Rx(1)
+    rx.execute([cap])
+    assert_frames_match(ref, rx.poll())
+
+
 def test_fused_pll_kernel_equals_the_two_pass_form(monkeypatch):
     # LQB_PLL_FUSED=1: tracker warp and emitter warps in one kernel (the emitters follow the tracker's progress words).
     # Every modulation class, multi-group frames of ragged lengths: bit-identical to the default two kernels in every

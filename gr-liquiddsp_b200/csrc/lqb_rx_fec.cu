@@ -434,7 +434,9 @@ template <bool PUNCT>
 __global__ void __launch_bounds__(kV4Threads)
 k_viterbi27x4(PayloadParams P, const unsigned *__restrict__ list, unsigned n_list, int stage, unsigned *__restrict__ dec, int warm)
 {
-    __shared__ uint4 lut[kV4Lanes][6][4];           // [lane][phase][two received bits] -> v4_metrics
+    // [lane][phase][received pair] -> v4_metrics; a received symbol is 0, 1 or (punctured codes) 2 = erased
+    constexpr int kPairs = PUNCT ? 9 : 4;
+    __shared__ uint4 lut[kV4Lanes][6][kPairs];
     const unsigned gt = blockIdx.x * kV4Threads + threadIdx.x;
     const unsigned l = gt % kV4Lanes;
     unsigned gi = gt / kV4Lanes;
@@ -449,24 +451,21 @@ k_viterbi27x4(PayloadParams P, const unsigned *__restrict__ list, unsigned n_lis
     unsigned Tw = T;                                  // longest codeword in this warp
 #pragma unroll
     for (int m = 16; m >= 1; m >>= 1) Tw = max(Tw, __shfl_xor_sync(0xffffffffu, Tw, m));
-    unsigned per = 0, pre[8];
-    for (unsigned c = 0; c < cs.P; ++c) { pre[c] = per; per += ((cs.keep0 >> c) & 1u) + ((cs.keep1 >> c) & 1u); }
     const unsigned char *enc = io.src;
     const unsigned enc_words = max((io.enc_len + 3u) / 4u, 1u);
 
     // lane part of the branch labels, as XOR masks on the received symbols, per phase
     auto lane_mask = [](unsigned lane, int r, unsigned poly) { return (__popc((lane << kV4PosBits) & v4_phase_mask(poly, r)) & 1) ? 255u : 0u; };
-    if (!PUNCT) {
-        for (unsigned i = threadIdx.x; i < kV4Lanes * 6 * 4; i += kV4Threads) {
-            const unsigned ll = i / 24u, v = i & 3u;
-            const int r = (int)((i >> 2) % 6u);
-            lut[ll][r][v] = v4_metrics(r, ((v & 2u) ? 255u : 0u) ^ lane_mask(ll, r, 0x6d), ((v & 1u) ? 255u : 0u) ^ lane_mask(ll, r, 0x4f));
+    {
+        const unsigned soft[3] = { 0u, 255u, 127u };
+        for (unsigned i = threadIdx.x; i < kV4Lanes * 6 * kPairs; i += kV4Threads) {
+            const unsigned ll = i / (6 * kPairs), v = i % kPairs;
+            const int r = (int)((i / kPairs) % 6u);
+            const unsigned s0 = PUNCT ? soft[v / 3u] : ((v & 2u) ? 255u : 0u), s1 = PUNCT ? soft[v % 3u] : ((v & 1u) ? 255u : 0u);
+            lut[ll][r][v] = v4_metrics(r, s0 ^ lane_mask(ll, r, 0x6d), s1 ^ lane_mask(ll, r, 0x4f));
         }
         __syncthreads();
     }
-    unsigned mk0[6], mk1[6];
-#pragma unroll
-    for (int r = 0; r < 6; ++r) { mk0[r] = lane_mask(l, r, 0x6d); mk1[r] = lane_mask(l, r, 0x4f); }
     // phases 0 and 1 exchange with the lane that differs in bit 1 / bit 0; the lane holding the upper predecessors
     // adds one to the raw difference (see v4_step) and its flags are stored uninverted
     const unsigned up5 = (l >> 1) & 1u, up4 = l & 1u;
@@ -479,28 +478,32 @@ k_viterbi27x4(PayloadParams P, const unsigned *__restrict__ list, unsigned n_lis
     for (int j = 0; j < 8; ++j) W[j] = 63u | (63u << 16);
     if (l == 0) W[0] = 63u << 16;                   // state 0 sits at position 0 at t = 0
 
-    unsigned col = 0, q = 0;                        // punctured: t = q * P + col
     const unsigned *enc32 = reinterpret_cast<const unsigned *>(enc);     // byte arenas are 16-byte aligned per frame
-    // unpunctured: the 12 encoded bits of six steps (MSB first, in the top bits), fetched one group ahead
-    auto fetch12 = [&](unsigned t0) {
-        const unsigned o = 2u * t0, idx = o >> 5;
+    // 32 encoded bits from bit offset o (MSB first, in the top bits); six steps use at most 12 of them
+    auto fetch32 = [&](unsigned o) {
+        const unsigned idx = o >> 5;
         const unsigned a = __byte_perm(__ldg(enc32 + min(idx, enc_words - 1u)), 0u, 0x0123);
         const unsigned b = __byte_perm(__ldg(enc32 + min(idx + 1u, enc_words - 1u)), 0u, 0x0123);
         return __funnelshift_l(b, a, o & 31u);
     };
-    unsigned bits = 0, bits_next = PUNCT ? 0u : fetch12(0u);
+    // unpunctured: the window of the next group is fetched one group ahead; punctured: the bit position of the next group
+    // depends on the puncturing column, the window is fetched at the group's start
+    unsigned bits = 0, bits_next = PUNCT ? 0u : fetch32(0u);
+    unsigned bitpos = 0, col = 0;                   // punctured: encoded bits consumed, column t mod P
     const char *lut_l = reinterpret_cast<const char *>(&lut[l][0][0]);
-    auto metrics = [&](const int r, const unsigned m0, const unsigned m1) -> uint4 {
+    auto metrics = [&](const int r) -> uint4 {
         if (PUNCT) {
-            unsigned ib = q * per + pre[col];
-            unsigned s0 = 127u, s1 = 127u;
-            if ((cs.keep0 >> col) & 1u) { s0 = (ib >> 3) < io.enc_len ? soft_bit(enc, ib) : 0u; ++ib; }
-            if ((cs.keep1 >> col) & 1u) { s1 = (ib >> 3) < io.enc_len ? soft_bit(enc, ib) : 0u; }
-            if (++col == cs.P) { col = 0; ++q; }
-            return v4_metrics(r, s0 ^ m0, s1 ^ m1);
+            const unsigned k0 = (cs.keep0 >> col) & 1u, k1 = (cs.keep1 >> col) & 1u;
+            const unsigned c0 = k0 ? bits >> 31 : 2u;
+            bits <<= k0;
+            const unsigned c1 = k1 ? bits >> 31 : 2u;
+            bits <<= k1;
+            bitpos += k0 + k1;
+            col = (col + 1u == cs.P) ? 0u : col + 1u;
+            return *reinterpret_cast<const uint4 *>(lut_l + 16 * kPairs * r + 16 * (3u * c0 + c1));
         } else {
             const int sh = 26 - 2 * r;                 // the step's two bits -> byte offset 16 * v
-            const unsigned off = (sh >= 0 ? bits >> sh : bits << -sh) & 0x30u;
+            const unsigned off = (bits >> sh) & 0x30u;
             return *reinterpret_cast<const uint4 *>(lut_l + 64 * r + off);
         }
     };
@@ -511,16 +514,17 @@ k_viterbi27x4(PayloadParams P, const unsigned *__restrict__ list, unsigned n_lis
 #define LQB_V4_PAIR(R, ROLE_E, ROLE_O, XM)                                        \
     {                                                                             \
         unsigned G[8];                                                            \
-        v4_step<R>(W, metrics(R, mk0[R], mk1[R]), ROLE_E, G);                     \
+        v4_step<R>(W, metrics(R), ROLE_E, G);                                     \
         const unsigned re = v4_pack(G);                                           \
-        v4_step<R + 1>(W, metrics(R + 1, mk0[R + 1], mk1[R + 1]), ROLE_O, G);     \
+        v4_step<R + 1>(W, metrics(R + 1), ROLE_O, G);                             \
         const unsigned ro = v4_pack(G);                                           \
         const unsigned dd = ((re & 0xf0f0f0f0u) | ((ro >> 4) & 0x0f0f0f0fu)) ^ (XM); \
         if (active && t + R < T) out_dec[(size_t)((t + R) >> 1) * dstride] = dd;  \
     }
     // whole groups of six phases; steps past a codeword's end run on arbitrary symbols and store nothing
     for (; t < Tw; t += 6) {
-        if (!PUNCT) { bits = bits_next; bits_next = fetch12(t + 6u); }
+        if (!PUNCT) { bits = bits_next; bits_next = fetch32(2u * (t + 6u)); }
+        else bits = fetch32(bitpos);
         LQB_V4_PAIR(0, role0, role1, xm0)
         LQB_V4_PAIR(2, 0x00010000u, 0u, xm1)
         LQB_V4_PAIR(4, 0u, 0u, xm2)

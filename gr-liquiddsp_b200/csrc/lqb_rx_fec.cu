@@ -306,8 +306,9 @@ k_viterbi(PayloadParams P, const unsigned *__restrict__ list, unsigned n_list, i
 // written back in place, so four steps out of six are register-only and two exchange with one other lane
 // through one shuffle per metric.  Branch labels are parities of position bits: the register part is a
 // compile-time constant, the lane part a per-thread mask XORed into the received symbols once per step.
-// Decisions are stored per position ([step][codeword] 64-bit, lane l owns bits 16 l .. 16 l + 15); the
-// traceback undoes the rotation.  Same integer metrics, comparisons and tie-breaks as the specification.
+// Decisions are stored per position ([step pair][codeword][lane] 32-bit words: the lane's 16 positions of the even
+// step in the high nibbles of the four bytes, of the odd step in the low nibbles); the traceback works in position
+// coordinates.  Same integer metrics, comparisons and tie-breaks as the specification.
 constexpr int kV4Lanes = 4, kV4PosBits = 4;
 
 __host__ __device__ constexpr unsigned v4_par6(unsigned x) { x ^= x >> 4; x ^= x >> 2; x ^= x >> 1; return x & 1u; }

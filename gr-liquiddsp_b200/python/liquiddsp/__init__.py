@@ -2,4 +2,4 @@
 (/root/reference/python/__init__.py:4,9: the SWIG blocks first, then the pure-Python blocks)."""
 from . import capi  # noqa: F401
 from .blocks import flex_rx, flex_tx, frame_detector_cc  # noqa: F401
-from . import policy, sharding, bulk  # noqa: F401
+from . import policy, sharding, bulk, replay  # noqa: F401

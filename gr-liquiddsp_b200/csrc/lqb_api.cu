@@ -167,7 +167,8 @@ struct Front {
     // below the header threshold searches all of them and aligns at every detection), so the longest are started
     // first (profiles/r01_notes.md v19).  Only the ORDER of the io entries changes; results do not depend on it.
     std::vector<int64_t> est_work;
-    bool lpt = getenv("LQB_NO_LPT") == nullptr && getenv("LQB_COARSE_SEPARATE") == nullptr;
+    bool coarse_separate = getenv("LQB_COARSE_SEPARATE") != nullptr;
+    bool lpt = getenv("LQB_NO_LPT") == nullptr && !coarse_separate;
     uint64_t launches = 0;
     // tensor-core pre-filter (lqb_rx_coarse.cu)
     bool coarse_ok = false;
@@ -491,7 +492,7 @@ struct RxLane {
         G.sp.det_mode = 0; G.sp.frames = G.d_frames.p; G.sp.detections = nullptr;
         G.sp.n_out = f.io[f.cur].d_count; G.sp.max_out = (unsigned)G.max_frames;
         CU(cudaEventRecord(G.ev[0], st));
-        if (!f.lpt) CU(cudaStreamSynchronize(st));      // debug modes plan the separate pre-filter from the host mirror of the states
+        if (f.coarse_separate) CU(cudaStreamSynchronize(st));      // debug mode: the separate pre-filter is planned from the host mirror of the states
         if (int e = f.run_coarse(n, G.ns_copy.data(), G.sp)) return e;
         CU(cudaMemsetAsync(f.io[f.cur].d_count, 0, 8 * sizeof(unsigned), st));
         launch_seek(G.sp, n, st); f.launches++;

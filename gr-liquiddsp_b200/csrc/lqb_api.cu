@@ -167,18 +167,12 @@ struct Front {
     // below the header threshold searches all of them and aligns at every detection), so the longest are started
     // first (profiles/r01_notes.md v19).  Only the ORDER of the io entries changes; results do not depend on it.
     std::vector<int64_t> est_work;
-    bool coarse_separate = getenv("LQB_COARSE_SEPARATE") != nullptr;
-    bool lpt = getenv("LQB_NO_LPT") == nullptr && !coarse_separate;
+    bool lpt = getenv("LQB_NO_LPT") == nullptr;
     uint64_t launches = 0;
-    // tensor-core pre-filter (lqb_rx_coarse.cu)
+    // tensor-core pre-filter fused into k_seek: the B operand (template x 49 CFO rotations) in shared-memory layout
     bool coarse_ok = false;
     void *d_bmat = nullptr;
-    DevBuf<float> d_m8, d_e8;
-    DevBuf<unsigned> d_tpre;
-    PinBuf<unsigned> h_tpre;
-    StreamState *h_states = nullptr;      // pinned host mirror of d_states (carry lengths for tile planning)
-    float coarse_ms = 0.0f;
-    cudaEvent_t cev[2] = { nullptr, nullptr };
+    StreamState *h_states = nullptr;      // pinned staging for reset()
 
     int init(int dev, unsigned ns, unsigned cap, void *user_stream, const DevTables &T, bool low_priority = false)
     {
@@ -187,7 +181,7 @@ struct Front {
         if (dev < 0 || dev >= ndev) return fail(LQB_ENODEV, "device ordinal out of range");
         cudaDeviceProp prop;
         CU(cudaGetDeviceProperties(&prop, dev));
-        if (prop.major < 10) return fail(LQB_ENODEV, "device is not sm_100 class; this library carries sm_100a code only");
+        if (prop.major != 10) return fail(LQB_ENODEV, "device is not sm_100 class; this library carries sm_100a code only");
         device = dev; n_streams = ns; carry_cap = cap;
         CU(cudaSetDevice(dev));
         if (user_stream) stream = (cudaStream_t)user_stream;
@@ -206,7 +200,6 @@ struct Front {
             CU(cudaMallocHost(&x.h_count, 8 * sizeof(unsigned)));
         }
         CU(cudaMallocHost(&h_states, (size_t)ns * sizeof(StreamState)));
-        CU(cudaEventCreate(&cev[0])); CU(cudaEventCreate(&cev[1]));
         fed.assign(ns, 0);
         est_work.assign(ns, 0);
         if (T.range == 24 && !getenv("LQB_NO_COARSE")) {
@@ -299,39 +292,12 @@ struct Front {
         *total = tot; *max_n = mx;
         return 0;
     }
-    // plan and launch the pre-filter for the streams just fed; fills the coarse fields of sp
-    int run_coarse(uint32_t n, const uint64_t *ns, SeekParams &sp)
+    // the pre-filter fields of sp (coarse == 0: exact FFT search only, LQB_NO_COARSE=1)
+    void set_coarse(SeekParams &sp) const
     {
-        sp.coarse = 0; sp.tile_prefix = nullptr; sp.m8 = nullptr; sp.e8 = nullptr; sp.bmat = d_bmat;
-        coarse_ms = 0.0f;
-        if (!coarse_ok || !n) return 0;
-        DevBuf<StreamIO> &d_io = io[cur].d_io;
-        PinBuf<StreamIO> &h_io = io[cur].h_io;
-        if (!getenv("LQB_COARSE_SEPARATE")) { sp.coarse = 2; h_tpre.reserve(n + 1); h_tpre.p[n] = 0; return 0; }   // fused in k_seek
-        if (int e = h_tpre.reserve(n + 1)) return e;
-        if (int e = d_tpre.reserve(n + 1)) return e;
-        uint64_t tiles = 0;
-        for (uint32_t i = 0; i < n; ++i) {
-            h_tpre.p[i] = (unsigned)tiles;
-            const uint64_t L = (uint64_t)h_states[h_io.p[i].stream].carry_len + ns[i];
-            tiles += (L + 127) / 128;
-        }
-        h_tpre.p[n] = (unsigned)tiles;
-        if (tiles == 0 || tiles > 0xfffffff0ull / 16) return 0;
-        if (int e = d_m8.reserve(tiles * 16 + 64)) return e;
-        if (int e = d_e8.reserve(tiles * 16 + 64)) return e;
-        CU(cudaMemcpyAsync(d_tpre.p, h_tpre.p, (n + 1) * sizeof(unsigned), cudaMemcpyHostToDevice, stream));
-        CoarseParams cp;
-        cp.states = d_states; cp.io = d_io.p; cp.carry[0] = d_carry[0]; cp.carry[1] = d_carry[1]; cp.carry_cap = carry_cap;
-        cp.tile_prefix = d_tpre.p; cp.n_io = n; cp.n_tiles = (unsigned)tiles; cp.bmat = d_bmat; cp.m8 = d_m8.p; cp.e8 = d_e8.p;
-        CU(cudaEventRecord(cev[0], stream));
-        launch_coarse(cp, stream); launches++;
-        CU(cudaEventRecord(cev[1], stream));
-        sp.coarse = 1; sp.tile_prefix = d_tpre.p; sp.m8 = d_m8.p; sp.e8 = d_e8.p;
-        return 0;
+        sp.bmat = d_bmat;
+        sp.coarse = coarse_ok ? 2 : 0;
     }
-    // refresh the host mirror of the stream states (call after launch_carry, before the final sync)
-    int mirror_states() { CU(cudaMemcpyAsync(h_states, d_states, (size_t)n_streams * sizeof(StreamState), cudaMemcpyDeviceToHost, stream)); return 0; }
 
     void destroy()
     {
@@ -345,10 +311,8 @@ struct Front {
             if (x.d_count) cudaFree(x.d_count);
             if (x.h_count) cudaFreeHost(x.h_count);
         }
-        d_m8.release(); d_e8.release(); d_tpre.release(); h_tpre.release();
         if (d_bmat) cudaFree(d_bmat);
         if (h_states) cudaFreeHost(h_states);
-        for (auto &e : cev) if (e) cudaEventDestroy(e);
         if (own_stream && stream) cudaStreamDestroy(stream);
     }
 };
@@ -386,13 +350,14 @@ struct RxGen {
     cudaEvent_t done = nullptr;           // results are on the host
     cudaEvent_t staged = nullptr;         // inputs and the I/O list are on the device
     cudaEvent_t seek_done = nullptr;      // the search has run and its counters are on the host
+    cudaEvent_t carry_done = nullptr;     // k_carry (the last reader of the caller's input buffers) has run
+    bool carry_pending = false;
     bool mf_pending = false;
     float ms[6] = {};
     uint64_t work[6] = {};
     SeekParams sp;
     size_t max_frames = 0;
     uint64_t total = 0;
-    std::vector<uint64_t> ns_copy;        // sample counts of the fed streams (separate pre-filter kernel only)
     void release()
     {
         d_frames.release(); h_frames.release(); d_syms.release(); h_syms.release();
@@ -403,6 +368,7 @@ struct RxGen {
         if (done) cudaEventDestroy(done);
         if (staged) cudaEventDestroy(staged);
         if (seek_done) cudaEventDestroy(seek_done);
+        if (carry_done) cudaEventDestroy(carry_done);
     }
 };
 
@@ -414,6 +380,10 @@ struct RxLane {
     unsigned flags = 0;
     unsigned lane = 0, n_lanes = 1;
     RxGen g[2];
+    // true while the other generation has no call in flight: buffers that grow are then grown for BOTH generations,
+    // so a caller alternating execute() calls pays every (slow, synchronising) pinned / device allocation once, on
+    // the first call of a size, not again on the second (bench: a 100 ms second step)
+    bool twin_idle = false;
     DevBuf<unsigned> d_ilv;
     size_t ilv_used = 0;
     std::unordered_map<unsigned, size_t> ilv_cache;
@@ -471,7 +441,16 @@ struct RxLane {
         if (int e = G.d_frames.reserve(G.max_frames)) return e;
         if (int e = G.h_frames.reserve(G.max_frames)) return e;
         if (int e = G.d_views.reserve(n)) return e;
-        G.ns_copy = ns;
+        if (twin_idle) {
+            RxGen &O = g[gen ^ 1u];
+            if (int e = O.d_frames.reserve(G.max_frames)) return e;
+            if (int e = O.h_frames.reserve(G.max_frames)) return e;
+            if (int e = O.d_views.reserve(n)) return e;
+            Front::IoSet &oi = f.io[gen ^ 1u];
+            if (int e = oi.h_io.reserve(n)) return e;
+            if (int e = oi.d_io.reserve(n)) return e;
+            if (mem == LQB_MEM_HOST) if (int e = oi.d_stage.reserve(G.total + 1)) return e;
+        }
         return 0;
     }
 
@@ -492,8 +471,7 @@ struct RxLane {
         G.sp.det_mode = 0; G.sp.frames = G.d_frames.p; G.sp.detections = nullptr;
         G.sp.n_out = f.io[f.cur].d_count; G.sp.max_out = (unsigned)G.max_frames;
         CU(cudaEventRecord(G.ev[0], st));
-        if (f.coarse_separate) CU(cudaStreamSynchronize(st));      // debug mode: the separate pre-filter is planned from the host mirror of the states
-        if (int e = f.run_coarse(n, G.ns_copy.data(), G.sp)) return e;
+        f.set_coarse(G.sp);
         CU(cudaMemsetAsync(f.io[f.cur].d_count, 0, 8 * sizeof(unsigned), st));
         launch_seek(G.sp, n, st); f.launches++;
         CU(cudaEventRecord(G.ev[1], st));
@@ -514,8 +492,10 @@ struct RxLane {
         RxGen &prev = g[gen ^ 1u];
         if (prev.mf_pending) { CU(cudaStreamWaitEvent(st, prev.mf_done, 0)); prev.mf_pending = false; }
         launch_carry(G.sp, n, st); f.launches++;
-        if (G.sp.coarse == 1)       // only the separate pre-filter kernel plans from the host mirror of the stream states
-            CU(cudaMemcpyAsync(f.h_states, f.d_states, (size_t)f.n_streams * sizeof(StreamState), cudaMemcpyDeviceToHost, st));
+        // k_carry reads the caller's input (or the staging copy of it) on the low-priority search stream, where nothing
+        // else orders it before collect(): the caller may touch its buffers once collect() returns, so collect waits
+        CU(cudaEventRecord(G.carry_done, st));
+        G.carry_pending = true;
         return 0;
     }
 
@@ -532,7 +512,7 @@ struct RxLane {
         g_trace.mark("seek done", lane);
         unsigned nf = std::min<unsigned>(f.io[f.cur].h_count[0], (unsigned)G.max_frames);
         G.work[0] = f.io[f.cur].h_count[1]; G.work[1] = f.io[f.cur].h_count[2]; G.work[2] = 0; G.work[3] = G.total; G.work[4] = f.io[f.cur].h_count[3];
-        G.work[5] = G.sp.coarse == 2 ? (uint64_t)f.io[f.cur].h_count[4] : (G.sp.coarse == 1 ? (uint64_t)f.h_tpre.p[n] : 0);
+        G.work[5] = f.io[f.cur].h_count[4];
         FrameDesc *fr = G.h_frames.p;
         if (nf) {
             // on the payload stream (idle: the chain of this generation's previous use has been collected), by kernel:
@@ -555,7 +535,7 @@ struct RxLane {
             // every detection costs an exact window and an alignment (about 3000 samples' worth of search); a frame with
             // a valid header lets the search skip its payload
             if (d.stream < f.est_work.size()) f.est_work[d.stream] += 3000 - (d.header_valid ? 2ll * d.n_sym : 0ll);
-            if (!d.header_valid) continue;
+            if (!d.header_valid || (d.flags & 1u)) continue;       // flags bit 0: dropped (longer than the carry), header only
             valid.push_back(i);
             d.sym_off = sym_total; sym_total += (d.n_sym + 1u) & ~1u;      // even: 16-byte aligned symbol rows
             unsigned bl = std::max(std::max(d.n1, d.n0), d.k0) + 16;
@@ -615,6 +595,22 @@ struct RxLane {
             for (auto p : parts) { loff.push_back(ltot); ltot += p->size(); }
             if (int e = G.h_lists.reserve(ltot + 1)) return e;
             if (int e = G.d_lists.reserve(ltot + 1)) return e;
+            if (twin_idle) {
+                RxGen &O = g[gen ^ 1u];
+                if (int e = O.d_syms.reserve(sym_total + 1)) return e;
+                if (int e = O.d_bufA.reserve(buf_total + 16)) return e;
+                if (int e = O.d_bufB.reserve(buf_total + 16)) return e;
+                if (int e = O.d_payload.reserve(pay_total + 16)) return e;
+                if (int e = O.d_dec.reserve(dec_total + 1)) return e;
+                if (int e = O.d_tilemap.reserve(12 * (n_tiles + 1))) return e;
+                if (int e = O.d_ckpt.reserve(ck_total + 1)) return e;
+                if (int e = O.h_lists.reserve(ltot + 1)) return e;
+                if (int e = O.d_lists.reserve(ltot + 1)) return e;
+                if (!(flags & LQB_RX_DEVICE_RESULTS)) {
+                    if (int e = O.h_payload.reserve(pay_total + 16)) return e;
+                    if (!(flags & LQB_RX_NO_FRAMESYMS)) if (int e = O.h_syms.reserve(sym_total + 1)) return e;
+                }
+            }
             for (size_t k = 0; k < parts.size(); ++k)
                 if (!parts[k]->empty()) std::memcpy(G.h_lists.p + loff[k], parts[k]->data(), parts[k]->size() * sizeof(unsigned));
             launch_copy(G.d_lists.p, G.h_lists.p, ltot * sizeof(unsigned), ps);
@@ -674,13 +670,13 @@ struct RxLane {
         RxGen &G = g[gen];
         if (!G.n_fed) return 0;
         CU(cudaEventSynchronize(G.done));
+        if (G.carry_pending) { CU(cudaEventSynchronize(G.carry_done)); G.carry_pending = false; }
         g_trace.mark("lane complete", lane);
         CU(cudaGetLastError());
         cudaEventElapsedTime(&G.ms[0], G.ev[0], G.ev[1]);
         for (int k = 1; k < 4; ++k) cudaEventElapsedTime(&G.ms[k], G.ev[k + 1], G.ev[k + 2]);
         cudaEventElapsedTime(&G.ms[4], G.ev[0], G.ev[6]);
         G.ms[5] = 0.0f;
-        if (G.sp.coarse == 1) cudaEventElapsedTime(&G.ms[5], f.cev[0], f.cev[1]);
         const FrameDesc *fr = G.h_frames.p;
         for (unsigned i = 0; i < G.n_frames; ++i) G.n_valid += fr[i].payload_valid ? 1 : 0;
         return 0;
@@ -813,6 +809,7 @@ lqb_rx lqb_rx_create(const lqb_rx_opts *o)
             ok = ok && cudaEventCreateWithFlags(&G.done, cudaEventDisableTiming) == cudaSuccess;
             ok = ok && cudaEventCreateWithFlags(&G.staged, cudaEventDisableTiming) == cudaSuccess;
             ok = ok && cudaEventCreateWithFlags(&G.seek_done, cudaEventDisableTiming) == cudaSuccess;
+            ok = ok && cudaEventCreateWithFlags(&G.carry_done, cudaEventDisableTiming) == cudaSuccess;
         }
     }
     delete T;
@@ -838,12 +835,13 @@ int lqb_rx_collect(lqb_rx h)
     h->n_frames = 0; h->n_valid = 0; h->order.clear();
     std::memset(h->ms, 0, sizeof h->ms);
     std::memset(h->work, 0, sizeof h->work);
+    for (auto *l : h->lanes) l->twin_idle = (h->pending == 0);       // (already decremented: nothing else in flight)
     int rc = h->plan(gen);
     if (!rc) for (auto *l : h->lanes) if ((rc = l->phase_finish(gen))) break;
     if (rc) {
         const std::string keep = g_err;
         h->sync_all(); cudaGetLastError();
-        for (auto *l : h->lanes) for (auto &G : l->g) { G.mf_pending = false; G.n_fed = 0; G.n_frames = 0; }
+        for (auto *l : h->lanes) for (auto &G : l->g) { G.mf_pending = false; G.carry_pending = false; G.n_fed = 0; G.n_frames = 0; }
         h->pending = 0;
         g_err = keep;
         return rc;
@@ -853,6 +851,7 @@ int lqb_rx_collect(lqb_rx h)
         for (unsigned l = 0; l < L; ++l) {
             CU(cudaEventRecord(h->ev_out[l], h->lanes[l]->pay));
             CU(cudaStreamWaitEvent(h->user_stream, h->ev_out[l], 0));
+            CU(cudaStreamWaitEvent(h->user_stream, h->lanes[l]->g[gen].carry_done, 0));    // last reader of the inputs
         }
     }
     std::vector<unsigned> &cnt = h->stream_count;        // frames per global stream, then running offsets
@@ -915,6 +914,7 @@ int lqb_rx_submit(lqb_rx h, uint32_t n, const uint32_t *ids, const float *const 
     }
     int rc = 0;
     g_trace.start();
+    for (auto *l : h->lanes) l->twin_idle = (h->pending == 0);
     // 1. the new samples start travelling (copy streams) while the previous call is still being searched;
     // 2. this call's search is queued behind its own copies (and behind the previous search, same stream);
     // 3. the previous call's search is awaited, its payload work planned and queued;
@@ -928,7 +928,7 @@ int lqb_rx_submit(lqb_rx h, uint32_t n, const uint32_t *ids, const float *const 
     if (rc) {
         const std::string keep = g_err;
         h->sync_all(); cudaGetLastError();
-        for (auto *l : h->lanes) for (auto &G : l->g) { G.mf_pending = false; G.n_fed = 0; G.n_frames = 0; }
+        for (auto *l : h->lanes) for (auto &G : l->g) { G.mf_pending = false; G.carry_pending = false; G.n_fed = 0; G.n_frames = 0; }
         h->pending = 0;
         g_err = keep;
         return rc;
@@ -981,7 +981,7 @@ int lqb_rx_poll(lqb_rx h, lqb_frame_result *out, uint32_t max_out, uint32_t *n_o
         r.stream = h->global_stream(ln->lane, d.stream); r.seq = d.seq; r.sample_index = d.F;
         std::memcpy(r.header, d.header, 20);
         r.header_valid = d.header_valid; r.payload_valid = d.payload_valid; r.payload_len = d.payload_len;
-        if (d.header_valid) {
+        if (d.header_valid && !(d.flags & 1u)) {
             r.payload = host_res ? G.h_payload.p + d.pay_off : G.d_payload.p + d.pay_off;
             if (h->flags & LQB_RX_DEVICE_RESULTS) r.framesyms = reinterpret_cast<const float *>(G.d_syms.p + d.sym_off);
             else if (!(h->flags & LQB_RX_NO_FRAMESYMS)) r.framesyms = reinterpret_cast<const float *>(G.h_syms.p + d.sym_off);
@@ -1085,11 +1085,10 @@ int lqb_det_execute(lqb_det h, uint32_t n, const uint32_t *ids, const float *con
     sp.det_mode = 1; sp.frames = nullptr; sp.detections = h->d_det.p; sp.views = nullptr;
     sp.n_out = f.io[0].d_count; sp.max_out = (unsigned)max_det;
     CU(cudaEventRecord(h->ev[0], st));
-    if (int e = f.run_coarse(n, ns, sp)) return e;
+    f.set_coarse(sp);
     CU(cudaMemsetAsync(f.io[0].d_count, 0, 8 * sizeof(unsigned), st));
     launch_seek(sp, n, st); f.launches++;
     launch_carry(sp, n, st); f.launches++;
-    if (int e = f.mirror_states()) return e;
     CU(cudaEventRecord(h->ev[1], st));
     CU(cudaMemcpyAsync(f.io[0].h_count, f.io[0].d_count, 4 * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));

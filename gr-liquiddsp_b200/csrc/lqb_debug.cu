@@ -69,40 +69,3 @@ extern "C" int lqb_dbg_fft512(const float *in_host, float *out_host, int dir)
     cudaFree(dW); cudaFree(din); cudaFree(dout);
     return e == cudaSuccess ? 0 : -5;
 }
-
-// one stream of n samples through the tensor-core pre-filter; returns m8 / e8 (n_tiles * 16 each)
-extern "C" int lqb_dbg_coarse(const float *x_host, unsigned n, float beta, float *m8_host, float *e8_host)
-{
-    using namespace lqb;
-    auto s = detector_template(beta);
-    std::vector<float> sre(156), sim(156);
-    for (int i = 0; i < 156; ++i) { sre[i] = s[i].re; sim[i] = s[i].im; }
-    std::vector<unsigned short> bm;
-    build_coarse_bmat(sre.data(), sim.data(), 24, bm);
-    const unsigned n_tiles = (n + 127) / 128;
-    StreamState st; std::memset(&st, 0, sizeof st);
-    float2 *dx = nullptr, *dcarry = nullptr; void *dB = nullptr; StreamState *dst = nullptr; StreamIO *dio = nullptr;
-    unsigned *dpre = nullptr; float *dm = nullptr, *de = nullptr;
-    if (cudaMalloc(&dx, (size_t)n * sizeof(float2)) != cudaSuccess) return -19;
-    cudaMalloc(&dcarry, 2048 * sizeof(float2)); cudaMalloc(&dB, bm.size() * 2); cudaMalloc(&dst, sizeof st);
-    cudaMalloc(&dio, sizeof(StreamIO)); cudaMalloc(&dpre, 2 * sizeof(unsigned));
-    cudaMalloc(&dm, (size_t)n_tiles * 16 * sizeof(float)); cudaMalloc(&de, (size_t)n_tiles * 16 * sizeof(float));
-    StreamIO io; io.in = dx; io.n_in = n; io.stream = 0; io.pad = 0;
-    unsigned pre[2] = { 0, n_tiles };
-    cudaMemcpy(dx, x_host, (size_t)n * sizeof(float2), cudaMemcpyHostToDevice);
-    cudaMemcpy(dB, bm.data(), bm.size() * 2, cudaMemcpyHostToDevice);
-    cudaMemcpy(dst, &st, sizeof st, cudaMemcpyHostToDevice);
-    cudaMemcpy(dio, &io, sizeof io, cudaMemcpyHostToDevice);
-    cudaMemcpy(dpre, pre, sizeof pre, cudaMemcpyHostToDevice);
-    CoarseParams P;
-    P.states = dst; P.io = dio; P.carry[0] = dcarry; P.carry[1] = dcarry; P.carry_cap = 2048;
-    P.tile_prefix = dpre; P.n_io = 1; P.n_tiles = n_tiles; P.bmat = dB; P.m8 = dm; P.e8 = de;
-    launch_coarse(P, 0);
-    cudaError_t e = cudaDeviceSynchronize();
-    if (e == cudaSuccess) e = cudaGetLastError();
-    cudaMemcpy(m8_host, dm, (size_t)n_tiles * 16 * sizeof(float), cudaMemcpyDeviceToHost);
-    cudaMemcpy(e8_host, de, (size_t)n_tiles * 16 * sizeof(float), cudaMemcpyDeviceToHost);
-    cudaFree(dx); cudaFree(dcarry); cudaFree(dB); cudaFree(dst); cudaFree(dio); cudaFree(dpre); cudaFree(dm); cudaFree(de);
-    if (e != cudaSuccess) { fprintf(stderr, "lqb_dbg_coarse: %s\n", cudaGetErrorString(e)); return -5; }
-    return 0;
-}

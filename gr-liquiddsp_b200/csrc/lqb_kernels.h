@@ -1,9 +1,36 @@
 // lqb_kernels.h -- launch interface between the C-ABI layer (lqb_api.cu) and the kernels.
 #pragma once
 #include "lqb_dev.cuh"
+#include <atomic>
 #include <vector>
 
 namespace lqb {
+
+// Function attributes and device properties belong to a DEVICE, not to the process: a handle on a second GPU of the
+// same process needs them again.  One bit per device ordinal; the first launch on a device (any thread) sees true.
+// Doing the set-up twice in a race is harmless, skipping it is not.
+inline bool first_launch_on_this_device(std::atomic<unsigned long long> &seen)
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (seen.load(std::memory_order_relaxed) & bit) return false;
+    seen.fetch_or(bit, std::memory_order_relaxed);
+    return true;
+}
+inline int sm_count_of_this_device()
+{
+    static std::atomic<int> cache[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int v = cache[dev & 63].load(std::memory_order_relaxed);
+    if (v <= 0) {
+        v = 148;
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        cache[dev & 63].store(v, std::memory_order_relaxed);
+    }
+    return v;
+}
 
 struct SeekParams {
     const DevTables *tables;
@@ -17,23 +44,9 @@ struct SeekParams {
     unsigned        *n_out;
     unsigned         max_out;
     StreamView      *views;         // [n_io] out: the sample view every fed stream was searched under (payload kernels read through it)
-    // tensor-core pre-filter results (lqb_rx_coarse.cu); coarse == 0 disables the shortcut
-    int              coarse;        // 0: off, 1: separate pre-filter kernel results in m8/e8, 2: fused in k_seek
-    const void      *bmat;          // fp16 B operand (coarse == 2)
-    const unsigned  *tile_prefix;   // [n_io + 1] first 128-lag tile of each fed stream
-    const float     *m8;            // per 8 lags: max over lags and CFO bins of |C|^2
-    const float     *e8;            // per 8 samples: energy
-};
-
-struct CoarseParams {
-    const StreamState *states;
-    const StreamIO    *io;
-    const float2      *carry[2];
-    unsigned           carry_cap;
-    const unsigned    *tile_prefix; // [n_io + 1]
-    unsigned           n_io, n_tiles;
-    const void        *bmat;        // fp16 B operand in shared-memory layout (71680 bytes)
-    float             *m8, *e8;     // [n_tiles * 16]
+    // tensor-core pre-filter fused into k_seek
+    int              coarse;        // 0: off (every window takes the exact 50-FFT evaluation), 2: on
+    const void      *bmat;          // B operand in shared-memory layout (build_coarse_bmat)
 };
 
 // CTA shapes of k_mf / k_pll_emit.  64-thread / 1024-symbol variants (14 KB / 13 KB of shared memory) were built to fit
@@ -68,7 +81,7 @@ struct PayloadParams {
 };
 
 void launch_seek(const SeekParams &P, unsigned n_io, cudaStream_t s);
-void launch_coarse(const CoarseParams &P, cudaStream_t s);
+// host: B operand of the pre-filter (template x CFO rotations) in the kernel's shared-memory layout
 void build_coarse_bmat(const float *s_re, const float *s_im, int range, std::vector<unsigned short> &out);
 void launch_carry(const SeekParams &P, unsigned n_io, cudaStream_t s);
 

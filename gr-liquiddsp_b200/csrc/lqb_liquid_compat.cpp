@@ -69,40 +69,43 @@ extern "C" flexframesync flexframesync_create(framesync_callback callback, void 
 extern "C" void flexframesync_destroy(flexframesync q) { if (q) { lqb_rx_destroy(q->rx); delete q; } }
 extern "C" void flexframesync_reset(flexframesync q) { if (q) { lqb_rx_reset(q->rx, -1); q->pend.clear(); q->q.clear(); } }
 
-extern "C" void flexframesync_execute(flexframesync q, liquid_float_complex *x, unsigned int n)
+namespace {
+// run the receiver over everything pending and queue the completed frames
+void run_pending(flexframesync q)
 {
-    if (!q) return;
-    const float *xf = reinterpret_cast<const float *>(x);
-    q->pend.insert(q->pend.end(), xf, xf + 2 * (size_t)n);
-    if (q->pend.size() / 2 >= q->batch) {
-        const float *p = q->pend.data();
-        uint64_t len = q->pend.size() / 2;
-        if (lqb_rx_execute(q->rx, 1, NULL, &p, &len, LQB_MEM_HOST) == 0) {
-            uint64_t frames = 0;
-            lqb_rx_counts(q->rx, &frames, NULL);
-            std::vector<lqb_frame_result> res((size_t)frames + 1);
-            uint32_t got = 0;
-            lqb_rx_poll(q->rx, res.data(), (uint32_t)frames, &got);
-            for (uint32_t i = 0; i < got && i < frames; ++i) {
-                const lqb_frame_result &r = res[i];
-                QueuedFrame f;
-                f.header.assign(r.header, r.header + 20);
-                if (r.payload) f.payload.assign(r.payload, r.payload + r.payload_len);
-                if (r.framesyms) {
-                    const liquid_float_complex *s = reinterpret_cast<const liquid_float_complex *>(r.framesyms);
-                    f.syms.assign(s, s + r.num_framesyms);
-                }
-                f.header_valid = r.header_valid; f.payload_valid = r.payload_valid;
-                f.stats.evm = r.evm; f.stats.rssi = r.rssi; f.stats.cfo = r.cfo;
-                f.stats.framesyms = NULL; f.stats.num_framesyms = r.header_valid ? r.num_framesyms : 0;
-                f.stats.mod_scheme = r.mod_scheme; f.stats.mod_bps = r.mod_bps; f.stats.check = r.check;
-                f.stats.fec0 = r.fec0; f.stats.fec1 = r.fec1;
-                q->q.push_back(std::move(f));
+    if (q->pend.empty()) return;
+    const float *p = q->pend.data();
+    uint64_t len = q->pend.size() / 2;
+    if (lqb_rx_execute(q->rx, 1, NULL, &p, &len, LQB_MEM_HOST) == 0) {
+        uint64_t frames = 0;
+        lqb_rx_counts(q->rx, &frames, NULL);
+        std::vector<lqb_frame_result> res((size_t)frames + 1);
+        uint32_t got = 0;
+        lqb_rx_poll(q->rx, res.data(), (uint32_t)frames, &got);
+        for (uint32_t i = 0; i < got && i < frames; ++i) {
+            const lqb_frame_result &r = res[i];
+            if (r.flags & 1u) continue;               // longer than the carry (cannot happen with the 4 Mi-sample carry used here)
+            QueuedFrame f;
+            f.header.assign(r.header, r.header + 20);
+            if (r.payload) f.payload.assign(r.payload, r.payload + r.payload_len);
+            if (r.framesyms) {
+                const liquid_float_complex *s = reinterpret_cast<const liquid_float_complex *>(r.framesyms);
+                f.syms.assign(s, s + r.num_framesyms);
             }
+            f.header_valid = r.header_valid; f.payload_valid = r.payload_valid;
+            f.stats.evm = r.evm; f.stats.rssi = r.rssi; f.stats.cfo = r.cfo;
+            f.stats.framesyms = NULL; f.stats.num_framesyms = r.header_valid ? r.num_framesyms : 0;
+            f.stats.mod_scheme = r.mod_scheme; f.stats.mod_bps = r.mod_bps; f.stats.check = r.check;
+            f.stats.fec0 = r.fec0; f.stats.fec1 = r.fec1;
+            q->q.push_back(std::move(f));
         }
-        q->pend.clear();
     }
-    if (!q->q.empty() && q->cb) {
+    q->pend.clear();
+}
+// deliver up to `budget` queued frames; the buffers of a delivered frame live until the next delivery (liquid's rule)
+void deliver(flexframesync q, size_t budget)
+{
+    while (budget-- && !q->q.empty() && q->cb) {
         q->cur = std::move(q->q.front());
         q->q.pop_front();
         QueuedFrame &f = q->cur;
@@ -110,6 +113,30 @@ extern "C" void flexframesync_execute(flexframesync q, liquid_float_complex *x, 
         q->cb(f.header.data(), f.header_valid, f.header_valid ? f.payload.data() : NULL,
               f.header_valid ? (unsigned)f.payload.size() : 0, f.payload_valid, f.stats, q->ud);
     }
+}
+}  // namespace
+
+// Samples are batched (LQB_COMPAT_BATCH, default 4096) before they go to the GPU, so callbacks come later than in
+// liquid-dsp but in the same order.  Delivery is paced at one callback per 256 samples of the current call: the
+// reference's loop (256 samples per call, one result slot, lib/flex_rx_impl.cc:212-251) therefore never sees two
+// callbacks in one call, while a caller that passes a large buffer gets every completed frame before execute returns
+// (a frame is at least 618 samples long, so the queue cannot grow).
+extern "C" void flexframesync_execute(flexframesync q, liquid_float_complex *x, unsigned int n)
+{
+    if (!q) return;
+    const float *xf = reinterpret_cast<const float *>(x);
+    q->pend.insert(q->pend.end(), xf, xf + 2 * (size_t)n);
+    if (q->pend.size() / 2 >= q->batch) run_pending(q);
+    deliver(q, ((size_t)n + 255) / 256);
+}
+
+// Extension (not in liquid-dsp): process the samples still waiting for a full batch and deliver every queued frame.
+// Call it at the end of a capture; liquid-dsp has nothing to flush because it works sample by sample.
+extern "C" void flexframesync_flush(flexframesync q)
+{
+    if (!q) return;
+    run_pending(q);
+    deliver(q, (size_t)-1);
 }
 
 // ------------------------------------------------------------------ flexframegen

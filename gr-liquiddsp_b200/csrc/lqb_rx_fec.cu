@@ -857,7 +857,7 @@ void launch_viterbi(const PayloadParams &P, const unsigned *list, unsigned n, in
 void launch_rs(const PayloadParams &P, const unsigned *blocks, unsigned n_blocks, int stage, cudaStream_t s)
 {
     if (!n_blocks) return;
-    static const int sms = [] { int dev = 0, v = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev); return v; }();
+    const int sms = sm_count_of_this_device();
     const unsigned want = (n_blocks + kRsWarps - 1) / kRsWarps, cap = (unsigned)sms * 6u;     // six 34 KB CTAs per SM
     k_rs<<<std::min(want, cap), 32 * kRsWarps, kRsSynBytes, s>>>(P, blocks, n_blocks, stage);
 }

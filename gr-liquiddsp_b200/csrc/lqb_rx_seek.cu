@@ -12,6 +12,7 @@
 #include "lqb_dev.cuh"
 #include "lqb_kernels.h"
 #include "lqb_tc.cuh"
+#include <cmath>
 
 namespace lqb {
 
@@ -493,52 +494,6 @@ __device__ int fused_scan(SeekShared &sh, const StreamView &sv, const DevTables 
     return result;
 }
 
-// Pre-filter test for the window starting r0 samples after the carry base: true when the tensor-core
-// correlation bound proves that no lag < 356 can exceed the threshold, i.e. the exact evaluation
-// could not trigger.  m8 = max |C|^2 per 8 lags (fp16 operands, error <= 1.4e-3 ||x_156|| ||s||),
-// e8 = energy per 8 samples.  Energy below uses only blocks fully inside the window (a lower bound,
-// so the rxy bound errs high); the superset sum guards the error term.
-__device__ bool coarse_rules_out(SeekShared &sh, const SeekParams &P, const DevTables *T, unsigned long long coff, long long r0, int tid)
-{
-    const int warp = tid >> 5, lane = tid & 31;
-    const long long b0 = r0 >> 3, b1 = (r0 + 355) >> 3;             // lag blocks touching [r0, r0+356)
-    const long long e0 = (r0 + 7) >> 3, e1 = ((r0 + 512) >> 3) - 1; // sample blocks inside [r0, r0+512)
-    const long long u0 = r0 >> 3, u1 = (r0 + 511) >> 3;             // sample blocks touching it
-    float m = 0.0f, el = 0.0f, eu = 0.0f;
-    for (long long b = b0 + tid; b <= b1; b += kThreads) m = fmaxf(m, P.m8[coff + b]);
-    for (long long b = u0 + tid; b <= u1; b += kThreads) {
-        const float e = P.e8[coff + b];
-        eu += e;
-        if (b >= e0 && b <= e1) el += e;
-    }
-#pragma unroll
-    for (int k = 16; k >= 1; k >>= 1) {
-        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, k));
-        el += __shfl_xor_sync(0xffffffffu, el, k);
-        eu += __shfl_xor_sync(0xffffffffu, eu, k);
-    }
-    wsync();                       // protect the reduction scratch against the previous use
-    float *red = reinterpret_cast<float *>(sh.best);
-    if (lane == 0) red[warp] = m;
-    __shared__ float red_el[kWarps], red_eu[kWarps];
-    if (lane == 0) { red_el[warp] = el; red_eu[warp] = eu; }
-    wsync();
-    if (tid == 0) {
-        float mm = 0.0f, l = 0.0f, u = 0.0f;
-        for (int w = 0; w < kWarps; ++w) { mm = fmaxf(mm, red[w]); l += red_el[w]; u += red_eu[w]; }
-        int skip = 0;
-        if (l > 0.0f && u <= 4.0f * l) {
-            const float ub = sqrtf(mm) / (sqrtf(l) * sqrtf(156.0f / 512.0f) * sqrtf(T->s2_sum));
-            skip = ub < T->threshold - 0.008f;
-        }
-        sh.trig = skip;
-    }
-    wsync();
-    const bool r = sh.trig != 0;
-    wsync();
-    return r;
-}
-
 // alignment on the 512 samples in sh.Xw (x[F .. F+512)) with CFO bin sh.off
 __device__ void align_frame(SeekShared &sh, const DevTables *T, int tid)
 {
@@ -862,7 +817,6 @@ k_seek(SeekParams P)
 
     unsigned n_windows = 0, n_aligns = 0, n_exact = 0, n_tc_tiles = 0;      // work counters (uniform across the workers)
     PROF_MARK(10);
-    const unsigned long long coff = P.coarse == 1 ? (unsigned long long)P.tile_prefix[blockIdx.x] * 16ull : 0ull;
     StreamView sv;
     sv.carry = P.carry[st.carry_sel] + (size_t)io.stream * P.carry_cap;
     sv.in = io.in;
@@ -891,11 +845,6 @@ k_seek(SeekParams P)
                 if (!fused_scan(sh, sv, T, st, tid, sc_, tc_pre, tc_pre_a0, ph_full, buf_w, n_windows, n_tc_tiles PROF_PASS)) break;
             } else {
                 ++n_windows;
-                if (P.coarse == 1 && st.wstart >= st.G && coarse_rules_out(sh, P, T, coff, st.wstart - sv.base, tid)) {
-                    if (tid == 0) st.wstart += 256;
-                    wsync();
-                    continue;
-                }
             }
             ++n_exact;
             PROF_MARK(7);
@@ -982,7 +931,22 @@ k_seek(SeekParams P)
                 // payload not complete yet: either wait for more samples or drop an oversized frame
                 long long need = last + 1 - (F > sv.G ? F : sv.G);
                 if (need > (long long)P.carry_cap) {
+                    // reported as a frame with flags bit 0 (header fields filled, no payload): the caller sees the drop
                     if (tid == 0) {
+                        unsigned slot = atomicAdd(P.n_out, 1u);
+                        if (slot < P.max_out) {
+                            FrameDesc &d = P.frames[slot];
+                            d = FrameDesc{};
+                            d.F = F; d.G = sv.G;
+                            d.stream = io.stream; d.seq = st.seq; d.io_index = blockIdx.x; d.flags = 1u;
+                            d.tau = sh.tau; d.gamma = sh.gamma; d.dphi = sh.dphi; d.phi = sh.phi; d.rxy = st.rxy;
+                            d.header_valid = 1; d.payload_len = plen; d.ms = ms; d.bps = modem_bps_hd(ms);
+                            d.check = check; d.fec0 = fec0; d.fec1 = fec1;
+                            d.rssi = __fmul_rn(20.0f, log10f(sh.gamma));
+                            d.cfo = nco_get_frequency_dev(sh.dtheta);
+                            for (int i = 0; i < 20; ++i) d.header[i] = hd[i];
+                        }
+                        st.seq++;
                         st.dropped++;
                         st.mode = 0; st.G = F + 512; st.wstart = st.G - 256;
                     }
@@ -1085,12 +1049,38 @@ __global__ void k_carry(SeekParams P)
 
 void launch_seek(const SeekParams &P, unsigned n_io, cudaStream_t s)
 {
-    static bool attr_set = false;
+    static std::atomic<unsigned long long> attr_seen{ 0 };
     const int dyn = tc::kBBytes + 256;
-    if (!attr_set) { cudaFuncSetAttribute(k_seek, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn); attr_set = true; }
+    if (first_launch_on_this_device(attr_seen)) cudaFuncSetAttribute(k_seek, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
     k_seek<<<n_io, kCtaThreads, P.coarse == 2 ? dyn : 0, s>>>(P);
 }
 void launch_carry(const SeekParams &P, unsigned n_io, cudaStream_t s) { k_carry<<<n_io, 256, 0, s>>>(P); }
+
+// host: B operand in the kernel's shared-memory layout (fp16).  s: 156 template samples; column nn = 2 b + part holds
+// the real (part 0) or imaginary (part 1) part of C[., b] for component c of x (0: re, 1: im).
+void build_coarse_bmat(const float *s_re, const float *s_im, int range, std::vector<unsigned short> &out)
+{
+    using namespace tc;
+    out.assign(kBBytes / 2, 0);
+    for (int c = 0; c < 2; ++c)
+        for (int j = 0; j < 10; ++j)
+            for (int q = 0; q < 2; ++q) {
+                const size_t chunk = (size_t)((c * 10 + j) * 2 + q) * (kBChunkBytes / 2);
+                for (int nn = 0; nn < 2 * kNBins; ++nn)
+                    for (int e = 0; e < 8; ++e) {
+                        const int n = 16 * j + 8 * q + e, b = nn >> 1, part = nn & 1;
+                        double val = 0.0;
+                        if (n < 156) {
+                            const double ph = 2.0 * 3.14159265358979323846 * (double)(b - range) * (double)n / 512.0;
+                            const double tr = s_re[n] * cos(ph) - s_im[n] * sin(ph), ti = s_re[n] * sin(ph) + s_im[n] * cos(ph);
+                            // C = sum (xr + j xi)(tr - j ti):  re = xr tr + xi ti,  im = xi tr - xr ti
+                            val = (part == 0) ? (c == 0 ? tr : ti) : (c == 0 ? -ti : tr);
+                        }
+                        __half hv = __float2half_rn((float)val);
+                        out[chunk + (size_t)nn * 8 + e] = *reinterpret_cast<unsigned short *>(&hv);
+                    }
+            }
+}
 
 #ifdef LQB_SEEK_PROF
 extern "C" int lqb_dbg_seek_prof(unsigned long long *out16, int reset)

@@ -424,6 +424,7 @@ struct lqb_tx_s {
     float2 *h_out = nullptr; size_t h_out_cap = 0;
     std::unordered_map<unsigned, size_t> ilv_cache;
     std::vector<unsigned> ilv_host;
+    size_t ilv_uploaded = 0;            // entries of ilv_host that are on the device
     uint64_t launches = 0;
 };
 
@@ -474,7 +475,7 @@ lqb_tx lqb_tx_create(const lqb_tx_opts *o)
     int dev = o ? o->device : 0;
     if (dev < 0 || dev >= ndev) { tx_fail(LQB_ENODEV, "device ordinal out of range"); return nullptr; }
     cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess || prop.major < 10) { tx_fail(LQB_ENODEV, "device is not sm_100 class"); return nullptr; }
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess || prop.major != 10) { tx_fail(LQB_ENODEV, "device is not sm_100 class"); return nullptr; }
     lqb_tx h = new lqb_tx_s;
     h->device = dev;
     cudaSetDevice(dev);
@@ -531,7 +532,6 @@ int lqb_tx_assemble(lqb_tx h, uint32_t n, const lqb_tx_props *props, const uint8
     if (grow_pinned(h->h_frames, h->h_frames_cap, n)) return tx_fail(LQB_ENOMEM, "cudaMallocHost failed");
     TxFrame *fr = h->h_frames;
     size_t pay_tot = 0, buf_tot = 0, sym_tot = 0, out_tot = 0;
-    bool new_maps = false;
     for (uint32_t i = 0; i < n; ++i) {
         const lqb_tx_props &p = props[i];
         uint32_t ns = 0;
@@ -558,7 +558,6 @@ int lqb_tx_assemble(lqb_tx h, uint32_t n, const lqb_tx_props *props, const uint8
                 off = h->ilv_host.size();
                 h->ilv_host.insert(h->ilv_host.end(), maps.begin(), maps.end());
                 h->ilv_cache.emplace(encs[s], off);
-                new_maps = true;
             } else off = it->second;
             (s ? f.ilv1_off : f.ilv0_off) = (unsigned)off;
         }
@@ -567,9 +566,14 @@ int lqb_tx_assemble(lqb_tx h, uint32_t n, const lqb_tx_props *props, const uint8
     if (grow(h->d_frames, h->frames_cap, n) || grow(h->d_A, h->buf_cap, buf_tot + 16)) return tx_fail(LQB_ENOMEM, "cudaMalloc failed");
     if (grow(h->d_B, h->bufB_cap, buf_tot + 16)) return tx_fail(LQB_ENOMEM, "cudaMalloc failed");
     if (grow(h->d_syms, h->sym_cap, sym_tot + 1)) return tx_fail(LQB_ENOMEM, "cudaMalloc failed");
-    if (new_maps || !h->d_ilv) {
+    // the device copy of the interleaver maps follows the host cache by COUNT, not by "this call added maps": a call
+    // that added maps and then failed (bad props further down the list, out of memory) leaves them to the next call
+    if (h->ilv_host.size() > h->ilv_uploaded || !h->d_ilv) {
         if (grow(h->d_ilv, h->ilv_cap, h->ilv_host.size() + 4)) return tx_fail(LQB_ENOMEM, "cudaMalloc failed");
-        if (!h->ilv_host.empty()) cudaMemcpyAsync(h->d_ilv, h->ilv_host.data(), h->ilv_host.size() * sizeof(unsigned), cudaMemcpyHostToDevice, st);
+        if (!h->ilv_host.empty() &&
+            cudaMemcpyAsync(h->d_ilv, h->ilv_host.data(), h->ilv_host.size() * sizeof(unsigned), cudaMemcpyHostToDevice, st) != cudaSuccess)
+            return tx_fail(LQB_ECUDA, "interleaver map upload failed");
+        h->ilv_uploaded = h->ilv_host.size();
     }
     // Device buffers are used in place: the kernel reads every payload and writes every frame through the caller's
     // pointers.  Host buffers are packed into one pinned staging area each way: one H2D and one D2H per call instead of

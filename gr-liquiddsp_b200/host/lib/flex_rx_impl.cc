@@ -47,6 +47,12 @@ int flex_rx_impl::outer_index(unsigned fec1)
 
 void flex_rx_impl::publish(const lqb_frame_result &r)
 {
+    if (r.flags & 1u) {
+        // a frame longer than the receiver's per-stream buffer (lqb_rx_opts.max_frame_samples) cannot be received:
+        // it is announced here instead of vanishing silently; no message goes out because there are no payload bytes
+        std::cout << "flex_rx: dropped a frame of " << r.payload_len << " payload bytes (longer than the receive buffer)" << std::endl;
+        return;
+    }
     // the constellation goes out for every frame, also when the header check failed (then it is empty)
     const gr_complex *syms = reinterpret_cast<const gr_complex *>(r.framesyms);
     message_port_pub(pmt::mp("constellation"), pmt::cons(pmt::PMT_NIL, pmt::init_c32vector(syms ? r.num_framesyms : 0, syms)));

@@ -153,6 +153,9 @@ class flex_rx(_MsgBlock):
         self._rx.execute(chunks)
         self.last_stats = self._rx.poll()
         for f in self.last_stats:
+            if f["flags"] & 1:            # longer than the receive buffer: announced, nothing to publish
+                print("flex_rx: dropped a frame of %d payload bytes (longer than the receive buffer)" % f["payload_len"])
+                continue
             self.message_port_pub("constellation", (None, f["framesyms"]))
             if not f["header_valid"]:
                 continue

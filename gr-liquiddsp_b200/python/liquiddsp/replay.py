@@ -58,6 +58,8 @@ def to_pdus(frame):
     """The messages `flex_rx` publishes for a frame, in publish order -- ('constellation', (None, complex64[])), then for a
     valid header ('payload_data', (None, bytes)) and ('packet_info', dict) -- lib/flex_rx_impl.cc:218-247."""
     from .blocks import MODULATION, INNER_CODE, OUTER_CODE, _index        # the block's own index tables
+    if frame.get("flags", 0) & 1:         # dropped (longer than the receive buffer): the block publishes nothing
+        return []
     syms = frame.get("framesyms")
     msgs = [("constellation", (None, np.asarray(syms if syms is not None else [], dtype=np.complex64)))]
     if frame["header_valid"]:

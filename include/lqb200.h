@@ -117,7 +117,7 @@ typedef struct {
                                     after the results); NULL = library-owned streams only */
     uint32_t n_lanes;            /* streams are split over this many independent pipeline lanes (a fixed, interleaved
                                     partition) whose search, payload kernels and copies overlap;
-                                    0 = automatic (env LQB_RX_LANES, else one per 128 streams, at most 4).  Results
+                                    0 = automatic (env LQB_RX_LANES, else one per 256 streams, at most 4).  Results
                                     do not depend on it. */
 } lqb_rx_opts;
 
@@ -139,7 +139,9 @@ typedef struct {
     float    rssi;               /* dB */
     float    cfo;                /* rad/sample */
     float    tau_hat, gamma_hat, dphi_hat, phi_hat, rxy;
-    uint32_t flags;              /* bit0: frame dropped (longer than max_frame_samples) */
+    uint32_t flags;              /* bit0: frame dropped -- its header decoded but the frame is longer than
+                                    max_frame_samples: header / scheme fields are valid, payload and framesyms are NULL,
+                                    payload_valid is 0 and the search resumed 512 samples after the frame start */
 } lqb_frame_result;
 
 lqb_rx lqb_rx_create(const lqb_rx_opts *opts);
@@ -159,8 +161,9 @@ int    lqb_rx_execute_dense(lqb_rx h, const float *iq, uint64_t stride_samples, 
  * so the H2D copy of call k+1 runs under the search of call k, and the payload work of call k (matched filter, PLL,
  * FEC, CRC, result copies) under the search of call k+1.  execute() == submit() + collect(); results are identical.
  * Host input buffers may be reused as soon as submit returns only if they are pageable; pinned host buffers and
- * device buffers must stay untouched until the matching collect() returns.  Result buffers of a collected call stay
- * valid until the next-but-one submit.  A third submit without a collect returns LQB_EBUSY. */
+ * device buffers must stay untouched until the matching collect() returns (collect waits for the last reader).  Result
+ * buffers of a collected call stay valid until the next submit / execute on the handle (with two calls in flight the
+ * next submit reuses the collected call's buffers).  A third submit without a collect returns LQB_EBUSY. */
 int    lqb_rx_submit(lqb_rx h, uint32_t n, const uint32_t *stream_ids,
                      const float *const *iq, const uint64_t *n_samples, int mem);
 int    lqb_rx_submit_dense(lqb_rx h, const float *iq, uint64_t stride_samples, uint64_t n_samples, int mem);

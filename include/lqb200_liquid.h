@@ -12,9 +12,13 @@
  * Every object here is a thin adapter over the batch C-ABI in lqb200.h with n_streams = 1 and
  * host buffers; the arithmetic runs on the GPU.  Differences from liquid-dsp that a caller can
  * observe (all about WHEN, never WHAT):
- *   - flexframesync_execute delivers at most one callback per call (the reference keeps a
- *     single-slot packet_info, lib/flex_rx_impl.cc:216-251); further completed frames are queued
- *     and delivered by the following calls, in order.
+ *   - flexframesync_execute batches samples before they go to the GPU, so a callback comes some
+ *     calls after the sample that completed its frame.  Delivery is paced at one callback per 256
+ *     samples of the current call: the reference's loop (256 samples per call, single-slot
+ *     packet_info, lib/flex_rx_impl.cc:212-251) never sees two callbacks in one call, a caller
+ *     passing a large buffer gets every completed frame before execute returns.  Samples still
+ *     waiting for a full batch at the end of a capture are processed by flexframesync_flush()
+ *     (an extension; liquid-dsp works sample by sample and has nothing to flush).
  *   - qdetector_cccf_execute reports a detection on the call that completes a 256-sample hop
  *     rather than on the exact sample; the count and the estimates are the same.
  *   - errors never exit(): create functions return NULL (see lqb_last_error()).
@@ -86,6 +90,7 @@ flexframesync flexframesync_create(framesync_callback callback, void *userdata);
 void flexframesync_destroy(flexframesync q);
 void flexframesync_reset(flexframesync q);
 void flexframesync_execute(flexframesync q, liquid_float_complex *x, unsigned int n);
+void flexframesync_flush(flexframesync q);      /* extension: process pending samples, deliver all queued frames */
 
 /* ---- frame generator ---- */
 typedef struct { unsigned int check, fec0, fec1, mod_scheme; } flexframegenprops_s;

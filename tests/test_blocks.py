@@ -254,6 +254,22 @@ def test_liquid_signature_veneer_loopback(gpu_required):
     L.flexframesync_destroy(fs)
     assert [g[2] for g in got] == sent and all(g[0] == 1 and g[1] == 1 for g in got)
     assert all(g[4] == util.PSK4 and g[5] == 11 and g[6] == 27 for g in got)
+    # one large buffer in one call: every completed frame is delivered before execute returns; the tail that does
+    # not fill a batch is processed by flexframesync_flush (no trailing zero padding this time)
+    L.flexframesync_flush.argtypes = [C.c_void_p]
+    got.clear()
+    fs = L.flexframesync_create(cbk, None)
+    cap = np.ascontiguousarray(util.build_capture(frames, rng, [800] * 3, snr_db=20.0))
+    cut = (len(cap) - 3000) // 256 * 256                 # the third frame ends 1700 samples before the end: inside the tail
+    L.flexframesync_execute(fs, cap.ctypes.data, cut)
+    assert len(got) == 2
+    tail = np.ascontiguousarray(cap[cut:])               # fewer samples than one batch: they wait
+    L.flexframesync_execute(fs, tail.ctypes.data, len(tail))
+    assert len(got) == 2
+    L.flexframesync_flush(fs)
+    assert len(got) == 3
+    L.flexframesync_destroy(fs)
+    assert [g[2] for g in got] == sent
 
 
 @pytest.mark.gpu

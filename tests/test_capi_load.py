@@ -27,6 +27,17 @@ def test_every_declared_symbol_is_exported():
     assert sorted(capi.DECLARED_SYMBOLS) == names
 
 
+def test_every_liquid_signature_symbol_is_exported():
+    """include/lqb200_liquid.h (liquid-dsp's own names) is part of the boundary too."""
+    txt = open(os.path.join(ROOT, "include", "lqb200_liquid.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    names = sorted(set(re.findall(r"\b((?:flexframesync|flexframegen|flexframegenprops|qdetector_cccf|msequence)_[a-z0-9_]+)\s*\(", txt)))
+    assert len(names) >= 20 and "flexframesync_flush" in names
+    L = capi.lib()
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+
+
 def test_no_gpu_means_loud_failure_not_fallback():
     L = capi.lib()
     if L.lqb_device_count() > 0:

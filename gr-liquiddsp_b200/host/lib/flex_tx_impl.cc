@@ -35,19 +35,19 @@ flex_tx_impl::~flex_tx_impl() { lqb_tx_destroy(d_tx); }
 
 void flex_tx_impl::set_modulation(unsigned int modulation)
 {
-    if (modulation < 11) { d_props.mod_scheme = tables::kModulation[modulation]; return; }
+    if (modulation < sizeof tables::kModulation / sizeof tables::kModulation[0]) { d_props.mod_scheme = tables::kModulation[modulation]; return; }
     std::cout << "Unsupported Modulation Defaulting to BPSK." << std::endl;
     d_props.mod_scheme = LQB_MODEM_PSK2;
 }
 void flex_tx_impl::set_inner_code(unsigned int inner_code)
 {
-    if (inner_code < 7) { d_props.fec0 = tables::kInner[inner_code]; return; }
+    if (inner_code < sizeof tables::kInner / sizeof tables::kInner[0]) { d_props.fec0 = tables::kInner[inner_code]; return; }
     std::cout << "Unsupported FEC Defaulting to none." << std::endl;
     d_props.fec0 = LQB_FEC_NONE;
 }
 void flex_tx_impl::set_outer_code(unsigned int outer_code)
 {
-    if (outer_code < 8) { d_props.fec1 = tables::kOuter[outer_code]; return; }
+    if (outer_code < sizeof tables::kOuter / sizeof tables::kOuter[0]) { d_props.fec1 = tables::kOuter[outer_code]; return; }
     std::cout << "Unsupported FEC Defaulting to none." << std::endl;
     d_props.fec1 = LQB_FEC_NONE;
 }

@@ -7,9 +7,13 @@ import numpy as np
 
 from . import capi
 
-MODULATION = [1, 2, 3, 4, 9, 10, 11, 18, 27, 28, 29]          # flex_tx index -> liquid modulation_scheme
-INNER_CODE = [1, 11, 15, 17, 18, 19, 20]                      # index -> fec0 (v27p34 is not offered)
-OUTER_CODE = [1, 7, 27, 4, 6, 8, 9, 10]                       # index -> fec1
+# flex_tx index -> liquid enum.  0..10 / 0..6 / 0..7 are the reference's numbering (lib/flex_tx_impl.cc:77-181) and do not
+# move; the entries after them are additive extensions: QAM128 / QAM256, the v27p34 rate the
+# reference skips, and the K = 9 family.  A reference transmitter cannot produce them.
+N_MOD_REF, N_INNER_REF, N_OUTER_REF = 11, 7, 8
+MODULATION = [1, 2, 3, 4, 9, 10, 11, 18, 27, 28, 29] + [30, 31]
+INNER_CODE = [1, 11, 15, 17, 18, 19, 20] + [16, 12, 21, 22, 23, 24, 25, 26]
+OUTER_CODE = [1, 7, 27, 4, 6, 8, 9, 10]
 CRC_24 = 5
 
 

@@ -46,6 +46,17 @@ class FrameResult(C.Structure):
                 ("phi_hat", C.c_float), ("rxy", C.c_float), ("flags", C.c_uint32)]
 
 
+# numpy view of lqb_frame_result (same field order; pointers as addresses)
+FRAME_DTYPE = np.dtype([("stream", "<u4"), ("seq", "<u4"), ("sample_index", "<i8"), ("header", "u1", (20,)),
+                        ("header_valid", "<i4"), ("payload_valid", "<i4"), ("payload_len", "<u4"),
+                        ("payload", "<u8"), ("framesyms", "<u8"), ("num_framesyms", "<u4"),
+                        ("mod_scheme", "<u4"), ("mod_bps", "<u4"), ("check", "<u4"), ("fec0", "<u4"), ("fec1", "<u4"),
+                        ("evm", "<f4"), ("rssi", "<f4"), ("cfo", "<f4"), ("tau_hat", "<f4"), ("gamma_hat", "<f4"),
+                        ("dphi_hat", "<f4"), ("phi_hat", "<f4"), ("rxy", "<f4"), ("flags", "<u4")], align=True)
+assert FRAME_DTYPE.itemsize == C.sizeof(FrameResult) and all(
+    FRAME_DTYPE.fields[k][1] == getattr(FrameResult, k).offset for k, _ in FrameResult._fields_)
+
+
 class TxOpts(C.Structure):
     _fields_ = [("device", C.c_int), ("flags", C.c_uint32), ("cuda_stream", C.c_void_p)]
 
@@ -209,6 +220,16 @@ class Rx:
         host = not (self.flags & RX_DEVICE_RESULTS)
         return [_frame_to_dict(arr[i], host) for i in range(nf)]
 
+    def poll_array(self):
+        """All frame records of the last execute / collect as one numpy structured array (fields of lqb_frame_result;
+        `payload` and `framesyms` are raw addresses valid until the next submit / execute).  No per-frame Python objects:
+        this is the form for callers that handle tens of thousands of frames per call."""
+        nf, _ = self.counts()
+        arr = (FrameResult * max(nf, 1))()
+        n = C.c_uint32(0)
+        _check(self._L.lqb_rx_poll(self._h, C.byref(arr), nf, C.byref(n)))
+        return np.frombuffer(arr, dtype=FRAME_DTYPE)[:nf]          # (the view keeps the ctypes array alive)
+
     def timing(self):
         ms = (C.c_float * 6)()
         _check(self._L.lqb_rx_last_timing(self._h, ms))
@@ -349,6 +370,18 @@ class Tx:
         op = (C.c_void_p * n)(*[o.ctypes.data for o in outs])
         _check(self._L.lqb_tx_assemble(self._h, n, P, hp, pp, lens, op, MEM_HOST))
         return outs
+
+    def assemble_device_arrays(self, props4, payload_ptrs, payload_lens, out_ptrs):
+        """Device-resident variant for large batches: numpy arrays in (no per-frame Python objects).
+        props4: uint32 [n, 4] rows (check, fec0, fec1, mod_scheme) = lqb_tx_props; payload_ptrs / out_ptrs: uint64 [n]
+        device addresses; payload_lens: uint32 [n].  Frames are written in place at out_ptrs."""
+        props4 = np.ascontiguousarray(props4, dtype=np.uint32)
+        pp = np.ascontiguousarray(payload_ptrs, dtype=np.uint64)
+        op = np.ascontiguousarray(out_ptrs, dtype=np.uint64)
+        ln = np.ascontiguousarray(payload_lens, dtype=np.uint32)
+        n = len(pp)
+        assert props4.shape == (n, 4) and len(op) == n and len(ln) == n
+        _check(self._L.lqb_tx_assemble(self._h, n, props4.ctypes.data, None, pp.ctypes.data, ln.ctypes.data, op.ctypes.data, MEM_DEVICE))
 
     def assemble_device(self, props, payload_ptrs, payload_lens, out_ptrs, header_ptrs=None):
         """Device-resident variant: raw device pointers in, frames written to out_ptrs."""

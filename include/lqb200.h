@@ -90,6 +90,12 @@ extern "C" {
 #define LQB_FEC_CONV_V27P56 18
 #define LQB_FEC_CONV_V27P67 19
 #define LQB_FEC_CONV_V27P78 20
+#define LQB_FEC_CONV_V29P23 21
+#define LQB_FEC_CONV_V29P34 22
+#define LQB_FEC_CONV_V29P45 23
+#define LQB_FEC_CONV_V29P56 24
+#define LQB_FEC_CONV_V29P67 25
+#define LQB_FEC_CONV_V29P78 26
 #define LQB_FEC_RS_M8 27
 #define LQB_CRC_NONE 1
 #define LQB_CRC_CHECKSUM 2

@@ -77,7 +77,10 @@ def test_index_tables_match_the_reference_numbering():
         assert L.blk_rx_index(1, fs) == i
     for i, fs in enumerate(util.OUTER):
         assert L.blk_rx_index(2, fs) == i
-    assert L.blk_rx_index(0, 31) == -1 and L.blk_rx_index(1, 16) == -1 and L.blk_rx_index(2, 5) == -1   # QAM256, v27p34, Hamming84
+    # additive extension indices sit AFTER the reference's ranges; schemes in neither stay -1
+    assert L.blk_rx_index(0, 30) == 11 and L.blk_rx_index(0, 31) == 12                                   # QAM128, QAM256
+    assert L.blk_rx_index(1, 16) == 7 and L.blk_rx_index(1, 12) == 8 and L.blk_rx_index(1, 26) == 14     # v27p34, v29, v29p78
+    assert L.blk_rx_index(0, 32) == -1 and L.blk_rx_index(1, 13) == -1 and L.blk_rx_index(2, 5) == -1    # APSK4, v39, Hamming84
     # config_id = mod*56 + inner*8 + outer + 1 covers 1..616 (python/cognitive_engine.py:87)
     ids = {m * 56 + i * 8 + oo + 1 for m in range(11) for i in range(7) for oo in range(8)}
     assert ids == set(range(1, 617))

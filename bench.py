@@ -536,22 +536,34 @@ def _parity_rows(torch, cap, rows, got_rec, cores):
     host = cap[rows].cpu().numpy()
     ref = oracle_frames(host, cores)
     frames = mism = 0
+    detail = []
     for k, r in enumerate(rows):
         mine = got_rec[got_rec["stream"] == r]
         mine = mine[np.argsort(mine["seq"], kind="stable")]
         frames += len(ref[k])
         if len(mine) != len(ref[k]):
             mism += abs(len(mine) - len(ref[k])) + 1
+            detail.append({"row": int(r), "oracle_frames": [(f["sample_index"], f["header_valid"], f["payload_valid"], f["mod_scheme"], f["fec0"], f["fec1"]) for f in ref[k]],
+                           "gpu_frames": [(int(b["sample_index"]), int(b["header_valid"]), int(b["payload_valid"]), int(b["mod_scheme"]), int(b["fec0"]), int(b["fec1"]), int(b["flags"])) for b in mine]})
             continue
         for a, b in zip(ref[k], mine):
-            same = (a["sample_index"] == int(b["sample_index"]) and a["header_valid"] == int(b["header_valid"])
-                    and a["payload_valid"] == int(b["payload_valid"]) and a["header"] == bytes(b["header"]))
-            if same and a["header_valid"]:
-                same = (a["mod_scheme"], a["fec0"], a["fec1"], a["payload_len"]) == (int(b["mod_scheme"]), int(b["fec0"]), int(b["fec1"]), int(b["payload_len"]))
-                if same and int(b["payload"]):
-                    same = a["payload"] == C.string_at(int(b["payload"]), int(b["payload_len"]))
-            mism += 0 if same else 1
-    return {"streams": len(rows), "frames": frames, "mismatches": mism}
+            why = [f for f in ("sample_index", "header_valid", "payload_valid") if a[f] != int(b[f])]
+            if a["header"] != bytes(b["header"]):
+                why.append("header")
+            if not why and a["header_valid"]:
+                why = [f for f in ("mod_scheme", "fec0", "fec1", "payload_len") if a[f] != int(b[f])]
+                if not why and int(b["payload"]):
+                    pb = C.string_at(int(b["payload"]), int(b["payload_len"]))
+                    if a["payload"] != pb:
+                        why.append("payload bytes (%d of %d differ)" % (sum(x != y for x, y in zip(a["payload"], pb)), len(pb)))
+            if why:
+                mism += 1
+                detail.append({"row": int(r), "sample_index": a["sample_index"], "scheme": (a["mod_scheme"], a["fec0"], a["fec1"]), "differs": why,
+                               "oracle": (a["header_valid"], a["payload_valid"], round(a["evm"], 3)), "gpu": (int(b["header_valid"]), int(b["payload_valid"]), round(float(b["evm"]), 3))})
+    out = {"streams": len(rows), "frames": frames, "mismatches": mism}
+    if detail:
+        out["detail"] = detail[:8]
+    return out
 
 
 def mixed_mod_arm(args, rank, local, world, steps=None, warmup=None, emit=True):
@@ -577,7 +589,9 @@ def mixed_mod_arm(args, rank, local, world, steps=None, warmup=None, emit=True):
     C_TOTAL, NM, PM, LEAD, GAP = 4096, 1 << 17, 256, 700, 900
     chans = np.arange(rank, C_TOTAL, world, dtype=np.int64)            # global ids of my channels (liquiddsp/sharding.py)
     S = len(chans)
-    cs = torch.cuda.current_stream(dev)
+    # a stream of our own: torch's default stream has handle 0, which the C-ABI reads as "no caller stream" (no ordering)
+    cs = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(cs)
     tx = capi.Tx(device=local, cuda_stream=cs.cuda_stream)
     rx = capi.Rx(S, device=local, max_frame_samples=65536, flags=capi.RX_NO_FRAMESYMS, cuda_stream=cs.cuda_stream)
     pol = policy.EpsilonGreedy(S, epsilon=0.25, seed=100 + rank, extended=True)
@@ -649,14 +663,15 @@ def mixed_mod_arm(args, rank, local, world, steps=None, warmup=None, emit=True):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dist.all_reduce(sm, op=dist.ReduceOp.SUM)
     rx.close(); tx.close()
+    torch.cuda.synchronize(dev)
+    torch.cuda.set_stream(torch.cuda.default_stream(dev))
     del cap, pool
     torch.cuda.empty_cache()
     if rank != 0:
         if world > 1 and standalone:
             dist.destroy_process_group()
         return None
-    if parity and parity["mismatches"]:
-        raise SystemExit("mixed_mod: GPU frames differ from the oracle's on the sampled channels: %r" % (parity,))
+    failed = "GPU frames differ from the oracle's on the sampled channels" if parity and parity["mismatches"] else None
     rx_s = float(tt[0]) / 1e3
     chans_all = float(sm[4])
     out = {
@@ -671,12 +686,14 @@ def mixed_mod_arm(args, rank, local, world, steps=None, warmup=None, emit=True):
         "loop_ms_per_step": {"flex_tx_batch": float(tt[2]) / steps, "awgn": float(tt[3]) / steps, "flex_rx_batch": float(tt[0]) / steps,
                              "policy_and_lists_host": float(tt[4]) / steps, "whole_loop": float(tt[1]) / steps},
         "closed_loop_msps": chans_all * NM * steps / (float(tt[1]) / 1e3) / 1e6,
-        "parity_sample": parity,
+        "parity_sample": parity, "failed": failed,
     }
     if emit:
         print(json.dumps(out))
     if world > 1 and standalone:
         dist.destroy_process_group()
+    if emit and failed:
+        raise SystemExit("mixed_mod: " + failed)
     return out
 
 
@@ -703,7 +720,8 @@ def tx_rx_per_arm(args, rank, local, world, steps=None, warmup=None, emit=True):
     S = len(chans)
     L = capi.Tx.frame_len(QAM16, CRC24, 1, 1, PAYLOAD)
     assert LEAD + NF * (L + GAP) <= NT
-    cs = torch.cuda.current_stream(dev)
+    cs = torch.cuda.Stream(dev)               # see mixed_mod_arm: handle 0 would mean "no caller stream"
+    torch.cuda.set_stream(cs)
     tx = capi.Tx(device=local, cuda_stream=cs.cuda_stream)
     rx = capi.Rx(S, device=local, max_frame_samples=16384, flags=capi.RX_NO_FRAMESYMS, cuda_stream=cs.cuda_stream)
     cap = torch.zeros((S, NT), dtype=torch.complex64, device=dev)
@@ -769,6 +787,8 @@ def tx_rx_per_arm(args, rank, local, world, steps=None, warmup=None, emit=True):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dist.all_reduce(sm, op=dist.ReduceOp.SUM)
     rx.close(); tx.close()
+    torch.cuda.synchronize(dev)
+    torch.cuda.set_stream(torch.cuda.default_stream(dev))
     del cap, pay
     torch.cuda.empty_cache()
     if rank != 0:
@@ -777,7 +797,7 @@ def tx_rx_per_arm(args, rank, local, world, steps=None, warmup=None, emit=True):
         return None
     sent_all, ok_all, chans_all = sm[:19].cpu().numpy(), sm[19:38].cpu().numpy(), float(sm[38])
     per = [round(float(1.0 - b / a), 5) if a else None for a, b in zip(sent_all, ok_all)]
-    oracle = None
+    oracle = failed = None
     if subs:
         from scipy.stats import beta as _beta
 
@@ -796,7 +816,7 @@ def tx_rx_per_arm(args, rank, local, world, steps=None, warmup=None, emit=True):
         oracle = {"channels": len(sub), "frames": int(o_frames), "per_by_snr_point": o_per, "points_with_overlapping_95pct_intervals": overlap,
                   "points": int((o_sent > 0).sum()), "channel_steps_with_identical_flags": int(o_same), "channel_steps": len(sub) * len(subs)}
         if overlap != oracle["points"] or o_same != oracle["channel_steps"]:
-            raise SystemExit("tx_rx_per: GPU PER / flags differ from the oracle's: %r" % (oracle,))
+            failed = "GPU PER / flags differ from the oracle's on the sampled channels"
     secs = float(tt[0]) / 1e3
     hbm_peak = float(load_peaks().get("hbm_gbs", 6650.0))
     tx_gbs = 8.0 * chans_all / world * NF * L * steps / (float(tt[1]) / 1e3) / 1e9 if tt[1] > 0 else None
@@ -811,12 +831,14 @@ def tx_rx_per_arm(args, rank, local, world, steps=None, warmup=None, emit=True):
         "ms_per_step_parts": {"flex_tx_batch": float(tt[1]) / steps, "flex_rx_batch": float(tt[2]) / steps},
         "roofline": {"bound": "hbm", "kernel": "k_tx", "achieved": tx_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": tx_gbs / hbm_peak if tx_gbs else None,
                      "traffic": None, "note": "16 B written per symbol; time = the whole lqb_tx_assemble call (plan + table upload + kernel)"},
-        "oracle_per": oracle,
+        "oracle_per": oracle, "failed": failed,
     }
     if emit:
         print(json.dumps(out))
     if world > 1 and standalone:
         dist.destroy_process_group()
+    if emit and failed:
+        raise SystemExit("tx_rx_per: " + failed)
     return out
 
 
@@ -854,6 +876,9 @@ def main():
         return
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
+    # all of this process's torch work and the library's caller-stream ordering use one explicit stream (torch's default
+    # stream has handle 0, which the C-ABI reads as "no caller stream")
+    torch.cuda.set_stream(torch.cuda.Stream(dev))
     near = bind_near_gpu(local) if world > 1 else 0
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
@@ -1120,451 +1145,6 @@ def main():
                   "compared": "sample_index, header_valid, payload_valid, header bytes, payload bytes; oracle vs one full-size GPU step"}
 
     out = {
-        "metric": "flex_rx_msps", "value": chans_all * NM * steps / rx_s / 1e6, "unit": "Msps", "n_gpus": world, "steps": steps, "warmup": warmup,
-        "ms_per_step": float(tt[0]) / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "flex_rx_mixed_mod_4096ch_policy_loop", "channels_total": C_TOTAL, "channels_per_gpu": S,
-                   "samples_per_channel_per_step": NM, "payload_bytes": PM, "schemes": "616 reference configurations + %d extension (non-reference) per channel and step" % (pol.n_cfg - 616),
-                   "snr_db": "4..26 per channel", "l2": "inputs (%.1f GB per step) larger than L2" % (S * NM * 8 / 1e9)},
-        "frames_per_s": float(sm[0]) / rx_s, "decoded_frames_per_s": float(sm[1]) / rx_s,
-        "frames_sent_per_step": float(sm[2]) / steps, "frames_found_per_step": float(sm[0]) / steps, "frames_valid_per_step": float(sm[1]) / steps,
-        "extension_frames_per_step": float(sm[3]) / steps, "distinct_configs_rank0": len(cfg_seen),
-        "loop_ms_per_step": {"flex_tx_batch": float(tt[2]) / steps, "awgn": float(tt[3]) / steps, "flex_rx_batch": float(tt[0]) / steps,
-                             "policy_and_lists_host": float(tt[4]) / steps, "whole_loop": float(tt[1]) / steps},
-        "closed_loop_msps": chans_all * NM * steps / (float(tt[1]) / 1e3) / 1e6,
-        "parity_sample": parity,
-    }
-    if emit:
-        print(json.dumps(out))
-    if world > 1 and standalone:
-        dist.destroy_process_group()
-    return out
-
-
-# ----------------------------------------------------------------------------- configs[4]: TX -> AWGN -> RX, PER vs SNR
-def tx_rx_per_arm(args, rank, local, world, steps=None, warmup=None, emit=True):
-    """BASELINE.json configs[4]: 8192 channels in total (channel c on rank c mod G), QAM16 / no FEC / CRC-24 / 1500-byte
-    frames GENERATED ON THE GPU by the flex_tx batch each step (fresh payloads), AWGN at the channel's SNR 6 .. 24 dB in
-    1 dB steps, received by the flex_rx batch; PER per SNR point from payload_valid, beside the oracle's PER on a
-    64-channel subsample of the same captures (95 % Clopper-Pearson intervals must overlap; flags are in fact equal)."""
-    import numpy as np
-    import torch
-    import torch.distributed as dist
-    from liquiddsp import capi
-    dev = torch.device("cuda", local)
-    torch.cuda.set_device(dev)
-    standalone = emit
-    steps = args.steps if steps is None else steps
-    warmup = args.warmup if warmup is None else warmup
-    if world > 1 and not dist.is_initialized():
-        dist.init_process_group("nccl", device_id=dev)
-    QAM16 = 27
-    C_TOTAL, NT, LEAD, GAP, NF = 8192, 1 << 14, 600, 1000, 2
-    chans = np.arange(rank, C_TOTAL, world, dtype=np.int64)
-    S = len(chans)
-    L = capi.Tx.frame_len(QAM16, CRC24, 1, 1, PAYLOAD)
-    assert LEAD + NF * (L + GAP) <= NT
-    cs = torch.cuda.current_stream(dev)
-    tx = capi.Tx(device=local, cuda_stream=cs.cuda_stream)
-    rx = capi.Rx(S, device=local, max_frame_samples=16384, flags=capi.RX_NO_FRAMESYMS, cuda_stream=cs.cuda_stream)
-    cap = torch.zeros((S, NT), dtype=torch.complex64, device=dev)
-    pay = torch.zeros((S * NF, 1504), dtype=torch.uint8, device=dev)
-    g = torch.Generator(device=dev).manual_seed(41 + rank)
-    point = (chans % 19).astype(np.int64)                                # SNR point of each channel: 6 + point dB
-    nstd = torch.tensor(10.0 ** (-(6.0 + point) / 20.0) / np.sqrt(2.0), dtype=torch.float32, device=dev)[:, None]
-    ch_of = np.repeat(np.arange(S), NF)
-    k_of = np.tile(np.arange(NF), S)
-    out_ptr = (cap.data_ptr() + 8 * (ch_of * NT + LEAD + k_of * (L + GAP))).astype(np.uint64)
-    pay_ptr = (pay.data_ptr() + 1504 * np.arange(S * NF)).astype(np.uint64)
-    props = np.tile(np.array([CRC24, 1, 1, QAM16], np.uint32), (S * NF, 1))
-    lens = np.full(S * NF, PAYLOAD, np.uint32)
-    sub = list(range(0, S, max(1, S // max(1, 64 // world))))[:max(1, 64 // world)] if rank == 0 else []
-    sent_pt, ok_pt = np.zeros(19), np.zeros(19)
-    o_sent, o_ok, o_same, o_frames = np.zeros(19), np.zeros(19), 0, 0
-    tx_ms = rx_ms = 0.0
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    subs = []
-    for it in range(warmup + steps):
-        if it == warmup:
-            torch.cuda.synchronize(dev)
-            if world > 1:
-                dist.barrier()
-            e0.record(cs)
-        pay.random_(0, 256, generator=g)
-        cap.zero_()
-        ev[0].record(cs)
-        tx.assemble_device_arrays(props, pay_ptr, lens, out_ptr)
-        ev[1].record(cs)
-        cap += nstd * torch.view_as_complex(torch.randn((S, NT, 2), generator=g, device=dev, dtype=torch.float32))
-        ev[2].record(cs)
-        rx.reset()                                # every step is a fresh capture (frames never straddle steps)
-        rx.execute_dense_ptr(cap.data_ptr(), NT, NT, capi.MEM_DEVICE)
-        ev[3].record(cs)
-        rec = rx.poll_array()
-        if it >= warmup:
-            okc = np.bincount(rec["stream"][rec["payload_valid"] != 0], minlength=S)
-            np.add.at(ok_pt, point, okc)
-            np.add.at(sent_pt, point, NF)
-            if sub and not args.no_cpu_baseline:
-                subs.append((cap[sub].cpu().numpy(), rec[np.isin(rec["stream"], sub)].copy()))
-            torch.cuda.synchronize(dev)
-            tx_ms += ev[0].elapsed_time(ev[1]); rx_ms += ev[2].elapsed_time(ev[3])
-    e1.record(cs)
-    torch.cuda.synchronize(dev)
-    ms = e0.elapsed_time(e1)
-    if subs:
-        cores = os.cpu_count() or 1
-        for host, mine in subs:
-            ref = oracle_frames(host, cores)
-            for k, r in enumerate(sub):
-                mr = mine[mine["stream"] == r]
-                o_sent[point[r]] += NF
-                o_ok[point[r]] += sum(1 for f in ref[k] if f["payload_valid"])
-                o_frames += len(ref[k])
-                o_same += int(len(mr) == len(ref[k]) and all(a["sample_index"] == int(b["sample_index"]) and a["payload_valid"] == int(b["payload_valid"])
-                                                             for a, b in zip(ref[k], mr[np.argsort(mr["seq"], kind="stable")])))
-    tt = torch.tensor([ms, tx_ms, rx_ms], dtype=torch.float64, device=dev)
-    sm = torch.tensor(np.concatenate([sent_pt, ok_pt, [float(S)]]), dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-    rx.close(); tx.close()
-    del cap, pay
-    torch.cuda.empty_cache()
-    if rank != 0:
-        if world > 1 and standalone:
-            dist.destroy_process_group()
-        return None
-    sent_all, ok_all, chans_all = sm[:19].cpu().numpy(), sm[19:38].cpu().numpy(), float(sm[38])
-    per = [round(float(1.0 - b / a), 5) if a else None for a, b in zip(sent_all, ok_all)]
-    oracle = None
-    if subs:
-        from scipy.stats import beta as _beta
-
-        def cp(k, n):          # 95 % Clopper-Pearson interval of k errors in n frames
-            lo = 0.0 if k == 0 else float(_beta.ppf(0.025, k, n - k + 1))
-            hi = 1.0 if k == n else float(_beta.ppf(0.975, k + 1, n - k))
-            return lo, hi
-        overlap, o_per = 0, []
-        for p_ in range(19):
-            if not o_sent[p_]:
-                o_per.append(None); continue
-            lo1, hi1 = cp(int(o_sent[p_] - o_ok[p_]), int(o_sent[p_]))
-            lo2, hi2 = cp(int(sent_all[p_] - ok_all[p_]), int(sent_all[p_]))
-            overlap += int(lo1 <= hi2 and lo2 <= hi1)
-            o_per.append(round(float(1.0 - o_ok[p_] / o_sent[p_]), 5))
-        oracle = {"channels": len(sub), "frames": int(o_frames), "per_by_snr_point": o_per, "points_with_overlapping_95pct_intervals": overlap,
-                  "points": int((o_sent > 0).sum()), "channel_steps_with_identical_flags": int(o_same), "channel_steps": len(sub) * len(subs)}
-        if overlap != oracle["points"] or o_same != oracle["channel_steps"]:
-            raise SystemExit("tx_rx_per: GPU PER / flags differ from the oracle's: %r" % (oracle,))
-    secs = float(tt[0]) / 1e3
-    hbm_peak = float(load_peaks().get("hbm_gbs", 6650.0))
-    tx_gbs = 8.0 * chans_all / world * NF * L * steps / (float(tt[1]) / 1e3) / 1e9 if tt[1] > 0 else None
-    out = {
-        "metric": "flex_tx_rx_msps", "value": chans_all * NT * steps / secs / 1e6, "unit": "Msps", "n_gpus": world, "steps": steps, "warmup": warmup,
-        "ms_per_step": float(tt[0]) / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "flex_tx_awgn_flex_rx_8192ch_qam16_1500B", "channels_total": C_TOTAL, "channels_per_gpu": S, "samples_per_channel_per_step": NT,
-                   "frames_per_channel_per_step": NF, "mod": "QAM16", "fec0": "none", "fec1": "none", "check": "crc24", "snr_db": "6..24 in 1 dB steps, one point per channel",
-                   "l2": "capture (%.1f GB per step) larger than L2" % (S * NT * 8 / 1e9)},
-        "frames_per_s": float(sent_all.sum()) / secs, "decoded_frames_per_s": float(ok_all.sum()) / secs,
-        "snr_db_points": [6 + k for k in range(19)], "per_by_snr_point": per, "frames_per_point": [int(a) for a in sent_all],
-        "ms_per_step_parts": {"flex_tx_batch": float(tt[1]) / steps, "flex_rx_batch": float(tt[2]) / steps},
-        "roofline": {"bound": "hbm", "kernel": "k_tx", "achieved": tx_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": tx_gbs / hbm_peak if tx_gbs else None,
-                     "traffic": None, "note": "16 B written per symbol; time = the whole lqb_tx_assemble call (plan + table upload + kernel)"},
-        "oracle_per": oracle,
-    }
-    if emit:
-        print(json.dumps(out))
-    if world > 1 and standalone:
-        dist.destroy_process_group()
-    return out
-
-
-# ----------------------------------------------------------------------------- our arm
-def main():
-    args = parse()
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if world == 1 and args.gpus > 1:
-        # convenience: relaunch under torchrun, one rank per GPU
-        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
-               "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__)] + sys.argv[1:]
-        sys.exit(subprocess.call(cmd))
-    if args.impl == "reference":
-        reference_arm(args, rank, world)
-        return
-
-    import torch
-    import torch.distributed as dist
-    from liquiddsp import capi
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
-    if args.workload == "detector":
-        detector_arm(args, rank, local, world)
-        return
-    if args.workload == "tx":
-        tx_arm(args, rank, local, world)
-        return
-    if args.workload == "mixed_mod":
-        mixed_mod_arm(args, rank, local, world)
-        return
-    if args.workload == "tx_rx_per":
-        tx_rx_per_arm(args, rank, local, world)
-        return
-    dev = torch.device("cuda", local)
-    torch.cuda.set_device(dev)
-    near = bind_near_gpu(local) if world > 1 else 0
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-
-    S, N = args.streams, args.samples
-    frames, payloads = clean_frames_ours(torch, dev, 1)
-    cap, sent = make_capture(torch, frames, S, N, 1, dev, stream_offset=rank * S)
-    torch.cuda.synchronize(dev)
-    cs = torch.cuda.current_stream(dev)
-    rx = capi.Rx(S, device=local, max_frame_samples=65536, flags=capi.RX_NO_FRAMESYMS, cuda_stream=cs.cuda_stream, lanes=args.lanes)
-    lanes = rx.lanes()
-
-    def step():
-        rx.execute_dense_ptr(cap.data_ptr(), N, N, capi.MEM_DEVICE)
-
-    for _ in range(args.warmup):
-        step()
-    torch.cuda.synchronize(dev)
-    pipelined = not args.no_pipeline
-    if world > 1:
-        dist.barrier()
-    clocks = ClockSampler(local)
-    clocks.start()
-    l0 = rx.launches()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kt = [0.0] * 6
-    work = dict(windows=0, aligns=0, symbols=0, samples=0, exact_windows=0, coarse_tiles=0)
-    fr_tot = va_tot = 0
-    def account():
-        nonlocal kt, fr_tot, va_tot
-        t = rx.timing()
-        kt = [a + b for a, b in zip(kt, t)]
-        w = rx.work()
-        for k in work:
-            work[k] += w[k]
-        f, v = rx.counts()
-        fr_tot += f; va_tot += v
-
-    torch.cuda.synchronize(dev)
-    t_wall = time.perf_counter()
-    e0.record(cs)
-    if pipelined:
-        # lqb_rx_submit / lqb_rx_collect: the payload work of step k runs under the search of step k+1; every
-        # one of the K steps is submitted AND collected (all its frames on the host side of the API) inside the region
-        for i in range(args.steps):
-            rx.submit_dense_ptr(cap.data_ptr(), N, N, capi.MEM_DEVICE)
-            if i:
-                rx.collect(); account()
-        rx.collect(); account()
-    else:
-        for _ in range(args.steps):
-            step()
-            account()
-    e1.record(cs)
-    torch.cuda.synchronize(dev)
-    t_wall = (time.perf_counter() - t_wall) * 1e3
-    if world > 1:
-        dist.barrier()
-    ms = max(e0.elapsed_time(e1), t_wall)      # the library works on its own streams: the host clock bounds the region too
-    clk = clocks.stop()
-    launches = rx.launches() - l0
-    tt = torch.tensor([ms, float(fr_tot), float(va_tot), float(launches), float(sent)], dtype=torch.float64, device=dev)
-    if world > 1:
-        mx = tt.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        sm = tt.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        ms = float(mx[0]); fr_all, va_all, launches_all, sent_all = float(sm[1]), float(sm[2]), float(sm[3]), float(sm[4])
-    else:
-        fr_all, va_all, launches_all, sent_all = float(fr_tot), float(va_tot), float(launches), float(sent)
-    secs = ms / 1e3
-    value = world * S * N * args.steps / secs / 1e6
-
-    # ---- per-kernel breakdown: in the timed region the lanes' kernels overlap on the GPU, so the kernel times
-    # used for the roofline come from the same K steps repeated with one lane (kernels back to back on one stream)
-    serial_ms = None
-    if lanes > 1:
-        rx.close()
-        rx = capi.Rx(S, device=local, max_frame_samples=65536, flags=capi.RX_NO_FRAMESYMS, cuda_stream=cs.cuda_stream, lanes=1)
-        step(); step()
-        torch.cuda.synchronize(dev)
-        kt = [0.0] * 6
-        work = {k: 0 for k in work}
-        e0.record(cs)
-        for _ in range(args.steps):
-            step()
-            t = rx.timing()
-            kt = [a + b for a, b in zip(kt, t)]
-            w = rx.work()
-            for k in work:
-                work[k] += w[k]
-        e1.record(cs)
-        torch.cuda.synchronize(dev)
-        serial_ms = e0.elapsed_time(e1) / args.steps
-    rx.close()
-
-    # ---- e2e: host buffers through the same C-ABI call (H2D + all results D2H inside the timed region)
-    e2e = None
-    if not args.no_e2e:
-        Ne = min(args.e2e_samples, N) if args.e2e_samples else N
-        host = torch.empty((S, Ne), dtype=torch.complex64).pin_memory()
-        host.copy_(cap[:, :Ne])
-        rx2 = capi.Rx(S, device=local, max_frame_samples=65536, flags=0, cuda_stream=cs.cuda_stream, lanes=args.e2e_lanes or args.lanes)
-        for _ in range(max(1, args.warmup)):
-            rx2.execute_dense_ptr(host.data_ptr(), Ne, Ne, capi.MEM_HOST)
-        torch.cuda.synchronize(dev)
-        if world > 1:
-            dist.barrier()
-        d2h = 0
-
-        def results():
-            arr, nf = rx2.poll(raw=True)
-            return sum(arr[i].payload_len + 8 * arr[i].num_framesyms + 256 for i in range(nf))
-
-        t0 = time.perf_counter()
-        e0.record(cs)
-        if pipelined:
-            for i in range(args.steps):
-                rx2.submit_dense_ptr(host.data_ptr(), Ne, Ne, capi.MEM_HOST)
-                if i:
-                    rx2.collect(); d2h += results()
-            rx2.collect(); d2h += results()
-        else:
-            for _ in range(args.steps):
-                rx2.execute_dense_ptr(host.data_ptr(), Ne, Ne, capi.MEM_HOST)
-                d2h += results()
-        e1.record(cs)
-        torch.cuda.synchronize(dev)
-        wall = time.perf_counter() - t0
-        ems = max(e0.elapsed_time(e1), wall * 1e3)
-        te = torch.tensor([ems], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * S * Ne * args.steps / (float(te[0]) / 1e3) / 1e6, "unit": "Msps",
-               "h2d_bytes_per_step": S * Ne * 8, "d2h_bytes_per_step": d2h // max(args.steps, 1),
-               "samples_per_stream_per_step": Ne, "lanes": rx2.lanes()}
-        rx2.close()
-        del host
-
-    # ---- CPU baseline + parity on a bounded sample of the same capture (rank 0, N = 1 only): the GPU's frame records of
-    # the sampled streams (fresh receiver, one full-size step, host results) are kept for the comparison below
-    cpu_sample = gpu_rec = None
-    if world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
-        Sc = min(S, 8 * cores, 256)
-        cpu_sample = cap[:Sc].cpu().numpy()
-        rx3 = capi.Rx(S, device=local, max_frame_samples=65536, flags=capi.RX_NO_FRAMESYMS, cuda_stream=cs.cuda_stream, lanes=args.lanes)
-        rx3.execute_dense_ptr(cap.data_ptr(), N, N, capi.MEM_DEVICE)
-        rec = rx3.poll_array()
-        rec = rec[rec["stream"] < Sc]
-        import ctypes as _C
-        gpu_rec = [(int(r["stream"]), int(r["seq"]), int(r["sample_index"]), int(r["header_valid"]), int(r["payload_valid"]), bytes(r["header"]),
-                    _C.string_at(int(r["payload"]), int(r["payload_len"])) if (r["header_valid"] and r["payload"]) else b"") for r in rec]
-        rx3.close()
-    del cap
-    torch.cuda.empty_cache()
-
-    # ---- the other BASELINE configurations, short runs (every rank takes part: they shard like the headline)
-    workloads = None
-    if not args.no_workloads:
-        workloads = {}
-        workloads["detector"] = detector_arm(args, rank, local, world, steps=3, warmup=1, emit=False)
-        workloads["mixed_mod"] = mixed_mod_arm(args, rank, local, world, steps=3, warmup=1, emit=False)
-        workloads["tx_rx_per"] = tx_rx_per_arm(args, rank, local, world, steps=5, warmup=1, emit=False)
-
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
-    # ---- roofline (per-kernel device times come from CUDA events on the launching stream, summed over the timed steps)
-    peaks = load_peaks()
-    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    names = ["seek_align_header", "matched_filter", "pll_demod", "fec_crc"]
-    t_seek, t_mf, t_pll, t_fec = [k / 1e3 for k in kt[:4]]
-    t_coarse = kt[5] / 1e3
-    win_bytes = 8.0 * 256.0 * work["windows"]                     # 8 B per new sample a detector window examines
-    win_flops = work["exact_windows"] * (50 * 9 * 256 * 10 + 49 * 512 * 9.0)
-    # tensor-core pre-filter: 128 lags x 320 (K) x 112 (N) x 2 flop per tile, fp16 in / fp32 accumulate
-    tc_flops = work["coarse_tiles"] * 128.0 * 320.0 * 112.0 * 2.0
-    tc_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
-    mf_bytes = 8.0 * (2.0 * work["symbols"]) + 8.0 * work["symbols"]   # 2 samples read + 1 symbol written per symbol
-    fp32_peak = 148 * 128 * 2 * (clk["sm_mhz"] or 1965.0) * 1e6 / 1e12
-    kernels = [
-        {"name": names[0], "ms_per_step": 1e3 * t_seek / args.steps, "bound": "fp32",
-         "hbm_gbs": win_bytes / t_seek / 1e9 if t_seek else None,
-         "hbm_frac": win_bytes / t_seek / 1e9 / hbm_peak if t_seek else None,
-         "fp32_tflops": win_flops / t_seek / 1e12 if t_seek else None,
-         "fp32_frac": win_flops / t_seek / 1e12 / fp32_peak if t_seek else None,
-         "windows_per_step": work["windows"] / args.steps, "exact_windows_per_step": work["exact_windows"] / args.steps,
-         "prefilter_ms_per_step": 1e3 * t_coarse / args.steps,
-         "prefilter_tensor_tflops": tc_flops / t_coarse / 1e12 if t_coarse else None,
-         "prefilter_tensor_frac": tc_flops / t_coarse / 1e12 / tc_peak if t_coarse else None,
-         "prefilter_hbm_gbs": (8.0 * work["samples"]) / t_coarse / 1e9 if t_coarse else None},
-        {"name": names[1], "ms_per_step": 1e3 * t_mf / args.steps, "bound": "hbm",
-         "hbm_gbs": mf_bytes / t_mf / 1e9 if t_mf else None, "hbm_frac": mf_bytes / t_mf / 1e9 / hbm_peak if t_mf else None},
-        {"name": names[2], "ms_per_step": 1e3 * t_pll / args.steps, "bound": "latency",
-         "hbm_gbs": 16.0 * work["symbols"] / t_pll / 1e9 if t_pll else None},
-        {"name": names[3], "ms_per_step": 1e3 * t_fec / args.steps, "bound": "int-alu"},
-    ]
-    # the search kernel is tensor-core work (pre-filter) plus a few exact FP32 windows: report it against the tensor peak
-    tc_in_seek = t_coarse == 0.0 and work["coarse_tiles"] > 0
-    if tc_in_seek:
-        kernels[0].update({"bound": "tensor", "tensor_tflops": tc_flops / t_seek / 1e12 if t_seek else None,
-                           "tensor_frac": tc_flops / t_seek / 1e12 / tc_peak if t_seek else None,
-                           "tensor_tiles_per_step": work["coarse_tiles"] / args.steps})
-    dom = max(range(4), key=lambda i: kt[i])
-    step_bytes = 8.0 * S * N * args.steps + 8.0 * work["symbols"]   # every input sample once + symbols written
-    if dom == 0 and tc_in_seek:
-        roof = {"bound": "tensor", "kernel": names[0], "achieved": kernels[0]["tensor_tflops"], "peak": tc_peak, "unit": "TFLOP/s",
-                "frac": kernels[0]["tensor_frac"], "traffic": None,
-                "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if "bf16_tflops_sustained" in peaks else "fallback 1400 TFLOP/s",
-                "note": "algorithmic flops = pre-filter tiles x 128 lags x 320 (K) x 112 (N) x 2 (fp16 in, fp32 accumulate); the kernel time also "
-                        "contains the exact FP32 FFT windows, alignment and header decode of every frame"}
-    elif dom == 1:
-        roof = {"bound": "hbm", "kernel": names[1], "achieved": kernels[1]["hbm_gbs"], "peak": hbm_peak, "unit": "GB/s",
-                "frac": kernels[1]["hbm_frac"], "traffic": None, "peak_source": peak_src}
-    else:
-        ach = win_bytes / t_seek / 1e9 if dom == 0 and t_seek else step_bytes / (kt[4] / 1e3) / 1e9
-        roof = {"bound": "hbm", "kernel": names[dom], "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
-                "note": "dominant kernel is the qdetector search, which is FP32-compute-bound (50 FFT-512 per 256 new samples), "
-                        "not HBM-bound: see kernels[0].fp32_frac; whole-step HBM fraction in step_hbm_frac"}
-    roof["step_hbm_gbs"] = step_bytes / secs / 1e9
-    roof["step_hbm_frac"] = roof["step_hbm_gbs"] / hbm_peak
-    # measured DRAM traffic of the dominant kernel (one `ncu --set full` capture of this workload, committed under
-    # profiles/): reported next to the algorithmic bytes so that wasted re-reads would show
-    try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
-        if tj["config"]["streams"] == S and tj["config"]["samples"] == N:
-            kname = {0: "k_seek", 1: "k_mf"}.get(dom)
-            if kname in tj["kernels"]:
-                roof["traffic"] = tj["kernels"][kname]["dram_gb_per_launch"] * 1e9
-                roof["traffic_unit"] = "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu)"
-                roof["algorithmic_bytes"] = (win_bytes if dom == 0 else mf_bytes) / args.steps
-                roof["traffic_source"] = "profiles/roofline_traffic.json"
-    except Exception:
-        pass
-
-    # ---- CPU baseline on a bounded sample of the same capture (rank 0, N = 1 only)
-    cpu = None
-    if world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
-        Sc = min(S, 8 * cores, 256)
-        Nc = N
-        sample = cap[:Sc, :Nc].cpu().numpy()
-        dt, f, v = cpu_rx(sample, cores)
-        cpu = {"value": Sc * Nc / dt / 1e6, "unit": "Msps", "cores": cores, "kind": "port",
-               "decoded_frames_per_s": v / dt,
-               "sample": "first %d streams x %d samples of the same capture, %d threads, %.1f s" % (Sc, Nc, cores, dt)}
-
-    out = {
         "metric": "flex_rx_msps", "value": value, "unit": "Msps", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
@@ -1586,6 +1166,9 @@ def main():
         dist.destroy_process_group()
     if parity and parity["mismatches"]:
         raise SystemExit("flex_rx: GPU frames differ from the oracle's on the sampled streams: %r" % (parity,))
+    bad = [k for k, v in (workloads or {}).items() if v and v.get("failed")]
+    if bad:
+        raise SystemExit("workloads failed their oracle check: %s" % ", ".join(bad))
 
 
 if __name__ == "__main__":

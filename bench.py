@@ -352,6 +352,7 @@ def detector_arm(args, rank, local, world, steps=None, warmup=None, emit=True):
         step()
         kms += det.timing()
         wins += det.windows()
+        srch = det.search()
     e1.record(cs)
     torch.cuda.synchronize(dev)
     found = det.poll()
@@ -419,7 +420,7 @@ def detector_arm(args, rank, local, world, steps=None, warmup=None, emit=True):
         "config": {"workload": "frame_detector_cc_bulk", "segments_per_gpu": S, "samples_per_segment": L, "overlap": 1024,
                    "frame_spacing": SP, "cfo": "+-0.05 rad/sample per frame", "snr_points": 64, "l2": "inputs (%.1f GB) larger than L2" % (S * L * 8 / 1e9)},
         "detections_per_s": nd * world * steps / secs if secs else None, "detections_per_step": nd,
-        "spurious_detections_per_step": extra, "pd_by_snr_point": pd, "snr_db_points": [-6.0 + 0.5 * i for i in range(64)],
+        "spurious_detections_per_step": extra, "search_work_last_step": srch, "pd_by_snr_point": pd, "snr_db_points": [-6.0 + 0.5 * i for i in range(64)],
         "clocks": clk, "gpu_launches": 2 * steps,
         "roofline": {"bound": "tensor", "kernel": "k_seek(detector)", "achieved": tflops, "peak": tc_peak, "unit": "TFLOP/s",
                      "frac": tflops / tc_peak if tflops else None, "traffic": None,
@@ -905,7 +906,7 @@ def main():
     l0 = rx.launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kt = [0.0] * 6
-    work = dict(windows=0, aligns=0, symbols=0, samples=0, exact_windows=0, coarse_tiles=0)
+    work = dict(windows=0, aligns=0, symbols=0, samples=0, exact_windows=0, coarse_tiles=0, exact_bins=0)
     fr_tot = va_tot = 0
     def account():
         nonlocal kt, fr_tot, va_tot
@@ -1068,6 +1069,7 @@ def main():
          "fp32_tflops": win_flops / t_seek / 1e12 if t_seek else None,
          "fp32_frac": win_flops / t_seek / 1e12 / fp32_peak if t_seek else None,
          "windows_per_step": work["windows"] / args.steps, "exact_windows_per_step": work["exact_windows"] / args.steps,
+         "cfo_bins_per_exact_window": work["exact_bins"] / max(1, work["exact_windows"]),
          "prefilter_ms_per_step": 1e3 * t_coarse / args.steps,
          "prefilter_tensor_tflops": tc_flops / t_coarse / 1e12 if t_coarse else None,
          "prefilter_tensor_frac": tc_flops / t_coarse / 1e12 / tc_peak if t_coarse else None,

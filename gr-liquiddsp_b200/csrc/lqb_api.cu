@@ -172,6 +172,7 @@ struct Front {
     // tensor-core pre-filter fused into k_seek: the B operand (template x 49 CFO rotations) in shared-memory layout
     bool coarse_ok = false;
     void *d_bmat = nullptr;
+    float b_err = 0.0f;                   // rounding error of B relative to ||s|| (enters the pre-filter's bound)
     StreamState *h_states = nullptr;      // pinned staging for reset()
 
     int init(int dev, unsigned ns, unsigned cap, void *user_stream, const DevTables &T, bool low_priority = false)
@@ -205,10 +206,10 @@ struct Front {
         if (T.range == 24 && !getenv("LQB_NO_COARSE")) {
             std::vector<float> sre(kSLen), sim(kSLen);
             for (unsigned i = 0; i < kSLen; ++i) { sre[i] = T.sconj[i].x; sim[i] = -T.sconj[i].y; }
-            std::vector<unsigned short> bm;
-            build_coarse_bmat(sre.data(), sim.data(), 24, bm);
-            CU(cudaMalloc(&d_bmat, bm.size() * sizeof(unsigned short)));
-            CU(cudaMemcpy(d_bmat, bm.data(), bm.size() * sizeof(unsigned short), cudaMemcpyHostToDevice));
+            std::vector<unsigned char> bm;
+            b_err = build_coarse_bmat(sre.data(), sim.data(), 24, bm);
+            CU(cudaMalloc(&d_bmat, bm.size()));
+            CU(cudaMemcpy(d_bmat, bm.data(), bm.size(), cudaMemcpyHostToDevice));
             coarse_ok = true;
         }
         return reset(-1);
@@ -296,6 +297,7 @@ struct Front {
     void set_coarse(SeekParams &sp) const
     {
         sp.bmat = d_bmat;
+        sp.b_err = b_err;
         sp.coarse = coarse_ok ? 2 : 0;
     }
 
@@ -355,6 +357,7 @@ struct RxGen {
     bool mf_pending = false;
     float ms[6] = {};
     uint64_t work[6] = {};
+    uint64_t bins = 0;                    // CFO bins the exact window evaluations visited (of 49 each)
     SeekParams sp;
     size_t max_frames = 0;
     uint64_t total = 0;
@@ -513,6 +516,7 @@ struct RxLane {
         unsigned nf = std::min<unsigned>(f.io[f.cur].h_count[0], (unsigned)G.max_frames);
         G.work[0] = f.io[f.cur].h_count[1]; G.work[1] = f.io[f.cur].h_count[2]; G.work[2] = 0; G.work[3] = G.total; G.work[4] = f.io[f.cur].h_count[3];
         G.work[5] = f.io[f.cur].h_count[4];
+        G.bins = f.io[f.cur].h_count[5];
         FrameDesc *fr = G.h_frames.p;
         if (nf) {
             // on the payload stream (idle: the chain of this generation's previous use has been collected), by kernel:
@@ -702,6 +706,7 @@ struct lqb_rx_s {
     uint64_t n_valid = 0;
     float ms[6] = {};
     uint64_t work[6] = {};
+    uint64_t bins = 0;
     // stream -> (lane, index inside the lane) and back (a fixed interleaved partition)
     std::vector<unsigned> lane_of, local_of;
     std::vector<std::vector<unsigned>> global_of;
@@ -835,6 +840,7 @@ int lqb_rx_collect(lqb_rx h)
     h->n_frames = 0; h->n_valid = 0; h->order.clear();
     std::memset(h->ms, 0, sizeof h->ms);
     std::memset(h->work, 0, sizeof h->work);
+    h->bins = 0;
     for (auto *l : h->lanes) l->twin_idle = (h->pending == 0);       // (already decremented: nothing else in flight)
     int rc = h->plan(gen);
     if (!rc) for (auto *l : h->lanes) if ((rc = l->phase_finish(gen))) break;
@@ -859,6 +865,7 @@ int lqb_rx_collect(lqb_rx h)
     for (unsigned l = 0; l < L; ++l) {
         const RxGen &G = h->lanes[l]->g[gen];
         for (int k = 0; k < 6; ++k) h->work[k] += G.work[k];
+        h->bins += G.bins;
         for (int k = 0; k < 6; ++k) if (k != 4) h->ms[k] += G.ms[k];
         h->ms[4] = std::max(h->ms[4], G.ms[4]);
         h->n_frames += G.n_frames; h->n_valid += G.n_valid;
@@ -1015,6 +1022,12 @@ int lqb_rx_last_work(lqb_rx h, uint64_t w[6])
     std::memcpy(w, h->work, sizeof h->work);
     return 0;
 }
+int lqb_rx_last_search_bins(lqb_rx h, uint64_t *bins)
+{
+    if (!h || !bins) return fail(LQB_EINVAL, "null handle");
+    *bins = h->bins;
+    return 0;
+}
 int lqb_rx_launch_count(lqb_rx h, uint64_t *l)
 {
     if (!h) return fail(LQB_EINVAL, "null handle");
@@ -1035,6 +1048,7 @@ struct lqb_det_s {
     std::vector<unsigned> order;
     unsigned n_det = 0;
     uint64_t windows = 0;
+    uint64_t search[4] = {};              // windows, alignments, exact window evaluations, CFO bins those visited
     cudaEvent_t ev[2] = {};
     float ms = 0.0f;
 };
@@ -1090,9 +1104,10 @@ int lqb_det_execute(lqb_det h, uint32_t n, const uint32_t *ids, const float *con
     launch_seek(sp, n, st); f.launches++;
     launch_carry(sp, n, st); f.launches++;
     CU(cudaEventRecord(h->ev[1], st));
-    CU(cudaMemcpyAsync(f.io[0].h_count, f.io[0].d_count, 4 * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(f.io[0].h_count, f.io[0].d_count, 8 * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     h->windows = f.io[0].h_count[1];
+    h->search[0] = f.io[0].h_count[1]; h->search[1] = f.io[0].h_count[2]; h->search[2] = f.io[0].h_count[3]; h->search[3] = f.io[0].h_count[5];
     unsigned nd = std::min<unsigned>(f.io[0].h_count[0], (unsigned)max_det);
     if (nd) {
         CU(cudaMemcpyAsync(h->h_det.p, h->d_det.p, nd * sizeof(Detection), cudaMemcpyDeviceToHost, st));
@@ -1136,6 +1151,12 @@ int lqb_det_last_timing(lqb_det h, float *ms)
 {
     if (!h) return fail(LQB_EINVAL, "null handle");
     *ms = h->ms;
+    return 0;
+}
+int lqb_det_last_search(lqb_det h, uint64_t out[4])
+{
+    if (!h || !out) return fail(LQB_EINVAL, "null handle");
+    std::memcpy(out, h->search, sizeof h->search);
     return 0;
 }
 int lqb_det_last_work(lqb_det h, uint64_t *windows)

@@ -47,6 +47,7 @@ struct SeekParams {
     // tensor-core pre-filter fused into k_seek
     int              coarse;        // 0: off (every window takes the exact 50-FFT evaluation), 2: on
     const void      *bmat;          // B operand in shared-memory layout (build_coarse_bmat)
+    float            b_err;         // max_b ||t_b - e4m3(t_b)|| / ||s|| of those bytes (error bound of the pre-filter)
 };
 
 // CTA shapes of k_mf / k_pll_emit.  64-thread / 1024-symbol variants (14 KB / 13 KB of shared memory) were built to fit
@@ -82,7 +83,7 @@ struct PayloadParams {
 
 void launch_seek(const SeekParams &P, unsigned n_io, cudaStream_t s);
 // host: B operand of the pre-filter (template x CFO rotations) in the kernel's shared-memory layout
-void build_coarse_bmat(const float *s_re, const float *s_im, int range, std::vector<unsigned short> &out);
+float build_coarse_bmat(const float *s_re, const float *s_im, int range, std::vector<unsigned char> &out);
 void launch_carry(const SeekParams &P, unsigned n_io, cudaStream_t s);
 
 // device <-> pinned-host copy of small control data by a kernel (never queues behind bulk DMA copies)

@@ -4,10 +4,16 @@
 // Replaces, for a batch of independent streams, the part of liquid-dsp's flexframesync
 // state machine that decides WHERE frames are (reference call site
 // lib/flex_rx_impl.cc:213 -> flexframesync_execute; lib/frame_detector_cc_impl.cc:77 ->
-// qdetector_cccf_execute).  One CTA (4 warps) walks one stream: every 256-sample hop it
-// evaluates the 512-sample window exactly as qdetector does (1 forward FFT + 49 frequency-
-// shifted inverse FFTs, each FFT done by one warp with 16 points per lane), and on a hit
-// runs the serial alignment / header steps before moving its hop grid past the frame.
+// qdetector_cccf_execute).  One CTA walks one stream's hop grid (a 512-sample window every 256
+// samples).  Every window first goes through a tensor-core PRE-FILTER: the correlation of its 356
+// linear lags with the template at all 49 CFO bins as one dense contraction (tcgen05.mma,
+// kind::f8f6f4: e4m3 operands, fp32 accumulators in TMEM, the Hankel operand never materialised),
+// with a RIGOROUS bound on what the e4m3 rounding can have changed.  A window the bound proves
+// unable to trigger is skipped; only the rest (the real detections plus a fraction of a percent)
+// take qdetector's exact evaluation (1 forward FFT + 49 frequency-shifted inverse FFTs, one warp
+// per FFT, 16 points per lane), so decisions are those of the specification.  On a hit the CTA runs
+// the serial alignment / header steps and moves its hop grid past the frame.  Four worker warps
+// stage samples and read accumulators, a fifth only issues MMAs; three CTAs share an SM.
 // The payload itself is left to the frame-parallel kernels in lqb_rx_payload.cu.
 #include "lqb_dev.cuh"
 #include "lqb_kernels.h"
@@ -18,6 +24,15 @@ namespace lqb {
 
 namespace {
 
+#ifndef LQB_SEEK_REORDER
+#define LQB_SEEK_REORDER 0               // stage A of block k+2 between the two tile read-outs of block k (0: after the decision; measured A/B on B200: 21.6 ms without, 22.8 ms with -- shared memory is the busy resource, not the wait)
+#endif
+#ifndef LQB_SEEK_BINS
+#define LQB_SEEK_BINS 1                  // exact windows visit only the CFO bins the tensor cores cannot rule out (0: all 49)
+#endif
+#ifndef LQB_SEEK_SLEEP
+#define LQB_SEEK_SLEEP 0                 // scale of the nanosleep back-off in mbarrier waits (0: plain polling)
+#endif
 constexpr int kWarps = 4;                 // worker warps (TMEM lane quarters: warp w reads accumulator rows 32w .. 32w+31)
 constexpr int kThreads = 32 * kWarps;     // worker threads
 constexpr int kCtaThreads = kThreads + 32; // + one warp that only issues tcgen05.mma
@@ -74,9 +89,13 @@ struct SeekShared {
     unsigned tmem_base;
     int    tc_cmd[2];         // tiles in strip b (0 = the MMA warp exits)
     int    tables_dirty;
-    float  part_max[2][kWarps], part_en[2][kWarps];
+    float  part_max[4][kWarps], part_en[4][kWarps];   // block statistics, four slots in rotation (three blocks are alive at a time)
+    float  chunk_e[16], chunk_d[16];  // per 32 staged samples: energy, e4m3 residual energy (scaled units)
+    float  span_e[4], span_d[4];      // per block: max over any 6 consecutive chunks (covers every lag's 156-sample span)
     float  red[kWarps][4];
     float  tc_red[2 * kWarps];
+    unsigned binmax[tc::kNBins + 7];  // bin_candidates: max over all 512 circular lags of |C_q|^2 per CFO bin (float bits)
+    unsigned long long cand;
     unsigned char hbytes[64]; // header: 54 demodulated bytes
     unsigned char hdec[32];   // decoded header (24 bytes incl. CRC)
 };
@@ -131,8 +150,9 @@ __device__ __forceinline__ void cross_ifft(SeekShared &sh, int off, float2 (&v)[
     fft512_warp<-1>(v, sh.W, sh.Wc, scratch, lane);
 }
 
-// evaluate the window in sh.Xw; thread 0 publishes trig/idx/off/rxy
-__device__ void eval_window(SeekShared &sh, const DevTables *T, int tid)
+// evaluate the window in sh.Xw; thread 0 publishes trig/idx/off/rxy.
+// cand: CFO bins (bit offi) that can hold the global maximum; the others are proven smaller (bin_candidates) and skipped.
+__device__ void eval_window(SeekShared &sh, const DevTables *T, int tid, unsigned long long cand)
 {
     const int warp = tid >> 5, lane = tid & 31;
     if (warp < 2) {
@@ -149,7 +169,11 @@ __device__ void eval_window(SeekShared &sh, const DevTables *T, int tid)
         // per-lane running maximum; strict '>' keeps the earliest (offset, lag) on ties within the lane
         float bv = 0.0f;
         unsigned border = 0;
-        for (int offi = kWarps - 1 - warp; offi <= 2 * range; offi += kWarps) {
+        // the candidate bins are dealt round-robin to the warps, each warp taking its bins in increasing order
+        int turn = 0;
+        for (int offi = 0; offi <= 2 * range; ++offi) {
+            if (!((cand >> offi) & 1ull)) continue;
+            if ((turn++ & (kWarps - 1)) != warp) continue;
             cross_ifft(sh, offi - range, v, sh.scr + warp * 544, lane);
             const unsigned obase = (unsigned)(offi * 512 + fft512_out_index(lane, 0));
 #pragma unroll
@@ -186,201 +210,278 @@ __device__ void eval_window(SeekShared &sh, const DevTables *T, int tid)
 
 // ------------------------------------------------------------------ fused tensor-core pre-filter (pipelined)
 // A block correlates n_t * 128 consecutive lags starting at absolute sample a0 against the template at
-// all 49 CFO bins on the tensor cores (fp16 operands, fp32 accumulation in TMEM; same implicit-Hankel
-// operand as lqb_rx_coarse.cu).  Work is split three ways so that the tensor pipe never waits for the
-// CUDA cores of its own CTA:
-//   tc_issue  (workers)  : stage the samples of block k+2 as fp16, build its Z strip, hand it to the MMA warp
-//   mma_warp  (warp 4)   : wait for strip + free accumulators, issue the 20 n_t MMAs of block k+1, commit
-//   tc_retire (workers)  : read the accumulators of block k (max_b |C|^2 per lag), release them, reduce
-// Strip layout: Z[c][8 m + e] = fp16(x_c[a0 + m + e] * 2^-ex), two components, 416 rows of 16 bytes.
+// all 49 CFO bins on the tensor cores (e4m3 operands, fp32 accumulation in TMEM).  Work is split three ways
+// so that the tensor pipe never waits for the CUDA cores of its own CTA:
+//   tc_stage_a / tc_stage_b (workers) : quantise the samples of block k+2 to e4m3 (A), build its Z strip and hand it to
+//                                       the MMA warp (B)
+//   mma_warp  (warp 4)                : per 128-lag tile: wait for the (single) accumulator to be free, issue 10 MMAs, commit
+//   tc_retire_tile (workers)          : per tile: read the accumulator (max_b |C|^2 per lag), release it
+// Strip layout: Z[c][16 m + e] = e4m3(x_c[a0 + m + e] * 2^(4 - ex)), two component planes, 416 rows of 16 bytes:
+// row m IS the K-major core-matrix row "16 consecutive samples from a0 + m", so a no-swizzle UMMA descriptor with
+// row-group stride 128 B and K-chunk stride 256 B reads the Hankel matrix A[lag][k] = x[a0 + lag + k] in place.
+//
+// Error bound (why skipping on the fp8 result is exact).  With x_q, t_q the quantised samples / template,
+//   |C[l,b] - C_q[l,b]| <= ||x_l - x_q,l|| ||t_b|| + ||x_q,l|| ||t_b - t_q,b||        (Cauchy-Schwarz over the 156-span)
+// The rounding residual v 2^k - e4m3(v 2^k) is exact in fp32, so its energy is ACCUMULATED EXACTLY while quantising,
+// per chunk of 32 samples; a lag's 156-sample span touches at most six consecutive chunks, so
+//   ||x_l - x_q,l||^2 <= D6 = max over six consecutive chunks of the residual energy, ||x_l||^2 <= E6 likewise,
+// ||t_b|| = ||s||, and max_b ||t_b - t_q,b|| / ||s|| = P.b_err is computed on the host from the very bytes of B.
+// With g0 = sqrt(E_window 156 / 512) (qdetector's normaliser):
+//   rxy <= rxy_q + (sqrt(D6) + (sqrt(E6) + sqrt(D6)) b_err) / g0
+// (typically 0.06; measured differences are several times smaller).  fp32 accumulation of 320 exact products adds
+// < 1e-4; the decision keeps a further 0.008 in hand.  Saturated blocks (scaled maximum >= 384) are not trusted.
 struct TcBlk {
-    long long a0, e_lo, e_hi, w;    // first lag; energy range; window this block belongs to
-    int n_t, cold, ex, buf;         // tiles; cold-start block of a hop grid; scale exponent; strip buffer
+    long long a0, e_lo, e_hi, w, next_a0;   // first lag; energy range; window this block belongs to; first lag of the block after it
+    int n_t, cold, ex, buf, slot;           // tiles; cold-start block of a hop grid; scale exponent; strip buffer; statistics slot
+    long long wrap_w;                       // >= LLONG_MIN + 1: samples are taken circularly from the 512-sample window at wrap_w
 };
-struct TcRes { float m0_all, m0_ge28, m1_all, m1_ge28, mx, en; };
+constexpr long long kNoWrap = -(1ll << 62);
+struct TcRes { float m0_all, m0_ge28, m1_all, m1_ge28, mx, en, span_e, span_d; };
+
+constexpr int kXsWords = 112;       // staged e4m3 samples: words per component plane (448 bytes >= 416 + 15 rows)
 
 __device__ __forceinline__ unsigned char *tc_strip(SeekShared &sh, int buf)
 {
     return buf ? sh.Z1 : reinterpret_cast<unsigned char *>(sh.scr);
+}
+__device__ __forceinline__ uint32_t *tc_xs(SeekShared &sh)
+{
+    return reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(sh.scr) + 2 * kTcZBytes);   // [2][kXsWords], behind strip 0
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(tc::smem_u32(bar)) : "memory");
 }
 
-// pre[] / pre_a0: samples already fetched for the block starting at pre_a0 (by the previous call);
-// next_a0: where the following block will start (its samples are requested before returning).
-__device__ void tc_issue(SeekShared &sh, const StreamView &sv, const TcBlk &b, int tid,
-                         float2 (&pre)[4], long long &pre_a0, long long next_a0)
+// Stage A of a block: quantise its samples to e4m3 into the staging planes `xs` and take its statistics (maximum, window
+// energy, per-span energy and residual maxima) into statistics slot b.slot.  Touches neither strip, so it can run while
+// the tensor core still reads the strip this block will later be built into.
+// pre[] / pre_a0: samples already fetched for the block starting at pre_a0 (by the previous stage B).
+// Thread t owns the four consecutive samples 4 t .. 4 t + 3 of the block (threads 106.. hold zeros).
+__device__ void tc_stage_a(SeekShared &sh, const StreamView &sv, const TcBlk &b, int tid, float2 (&pre)[4], long long pre_a0 PROF_ARGS)
 {
-    using namespace tc;
     const int warp = tid >> 5, lane = tid & 31;
-    unsigned char *Z = tc_strip(sh, b.buf);
-    uint32_t *xs = reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(sh.scr) + 2 * kTcZBytes);   // [2][216] half pairs
+    uint32_t *xs = tc_xs(sh);
     const int n_samp = 128 * b.n_t + 168;
-    const float sc = __uint_as_float((uint32_t)(127 - b.ex) << 23);          // exact power of two
+    const float sc = __uint_as_float((uint32_t)(127 + 4 - b.ex) << 23);      // exact power of two: block maximum -> [16, 32)
     wsync();                                   // the previous strip build has finished reading xs
-    float mx = 0.0f, en = 0.0f;
-    __half *xh = reinterpret_cast<__half *>(xs);
-    if (pre_a0 != b.a0) {                      // (uniform) nothing usable was prefetched: fetch now
+    float mx = 0.0f, en = 0.0f, dd = 0.0f, ee = 0.0f;
+    if (b.wrap_w != kNoWrap) {                 // (uniform) circular lags of one window: sample index modulo 512
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const int i = tid + kThreads * k;
+            const int i = 4 * tid + k;
+            pre[k] = (i < 424) ? sv.at(b.wrap_w + (((b.a0 - b.wrap_w) + i) & 511)) : make_float2(0.0f, 0.0f);
+        }
+    } else if (pre_a0 != b.a0) {               // (uniform) nothing usable was prefetched: fetch now
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int i = 4 * tid + k;
             pre[k] = (i < 424) ? sv.at(b.a0 + i) : make_float2(0.0f, 0.0f);
         }
     }
+    uint32_t pk[2] = { 0u, 0u };               // (re0 im0 re1 im1), (re2 im2 re3 im3) as e4m3 bytes
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const int i = tid + kThreads * k;
+        const int i = 4 * tid + k;
         const long long n = b.a0 + i;
         float2 v = pre[k];
         if (i >= n_samp) v = make_float2(0.0f, 0.0f);
         mx = fmaxf(mx, fmaxf(fabsf(v.x), fabsf(v.y)));
-        if (i < n_samp && n >= b.e_lo && n < b.e_hi) en += fmaf(v.y, v.y, v.x * v.x);
-        if (i < 432) { xh[i] = __float2half_rn(v.x * sc); xh[432 + i] = __float2half_rn(v.y * sc); }
+        const float a2 = fmaf(v.y, v.y, v.x * v.x);
+        if (i < n_samp && n >= b.e_lo && n < b.e_hi) en += a2;
+        ee += a2;
+        const float2 vs = make_float2(v.x * sc, v.y * sc);
+        const __nv_fp8x2_storage_t q = __nv_cvt_float2_to_fp8x2(vs, __NV_SATFINITE, __NV_E4M3);      // low byte: re
+        const __half2_raw hb = __nv_cvt_fp8x2_to_halfraw2(q, __NV_E4M3);
+        const float2 back = __half22float2(*reinterpret_cast<const __half2 *>(&hb));
+        const float rx = vs.x - back.x, ry = vs.y - back.y;                  // exact: what the tensor core will not see
+        dd += fmaf(ry, ry, rx * rx);
+        pk[k >> 1] |= (uint32_t)q << (16 * (k & 1));
+    }
+    if (tid < kXsWords) {
+        xs[tid] = __byte_perm(pk[0], pk[1], 0x6420);                         // re plane: bytes 0, 2 of each word
+        xs[kXsWords + tid] = __byte_perm(pk[0], pk[1], 0x7531);              // im plane
     }
     // non-negative floats order like their bit patterns: one REDUX instead of five shuffle + max rounds
     mx = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(mx)));
+    // chunk sums: eight consecutive lanes hold one chunk of 32 samples
+#pragma unroll
+    for (int m = 1; m <= 4; m <<= 1) { ee += __shfl_xor_sync(0xffffffffu, ee, m); dd += __shfl_xor_sync(0xffffffffu, dd, m); }
+    if ((lane & 7) == 0) { sh.chunk_e[tid >> 3] = ee; sh.chunk_d[tid >> 3] = dd; }
 #pragma unroll
     for (int m = 16; m >= 1; m >>= 1) en += __shfl_xor_sync(0xffffffffu, en, m);
-    if (lane == 0) { sh.part_max[b.buf][warp] = mx; sh.part_en[b.buf][warp] = en; }
+    if (lane == 0) { sh.part_max[b.slot][warp] = mx; sh.part_en[b.slot][warp] = en; }
     wsync();
-    // ---- Z[c][8 m + e] = xs[c][m + e]: row m is the 16 bytes at half offset m (word aligned for even m)
+    if (warp == 0) {
+        // lag p (0 .. 255) spans samples p .. p + 155 = chunks p / 32 .. (p + 155) / 32: six consecutive chunks from j = 0 .. 7
+        float se = 0.0f, sd = 0.0f;
+        if (lane < 9) {
+#pragma unroll
+            for (int q = 0; q < 6; ++q) { if (lane + q < 16) { se += sh.chunk_e[lane + q]; sd += sh.chunk_d[lane + q]; } }
+        }
+        se = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(se)));
+        sd = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(sd)));
+        if (lane == 0) { sh.span_e[b.slot] = se; sh.span_d[b.slot] = sd; }
+    }
+    PROF_MARK(1);
+}
+
+// Stage B: build the block's Z strip from the staging planes, hand it to the MMA warp, request the samples of the block
+// that will be staged next (they travel while this one is multiplied).
+__device__ void tc_stage_b(SeekShared &sh, const StreamView &sv, const TcBlk &b, int tid, float2 (&pre)[4], long long &pre_a0 PROF_ARGS)
+{
+    using namespace tc;
+    unsigned char *Z = tc_strip(sh, b.buf);
+    const uint32_t *xs = tc_xs(sh);
+    // ---- Z[c][16 m + e] = xs[c][m + e]: row m is the 16 bytes at byte offset m of the plane
     const int rows = 128 * b.n_t + 160;
     for (int m = tid; m < rows; m += kThreads) {
-        const int w0 = m >> 1;
-        const unsigned sh16 = (m & 1) ? 16u : 0u;
+        const int w0 = m >> 2;
+        const unsigned sh8 = 8u * (unsigned)(m & 3);
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
-            const uint32_t *s = xs + 216 * c + w0;
+            const uint32_t *s = xs + kXsWords * c + w0;
             const uint32_t q0 = s[0], q1 = s[1], q2 = s[2], q3 = s[3], q4 = s[4];
             uint4 o;
-            o.x = __funnelshift_r(q0, q1, sh16); o.y = __funnelshift_r(q1, q2, sh16);
-            o.z = __funnelshift_r(q2, q3, sh16); o.w = __funnelshift_r(q3, q4, sh16);
+            o.x = __funnelshift_r(q0, q1, sh8); o.y = __funnelshift_r(q1, q2, sh8);
+            o.z = __funnelshift_r(q2, q3, sh8); o.w = __funnelshift_r(q3, q4, sh8);
             *reinterpret_cast<uint4 *>(Z + c * kTcZBytes + 16 * m) = o;
         }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     if (tid == 0) sh.tc_cmd[b.buf] = b.n_t;
     mbar_arrive(&sh.z_full[b.buf]);
-    // the samples of the block that will be staged next travel while this one is multiplied; a block that lies
-    // wholly inside the new input (the usual case) is read straight through the pointer
-    {
+    PROF_MARK(2);
+    // a block that lies wholly inside the new input (the usual case) is read straight through the pointer
+    if (b.next_a0 == kNoWrap) pre_a0 = kNoWrap;        // (nothing follows: bin_candidates)
+    else {
+        const long long next_a0 = b.next_a0;
         const long long i0 = next_a0 - sv.base - (long long)sv.carry_len;
         if (i0 >= 0 && next_a0 >= sv.G && next_a0 + 424 <= sv.end) {
             const float2 *src = sv.in + i0;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const int i = tid + kThreads * k;
+                const int i = 4 * tid + k;
                 pre[k] = (i < 424) ? __ldg(src + i) : make_float2(0.0f, 0.0f);
             }
         } else {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const int i = tid + kThreads * k;
+                const int i = 4 * tid + k;
                 pre[k] = (i < 424) ? sv.at(next_a0 + i) : make_float2(0.0f, 0.0f);
             }
         }
+        pre_a0 = next_a0;
     }
-    pre_a0 = next_a0;
+    PROF_MARK(3);
 }
 
-// the MMA warp: one lane issues, the warp only ever waits on mbarriers
+// the MMA warp: one lane issues, the warp only ever waits on mbarriers.  One accumulator tile (128 lags x 112
+// columns, 128 TMEM columns per CTA so that three CTAs fit an SM): a tile's MMAs start when the workers have read
+// the previous tile out; the tensor pipe is kept busy by the other CTAs of the SM meanwhile.
 __device__ void mma_warp(SeekShared &sh, const unsigned char *Bsm, int lane)
 {
     using namespace tc;
-    unsigned pz[2] = { 0u, 0u }, pe = 1u;      // parity 1 on a fresh barrier: "the accumulators start out free"
+    unsigned pz[2] = { 0u, 0u }, pe = 1u;      // parity 1 on a fresh barrier: "the accumulator starts out free"
     int buf = 0;
     const uint32_t tmem = sh.tmem_base;
+    // instruction descriptor: D = f32 (bit 4), A = B = e4m3 (format 0), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
     const uint32_t idesc = (1u << 4) | ((uint32_t)(kN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const uint32_t b_addr = smem_u32(Bsm);
     while (true) {
-        mbar_wait(&sh.z_full[buf], pz[buf]);
+        mbar_wait(&sh.z_full[buf], pz[buf], 200u * LQB_SEEK_SLEEP);
         pz[buf] ^= 1u;
         const int n_t = *reinterpret_cast<volatile int *>(&sh.tc_cmd[buf]);
         if (n_t == 0) break;
-        mbar_wait(&sh.acc_empty, pe);
-        pe ^= 1u;
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (lane == 0) {
-            const unsigned char *Z = tc_strip(sh, buf);
-            for (int t = 0; t < n_t; ++t) {
+        const unsigned char *Z = tc_strip(sh, buf);
+        for (int t = 0; t < n_t; ++t) {
+            mbar_wait(&sh.acc_empty, pe, 100u * LQB_SEEK_SLEEP);
+            pe ^= 1u;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (lane == 0) {
                 uint32_t acc = 0;
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
-                    const uint32_t za = smem_u32(Z + c * kTcZBytes) + 2048u * t;
+                    const uint32_t za = smem_u32(Z + c * kTcZBytes) + 2048u * t;        // 128 lags further: 128 rows
 #pragma unroll
-                    for (int j = 0; j < 10; ++j) {
-                        mma_f16(tmem + 128u * t, make_desc(za + 256u * j, 128u, 128u),
-                                make_desc(b_addr + (uint32_t)((c * 10 + j) * 2) * kBChunkBytes, kBChunkBytes, 128u), idesc, acc);
+                    for (int j = 0; j < kMmaPerComp; ++j) {
+                        // A: K-chunk (16 samples) stride 256 B, row-group (8 lags) stride 128 B; 32 samples per MMA = 512 B
+                        mma_f8(tmem, make_desc(za + 512u * j, 256u, 128u),
+                               make_desc(b_addr + (uint32_t)((c * kMmaPerComp + j) * 2) * kBChunkBytes, kBChunkBytes, 128u), idesc, acc);
                         acc = 1;
                     }
                 }
+                mma_commit(&sh.acc_full);
             }
-            mma_commit(&sh.acc_full);
+            __syncwarp();
         }
-        __syncwarp();
         buf ^= 1;
     }
 }
 
-// wait for block b, reduce max_b |C|^2 per lag to the four range maxima the decisions need
-__device__ void tc_retire(SeekShared &sh, const TcBlk &b, unsigned &ph_full, int tid, TcRes &r, bool discard PROF_ARGS)
+// wait for the next accumulator tile, take max_b |C|^2 of this thread's lag, release the accumulator.
+// Columns: re of bin b at column b, im at column 56 + b (b < 49; the padding columns of B are zero).
+__device__ float tc_retire_tile(SeekShared &sh, unsigned &ph_full, int tid, bool discard PROF_ARGS)
 {
     using namespace tc;
-    const int warp = tid >> 5, lane = tid & 31;
     PROF_MARK(0);
-    mbar_wait(&sh.acc_full, ph_full);
+    mbar_wait(&sh.acc_full, ph_full, 40u * LQB_SEEK_SLEEP);
     ph_full ^= 1u;
     PROF_MARK(4);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    float best[2] = { 0.0f, 0.0f };
+    float best = 0.0f;
     if (!discard) {
-        const uint32_t tmem = sh.tmem_base;
+        const uint32_t taddr = sh.tmem_base + ((uint32_t)((tid >> 5) * 32) << 16);
+        float bt0 = 0.0f, bt1 = 0.0f, bt2 = 0.0f, bt3 = 0.0f;       // independent running maxima: no single dependent chain
 #pragma unroll
-        for (int t = 0; t < 2; ++t) {
-            if (t >= b.n_t) break;
-            const uint32_t taddr = tmem + 128u * t + ((uint32_t)(warp * 32) << 16);
-            float bt = 0.0f;
+        for (int round = 0; round < 4; ++round) {
+            uint32_t re[2][8], im[2][8];
+            const int nc = (round == 3) ? 1 : 2;
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                uint32_t q[4][16];
-                const int q0 = half * 4, nq = half ? 3 : 4;
-#pragma unroll
-                for (int u = 0; u < 4; ++u) if (u < nq) tmem_ld16(taddr + 16u * (q0 + u), q[u]);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if (u >= nq) continue;
-#pragma unroll
-                    for (int k = 0; k < 16; k += 2) {
-                        if (16 * (q0 + u) + k < 2 * kNBins) {
-                            const float re = __uint_as_float(q[u][k]), im = __uint_as_float(q[u][k + 1]);
-                            bt = fmaxf(bt, fmaf(im, im, re * re));
-                        }
-                    }
-                }
+            for (int u = 0; u < 2; ++u) {
+                if (u < nc) { tmem_ld8(taddr + 8u * (2 * round + u), re[u]); tmem_ld8(taddr + 56u + 8u * (2 * round + u), im[u]); }
             }
-            best[t] = bt;
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                if (u >= nc) continue;
+                float2 a[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float2 r2 = make_float2(__uint_as_float(re[u][2 * k]), __uint_as_float(re[u][2 * k + 1]));
+                    const float2 i2 = make_float2(__uint_as_float(im[u][2 * k]), __uint_as_float(im[u][2 * k + 1]));
+                    a[k] = __ffma2_rn(i2, i2, __fmul2_rn(r2, r2));           // two bins per instruction (FMUL2 / FFMA2)
+                }
+                bt0 = max3f(bt0, a[0].x, a[0].y); bt1 = max3f(bt1, a[1].x, a[1].y);
+                bt2 = max3f(bt2, a[2].x, a[2].y); bt3 = max3f(bt3, a[3].x, a[3].y);
+            }
         }
+        best = fmaxf(fmaxf(bt0, bt1), fmaxf(bt2, bt3));
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     mbar_arrive(&sh.acc_empty);
     PROF_MARK(5);
-    if (discard) return;
+    return best;
+}
+
+// reduce the per-lag maxima of a block's tiles to the four range maxima the decisions need, and fetch its statistics
+__device__ void tc_retire_reduce(SeekShared &sh, const TcBlk &b, float best0, float best1, int tid, TcRes &r PROF_ARGS)
+{
+    const int warp = tid >> 5, lane = tid & 31;
     // |C|^2 >= 0: the maxima are taken on the bit patterns with one REDUX each
-    const float a = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(best[0])));
-    const float bb = __uint_as_float(__reduce_max_sync(0xffffffffu, tid >= 28 ? __float_as_uint(best[0]) : 0u));
-    const float c = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(best[1])));
-    const float d = __uint_as_float(__reduce_max_sync(0xffffffffu, tid >= 28 ? __float_as_uint(best[1]) : 0u));
+    const float a = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(best0)));
+    const float bb = __uint_as_float(__reduce_max_sync(0xffffffffu, tid >= 28 ? __float_as_uint(best0) : 0u));
+    const float c = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(best1)));
+    const float d = __uint_as_float(__reduce_max_sync(0xffffffffu, tid >= 28 ? __float_as_uint(best1) : 0u));
     if (lane == 0) { sh.red[warp][0] = a; sh.red[warp][1] = bb; sh.red[warp][2] = c; sh.red[warp][3] = d; }
     wsync();
     r.m0_all = 0.0f; r.m0_ge28 = 0.0f; r.m1_all = 0.0f; r.m1_ge28 = 0.0f; r.mx = 0.0f; r.en = 0.0f;
+    r.span_e = sh.span_e[b.slot]; r.span_d = sh.span_d[b.slot];
 #pragma unroll
     for (int w = 0; w < kWarps; ++w) {
         r.m0_all = fmaxf(r.m0_all, sh.red[w][0]); r.m0_ge28 = fmaxf(r.m0_ge28, sh.red[w][1]);
         r.m1_all = fmaxf(r.m1_all, sh.red[w][2]); r.m1_ge28 = fmaxf(r.m1_ge28, sh.red[w][3]);
-        r.mx = fmaxf(r.mx, sh.part_max[b.buf][w]); r.en += sh.part_en[b.buf][w];
+        r.mx = fmaxf(r.mx, sh.part_max[b.slot][w]); r.en += sh.part_en[b.slot][w];
     }
     wsync();
     PROF_MARK(6);
@@ -391,23 +492,41 @@ struct ScanCarry {
     bool valid, unsafe, ex_valid;
     long long w;            // window the carried tail / half-energy belong to
     float tail, half;       // max |C|^2 over its first 100 lags; energy of its first 256 samples
+    float tail_d, tail_e;   // of the block that produced the tail: largest residual energy / energy of a 156-sample span
     int ex;                 // scale exponent for the next strips
 };
 
+__device__ __forceinline__ float fast_sqrt(float x)
+{
+    float y;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// the scale is only a choice (any power of two keeps the bound exact); clamped so that the factors below stay normal
 __device__ __forceinline__ int exponent_of(float mx)
 {
     int ex = 0;
     if (mx > 0.0f) ex = (int)((__float_as_uint(mx) >> 23) & 0xffu) - 127;
-    return max(-100, min(100, ex));
+    return max(-40, min(40, ex));
 }
 
 // Walk the hop grid from st.wstart with the pre-filter while windows can be ruled out.
 // Returns 1 when window st.wstart (updated) needs the exact evaluation, 0 when the input is exhausted.
 // The pipeline is empty on return.
-__device__ int fused_scan(SeekShared &sh, const StreamView &sv, const DevTables *T, StreamState &st, int tid,
+//
+// Order of work per window (block k is being decided, k+1 is staged, k+2 is new), chosen so that the workers never idle
+// while the tensor core multiplies -- a CTA has ONE accumulator tile, so tile 1 of block k can only be multiplied once
+// tile 0 has been read out:
+//   read tile 0 of k | quantise k+2 (stage A: no strip touched) while tile 1 of k is multiplied | read tile 1 of k |
+//   decide k | build the strip of k+2 in the buffer k used (stage B) -- tile 0 of k+1 is multiplied meanwhile.
+__device__ int fused_scan(SeekShared &sh, const StreamView &sv, const DevTables *T, float b_err, StreamState &st, int tid,
                           ScanCarry &c, float2 (&pre)[4], long long &pre_a0, unsigned &ph_full, int &buf_w,
-                          unsigned &n_windows, unsigned &n_tiles PROF_ARGS)
+                          unsigned &n_windows, unsigned &n_tiles, float &rxy_q PROF_ARGS)
 {
+    rxy_q = 0.0f;                                      // pre-filter's estimate of rxy for the window that needs the exact evaluation
+    const float s_norm = sqrtf(T->s2_sum);             // (once per scan, not per window)
+    const float k_err = s_norm, k_thr = (T->threshold - 0.008f) * sqrtf(156.0f / 512.0f) * s_norm;
     long long g_w = st.wstart;                         // block generator: next window to stage
     bool g_cold = !(c.valid && c.w == g_w);
     long long w_done = g_w;                            // first window not yet decided
@@ -432,66 +551,206 @@ __device__ int fused_scan(SeekShared &sh, const StreamView &sv, const DevTables 
         c.ex = exponent_of(mx);
         c.ex_valid = true;
     }
-    TcBlk q0, q1;                                       // in flight, q0 the older
-    int inflight = 0, result = 0;
-    auto gen = [&](TcBlk &b, long long &next_a0) {
-        b.w = g_w; b.ex = c.ex; b.buf = buf_w; buf_w ^= 1;
-        if (g_cold) { b.a0 = g_w - 28; b.n_t = 1; b.e_lo = g_w; b.e_hi = g_w + 256; b.cold = 1; next_a0 = g_w + 100; g_cold = false; }
-        else { b.a0 = g_w + 100; b.n_t = 2; b.e_lo = g_w + 256; b.e_hi = g_w + 512; b.cold = 0; next_a0 = g_w + 356; g_w += 256; }
+    TcBlk q0, q1, nb;                                   // q0, q1: handed to the MMA warp (q0 the older); nb: stage A done only
+    int inflight = 0, result = 0, slot_w = 0;
+    auto gen = [&](TcBlk &b) {
+        b.w = g_w; b.ex = c.ex; b.buf = buf_w; buf_w ^= 1; b.slot = slot_w; slot_w = (slot_w + 1) & 3; b.wrap_w = kNoWrap;
+        if (g_cold) { b.a0 = g_w - 28; b.n_t = 1; b.e_lo = g_w; b.e_hi = g_w + 256; b.cold = 1; b.next_a0 = g_w + 100; g_cold = false; }
+        else { b.a0 = g_w + 100; b.n_t = 2; b.e_lo = g_w + 256; b.e_hi = g_w + 512; b.cold = 0; b.next_a0 = g_w + 356; g_w += 256; }
         n_tiles += (unsigned)b.n_t;
     };
     auto more = [&]() { return g_w + 512 <= sv.end; };
+    auto block_max = [&](const TcBlk &b) {
+        return fmaxf(fmaxf(sh.part_max[b.slot][0], sh.part_max[b.slot][1]), fmaxf(sh.part_max[b.slot][2], sh.part_max[b.slot][3]));
+    };
     while (inflight < 2 && more()) {
         TcBlk &b = inflight ? q1 : q0;
-        long long na;
-        gen(b, na);
-        tc_issue(sh, sv, b, tid, pre, pre_a0, na);
+        gen(b);
+        tc_stage_a(sh, sv, b, tid, pre, pre_a0 PROF_PASS);
+        tc_stage_b(sh, sv, b, tid, pre, pre_a0 PROF_PASS);
+        // the scale of the following blocks follows the samples (statistics are visible: stage A ends behind a barrier)
+        c.ex = exponent_of(block_max(b));
         ++inflight;
     }
-    PROF_MARK(1);
     while (inflight) {
-        TcRes r;
-        tc_retire(sh, q0, ph_full, tid, r, false PROF_PASS);
         const TcBlk d = q0;
+        const float best0 = tc_retire_tile(sh, ph_full, tid, false PROF_PASS);
+        bool have_nb = false;
+#if LQB_SEEK_REORDER
+        if (more()) {
+            gen(nb);
+            tc_stage_a(sh, sv, nb, tid, pre, pre_a0 PROF_PASS);          // runs while tile 1 of d is multiplied
+            have_nb = true;
+        }
+#endif
+        const float best1 = d.n_t == 2 ? tc_retire_tile(sh, ph_full, tid, false PROF_PASS) : 0.0f;
+        TcRes r;
+        tc_retire_reduce(sh, d, best0, best1, tid, r PROF_PASS);
         q0 = q1; --inflight;
-        const float s2 = __uint_as_float((uint32_t)(127 + 2 * d.ex) << 23);
-        const float scaled_mx = r.mx * __uint_as_float((uint32_t)(127 - d.ex) << 23);
-        // outside this range fp16 staging loses the error bound (overflow / everything subnormal): do not trust the block
-        const bool unsafe_blk = !(scaled_mx < 32768.0f) || (r.mx > 0.0f && scaled_mx < 0.001953125f);
-        c.ex = exponent_of(r.mx);
+        // accumulators hold sum (x 2^(4-ex)) (t 2^5): |C|^2 = acc^2 2^(2 ex - 18); residual energy in sample units: 2^(2 ex - 8)
+        const float s2 = __uint_as_float((uint32_t)(127 + 2 * d.ex - 8 - 2 * tc::kBScaleLog2) << 23);
+        const float d_true = r.span_d * __uint_as_float((uint32_t)(127 + 2 * d.ex - 8) << 23);
+        const float scaled_mx = r.mx * __uint_as_float((uint32_t)(127 + 4 - d.ex) << 23);
+        // a block whose scaled maximum reaches e4m3's saturation (448) has an unbounded rounding error: do not trust it
+        // (small values need no such test: their rounding error, including flush to zero, is inside the residual)
+        const bool unsafe_blk = !(scaled_mx < 384.0f);
+        bool skip = true;
         if (d.cold) {
-            c.tail = r.m0_ge28 * s2; c.half = r.en; c.unsafe = unsafe_blk; c.w = d.w; c.valid = true;
+            c.tail = r.m0_ge28 * s2; c.tail_d = d_true; c.tail_e = r.span_e; c.half = r.en; c.unsafe = unsafe_blk; c.w = d.w; c.valid = true;
         } else {
             ++n_windows;
             const float mm = fmaxf(c.tail, fmaxf(r.m0_all, r.m1_all) * s2), E = c.half + r.en;
-            bool skip = false;
+            skip = false;
             if (E > 0.0f && !c.unsafe && !unsafe_blk) {
-                const float ub = sqrtf(mm) / (sqrtf(E) * sqrtf(156.0f / 512.0f) * sqrtf(T->s2_sum));
-                skip = ub < T->threshold - 0.008f;
+                // rxy_q + margin < thr - 0.008, multiplied through by g0 ||s|| (no division, four approximate square
+                // roots -- their 2^-22 relative error and the rounding of the sums are covered by the factor 1.001):
+                //   sqrt(mm) + ||s|| (sqrt(D6) + (sqrt(E6) + sqrt(D6)) b_err) < (thr - 0.008) sqrt(156 / 512) ||s|| sqrt(E)
+                const float rd = fast_sqrt(fmaxf(c.tail_d, d_true)), re = fast_sqrt(fmaxf(c.tail_e, r.span_e));
+                const float lhs = fast_sqrt(mm) + k_err * (rd + (re + rd) * b_err);
+                skip = lhs * 1.001f < k_thr * fast_sqrt(E);
+                if (!skip) rxy_q = fast_sqrt(mm) / (fast_sqrt(E) * sqrtf(156.0f / 512.0f) * s_norm);
             }
-            c.tail = r.m1_ge28 * s2; c.half = r.en; c.unsafe = unsafe_blk; c.w = d.w + 256; c.valid = true;
-            if (!skip) {
-                // speculative blocks behind this one are dropped (their accumulators are released unread)
-                while (inflight) { TcRes dummy; tc_retire(sh, q0, ph_full, tid, dummy, true PROF_PASS); q0 = q1; --inflight; }
-                w_done = d.w;
-                result = 1;
-                break;
-            }
-            w_done = d.w + 256;
+            c.tail = r.m1_ge28 * s2; c.tail_d = d_true; c.tail_e = r.span_e; c.half = r.en; c.unsafe = unsafe_blk; c.w = d.w + 256; c.valid = true;
         }
+        if (!skip) {
+            // speculative work behind this window is dropped: a block that only went through stage A was never handed
+            // to the MMA warp (undo its strip-buffer turn), handed-over blocks have their accumulators released unread
+            if (have_nb) { buf_w ^= 1; n_tiles -= (unsigned)nb.n_t; }
+            while (inflight) {
+                for (int t = 0; t < q0.n_t; ++t) (void)tc_retire_tile(sh, ph_full, tid, true PROF_PASS);
+                q0 = q1; --inflight;
+            }
+            w_done = d.w;
+            result = 1;
+            break;
+        }
+        if (!d.cold) w_done = d.w + 256;
+#if !LQB_SEEK_REORDER
         if (more()) {
-            TcBlk &b = inflight ? q1 : q0;
-            long long na;
-            gen(b, na);
-            PROF_MARK(0);
-            tc_issue(sh, sv, b, tid, pre, pre_a0, na);
-            PROF_MARK(2);
+            gen(nb);
+            tc_stage_a(sh, sv, nb, tid, pre, pre_a0 PROF_PASS);
+            have_nb = true;
+        }
+#endif
+        if (have_nb) {
+            tc_stage_b(sh, sv, nb, tid, pre, pre_a0 PROF_PASS);          // into the strip buffer d used: its MMAs are complete
+            c.ex = exponent_of(block_max(nb));
+            if (inflight) q1 = nb; else q0 = nb;
             ++inflight;
         }
     }
     if (tid == 0) st.wstart = w_done;
     wsync();
     return result;
+}
+
+// per-bin form of the accumulator read-out: every thread keeps max |C_q|^2 per CFO bin over ITS lag of each of the four
+// tiles in registers (acc[b], float bit patterns); the reduction over the 128 lags happens once, after the last tile.
+__device__ void tc_retire_tile_bins(SeekShared &sh, unsigned &ph_full, int tid, unsigned (&acc)[tc::kNBins])
+{
+    using namespace tc;
+    mbar_wait(&sh.acc_full, ph_full, 40u * LQB_SEEK_SLEEP);
+    ph_full ^= 1u;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t taddr = sh.tmem_base + ((uint32_t)((tid >> 5) * 32) << 16);
+#pragma unroll
+    for (int c8 = 0; c8 < 7; ++c8) {
+        uint32_t re[8], im[8];
+        tmem_ld8(taddr + 8u * c8, re);
+        tmem_ld8(taddr + (uint32_t)kImCol0 + 8u * c8, im);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int bin = 8 * c8 + k;                                          // compile-time
+            if (bin < kNBins) {
+                const float r_ = __uint_as_float(re[k]), i_ = __uint_as_float(im[k]);
+                acc[bin] = max(acc[bin], __float_as_uint(fmaf(i_, i_, r_ * r_)));
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    mbar_arrive(&sh.acc_empty);
+}
+
+// Which CFO bins can hold the global maximum of the window at w (the exact evaluation's arg max over all 512 CIRCULAR
+// lags x 49 bins)?  The window is not skippable, so its exact evaluation would cost 49 inverse FFTs; the tensor cores
+// first correlate all 512 circular lags (two 256-lag blocks, the second reading the window modulo 512), keep the
+// maximum per bin, and the same rigorous e4m3 error bound as the pre-filter's rules out every bin whose largest
+// possible value lies below the smallest possible value of the best bin.  Typically 3 .. 7 bins survive.
+// Returns the bin mask (all bins when a block cannot be trusted).  The MMA pipeline must be empty on entry and is on exit.
+__device__ unsigned long long bin_candidates(SeekShared &sh, const StreamView &sv, const DevTables *T, float b_err, long long w,
+                                             int tid, float2 (&pre)[4], long long &pre_a0, unsigned &ph_full, int &buf_w,
+                                             unsigned &n_tiles PROF_ARGS)
+{
+    const unsigned long long all = (1ull << (2 * T->range + 1)) - 1ull;
+    for (int i = tid; i < tc::kNBins + 7; i += kThreads) sh.binmax[i] = 0u;
+    // the scale comes from the window itself (a window that is not skippable usually holds the start of a frame, whose
+    // level the pre-filter's running scale has not seen yet)
+    int ex;
+    {
+        float m = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float2 v = sv.at(w + tid + kThreads * k);
+            m = fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y)));
+        }
+        m = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(m)));
+        wsync();
+        if ((tid & 31) == 0) sh.tc_red[tid >> 5] = m;
+        wsync();
+        ex = exponent_of(fmaxf(fmaxf(sh.tc_red[0], sh.tc_red[1]), fmaxf(sh.tc_red[2], sh.tc_red[3])));
+    }
+    TcBlk b[2];
+    float worst_d = 0.0f, worst_e = 0.0f, mx = 0.0f, en = 0.0f;
+    for (int h = 0; h < 2; ++h) {
+        TcBlk &q = b[h];
+        q.w = w; q.a0 = w + 256 * h; q.e_lo = q.a0; q.e_hi = q.a0 + 256; q.next_a0 = kNoWrap;
+        q.n_t = 2; q.cold = 0; q.ex = ex; q.buf = buf_w; buf_w ^= 1; q.slot = h; q.wrap_w = w;
+        n_tiles += 2u;
+        tc_stage_a(sh, sv, q, tid, pre, pre_a0 PROF_PASS);
+        tc_stage_b(sh, sv, q, tid, pre, pre_a0 PROF_PASS);
+    }
+    {
+        unsigned acc[tc::kNBins];
+#pragma unroll
+        for (int i = 0; i < tc::kNBins; ++i) acc[i] = 0u;
+        for (int t = 0; t < 4; ++t) tc_retire_tile_bins(sh, ph_full, tid, acc);
+        const int lane = tid & 31;
+        unsigned mine0 = 0u, mine1 = 0u;               // lane b & 31 collects bin b
+#pragma unroll
+        for (int i = 0; i < tc::kNBins; ++i) {
+            const unsigned m = __reduce_max_sync(0xffffffffu, acc[i]);
+            if (i < 32) mine0 = (lane == i) ? m : mine0; else mine1 = (lane == i - 32) ? m : mine1;
+        }
+        atomicMax(&sh.binmax[lane], mine0);                    // four warps x two instructions
+        if (lane < tc::kNBins - 32) atomicMax(&sh.binmax[32 + lane], mine1);
+    }
+    wsync();
+    for (int h = 0; h < 2; ++h) {
+        worst_d = fmaxf(worst_d, sh.span_d[h]); worst_e = fmaxf(worst_e, sh.span_e[h]);
+#pragma unroll
+        for (int k = 0; k < kWarps; ++k) { mx = fmaxf(mx, sh.part_max[h][k]); en += sh.part_en[h][k]; }
+    }
+    const float scaled_mx = mx * __uint_as_float((uint32_t)(127 + 4 - ex) << 23);
+    unsigned long long cand = all;
+    if (scaled_mx < 384.0f && en > 0.0f) {
+        // everything in |C| units: |C_q| = sqrt(binmax) 2^(ex - 9); err as in fused_scan; slack for the fp32 rounding of
+        // the exact evaluation itself (0.004 in rxy units on either side)
+        const float s2 = __uint_as_float((uint32_t)(127 + 2 * ex - 8 - 2 * tc::kBScaleLog2) << 23);
+        const float d_true = worst_d * __uint_as_float((uint32_t)(127 + 2 * ex - 8) << 23);
+        const float s_norm = sqrtf(T->s2_sum);
+        const float rd = fast_sqrt(d_true), re = fast_sqrt(worst_e);
+        const float err = (s_norm * (rd + (re + rd) * b_err) + 0.004f * fast_sqrt(en * (156.0f / 512.0f)) * s_norm) * 1.001f;
+        float best = 0.0f;
+        for (int i = 0; i < tc::kNBins; ++i) best = fmaxf(best, __uint_as_float(sh.binmax[i]));
+        const float floor_ = fast_sqrt(best * s2) - err;
+        cand = 0ull;
+        for (int i = 0; i <= 2 * T->range; ++i)
+            if (fast_sqrt(__uint_as_float(sh.binmax[i]) * s2) + err >= floor_) cand |= 1ull << i;
+        if (!cand) cand = all;
+    }
+    wsync();                                   // binmax / statistics slots are free again
+    return cand;
 }
 
 // alignment on the 512 samples in sh.Xw (x[F .. F+512)) with CFO bin sh.off
@@ -760,7 +1019,7 @@ __device__ void decode_header(SeekShared &sh, const DevTables *T, const StreamVi
 // ------------------------------------------------------------------ the kernel
 // 4 worker warps walk the stream's state machine; a fifth warp only issues tcgen05.mma for the
 // pre-filter pipeline (fused mode) and otherwise idles until the end of the CTA.
-__global__ void __launch_bounds__(kCtaThreads, 2)
+__global__ void __launch_bounds__(kCtaThreads, 3)
 k_seek(SeekParams P)
 {
     __shared__ SeekShared sh;
@@ -784,7 +1043,7 @@ k_seek(SeekParams P)
             sh.tc_cmd[0] = 0; sh.tc_cmd[1] = 0;
         }
         if (tid < 32) {
-            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tc::smem_u32(&sh.tmem_base)), "r"(256));
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tc::smem_u32(&sh.tmem_base)), "r"(128));
             asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -807,15 +1066,16 @@ k_seek(SeekParams P)
     }
     wsync();
     ScanCarry sc_;
-    sc_.valid = false; sc_.unsafe = false; sc_.ex_valid = false; sc_.w = 0; sc_.tail = 0.0f; sc_.half = 0.0f; sc_.ex = 0;
+    sc_.valid = false; sc_.unsafe = false; sc_.ex_valid = false; sc_.w = 0; sc_.tail = 0.0f; sc_.tail_d = 0.0f; sc_.tail_e = 0.0f; sc_.half = 0.0f; sc_.ex = 0;
     float2 tc_pre[4];
     long long tc_pre_a0 = -(1ll << 62);
 #pragma unroll
     for (int k = 0; k < 4; ++k) tc_pre[k] = make_float2(0.0f, 0.0f);
     unsigned ph_full = 0u;
     int buf_w = 0;
+    float rxy_q = 0.0f;
 
-    unsigned n_windows = 0, n_aligns = 0, n_exact = 0, n_tc_tiles = 0;      // work counters (uniform across the workers)
+    unsigned n_windows = 0, n_aligns = 0, n_exact = 0, n_tc_tiles = 0, n_bins = 0;      // work counters (uniform across the workers)
     PROF_MARK(10);
     StreamView sv;
     sv.carry = P.carry[st.carry_sel] + (size_t)io.stream * P.carry_cap;
@@ -842,16 +1102,27 @@ k_seek(SeekParams P)
         if (st.mode == 0) {
             if (st.wstart + 512 > sv.end) break;
             if (fused) {
-                if (!fused_scan(sh, sv, T, st, tid, sc_, tc_pre, tc_pre_a0, ph_full, buf_w, n_windows, n_tc_tiles PROF_PASS)) break;
+                if (!fused_scan(sh, sv, T, P.b_err, st, tid, sc_, tc_pre, tc_pre_a0, ph_full, buf_w, n_windows, n_tc_tiles, rxy_q PROF_PASS)) break;
             } else {
                 ++n_windows;
             }
             ++n_exact;
             PROF_MARK(7);
+            // (uniform) which CFO bins the exact evaluation has to visit
+            unsigned long long cand = (1ull << (2 * T->range + 1)) - 1ull;
+            // Worth it only when the pre-filter saw a peak well above the threshold (a real preamble: 3 .. 9 bins
+            // survive); a window that merely could not be ruled out has a noise-like spectrum in which nearly every bin
+            // stays a candidate, and the scan would be pure overhead.  Measured (B200): flex_rx search 22.1 -> 20.9 ms;
+            // the bare detector, where two of three exact windows are of the second kind, 87.3 -> 89.6 ms: off there.
+            if (fused && LQB_SEEK_BINS && !P.det_mode && rxy_q > T->threshold + 0.1f) {
+                cand = bin_candidates(sh, sv, T, P.b_err, st.wstart, tid, tc_pre, tc_pre_a0, ph_full, buf_w, n_tc_tiles PROF_PASS);
+                sh.tables_dirty = 1;
+            }
+            n_bins += (unsigned)__popcll(cand);
             restore_tables();
             load_window(sh, sv, st.wstart, tid);
             wsync();
-            eval_window(sh, T, tid);
+            eval_window(sh, T, tid, cand);
             PROF_MARK(8);
             if (!sh.trig) {
                 if (tid == 0) st.wstart += 256;
@@ -1008,6 +1279,7 @@ k_seek(SeekParams P)
         atomicAdd(P.n_out + 2, n_aligns);
         atomicAdd(P.n_out + 3, n_exact);
         atomicAdd(P.n_out + 4, n_tc_tiles);
+        atomicAdd(P.n_out + 5, n_bins);
 #ifdef LQB_SEEK_PROF
         for (int i = 0; i < 12; ++i) atomicAdd(&g_seek_prof[i], (unsigned long long)prof_acc[i]);
 #endif
@@ -1017,7 +1289,7 @@ k_seek(SeekParams P)
     if (fused) {
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
-        if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(sh.tmem_base), "r"(256));
+        if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(sh.tmem_base), "r"(128));
     }
 }
 
@@ -1050,36 +1322,47 @@ __global__ void k_carry(SeekParams P)
 void launch_seek(const SeekParams &P, unsigned n_io, cudaStream_t s)
 {
     static std::atomic<unsigned long long> attr_seen{ 0 };
-    const int dyn = tc::kBBytes + 256;
+    const int dyn = tc::kBBytes + 256;       // three CTAs per SM: 3 x (34 KB static + 35 KB B) fits 227 KB
     if (first_launch_on_this_device(attr_seen)) cudaFuncSetAttribute(k_seek, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
     k_seek<<<n_io, kCtaThreads, P.coarse == 2 ? dyn : 0, s>>>(P);
 }
 void launch_carry(const SeekParams &P, unsigned n_io, cudaStream_t s) { k_carry<<<n_io, 256, 0, s>>>(P); }
 
-// host: B operand in the kernel's shared-memory layout (fp16).  s: 156 template samples; column nn = 2 b + part holds
-// the real (part 0) or imaginary (part 1) part of C[., b] for component c of x (0: re, 1: im).
-void build_coarse_bmat(const float *s_re, const float *s_im, int range, std::vector<unsigned short> &out)
+// host: B operand in the kernel's shared-memory layout (e4m3 bytes, values x 32).  s: 156 template samples; column
+// b holds the real part of C[., b], column 56 + b the imaginary part, for component c of x (0: re, 1: im).
+// Layout: [component][MMA j][K chunk q][column nn][16 k-values], k = 32 j + 16 q + e.
+// Returns max_b || t_b - t_q,b || / || s || of the bytes it produced (the B term of the pre-filter's error bound).
+float build_coarse_bmat(const float *s_re, const float *s_im, int range, std::vector<unsigned char> &out)
 {
     using namespace tc;
-    out.assign(kBBytes / 2, 0);
-    for (int c = 0; c < 2; ++c)
-        for (int j = 0; j < 10; ++j)
-            for (int q = 0; q < 2; ++q) {
-                const size_t chunk = (size_t)((c * 10 + j) * 2 + q) * (kBChunkBytes / 2);
-                for (int nn = 0; nn < 2 * kNBins; ++nn)
-                    for (int e = 0; e < 8; ++e) {
-                        const int n = 16 * j + 8 * q + e, b = nn >> 1, part = nn & 1;
-                        double val = 0.0;
-                        if (n < 156) {
-                            const double ph = 2.0 * 3.14159265358979323846 * (double)(b - range) * (double)n / 512.0;
-                            const double tr = s_re[n] * cos(ph) - s_im[n] * sin(ph), ti = s_re[n] * sin(ph) + s_im[n] * cos(ph);
-                            // C = sum (xr + j xi)(tr - j ti):  re = xr tr + xi ti,  im = xi tr - xr ti
-                            val = (part == 0) ? (c == 0 ? tr : ti) : (c == 0 ? -ti : tr);
-                        }
-                        __half hv = __float2half_rn((float)val);
-                        out[chunk + (size_t)nn * 8 + e] = *reinterpret_cast<unsigned short *>(&hv);
-                    }
-            }
+    out.assign(kBBytes, 0);
+    auto quant = [](double v, unsigned char &byte) {
+        byte = (unsigned char)__nv_cvt_float_to_fp8((float)(v * (double)kBScale), __NV_SATFINITE, __NV_E4M3);
+        const __half_raw hr = __nv_cvt_fp8_to_halfraw(byte, __NV_E4M3);
+        return (double)__half2float(__half(hr)) / (double)kBScale;
+    };
+    double s2 = 0.0, worst = 0.0;
+    for (int n = 0; n < 156; ++n) s2 += (double)s_re[n] * s_re[n] + (double)s_im[n] * s_im[n];
+    for (int b = 0; b < kNBins; ++b) {
+        double err2 = 0.0;
+        for (int n = 0; n < kKPad; ++n) {
+            if (n >= 156) continue;                          // padding rows stay zero
+            const double ph = 2.0 * 3.14159265358979323846 * (double)(b - range) * (double)n / 512.0;
+            const double tr = s_re[n] * cos(ph) - s_im[n] * sin(ph), ti = s_re[n] * sin(ph) + s_im[n] * cos(ph);
+            const int j = n >> 5, q = (n >> 4) & 1, e = n & 15;
+            unsigned char byte = 0;
+            // C = sum (xr + j xi)(tr - j ti):  re = xr tr + xi ti,  im = xi tr - xr ti
+            for (int c = 0; c < 2; ++c)
+                for (int part = 0; part < 2; ++part) {
+                    const double val = (part == 0) ? (c == 0 ? tr : ti) : (c == 0 ? -ti : tr);
+                    const double back = quant(val, byte);
+                    out[(size_t)((c * kMmaPerComp + j) * 2 + q) * kBChunkBytes + (size_t)(kImCol0 * part + b) * 16 + e] = byte;
+                    if (c == 0) err2 += (val - back) * (val - back);       // tr and ti once each (c = 1 holds the same two numbers)
+                }
+        }
+        worst = std::max(worst, err2);
+    }
+    return (float)(std::sqrt(worst / s2) * 1.0001);
 }
 
 #ifdef LQB_SEEK_PROF

@@ -20,10 +20,10 @@ DECLARED_SYMBOLS = [
     "lqb_last_error", "lqb_device_count", "lqb_version",
     "lqb_rx_create", "lqb_rx_destroy", "lqb_rx_reset", "lqb_rx_execute", "lqb_rx_execute_dense",
     "lqb_rx_submit", "lqb_rx_submit_dense", "lqb_rx_collect",
-    "lqb_rx_poll", "lqb_rx_counts", "lqb_rx_last_timing", "lqb_rx_launch_count", "lqb_rx_last_work", "lqb_rx_lane_count",
+    "lqb_rx_poll", "lqb_rx_counts", "lqb_rx_last_timing", "lqb_rx_launch_count", "lqb_rx_last_work", "lqb_rx_last_search_bins", "lqb_rx_lane_count",
     "lqb_tx_create", "lqb_tx_destroy", "lqb_tx_props_init_default", "lqb_tx_frame_len", "lqb_tx_assemble",
     "lqb_det_create", "lqb_det_destroy", "lqb_det_reset", "lqb_det_execute", "lqb_det_execute_dense",
-    "lqb_det_poll", "lqb_det_last_timing", "lqb_det_last_work",
+    "lqb_det_poll", "lqb_det_last_timing", "lqb_det_last_work", "lqb_det_last_search",
     "lqb_tab_interp_taps", "lqb_tab_pfb_banks", "lqb_tab_detector_template", "lqb_tab_nco_sintab",
     "lqb_tab_packet_len",
 ]
@@ -102,7 +102,9 @@ def lib():
     L.lqb_rx_launch_count.argtypes = [vp, C.POINTER(u64)]
     L.lqb_rx_last_work.argtypes = [vp, C.POINTER(u64)]
     L.lqb_rx_lane_count.argtypes = [vp]
+    L.lqb_rx_last_search_bins.argtypes = [vp, C.POINTER(u64)]
     L.lqb_det_last_work.argtypes = [vp, C.POINTER(u64)]
+    L.lqb_det_last_search.argtypes = [vp, C.POINTER(u64)]
     if hasattr(L, "lqb_tx_create"):
         L.lqb_tx_create.restype = vp
         L.lqb_tx_create.argtypes = [C.POINTER(TxOpts)]
@@ -246,8 +248,10 @@ class Rx:
     def work(self):
         w = (C.c_uint64 * 6)()
         _check(self._L.lqb_rx_last_work(self._h, w))
+        b = C.c_uint64(0)
+        _check(self._L.lqb_rx_last_search_bins(self._h, C.byref(b)))
         return dict(windows=int(w[0]), aligns=int(w[1]), symbols=int(w[2]), samples=int(w[3]),
-                    exact_windows=int(w[4]), coarse_tiles=int(w[5]))
+                    exact_windows=int(w[4]), coarse_tiles=int(w[5]), exact_bins=int(b.value))
 
 
 class Det:
@@ -298,6 +302,11 @@ class Det:
         w = C.c_uint64(0)
         _check(self._L.lqb_det_last_work(self._h, C.byref(w)))
         return int(w.value)
+
+    def search(self):
+        w = (C.c_uint64 * 4)()
+        _check(self._L.lqb_det_last_search(self._h, w))
+        return dict(windows=int(w[0]), aligns=int(w[1]), exact_windows=int(w[2]), exact_bins=int(w[3]))
 
 
 def tab_interp_taps(beta):

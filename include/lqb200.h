@@ -190,6 +190,8 @@ int    lqb_rx_lane_count(lqb_rx h);                         /* pipeline lanes of
  * [2] payload symbols matched-filtered/demodulated, [3] input samples consumed,
  * [4] windows that needed the exact 50-FFT evaluation, [5] 128-lag pre-filter tiles */
 int    lqb_rx_last_work(lqb_rx h, uint64_t work[6]);
+/* CFO bins the exact window evaluations of the last execute visited (49 per window without the tensor-core bin filter) */
+int    lqb_rx_last_search_bins(lqb_rx h, uint64_t *bins);
 
 /* ------------------------------------------------------------------ TX (flex_tx / flexframegen) */
 typedef struct lqb_tx_s *lqb_tx;
@@ -236,6 +238,9 @@ int     lqb_det_execute_dense(lqb_det h, const float *iq, uint64_t stride_sample
 int     lqb_det_poll(lqb_det h, lqb_detection *out, uint32_t max_out, uint32_t *n_out);
 int     lqb_det_last_timing(lqb_det h, float *ms);
 int     lqb_det_last_work(lqb_det h, uint64_t *windows);   /* detector windows evaluated by the last execute */
+/* search work of the last execute: [0] windows, [1] alignments (= detections), [2] windows that needed the exact
+ * evaluation, [3] CFO bins those evaluations visited (49 per window without the tensor-core bin filter) */
+int     lqb_det_last_search(lqb_det h, uint64_t out[4]);
 
 /* ------------------------------------------------------------------ host-side tables (no GPU needed) */
 /* exposed so tests can check the product's own filter/table design against the oracle */

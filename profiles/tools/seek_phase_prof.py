@@ -22,7 +22,7 @@ out = (C.c_uint64 * 16)()
 for it in range(2):
     rx.execute_dense_ptr(cap.data_ptr(), N, N, capi.MEM_DEVICE)
     L.lqb_dbg_seek_prof(out, 1)
-names = ["between blocks", "stage samples", "build Z", "issue MMA+prefetch", "wait MMA", "epilogue", "rowmax+decide",
+names = ["between blocks", "quantise + sums", "build Z", "prefetch issue", "wait MMA", "epilogue", "rowmax+decide",
          "loop misc", "exact window", "align+header", "prologue", "-"]
 tot = sum(out[i] for i in range(12))
 w = rx.work(); t = rx.timing()

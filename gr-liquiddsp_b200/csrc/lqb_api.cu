@@ -139,6 +139,17 @@ int build_tables(DevTables &T, float beta, float threshold, float dphi_max)
     return 0;
 }
 
+// interleaved int16 (re, im) -> complex64, value / 32768 (exact): two samples per thread and step
+__global__ void k_sc16_to_c32(const int2 *__restrict__ in, float4 *__restrict__ out, size_t n_pairs)
+{
+    const float k = 1.0f / 32768.0f;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pairs; i += (size_t)gridDim.x * blockDim.x) {
+        const int2 v = in[i];
+        out[i] = make_float4((float)(short)(v.x & 0xffff) * k, (float)(short)(v.x >> 16) * k,
+                             (float)(short)(v.y & 0xffff) * k, (float)(short)(v.y >> 16) * k);
+    }
+}
+
 bool is_conv(unsigned fs) { return fs == FEC_CONV_V27 || fs == FEC_CONV_V29 || (fs >= FEC_CONV_V27P23 && fs <= FEC_CONV_V29P78); }
 unsigned conv_K(unsigned fs) { return (fs == FEC_CONV_V29 || fs >= FEC_CONV_V29P23) ? 9u : 7u; }
 
@@ -157,6 +168,7 @@ struct Front {
         DevBuf<StreamIO> d_io;
         PinBuf<StreamIO> h_io;
         DevBuf<float2> d_stage;
+        DevBuf<int> d_stage16;            // raw sc16 samples (one int = one complex sample) before conversion
         unsigned *d_count = nullptr;
         unsigned *h_count = nullptr;
     } io[2];
@@ -253,7 +265,36 @@ struct Front {
             if (ns[i] && !iq[i]) return fail(LQB_EINVAL, "null sample pointer");
             tot += ns[i]; mx = std::max<uint64_t>(mx, ns[i]);
         }
-        if (mem == LQB_MEM_HOST) {
+        const bool sc16 = (mem == LQB_MEM_HOST_SC16 || mem == LQB_MEM_DEVICE_SC16);
+        if (sc16) {
+            // int16 pairs travel as they are (half the bytes of complex64 over PCIe) and are widened on the device:
+            // packed back to back in feed order, then one conversion kernel on the same stream
+            DevBuf<int> &d_raw = io[cur].d_stage16;
+            if (int e = d_stage.reserve(tot + 2)) return e;
+            if (int e = d_raw.reserve(tot + 2)) return e;
+            const cudaMemcpyKind kind = mem == LQB_MEM_HOST_SC16 ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+            bool regular = n >= 2 && ns[0] > 0;
+            const ptrdiff_t pitch = regular ? (reinterpret_cast<const int *>(iq[1]) - reinterpret_cast<const int *>(iq[0])) : 0;
+            for (uint32_t i = 1; i < n && regular; ++i)
+                regular = ns[i] == ns[0] && (reinterpret_cast<const int *>(iq[i]) - reinterpret_cast<const int *>(iq[i - 1])) == pitch;
+            regular = regular && pitch >= (ptrdiff_t)ns[0];
+            uint64_t off = 0;
+            if (regular) {
+                const size_t row = ns[0] * sizeof(int);
+                CU(cudaMemcpy2DAsync(d_raw.p, row, iq[0], (size_t)pitch * sizeof(int), row, n, kind, stream));
+            }
+            for (uint32_t k = 0; k < n; ++k) {
+                if (!regular && ns[k]) CU(cudaMemcpyAsync(d_raw.p + off, iq[k], ns[k] * sizeof(int), kind, stream));
+                h_io.p[k].in = d_stage.p + off; h_io.p[k].n_in = ns[k]; h_io.p[k].stream = ids ? ids[k] : k; h_io.p[k].pad = 0;
+                off += ns[k];
+            }
+            const size_t pairs = (size_t)((tot + 1) / 2);
+            if (pairs) {
+                const unsigned grid = (unsigned)std::min<size_t>((pairs + 255) / 256, 148u * 16u);
+                k_sc16_to_c32<<<grid, 256, 0, stream>>>(reinterpret_cast<const int2 *>(d_raw.p), reinterpret_cast<float4 *>(d_stage.p), pairs);
+                launches++;
+            }
+        } else if (mem == LQB_MEM_HOST) {
             if (int e = d_stage.reserve(tot + 1)) return e;
             // equal-length streams at a constant pitch in host memory (the dense layout, also after the lane split):
             // one strided 2-D copy instead of one call per stream
@@ -309,7 +350,7 @@ struct Front {
         if (d_states) cudaFree(d_states);
         for (int k = 0; k < 2; ++k) if (d_carry[k]) cudaFree(d_carry[k]);
         for (auto &x : io) {
-            x.d_io.release(); x.h_io.release(); x.d_stage.release();
+            x.d_io.release(); x.h_io.release(); x.d_stage.release(); x.d_stage16.release();
             if (x.d_count) cudaFree(x.d_count);
             if (x.h_count) cudaFreeHost(x.h_count);
         }
@@ -452,7 +493,8 @@ struct RxLane {
             Front::IoSet &oi = f.io[gen ^ 1u];
             if (int e = oi.h_io.reserve(n)) return e;
             if (int e = oi.d_io.reserve(n)) return e;
-            if (mem == LQB_MEM_HOST) if (int e = oi.d_stage.reserve(G.total + 1)) return e;
+            if (mem != LQB_MEM_DEVICE) if (int e = oi.d_stage.reserve(G.total + 2)) return e;
+            if (mem == LQB_MEM_HOST_SC16 || mem == LQB_MEM_DEVICE_SC16) if (int e = oi.d_stage16.reserve(G.total + 2)) return e;
         }
         return 0;
     }
@@ -960,7 +1002,7 @@ int lqb_rx_execute_dense(lqb_rx h, const float *iq, uint64_t stride, uint64_t ns
     unsigned n = h->n_streams;
     std::vector<const float *> ptr(n);
     std::vector<uint64_t> len(n, ns);
-    for (unsigned s = 0; s < n; ++s) ptr[s] = iq + 2 * (size_t)s * stride;
+    for (unsigned s = 0; s < n; ++s) ptr[s] = iq + (mem >= LQB_MEM_HOST_SC16 ? 1 : 2) * (size_t)s * stride;   // a sample is 2 floats, or 1 float-sized int16 pair
     return lqb_rx_execute(h, n, nullptr, ptr.data(), len.data(), mem);
 }
 
@@ -970,7 +1012,7 @@ int lqb_rx_submit_dense(lqb_rx h, const float *iq, uint64_t stride, uint64_t ns,
     unsigned n = h->n_streams;
     std::vector<const float *> ptr(n);
     std::vector<uint64_t> len(n, ns);
-    for (unsigned s = 0; s < n; ++s) ptr[s] = iq + 2 * (size_t)s * stride;
+    for (unsigned s = 0; s < n; ++s) ptr[s] = iq + (mem >= LQB_MEM_HOST_SC16 ? 1 : 2) * (size_t)s * stride;   // a sample is 2 floats, or 1 float-sized int16 pair
     return lqb_rx_submit(h, n, nullptr, ptr.data(), len.data(), mem);
 }
 
@@ -1131,7 +1173,7 @@ int lqb_det_execute_dense(lqb_det h, const float *iq, uint64_t stride, uint64_t 
     unsigned n = h->f.n_streams;
     std::vector<const float *> ptr(n);
     std::vector<uint64_t> len(n, ns);
-    for (unsigned s = 0; s < n; ++s) ptr[s] = iq + 2 * (size_t)s * stride;
+    for (unsigned s = 0; s < n; ++s) ptr[s] = iq + (mem >= LQB_MEM_HOST_SC16 ? 1 : 2) * (size_t)s * stride;   // a sample is 2 floats, or 1 float-sized int16 pair
     return lqb_det_execute(h, n, nullptr, ptr.data(), len.data(), mem);
 }
 

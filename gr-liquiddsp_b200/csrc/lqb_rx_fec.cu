@@ -237,14 +237,31 @@ k_viterbi(PayloadParams P, const unsigned *__restrict__ list, unsigned n_list, i
     if (lane == 0) m[0][0] = 0u;
     __syncwarp();
 
+    // The received bits are consumed in order, so they are read as 32-bit big-endian words, the next word always
+    // requested one word ahead: a byte load per trellis step put a global-memory round trip on every step's critical
+    // path (this kernel was 15x slower per frame than the K = 7 one, profiles/r01_notes.md v29).
+    const unsigned enc_words = (io.enc_len + 3u) >> 2;
+    auto load_word = [&](unsigned w) -> unsigned {
+        if (w >= enc_words) return 0u;
+        const unsigned char *p = io.src + 4u * w;
+        unsigned v = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v = (v << 8) | ((4u * w + k < io.enc_len) ? (unsigned)p[k] : 0u);
+        return v;
+    };
+    unsigned wbase = 0, wcur = load_word(0), wnext = load_word(1);
+    auto take_bit = [&](unsigned ib) -> unsigned {               // ib never decreases
+        while ((ib >> 5) != wbase) { ++wbase; wcur = wnext; wnext = load_word(wbase + 1); }
+        return ((wcur >> (31u - (ib & 31u))) & 1u) ? 255u : 0u;
+    };
     // branch labels for this lane's butterflies (state pair i, i+half -> 2i, 2i+1)
     unsigned cur = 0;
     for (unsigned t = 0; t < T; ++t) {
         const unsigned col = t % cs.P;
         unsigned ib = (t / cs.P) * per + pre[col];
         unsigned sym0 = 127u, sym1 = 127u;
-        if ((cs.keep0 >> col) & 1u) { sym0 = soft_bit(io.src, ib); ++ib; }
-        if ((cs.keep1 >> col) & 1u) { sym1 = soft_bit(io.src, ib); }
+        if ((cs.keep0 >> col) & 1u) { sym0 = take_bit(ib); ++ib; }
+        if ((cs.keep1 >> col) & 1u) { sym1 = take_bit(ib); }
         const unsigned *mo = m[cur];
         unsigned *mn = m[cur ^ 1];
         for (unsigned q = 0; q < half; q += 32) {

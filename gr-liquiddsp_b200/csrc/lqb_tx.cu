@@ -27,6 +27,7 @@ struct TxTables {
     float2   psk_map[8 * 256];
     uint32_t crc_tab[8][256];
     uint16_t ilv54[4][28], ilv27[4][16];
+    uint16_t hperm27f[216], hperm54f[432];   // the header's two interleavers as bit gathers: out bit i = in bit perm[i]
     uint8_t  secded_col[64];
     uint8_t  gf_exp[512], gf_log[256], rs_gen[64];
 };
@@ -42,7 +43,13 @@ struct TxFrame {               // one frame's plan (host-built)
 
 namespace {
 
-constexpr int kTxThreads = 256;
+// Threads per frame.  The header encode and the payload check are serial sections (one thread each, side by side);
+// the fewer threads wait for them, the more frames an SM keeps in flight to cover them: 64 threads = 32 frames per SM.
+#ifndef LQB_TX_THREADS
+#define LQB_TX_THREADS 64
+#endif
+constexpr int kTxThreads = LQB_TX_THREADS;
+static_assert(kTxThreads >= 64 && kTxThreads % 32 == 0, "warp 0 encodes the header while warp 1 checks the payload");
 constexpr float kPiF = 3.14159274f;
 constexpr float kTwoPiF = 6.28318548f;
 
@@ -252,8 +259,9 @@ __device__ float2 modulate(const TxTables *T, unsigned ms, unsigned bps, unsigne
 __global__ void __launch_bounds__(kTxThreads)
 k_tx(const TxTables *T, const TxFrame *frames, unsigned char *bufA, unsigned char *bufB, const unsigned *ilv, float2 *syms)
 {
-    __shared__ unsigned char hb[64];
+    __shared__ unsigned char hb[64], hd[32], he[32], hraw[64];  // header: 54 coded bytes; 24 data bytes; 27 SECDED bytes; 54 before the last interleaver
     __shared__ unsigned crc4[4][256];                 // slicing-by-4 tables of the frame's check
+    __shared__ float2 smap[256];                      // the frame's symbol map (the scale's divide and square root once per point)
     const int tid = threadIdx.x;
     const TxFrame &f = frames[blockIdx.x];
     unsigned char *A = bufA + f.buf_off, *B = bufB + f.buf_off;
@@ -275,53 +283,132 @@ k_tx(const TxTables *T, const TxFrame *frames, unsigned char *bufA, unsigned cha
         }
     }
 
+    if (!(f.ms >= 9 && f.ms <= 16))
+        for (unsigned i = tid; i < (1u << f.bps); i += kTxThreads) smap[i] = modulate(T, f.ms, f.bps, i);
+
     // ---------------- payload bytes into the work buffer
     const unsigned plen = f.payload_len, cl = f.k0 - plen;
     const unsigned char *pay = f.pay;
-    for (unsigned i = tid; i < plen; i += kTxThreads) A[i] = pay[i];
-    __syncthreads();
-    // ---------------- the two serial sections run side by side: header on warp 0, payload check on warp 1
-    if (tid == 0) {
-        unsigned char d[28], e27[28];
-        for (int i = 0; i < 14; ++i) d[i] = f.header[i];
-        d[14] = 102; d[15] = (unsigned char)(f.payload_len >> 8); d[16] = (unsigned char)f.payload_len;
-        d[17] = (unsigned char)f.ms; d[18] = (unsigned char)(((f.check & 7u) << 5) | (f.fec0 & 0x1fu)); d[19] = (unsigned char)(f.fec1 & 0x1fu);
-        unsigned key = 0xffffffffu;
-        for (int i = 0; i < 20; ++i) key = (key >> 8) ^ T->crc_tab[6][(key ^ d[i]) & 0xffu];
-        key = ~key;
-        d[20] = (unsigned char)(key >> 24); d[21] = (unsigned char)(key >> 16); d[22] = (unsigned char)(key >> 8); d[23] = (unsigned char)key;
-        const unsigned char mask[4] = { 0xb4, 0x6a, 0x8b, 0xc5 };
-        for (int i = 0; i < 24; ++i) d[i] ^= mask[i & 3];
-        for (int b = 0; b < 3; ++b) {
-            e27[9 * b] = (unsigned char)secded_parity(T, d + 8 * b, 8, 7);
-            for (int q = 0; q < 8; ++q) e27[9 * b + 1 + q] = d[8 * b + q];
-        }
-        ilv_small(e27, T->ilv27[0], 13, 0xff); ilv_small(e27, T->ilv27[1], 13, 0x0f);
-        ilv_small(e27, T->ilv27[2], 13, 0x55); ilv_small(e27, T->ilv27[3], 13, 0x33);
-        for (int i = 0; i < 27; ++i) { hb[2 * i] = c_h84[e27[i] >> 4]; hb[2 * i + 1] = c_h84[e27[i] & 15u]; }
-        ilv_small(hb, T->ilv54[0], 27, 0xff); ilv_small(hb, T->ilv54[1], 27, 0x0f);
-        ilv_small(hb, T->ilv54[2], 27, 0x55); ilv_small(hb, T->ilv54[3], 27, 0x33);
+    // payload -> work buffer, whitened on the way (the check below reads the caller's bytes, not these)
+    if ((reinterpret_cast<uintptr_t>(pay) & 3u) == 0) {
+        const unsigned *p4 = reinterpret_cast<const unsigned *>(pay);
+        unsigned *a4 = reinterpret_cast<unsigned *>(A);                           // buf_off is a multiple of 16
+        for (unsigned i = tid; i < (plen >> 2); i += kTxThreads) a4[i] = p4[i] ^ 0xc58b6ab4u;      // b4 6a 8b c5, little endian
+        for (unsigned i = (plen & ~3u) + tid; i < plen; i += kTxThreads)
+            A[i] = pay[i] ^ (unsigned char)(0xc58b6ab4u >> (8u * (i & 3u)));
+    } else {
+        for (unsigned i = tid; i < plen; i += kTxThreads) A[i] = pay[i] ^ (unsigned char)(0xc58b6ab4u >> (8u * (i & 3u)));
     }
-    if (tid == 32) {
+    __syncthreads();                                      // (crc4 / smap tables are complete)
+    // ---------------- the two serial sections run side by side: header on warp 0, payload check on warp 1
+    if (tid < 32) {
+        // header on warp 0, every step across the lanes (it used to be one thread walking 160 interleaver swaps and 192
+        // parity bits through local memory: ~50 us per frame)
+        const unsigned lane = (unsigned)tid;
+        if (lane < 14) hd[lane] = f.header[lane];
+        if (lane == 14) {
+            hd[14] = 102; hd[15] = (unsigned char)(f.payload_len >> 8); hd[16] = (unsigned char)f.payload_len;
+            hd[17] = (unsigned char)f.ms; hd[18] = (unsigned char)(((f.check & 7u) << 5) | (f.fec0 & 0x1fu)); hd[19] = (unsigned char)(f.fec1 & 0x1fu);
+        }
+        __syncwarp();
+        if (lane == 0) {
+            unsigned key = 0xffffffffu;
+            for (int i = 0; i < 20; ++i) key = (key >> 8) ^ T->crc_tab[6][(key ^ hd[i]) & 0xffu];
+            key = ~key;
+            hd[20] = (unsigned char)(key >> 24); hd[21] = (unsigned char)(key >> 16); hd[22] = (unsigned char)(key >> 8); hd[23] = (unsigned char)key;
+        }
+        __syncwarp();
+        if (lane < 24) hd[lane] ^= (unsigned char)(lane & 3u) == 0 ? 0xb4u : (lane & 3u) == 1 ? 0x6au : (lane & 3u) == 2 ? 0x8bu : 0xc5u;
+        __syncwarp();
+        // SECDED(72,64): parity of block b = XOR of the columns of its set bits; lane handles bits lane and lane + 32
+        for (unsigned b = 0; b < 3; ++b) {
+            unsigned p = 0, ones = 0;
+#pragma unroll
+            for (unsigned h2 = 0; h2 < 2; ++h2) {
+                const unsigned bit = lane + 32u * h2;
+                if ((hd[8 * b + (bit >> 3)] >> (7 - (bit & 7))) & 1u) { p ^= T->secded_col[bit]; ones ^= 1u; }
+            }
+#pragma unroll
+            for (int m = 16; m >= 1; m >>= 1) { p ^= __shfl_xor_sync(0xffffffffu, p, m); ones ^= __shfl_xor_sync(0xffffffffu, ones, m); }
+            ones ^= (unsigned)__popc(p) & 1u;
+            if (lane == 0) he[9 * b] = (unsigned char)(p | (ones << 7));
+            if (lane < 8) he[9 * b + 1 + lane] = hd[8 * b + lane];
+        }
+        __syncwarp();
+        // interleave(27) as one bit gather, then Hamming(8,4), then interleave(54) as one bit gather
+        unsigned char v27 = 0;
+        if (lane < 27) {
+            unsigned v = 0;
+#pragma unroll
+            for (unsigned bit = 0; bit < 8; ++bit) {
+                const unsigned src = T->hperm27f[8 * lane + bit];
+                v |= ((he[src >> 3] >> (src & 7u)) & 1u) << bit;
+            }
+            v27 = (unsigned char)v;
+        }
+        __syncwarp();
+        if (lane < 27) { hraw[2 * lane] = c_h84[v27 >> 4]; hraw[2 * lane + 1] = c_h84[v27 & 15u]; }
+        __syncwarp();
+        for (unsigned o = lane; o < 54; o += 32) {
+            unsigned v = 0;
+#pragma unroll
+            for (unsigned bit = 0; bit < 8; ++bit) {
+                const unsigned src = T->hperm54f[8 * o + bit];
+                v |= ((hraw[src >> 3] >> (src & 7u)) & 1u) << bit;
+            }
+            hb[o] = (unsigned char)v;
+        }
+    }
+    if (tid >= 32 && tid < 64) {
+        // payload check on warp 1, over the caller's bytes.  A CRC is linear over GF(2): lane i runs the table recurrence
+        // over its own 1/32 of the message (lane 0 from the all-ones preset, the others from zero); "advance a state by L
+        // zero bytes" is a 32 x 32 bit matrix whose column j lane j obtains by running 1 << j through L zero bytes; the
+        // lanes' states are then folded in order (Horner), each fold one select and an XOR reduction by shuffle.
+        // ~1.1 k warp instructions per 1500-byte frame; the serial slicing-by-4 loop was 6.5 k, a third of the kernel.
+        const unsigned lane = (unsigned)tid - 32u;
         unsigned key = 0;
         if (f.check == 2) {
             unsigned sum = 0;
-            for (unsigned i = 0; i < plen; ++i) sum += A[i];
+            for (unsigned i = lane; i < plen; i += 32) sum += pay[i];
+#pragma unroll
+            for (int m = 16; m >= 1; m >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, m);
             key = (~sum + 1u) & 0xffu;
         } else if (f.check >= 3 && f.check <= 6) {
-            // four bytes per dependent step (the byte-at-a-time loop was 39 % of the kernel's stall samples)
-            unsigned k = 0xffffffffu;
-            const unsigned *A4 = reinterpret_cast<const unsigned *>(A);          // buf_off is a multiple of 16
-            const unsigned nw = plen >> 2;
-            for (unsigned i = 0; i < nw; ++i) {
-                k ^= A4[i];
-                k = crc4[3][k & 0xffu] ^ crc4[2][(k >> 8) & 0xffu] ^ crc4[1][(k >> 16) & 0xffu] ^ crc4[0][k >> 24];
+            const unsigned *tab = crc4[0];
+            const unsigned L = max(4u, (((plen + 31u) >> 5) + 3u) & ~3u);          // bytes per lane
+            const unsigned F = plen / L, r = plen - F * L;                      // full lanes; bytes of lane F
+            unsigned st = lane == 0 ? 0xffffffffu : 0u;
+            {
+                const unsigned b0 = lane * L, b1 = min(plen, b0 + L);
+                for (unsigned i = b0; i < b1; ++i) st = (st >> 8) ^ tab[(st ^ pay[i]) & 0xffu];
             }
-            for (unsigned i = 4 * nw; i < plen; ++i) k = (k >> 8) ^ crc4[0][(k ^ A[i]) & 0xffu];
+            unsigned colL = 1u << lane, colr = 1u << lane;
+            for (unsigned i = 0; i < L; ++i) {
+                colL = (colL >> 8) ^ tab[colL & 0xffu];
+                if (i < r) colr = (colr >> 8) ^ tab[colr & 0xffu];
+            }
+            auto matvec = [&](unsigned col, unsigned v) {
+                unsigned y = ((v >> lane) & 1u) ? col : 0u;
+#pragma unroll
+                for (int m = 16; m >= 1; m >>= 1) y ^= __shfl_xor_sync(0xffffffffu, y, m);
+                return y;
+            };
+            unsigned k;
+            if (F == 0) k = __shfl_sync(0xffffffffu, st, 0);                    // (plen < L: everything in lane 0)
+            else {
+                k = __shfl_sync(0xffffffffu, st, 0);
+                for (unsigned i = 1; i < F; ++i) k = matvec(colL, k) ^ __shfl_sync(0xffffffffu, st, (int)i);
+                if (r) k = matvec(colr, k) ^ __shfl_sync(0xffffffffu, st, (int)F);
+            }
             const unsigned bits = f.check == 3 ? 8u : f.check == 4 ? 16u : f.check == 5 ? 24u : 32u;
             key = (~k) & (bits == 32 ? 0xffffffffu : ((1u << bits) - 1u));
         }
-        for (unsigned i = 0; i < cl; ++i) { A[plen + cl - i - 1] = (unsigned char)(key & 0xffu); key >>= 8; }
+        if (lane == 0)
+            for (unsigned i = 0; i < cl; ++i) {           // big endian behind the payload, whitened like the payload
+                const unsigned pos = plen + cl - i - 1;
+                A[pos] = (unsigned char)((key & 0xffu) ^ (0xc58b6ab4u >> (8u * (pos & 3u))));
+                key >>= 8;
+            }
     }
     __syncthreads();
     for (int i = tid; i < 231; i += kTxThreads) {
@@ -333,16 +420,20 @@ k_tx(const TxTables *T, const TxFrame *frames, unsigned char *bufA, unsigned cha
         }
     }
 
-    for (unsigned i = tid; i < f.k0; i += kTxThreads) {
-        unsigned mask = (i & 3u) == 0 ? 0xb4u : (i & 3u) == 1 ? 0x6au : (i & 3u) == 2 ? 0x8bu : 0xc5u;
-        A[i] ^= (unsigned char)mask;
-    }
     __syncthreads();
-    // ---------------- fec0 / interleave / fec1 / interleave
-    fec_encode(T, f.fec0, f.k0, f.n0, A, B, tid);
-    if (f.fec0 != 1) ilv_forward(B, f.n0, ilv + f.ilv0_off, tid);
-    fec_encode(T, f.fec1, f.n0, f.n1, B, A, tid);
-    if (f.fec1 != 1) ilv_forward(A, f.n1, ilv + f.ilv1_off, tid);
+    // ---------------- fec0 / interleave / fec1 / interleave ("no code" moves nothing: the buffers just keep their roles)
+    unsigned char *cur = A, *oth = B;
+    if (f.fec0 != 1) {
+        fec_encode(T, f.fec0, f.k0, f.n0, cur, oth, tid);
+        ilv_forward(oth, f.n0, ilv + f.ilv0_off, tid);
+        unsigned char *t_ = cur; cur = oth; oth = t_;
+    }
+    if (f.fec1 != 1) {
+        fec_encode(T, f.fec1, f.n0, f.n1, cur, oth, tid);
+        ilv_forward(oth, f.n1, ilv + f.ilv1_off, tid);
+        unsigned char *t_ = cur; cur = oth; oth = t_;
+    }
+    A = cur;                                              // the encoded message
 
     // ---------------- bits -> symbols
     const unsigned bps = f.bps, nbits = 8 * f.n1;
@@ -368,7 +459,7 @@ k_tx(const TxTables *T, const TxFrame *frames, unsigned char *bufA, unsigned cha
             unsigned w = ((unsigned)A[byte] << 8) | (byte + 1 < f.n1 ? (unsigned)A[byte + 1] : 0u);
             unsigned s = (w >> (16u - (pos & 7u) - bps)) & ((1u << bps) - 1u);
             if (pos + bps > nbits) s &= ~((1u << (pos + bps - nbits)) - 1u);
-            psym[i] = modulate(T, f.ms, bps, s);
+            psym[i] = smap[s];
         }
     }
     __syncthreads();
@@ -418,8 +509,17 @@ struct lqb_tx_s {
     unsigned char *d_pay = nullptr, *d_A = nullptr, *d_B = nullptr; size_t pay_cap = 0, buf_cap = 0, bufB_cap = 0;
     float2 *d_syms = nullptr, *d_out = nullptr; size_t sym_cap = 0, out_cap = 0;
     unsigned *d_ilv = nullptr; size_t ilv_cap = 0, ilv_used = 0;
-    // pinned staging: frame plans, host payloads packed back to back (one H2D instead of one copy per frame), host outputs
-    TxFrame *h_frames = nullptr; size_t h_frames_cap = 0;
+    // pinned staging: frame plans (two tables in rotation: the host fills one while the upload of the other may still be in
+    // flight), host payloads packed back to back (one H2D instead of one copy per frame), host outputs
+    TxFrame *h_tab[2] = { nullptr, nullptr }; size_t h_tab_cap[2] = { 0, 0 };
+    cudaEvent_t tab_ev[2] = { nullptr, nullptr }; bool tab_busy[2] = { false, false };
+    unsigned tab_next = 0;
+    // a submitted call that still has to be collected
+    bool pending = false, pending_host = false;
+    uint32_t pend_n = 0; unsigned pend_tab = 0;
+    std::vector<float *> pend_out;
+    cudaEvent_t k_ev[2] = { nullptr, nullptr };
+    float kernel_ms = 0.0f;
     unsigned char *h_pay = nullptr; size_t h_pay_cap = 0;
     float2 *h_out = nullptr; size_t h_out_cap = 0;
     std::unordered_map<unsigned, size_t> ilv_cache;
@@ -497,6 +597,22 @@ lqb_tx lqb_tx_create(const lqb_tx_opts *o)
         for (unsigned i = 0; i < 27; ++i) T->ilv54[p][i] = (uint16_t)m54[p * 27 + i];
         for (unsigned i = 0; i < 13; ++i) T->ilv27[p][i] = (uint16_t)m27[p * 13 + i];
     }
+    // the interleaver (passes 0, 1, 2, 3 of masked swaps between byte pairs) moves bits without changing them: run it
+    // once on bit labels and keep the permutation, so the device can gather every output byte at once
+    auto compose = [](const std::vector<uint32_t> &maps, unsigned n, uint16_t *perm) {
+        const unsigned n2 = n / 2, masks[4] = { 0xffu, 0x0fu, 0x55u, 0x33u };
+        std::vector<uint16_t> lab(8 * n);
+        for (unsigned i = 0; i < 8 * n; ++i) lab[i] = (uint16_t)i;
+        for (int pass = 0; pass < 4; ++pass)
+            for (unsigned i = 0; i < n2; ++i) {
+                const unsigned j = maps[(size_t)pass * n2 + i];
+                for (unsigned b = 0; b < 8; ++b)
+                    if ((masks[pass] >> b) & 1u) std::swap(lab[8 * (2 * j + 1) + b], lab[8 * (2 * i) + b]);
+            }
+        for (unsigned i = 0; i < 8 * n; ++i) perm[i] = lab[i];
+    };
+    compose(m27, 27, T->hperm27f);
+    compose(m54, 54, T->hperm54f);
     secded_cols(T->secded_col);
     uint8_t gen[33];
     gf256_tables(T->gf_exp, T->gf_log, gen);
@@ -504,6 +620,10 @@ lqb_tx lqb_tx_create(const lqb_tx_opts *o)
     cudaError_t e = cudaMalloc(&h->d_tables, sizeof(TxTables));
     if (e == cudaSuccess) e = cudaMemcpy(h->d_tables, T, sizeof(TxTables), cudaMemcpyHostToDevice);
     delete T;
+    for (int k = 0; k < 2 && e == cudaSuccess; ++k) {
+        e = cudaEventCreateWithFlags(&h->tab_ev[k], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreate(&h->k_ev[k]);
+    }
     if (e != cudaSuccess) { tx_fail(LQB_ECUDA, cudaGetErrorString(e)); lqb_tx_destroy(h); return nullptr; }
     return h;
 }
@@ -515,60 +635,106 @@ void lqb_tx_destroy(lqb_tx h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->d_tables); cudaFree(h->d_frames); cudaFree(h->d_pay); cudaFree(h->d_A); cudaFree(h->d_B);
     cudaFree(h->d_syms); cudaFree(h->d_out); cudaFree(h->d_ilv);
-    if (h->h_frames) cudaFreeHost(h->h_frames);
+    for (int k = 0; k < 2; ++k) {
+        if (h->h_tab[k]) cudaFreeHost(h->h_tab[k]);
+        if (h->tab_ev[k]) cudaEventDestroy(h->tab_ev[k]);
+        if (h->k_ev[k]) cudaEventDestroy(h->k_ev[k]);
+    }
     if (h->h_pay) cudaFreeHost(h->h_pay);
     if (h->h_out) cudaFreeHost(h->h_out);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
 
-int lqb_tx_assemble(lqb_tx h, uint32_t n, const lqb_tx_props *props, const uint8_t *const *headers,
-                    const uint8_t *const *payloads, const uint32_t *lens, float *const *out, int mem)
+// wait for everything submitted; host-memory frames are copied out to the caller's buffers
+int lqb_tx_collect(lqb_tx h)
+{
+    if (!h) return LQB_EINVAL;
+    if (!h->pending) return 0;
+    if (cudaSetDevice(h->device) != cudaSuccess) return LQB_ECUDA;
+    cudaError_t e = cudaStreamSynchronize(h->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    h->pending = false;
+    h->tab_busy[0] = h->tab_busy[1] = false;
+    if (e != cudaSuccess) { h->pending_host = false; return tx_fail(LQB_ECUDA, cudaGetErrorString(e)); }
+    cudaEventElapsedTime(&h->kernel_ms, h->k_ev[0], h->k_ev[1]);
+    if (h->pending_host) {
+        const TxFrame *fr = h->h_tab[h->pend_tab];
+        for (uint32_t i = 0; i < h->pend_n; ++i) std::memcpy(h->pend_out[i], h->h_out + fr[i].out_off, (size_t)fr[i].n_samples * sizeof(float2));
+        h->pending_host = false;
+    }
+    return 0;
+}
+
+int lqb_tx_last_timing(lqb_tx h, float *kernel_ms)
+{
+    if (!h || !kernel_ms) return LQB_EINVAL;
+    *kernel_ms = h->kernel_ms;
+    return 0;
+}
+
+// Queue the assembly of n frames on the handle's stream and return.  With device buffers nothing waits: frames are
+// complete in stream order (the caller's stream when the handle was created on one), and further submits may follow at
+// once.  With host buffers the frames reach the caller's memory in lqb_tx_collect().
+int lqb_tx_submit(lqb_tx h, uint32_t n, const lqb_tx_props *props, const uint8_t *const *headers,
+                  const uint8_t *const *payloads, const uint32_t *lens, float *const *out, int mem)
 {
     if (!h || !props || !payloads || !lens || !out) return LQB_EINVAL;
+    if (mem != LQB_MEM_HOST && mem != LQB_MEM_DEVICE) return tx_fail(LQB_EINVAL, "frames are complex64 in host or device memory");
     if (!n) return 0;
     if (cudaSetDevice(h->device) != cudaSuccess) return LQB_ECUDA;
+    const bool dev_io = (mem == LQB_MEM_DEVICE);
+    if (h->pending_host || (!dev_io && h->pending)) if (int e = lqb_tx_collect(h)) return e;      // one host-memory call at a time
     cudaStream_t st = h->stream;
-    if (grow_pinned(h->h_frames, h->h_frames_cap, n)) return tx_fail(LQB_ENOMEM, "cudaMallocHost failed");
-    TxFrame *fr = h->h_frames;
+    const unsigned tab = h->tab_next;
+    if (h->tab_busy[tab]) { if (cudaEventSynchronize(h->tab_ev[tab]) != cudaSuccess) return tx_fail(LQB_ECUDA, "event wait failed"); h->tab_busy[tab] = false; }
+    if (grow_pinned(h->h_tab[tab], h->h_tab_cap[tab], n)) return tx_fail(LQB_ENOMEM, "cudaMallocHost failed");
+    // (the other table too, while it is idle: a pinned allocation in the middle of a run of submits stalls it for milliseconds)
+    if (!h->tab_busy[tab ^ 1u] && grow_pinned(h->h_tab[tab ^ 1u], h->h_tab_cap[tab ^ 1u], n)) return tx_fail(LQB_ENOMEM, "cudaMallocHost failed");
+    TxFrame *fr = h->h_tab[tab];
     size_t pay_tot = 0, buf_tot = 0, sym_tot = 0, out_tot = 0;
     for (uint32_t i = 0; i < n; ++i) {
         const lqb_tx_props &p = props[i];
-        uint32_t ns = 0;
-        if (int e = lqb_tx_frame_len(&p, lens[i], &ns)) return tx_fail(e, "unsupported props or payload length");
         if (lens[i] && !payloads[i]) return tx_fail(LQB_EINVAL, "null payload");
         TxFrame &f = fr[i];
-        std::memset(&f, 0, sizeof f);
-        f.payload_len = lens[i]; f.check = p.check; f.fec0 = p.fec0; f.fec1 = p.fec1; f.ms = p.mod_scheme; f.bps = modem_bps(p.mod_scheme);
-        f.k0 = lens[i] + crc_len(p.check); f.n0 = fec_enc_len(p.fec0, f.k0); f.n1 = fec_enc_len(p.fec1, f.n0);
-        f.n_sym = (8 * f.n1 + f.bps - 1) / f.bps; f.n_samples = ns;
-        f.buf_len = ((std::max(std::max(f.n1, f.n0), f.k0) + 16) + 15u) & ~15u;
+        if (i && lens[i] == lens[i - 1] && std::memcmp(&p, &props[i - 1], sizeof p) == 0) {
+            f = fr[i - 1];                 // same scheme and length as the frame before: same plan, new offsets
+            std::memset(f.header, 0, sizeof f.header);
+        } else {
+            uint32_t ns = 0;
+            if (int e = lqb_tx_frame_len(&p, lens[i], &ns)) return tx_fail(e, "unsupported props or payload length");
+            std::memset(&f, 0, sizeof f);
+            f.payload_len = lens[i]; f.check = p.check; f.fec0 = p.fec0; f.fec1 = p.fec1; f.ms = p.mod_scheme; f.bps = modem_bps(p.mod_scheme);
+            f.k0 = lens[i] + crc_len(p.check); f.n0 = fec_enc_len(p.fec0, f.k0); f.n1 = fec_enc_len(p.fec1, f.n0);
+            f.n_sym = (8 * f.n1 + f.bps - 1) / f.bps; f.n_samples = ns;
+            f.buf_len = ((std::max(std::max(f.n1, f.n0), f.k0) + 16) + 15u) & ~15u;
+            const unsigned encs[2] = { f.n0, f.n1 }, fss[2] = { f.fec0, f.fec1 };
+            for (int s = 0; s < 2; ++s) {
+                if (fss[s] == FEC_NONE) continue;
+                auto it = h->ilv_cache.find(encs[s]);
+                size_t off;
+                if (it == h->ilv_cache.end()) {
+                    auto maps = ilv_maps(encs[s]);
+                    off = h->ilv_host.size();
+                    h->ilv_host.insert(h->ilv_host.end(), maps.begin(), maps.end());
+                    h->ilv_cache.emplace(encs[s], off);
+                } else off = it->second;
+                (s ? f.ilv1_off : f.ilv0_off) = (unsigned)off;
+            }
+        }
         f.pay_off = pay_tot; pay_tot += (lens[i] + 15u) & ~15u;
         f.buf_off = buf_tot; buf_tot += f.buf_len;
         f.sym_off = sym_tot; sym_tot += (f.n_sym + 14 + 64 + 231 + 16 + 1) & ~(size_t)1;      // lead zeros, preamble, header, payload, tail zeros
-        f.out_off = out_tot; out_tot += ns;
+        f.out_off = out_tot; out_tot += f.n_samples;
         if (headers && headers[i]) std::memcpy(f.header, headers[i], 14);
-        const unsigned encs[2] = { f.n0, f.n1 }, fss[2] = { f.fec0, f.fec1 };
-        for (int s = 0; s < 2; ++s) {
-            if (fss[s] == FEC_NONE) continue;
-            auto it = h->ilv_cache.find(encs[s]);
-            size_t off;
-            if (it == h->ilv_cache.end()) {
-                auto maps = ilv_maps(encs[s]);
-                off = h->ilv_host.size();
-                h->ilv_host.insert(h->ilv_host.end(), maps.begin(), maps.end());
-                h->ilv_cache.emplace(encs[s], off);
-            } else off = it->second;
-            (s ? f.ilv1_off : f.ilv0_off) = (unsigned)off;
-        }
     }
-    const bool dev_io = (mem == LQB_MEM_DEVICE);
     if (grow(h->d_frames, h->frames_cap, n) || grow(h->d_A, h->buf_cap, buf_tot + 16)) return tx_fail(LQB_ENOMEM, "cudaMalloc failed");
     if (grow(h->d_B, h->bufB_cap, buf_tot + 16)) return tx_fail(LQB_ENOMEM, "cudaMalloc failed");
     if (grow(h->d_syms, h->sym_cap, sym_tot + 1)) return tx_fail(LQB_ENOMEM, "cudaMalloc failed");
     // the device copy of the interleaver maps follows the host cache by COUNT, not by "this call added maps": a call
     // that added maps and then failed (bad props further down the list, out of memory) leaves them to the next call
     if (h->ilv_host.size() > h->ilv_uploaded || !h->d_ilv) {
+        if (h->pending) cudaStreamSynchronize(st);          // growing frees the old arena: no queued kernel may still read it
         if (grow(h->d_ilv, h->ilv_cap, h->ilv_host.size() + 4)) return tx_fail(LQB_ENOMEM, "cudaMalloc failed");
         if (!h->ilv_host.empty() &&
             cudaMemcpyAsync(h->d_ilv, h->ilv_host.data(), h->ilv_host.size() * sizeof(unsigned), cudaMemcpyHostToDevice, st) != cudaSuccess)
@@ -590,15 +756,28 @@ int lqb_tx_assemble(lqb_tx h, uint32_t n, const lqb_tx_props *props, const uint8
         if (pay_tot) cudaMemcpyAsync(h->d_pay, h->h_pay, pay_tot, cudaMemcpyHostToDevice, st);
     }
     cudaMemcpyAsync(h->d_frames, fr, n * sizeof(TxFrame), cudaMemcpyHostToDevice, st);
+    cudaEventRecord(h->tab_ev[tab], st);
+    h->tab_busy[tab] = true;
+    h->tab_next = tab ^ 1u;
+    cudaEventRecord(h->k_ev[0], st);
     k_tx<<<n, kTxThreads, 0, st>>>(h->d_tables, h->d_frames, h->d_A, h->d_B, h->d_ilv, h->d_syms);
+    cudaEventRecord(h->k_ev[1], st);
     h->launches++;
-    if (!dev_io) cudaMemcpyAsync(h->h_out, h->d_out, out_tot * sizeof(float2), cudaMemcpyDeviceToHost, st);
-    cudaError_t e = cudaStreamSynchronize(st);
-    if (e == cudaSuccess) e = cudaGetLastError();
-    if (e != cudaSuccess) return tx_fail(LQB_ECUDA, cudaGetErrorString(e));
-    if (!dev_io)
-        for (uint32_t i = 0; i < n; ++i) std::memcpy(out[i], h->h_out + fr[i].out_off, (size_t)fr[i].n_samples * sizeof(float2));
+    h->pending = true;
+    if (!dev_io) {
+        cudaMemcpyAsync(h->h_out, h->d_out, out_tot * sizeof(float2), cudaMemcpyDeviceToHost, st);
+        h->pending_host = true; h->pend_n = n; h->pend_tab = tab;
+        h->pend_out.assign(out, out + n);
+    }
+    if (cudaGetLastError() != cudaSuccess) return tx_fail(LQB_ECUDA, "k_tx launch failed");
     return 0;
+}
+
+int lqb_tx_assemble(lqb_tx h, uint32_t n, const lqb_tx_props *props, const uint8_t *const *headers,
+                    const uint8_t *const *payloads, const uint32_t *lens, float *const *out, int mem)
+{
+    if (int e = lqb_tx_submit(h, n, props, headers, payloads, lens, out, mem)) return e;
+    return lqb_tx_collect(h);
 }
 
 }  // extern "C"

@@ -13,7 +13,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("LQB_LIB") or os.path.normpath(os.path.join(_HERE, "..", "..", "lib", "liblqb200.so"))
 
-MEM_HOST, MEM_DEVICE = 0, 1
+MEM_HOST, MEM_DEVICE, MEM_HOST_SC16, MEM_DEVICE_SC16 = 0, 1, 2, 3
 RX_NO_FRAMESYMS, RX_DEVICE_RESULTS = 1, 2
 
 DECLARED_SYMBOLS = [
@@ -21,7 +21,7 @@ DECLARED_SYMBOLS = [
     "lqb_rx_create", "lqb_rx_destroy", "lqb_rx_reset", "lqb_rx_execute", "lqb_rx_execute_dense",
     "lqb_rx_submit", "lqb_rx_submit_dense", "lqb_rx_collect",
     "lqb_rx_poll", "lqb_rx_counts", "lqb_rx_last_timing", "lqb_rx_launch_count", "lqb_rx_last_work", "lqb_rx_last_search_bins", "lqb_rx_lane_count",
-    "lqb_tx_create", "lqb_tx_destroy", "lqb_tx_props_init_default", "lqb_tx_frame_len", "lqb_tx_assemble",
+    "lqb_tx_create", "lqb_tx_destroy", "lqb_tx_props_init_default", "lqb_tx_frame_len", "lqb_tx_assemble", "lqb_tx_submit", "lqb_tx_collect", "lqb_tx_last_timing",
     "lqb_det_create", "lqb_det_destroy", "lqb_det_reset", "lqb_det_execute", "lqb_det_execute_dense",
     "lqb_det_poll", "lqb_det_last_timing", "lqb_det_last_work", "lqb_det_last_search",
     "lqb_tab_interp_taps", "lqb_tab_pfb_banks", "lqb_tab_detector_template", "lqb_tab_nco_sintab",
@@ -112,6 +112,9 @@ def lib():
         L.lqb_tx_props_init_default.argtypes = [C.POINTER(TxProps)]
         L.lqb_tx_frame_len.argtypes = [C.POINTER(TxProps), u32, C.POINTER(u32)]
         L.lqb_tx_assemble.argtypes = [vp, u32, vp, vp, vp, vp, vp, C.c_int]
+        L.lqb_tx_submit.argtypes = [vp, u32, vp, vp, vp, vp, vp, C.c_int]
+        L.lqb_tx_collect.argtypes = [vp]
+        L.lqb_tx_last_timing.argtypes = [vp, C.POINTER(C.c_float)]
     L.lqb_det_create.restype = vp
     L.lqb_det_create.argtypes = [C.POINTER(DetOpts)]
     L.lqb_det_destroy.argtypes = [vp]
@@ -186,6 +189,15 @@ class Rx:
 
     def execute_dense_ptr(self, ptr, stride, n_samples, mem):
         _check(self._L.lqb_rx_execute_dense(self._h, C.c_void_p(ptr), stride, n_samples, mem))
+
+    def execute_sc16(self, chunks, stream_ids=None):
+        """chunks: list of int16 arrays of shape [n, 2] (re, im); a sample is value / 32768 (LQB_MEM_HOST_SC16)."""
+        n = len(chunks)
+        arrs = [np.ascontiguousarray(c, dtype=np.int16).reshape(-1, 2) for c in chunks]
+        ptrs = (C.c_void_p * n)(*[a.ctypes.data for a in arrs])
+        lens = (C.c_uint64 * n)(*[len(a) for a in arrs])
+        ids = None if stream_ids is None else (C.c_uint32 * n)(*stream_ids)
+        _check(self._L.lqb_rx_execute(self._h, n, ids, ptrs, lens, MEM_HOST_SC16))
 
     # pipelined form: submit() returns when the search is done, collect() makes the oldest submitted call current
     def submit(self, chunks, stream_ids=None):
@@ -380,7 +392,15 @@ class Tx:
         _check(self._L.lqb_tx_assemble(self._h, n, P, hp, pp, lens, op, MEM_HOST))
         return outs
 
-    def assemble_device_arrays(self, props4, payload_ptrs, payload_lens, out_ptrs):
+    def kernel_ms(self):
+        v = C.c_float(0)
+        _check(self._L.lqb_tx_last_timing(self._h, C.byref(v)))
+        return float(v.value)
+
+    def collect(self):
+        _check(self._L.lqb_tx_collect(self._h))
+
+    def assemble_device_arrays(self, props4, payload_ptrs, payload_lens, out_ptrs, wait=True):
         """Device-resident variant for large batches: numpy arrays in (no per-frame Python objects).
         props4: uint32 [n, 4] rows (check, fec0, fec1, mod_scheme) = lqb_tx_props; payload_ptrs / out_ptrs: uint64 [n]
         device addresses; payload_lens: uint32 [n].  Frames are written in place at out_ptrs."""
@@ -390,7 +410,8 @@ class Tx:
         ln = np.ascontiguousarray(payload_lens, dtype=np.uint32)
         n = len(pp)
         assert props4.shape == (n, 4) and len(op) == n and len(ln) == n
-        _check(self._L.lqb_tx_assemble(self._h, n, props4.ctypes.data, None, pp.ctypes.data, ln.ctypes.data, op.ctypes.data, MEM_DEVICE))
+        fn = self._L.lqb_tx_assemble if wait else self._L.lqb_tx_submit      # wait=False: complete in stream order (lqb_tx_submit)
+        _check(fn(self._h, n, props4.ctypes.data, None, pp.ctypes.data, ln.ctypes.data, op.ctypes.data, MEM_DEVICE))
 
     def assemble_device(self, props, payload_ptrs, payload_lens, out_ptrs, header_ptrs=None):
         """Device-resident variant: raw device pointers in, frames written to out_ptrs."""

@@ -55,6 +55,12 @@ extern "C" {
 
 #define LQB_MEM_HOST   0
 #define LQB_MEM_DEVICE 1
+/* Additive input formats for the receiver and the detector (the reference's blocks only know complex64): the iq
+ * pointers address interleaved int16 pairs (re, im) -- what SDR front ends deliver natively -- and a sample is
+ * value / 32768.  Half the bytes of complex64 over PCIe; widened on the device, results identical to feeding the
+ * widened floats. */
+#define LQB_MEM_HOST_SC16   2
+#define LQB_MEM_DEVICE_SC16 3
 
 /* liquid-dsp wire enums carried in the frame header (only the values the blocks use are named) */
 #define LQB_MODEM_PSK2 1
@@ -154,7 +160,7 @@ lqb_rx lqb_rx_create(const lqb_rx_opts *opts);
 void   lqb_rx_destroy(lqb_rx h);
 int    lqb_rx_reset(lqb_rx h, int stream /* -1 = all */);
 /* Feed n_samples[i] new samples to stream stream_ids[i] (each stream at most once per call).
- * iq[i] points at interleaved complex64.  Runs the whole receive chain for every frame that
+ * iq[i] points at interleaved complex64 (interleaved int16 pairs cast to float* for the *_SC16 kinds).  Runs the whole receive chain for every frame that
  * completes inside the data seen so far; partial frames are carried to the next call. */
 int    lqb_rx_execute(lqb_rx h, uint32_t n, const uint32_t *stream_ids,
                       const float *const *iq, const uint64_t *n_samples, int mem);
@@ -212,6 +218,16 @@ int    lqb_tx_frame_len(const lqb_tx_props *p, uint32_t payload_len, uint32_t *n
 int    lqb_tx_assemble(lqb_tx h, uint32_t n, const lqb_tx_props *props,
                        const uint8_t *const *headers, const uint8_t *const *payloads,
                        const uint32_t *payload_lens, float *const *out, int mem);
+/* Asynchronous form: submit() queues the batch on the handle's stream and returns; with LQB_MEM_DEVICE the frames are
+ * complete in stream order (on the caller's stream when the handle was created on one) and further submits may follow
+ * without waiting; with LQB_MEM_HOST the frames reach `out` in collect().  collect() waits for everything submitted.
+ * assemble() == submit() + collect().  The argument arrays may be reused as soon as submit returns. */
+int    lqb_tx_submit(lqb_tx h, uint32_t n, const lqb_tx_props *props,
+                     const uint8_t *const *headers, const uint8_t *const *payloads,
+                     const uint32_t *payload_lens, float *const *out, int mem);
+int    lqb_tx_collect(lqb_tx h);
+/* device time (ms) of the frame generator kernel of the last collected batch (CUDA events on the handle's stream) */
+int    lqb_tx_last_timing(lqb_tx h, float *kernel_ms);
 
 /* ------------------------------------------------------------------ detector (frame_detector_cc / qdetector_cccf) */
 typedef struct lqb_det_s *lqb_det;

@@ -1,12 +1,4 @@
-for v in liblqb200 v_b0; do
-  LQB_LIB=gr-liquiddsp_b200/lib/$v.so timeout -s KILL 200 python bench.py --steps 8 --warmup 3 --no-workloads --no-e2e --no-cpu-baseline > gpurun_out/ab_$v.json 2> gpurun_out/ab_$v.err
-  LQB_LIB=gr-liquiddsp_b200/lib/$v.so timeout -s KILL 200 python bench.py --workload detector --steps 3 --warmup 1 --no-cpu-baseline > gpurun_out/abd_$v.json 2> gpurun_out/abd_$v.err
-  python - <<PY
-import json
-d=json.load(open('gpurun_out/ab_$v.json'))
-print('$v', round(d['ms_per_step'],2), [round(k['ms_per_step'],2) for k in d['kernels']], d['frames_found_per_step'], d['frames_valid_per_step'], d['kernels'][0].get('cfo_bins_per_exact_window'))
-d=json.load(open('gpurun_out/abd_$v.json'))
-print('   det', round(d['ms_per_step'],2), d['detections_per_step'], d['search_work_last_step'])
-PY
-done
-timeout -s KILL 300 python -m pytest tests -m gpu -x -q 2>&1 | tail -2
+timeout -s KILL 300 python -m pytest tests/test_gpu_tx_det.py tests/test_blocks.py tests/test_python_layer.py tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -2
+timeout -s KILL 200 python bench.py --workload tx --steps 10 --warmup 3 --no-cpu-baseline 2>gpurun_out/e1.err | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('tx', round(d['ms_per_step'],3), d['kernel_ms_per_step'], d['roofline']['frac'])"
+timeout -s KILL 200 python bench.py --workload tx_rx_per --steps 5 --warmup 2 2>gpurun_out/e2.err | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('per', d['value'], d['ms_per_step'], d['ms_per_step_parts'], d['roofline']['frac'], d['failed'])"
+tail -c 300 gpurun_out/e1.err gpurun_out/e2.err

@@ -134,3 +134,30 @@ def test_receivers_on_two_devices_in_one_process():
         det.execute([cap])
         assert len(det.poll()) >= 1
         det.close()
+
+
+def test_sc16_input_equals_the_widened_floats():
+    """LQB_MEM_HOST_SC16 (interleaved int16 pairs, value / 32768 -- additive to the reference's complex64): the receiver
+    and the detector give exactly what they give for the widened floats, which is what the oracle gives for them."""
+    rng = np.random.default_rng(307)
+    pls = [rng.integers(0, 256, 400, dtype=np.uint8) for _ in range(3)]
+    frames = [o.tx_frame(util.PSK4, util.CRC24, V27, RS8, p) for p in pls]
+    cap = util.build_capture(frames, rng, [1500] * 3, snr_db=12.0, cfo=0.015, tau=0.3, gain=0.9)
+    q = np.clip(np.round(np.stack([cap.real, cap.imag], axis=1) * 6000.0), -32768, 32767).astype(np.int16)
+    wide = (q[:, 0].astype(np.float32) / 32768.0 + 1j * (q[:, 1].astype(np.float32) / 32768.0)).astype(np.complex64)
+    ref = o.rx_capture(wide)
+    assert len(ref) == 3 and all(r["payload_valid"] for r in ref)
+    rx = capi.Rx(2)
+    rx.execute_sc16([q, q[:4001]])                       # second stream: a ragged, odd-length piece of the same capture
+    got = rx.poll()
+    assert_frames_match(ref, [g for g in got if g["stream"] == 0])
+    rx2 = capi.Rx(1)
+    rx2.execute([wide])
+    assert_frames_match(ref, rx2.poll())
+    # streamed in odd-sized chunks through the same format
+    rx3 = capi.Rx(1)
+    got3 = []
+    for i in range(0, len(q), 3001):
+        rx3.execute_sc16([q[i:i + 3001]])
+        got3 += rx3.poll()
+    assert_frames_match(ref, got3)

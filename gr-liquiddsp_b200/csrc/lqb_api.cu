@@ -386,6 +386,10 @@ struct RxGen {
     DevBuf<unsigned> d_lists, d_tilemap;
     PinBuf<unsigned> h_lists;
     DevBuf<StreamView> d_views;
+    // soft-decision path (LQB_RX_SOFT): soft bytes in transmission order, deinterleaved soft bytes, per-frame descriptors
+    DevBuf<unsigned char> d_soft_raw, d_soft_d;
+    DevBuf<SoftDesc> d_softdesc;
+    PinBuf<SoftDesc> h_softdesc;
     unsigned n_frames = 0, n_fed = 0;
     uint64_t n_valid = 0;
     cudaEvent_t ev[7] = {};
@@ -407,6 +411,7 @@ struct RxGen {
         d_frames.release(); h_frames.release(); d_syms.release(); h_syms.release();
         d_bufA.release(); d_bufB.release(); d_payload.release(); h_payload.release();
         d_dec.release(); d_ckpt.release(); d_lists.release(); h_lists.release(); d_tilemap.release(); d_views.release();
+        d_soft_raw.release(); d_soft_d.release(); d_softdesc.release(); h_softdesc.release();
         for (auto &e : ev) if (e) cudaEventDestroy(e);
         if (mf_done) cudaEventDestroy(mf_done);
         if (done) cudaEventDestroy(done);
@@ -431,6 +436,9 @@ struct RxLane {
     DevBuf<unsigned> d_ilv;
     size_t ilv_used = 0;
     std::unordered_map<unsigned, size_t> ilv_cache;
+    DevBuf<unsigned> d_bitperm;           // soft-decision path: bit permutations of the deinterleaver, by block length
+    size_t bitperm_used = 0;
+    std::unordered_map<unsigned, size_t> bitperm_cache;
     // per-call input lists (lane-local stream ids)
     std::vector<uint32_t> ids;
     std::vector<const float *> iq;
@@ -442,7 +450,7 @@ struct RxLane {
         if (f.stream) cudaStreamSynchronize(f.stream);
         if (pay) cudaStreamSynchronize(pay);
         for (auto &x : g) x.release();
-        d_ilv.release();
+        d_ilv.release(); d_bitperm.release();
         if (own_pay && pay) cudaStreamDestroy(pay);
         if (copy) { cudaStreamSynchronize(copy); cudaStreamDestroy(copy); }
         f.destroy();
@@ -461,6 +469,22 @@ struct RxLane {
         cudaStreamSynchronize(pay);         // maps is a local; finish the copy before it dies
         ilv_used = off + maps.size();
         ilv_cache.emplace(n, off);
+        return off;
+    }
+
+    size_t bitperm_offset(unsigned n)
+    {
+        auto it = bitperm_cache.find(n);
+        if (it != bitperm_cache.end()) return it->second;
+        std::vector<uint32_t> perm = ilv_bit_perm(n);
+        size_t off = bitperm_used;
+        if (off + perm.size() + 4 > d_bitperm.cap) cudaStreamSynchronize(pay);   // growing frees the old arena: no chain may still read it
+        if (d_bitperm.reserve(off + perm.size() + 4, true, pay)) return (size_t)-1;
+        if (!perm.empty())
+            cudaMemcpyAsync(d_bitperm.p + off, perm.data(), perm.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, pay);
+        cudaStreamSynchronize(pay);         // perm is a local; finish the copy before it dies
+        bitperm_used = off + perm.size();
+        bitperm_cache.emplace(n, off);
         return off;
     }
 
@@ -571,7 +595,16 @@ struct RxLane {
         g_trace.mark("frame list on host", lane);
         // ---------------- plan
         size_t sym_total = 0, buf_total = 0, pay_total = 0, dec_total = 0, n_tiles = 0, ck_total = 0;
-        std::vector<unsigned> tile_start(nf + 1, 0), valid, deint[2], blk[2], vit[2], vit9[2], rsb[2];
+        std::vector<unsigned> tile_start(nf + 1, 0), valid, deint[2], blk[2], vit[2], vit9[2], rsb[2], softl, vsoft[2];
+        const bool soft_on = (flags & LQB_RX_SOFT) != 0;
+        size_t soft_raw_total = 0, soft_d_total = 0;
+        unsigned soft_max_syms = 0, soft_max_bits = 0;
+        SoftDesc *sdesc = nullptr;
+        if (soft_on && nf) {
+            if (int e = G.h_softdesc.reserve(nf)) return e;
+            sdesc = G.h_softdesc.p;
+            for (unsigned i = 0; i < nf; ++i) { sdesc[i].raw_off = 0; sdesc[i].d_off = 0; sdesc[i].perm_off = 0; sdesc[i].stage = -1; }
+        }
         size_t tmax7[2] = { 0, 0 };
         bool punct7[2] = { false, false };
         std::fill(f.est_work.begin(), f.est_work.end(), 0);
@@ -592,7 +625,26 @@ struct RxLane {
             d.ck_off = (unsigned)ck_total; ck_total += (d.n_sym + 31) / 32;
             const unsigned fs[2] = { d.fec0, d.fec1 }, enc[2] = { d.n0, d.n1 }, dl[2] = { d.k0, d.n0 };
             size_t need_dec = 0;
+            // soft decisions: the stage nearest the channel, when it is convolutional and the modem has a soft demodulator
+            int sstage = -1;
+            if (soft_on && !(d.ms >= 9 && d.ms <= 16)) {
+                const int st = (d.fec1 != FEC_NONE) ? 1 : 0;
+                if (is_conv(fs[st])) sstage = st;
+            }
+            if (sstage >= 0) {
+                const size_t off = bitperm_offset(enc[sstage]);
+                if (off == (size_t)-1) return LQB_ENOMEM;
+                SoftDesc &sd = sdesc[i];
+                sd.stage = sstage; sd.perm_off = (unsigned)off;
+                sd.raw_off = soft_raw_total; soft_raw_total += ((size_t)d.n_sym * d.bps + 31u) & ~(size_t)15u;
+                sd.d_off = soft_d_total; soft_d_total += ((size_t)8 * enc[sstage] + 31u) & ~(size_t)15u;
+                soft_max_syms = std::max(soft_max_syms, d.n_sym); soft_max_bits = std::max(soft_max_bits, 8u * enc[sstage]);
+                softl.push_back(i); vsoft[sstage].push_back(i);
+                const size_t T = (size_t)8 * dl[sstage] + conv_K(fs[sstage]) - 1;
+                need_dec = std::max(need_dec, T * (conv_K(fs[sstage]) == 7 ? 1u : 4u));        // 2 or 8 decision words per step
+            }
             for (int stg = 1; stg >= 0; --stg) {
+                if (stg == sstage) continue;              // deinterleaved and decoded from soft bytes instead
                 if (fs[stg] != FEC_NONE) {
                     size_t off = ilv_offset(enc[stg]);
                     if (off == (size_t)-1) return LQB_ENOMEM;
@@ -635,7 +687,8 @@ struct RxLane {
             if (int e = G.d_ckpt.reserve(ck_total + 1)) return e;
             // one list arena: tile_start | pll | valid | deint1 | blk1 | vit1 | rs1 | deint0 | blk0 | vit0 | rs0
             std::vector<const std::vector<unsigned> *> parts = { &tile_start, &pll, &valid, &deint[1], &blk[1], &vit[1], &rsb[1],
-                                                                 &deint[0], &blk[0], &vit[0], &rsb[0], &vit9[1], &vit9[0], &span_start };
+                                                                 &deint[0], &blk[0], &vit[0], &rsb[0], &vit9[1], &vit9[0], &span_start,
+                                                                 &softl, &vsoft[1], &vsoft[0] };
             size_t ltot = 0;
             std::vector<size_t> loff;
             for (auto p : parts) { loff.push_back(ltot); ltot += p->size(); }
@@ -668,6 +721,14 @@ struct RxLane {
             pp.tile_start = G.d_lists.p + loff[0]; pp.n_tiles = (unsigned)n_tiles; pp.tile_rec = reinterpret_cast<uint4 *>(G.d_tilemap.p);
             pp.syms = G.d_syms.p; pp.bufA = G.d_bufA.p; pp.bufB = G.d_bufB.p; pp.payload = G.d_payload.p;
             pp.ilv_maps = d_ilv.p; pp.decisions = G.d_dec.p; pp.pll_ckpt = G.d_ckpt.p;
+            pp.soft = nullptr; pp.soft_raw = nullptr; pp.soft_d = nullptr; pp.bitperm = d_bitperm.p;
+            if (!softl.empty()) {
+                if (int e = G.d_soft_raw.reserve(soft_raw_total + 64)) return e;
+                if (int e = G.d_soft_d.reserve(soft_d_total + 64)) return e;
+                if (int e = G.d_softdesc.reserve(nf)) return e;
+                launch_copy(G.d_softdesc.p, sdesc, nf * sizeof(SoftDesc), ps);
+                pp.soft = G.d_softdesc.p; pp.soft_raw = G.d_soft_raw.p; pp.soft_d = G.d_soft_d.p;
+            }
 
             CU(cudaEventRecord(G.ev[2], ps));
             launch_mf(pp, ps); f.launches += n_tiles ? 2 : 0;
@@ -677,8 +738,10 @@ struct RxLane {
             launch_pll(pp, G.d_lists.p + loff[1], G.d_lists.p + loff[13], (unsigned)pll.size(), span_start.back(), ps);
             f.launches += getenv("LQB_PLL_FUSED") ? 1 : 2;          // tracker + emitter kernels (one fused kernel on request)
             CU(cudaEventRecord(G.ev[4], ps));
+            if (!softl.empty()) { launch_soft_demod(pp, G.d_lists.p + loff[14], (unsigned)softl.size(), soft_max_syms, soft_max_bits, ps); f.launches += 2; }
             for (int stg = 1; stg >= 0; --stg) {
                 const size_t base = stg ? 3 : 7;
+                if (!vsoft[stg].empty()) { launch_viterbi_soft(pp, G.d_lists.p + loff[stg ? 15 : 16], (unsigned)vsoft[stg].size(), stg, ps); f.launches++; }
                 if (!deint[stg].empty()) { launch_deinterleave(pp, G.d_lists.p + loff[base], (unsigned)deint[stg].size(), stg, ps); f.launches++; }
                 if (!blk[stg].empty()) { launch_blockfec(pp, G.d_lists.p + loff[base + 1], (unsigned)blk[stg].size(), stg, ps); f.launches++; }
                 if (!vit[stg].empty()) { launch_viterbi(pp, G.d_lists.p + loff[base + 2], (unsigned)vit[stg].size(), stg, 7, punct7[stg], ps); f.launches++; }
@@ -1213,6 +1276,13 @@ int lqb_tab_interp_taps(float beta, float *h30) { auto h = interp_taps(beta); st
 int lqb_tab_pfb_banks(float beta, float *b) { auto v = pfb_banks(beta); std::memcpy(b, v.data(), v.size() * sizeof(float)); return 0; }
 int lqb_tab_detector_template(float beta, float *s) { auto v = detector_template(beta); std::memcpy(s, v.data(), v.size() * sizeof(cf)); return 0; }
 int lqb_tab_nco_sintab(float *t) { std::memcpy(t, nco_sintab(), 1024 * sizeof(float)); return 0; }
+int lqb_tab_ilv_bit_perm(uint32_t n, uint32_t *perm)
+{
+    if (!perm) return fail(LQB_EINVAL, "null pointer");
+    auto v = ilv_bit_perm(n);
+    std::memcpy(perm, v.data(), v.size() * sizeof(uint32_t));
+    return 0;
+}
 int lqb_tab_packet_len(uint32_t n, uint32_t check, uint32_t fec0, uint32_t fec1, uint32_t ms, uint32_t *enc, uint32_t *nsym)
 {
     if (!modem_supported(ms) || !fec_supported(fec0) || !fec_supported(fec1) || check == 0 || check >= CRC_NUM) return fail(LQB_EINVAL, "unsupported scheme");

@@ -103,6 +103,30 @@ __device__ __forceinline__ float2 cmulf(float2 a, float2 b)
 __device__ __forceinline__ float abs2f(float2 a) { return __fmaf_rn(a.y, a.y, __fmul_rn(a.x, a.x)); }
 __device__ __forceinline__ float cabsf_(float2 a) { return __fsqrt_rn(abs2f(a)); }
 
+// constellation point of symbol s (the modulator's map; the same operations as the host-built tables of the
+// specification, so the points are bit-identical to the oracle's).  psk_map: [8][256] PSK-2^b rows.
+__device__ __forceinline__ unsigned gray_decode_dev(unsigned s) { unsigned r = s; for (unsigned sh = 1; sh < 32; sh <<= 1) r ^= r >> sh; return r; }
+__device__ inline float2 modem_point(const float2 *psk_map, unsigned ms, unsigned bps, unsigned s)
+{
+    const unsigned M = 1u << bps;
+    if (ms >= 1 && ms <= 8) return psk_map[(bps - 1) * 256 + s];
+    if (ms >= 17 && ms <= 24) {
+        const float c[9] = { 0, 1.0f, 5.0f, 21.0f, 85.0f, 341.0f, 1365.0f, 5461.0f, 21845.0f };
+        const float alpha = __fdiv_rn(1.0f, __fsqrt_rn(c[bps]));
+        return make_float2(__fmul_rn((float)(2 * (int)gray_decode_dev(s) - (int)M + 1), alpha), 0.0f);
+    }
+    if (ms >= 25 && ms <= 31) {
+        const float c[9] = { 0, 0, 2.0f, 6.0f, 10.0f, 26.0f, 42.0f, 106.0f, 170.0f };
+        const float alpha = __fdiv_rn(1.0f, __fsqrt_rn(c[bps]));
+        const unsigned m_i = (bps + 1) >> 1, m_q = bps >> 1;
+        const unsigned si = gray_decode_dev(s >> m_q), sq = gray_decode_dev(s & ((1u << m_q) - 1u));
+        return make_float2(__fmul_rn((float)(2 * (int)si - (int)(1u << m_i) + 1), alpha),
+                           __fmul_rn((float)(2 * (int)sq - (int)(1u << m_q) + 1), alpha));
+    }
+    if (ms == 39) return make_float2(s ? -1.0f : 1.0f, 0.0f);
+    return make_float2((s & 1u) ? -0.707106769f : 0.707106769f, (s & 2u) ? -0.707106769f : 0.707106769f);
+}
+
 __device__ __forceinline__ uint32_t nco_constrain_dev(float theta)
 {
     // identical to: p = theta/(2 pi); f = p - trunc(p); f < 0 ? f + 1; (uint32)(int64)(f * 2^32)

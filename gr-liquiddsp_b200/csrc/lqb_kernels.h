@@ -64,6 +64,14 @@ constexpr unsigned kMfTileSyms = 8 * LQB_MF_THREADS;   // payload symbols per ma
 // work list entry for kernels that run per FEC stage
 struct StageItem { unsigned frame; unsigned pad; };
 
+// soft-decision frames (LQB_RX_SOFT): where a frame's soft bits live and which stage consumes them
+struct SoftDesc {
+    unsigned long long raw_off;     // soft bytes in transmission order, n_sym * bps of them
+    unsigned long long d_off;       // deinterleaved soft bytes, 8 * enc_len of the soft stage
+    unsigned perm_off;              // bit permutation of that length in the bitperm arena
+    int      stage;                 // 1: fec1, 0: fec0 (fec1 is "none"), -1: hard decisions only
+};
+
 struct PayloadParams {
     const DevTables   *tables;
     const StreamView  *views;       // [n_io] written by k_seek: carry / input pointers and bounds as of this call
@@ -79,6 +87,10 @@ struct PayloadParams {
     const unsigned    *ilv_maps;    // interleaver map arena
     unsigned long long *decisions;  // Viterbi decision arena
     void              *pll_ckpt;    // PLL checkpoints, 16 bytes per 32 payload symbols (FrameDesc::ck_off)
+    // soft-decision path (null without LQB_RX_SOFT)
+    const SoftDesc    *soft;        // [n_frames]
+    unsigned char     *soft_raw, *soft_d;
+    const unsigned    *bitperm;
 };
 
 void launch_seek(const SeekParams &P, unsigned n_io, cudaStream_t s);
@@ -99,6 +111,10 @@ void launch_blockfec(const PayloadParams &P, const unsigned *list, unsigned n, i
 void launch_viterbi(const PayloadParams &P, const unsigned *list, unsigned n, int stage, unsigned K, bool punct, cudaStream_t s);
 void launch_rs(const PayloadParams &P, const unsigned *blocks /* pairs (frame, block) */, unsigned n_blocks, int stage, cudaStream_t s);
 void launch_crc(const PayloadParams &P, const unsigned *list, unsigned n, cudaStream_t s);
+// soft decisions for the listed frames: demodulate the stored constellation points to soft bytes, deinterleave them
+// through the bit permutation, then (launch_viterbi_soft, per stage) the soft-input Viterbi decoder
+void launch_soft_demod(const PayloadParams &P, const unsigned *list, unsigned n, unsigned max_syms, unsigned max_bits, cudaStream_t s);
+void launch_viterbi_soft(const PayloadParams &P, const unsigned *list, unsigned n, int stage, cudaStream_t s);
 
 // debug / unit-test hooks (single launches on tiny inputs)
 void launch_dbg_fft512(const DevTables *T, const float2 *in, float2 *out, int dir, cudaStream_t s);

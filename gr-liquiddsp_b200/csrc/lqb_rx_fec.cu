@@ -213,6 +213,8 @@ __device__ __forceinline__ unsigned soft_bit(const unsigned char *enc, unsigned 
 
 constexpr int kVitWarps = 4;
 
+// SOFT: the received values are bytes (one per kept coded bit, already deinterleaved: LQB_RX_SOFT) instead of bits
+template <bool SOFT>
 __global__ void __launch_bounds__(32 * kVitWarps)
 k_viterbi(PayloadParams P, const unsigned *__restrict__ list, unsigned n_list, int stage)
 {
@@ -221,7 +223,8 @@ k_viterbi(PayloadParams P, const unsigned *__restrict__ list, unsigned n_list, i
     const unsigned gi = blockIdx.x * kVitWarps + warp;
     if (gi >= n_list) return;
     const FrameDesc &d = P.frames[list[gi]];
-    const StageIO io = stage_io(P, d, stage);
+    StageIO io = stage_io(P, d, stage);
+    if (SOFT) { io.src = P.soft_d + P.soft[list[gi]].d_off; io.enc_len *= 8u; }     // one byte per coded bit
     const ConvSpec cs = conv_spec(io.fs);
     const unsigned ns = 1u << (cs.K - 1), half = ns >> 1, words = ns >> 5;
     const unsigned nbits = 8 * io.dec_len, T = nbits + cs.K - 1;
@@ -251,6 +254,10 @@ k_viterbi(PayloadParams P, const unsigned *__restrict__ list, unsigned n_list, i
     };
     unsigned wbase = 0, wcur = load_word(0), wnext = load_word(1);
     auto take_bit = [&](unsigned ib) -> unsigned {               // ib never decreases
+        if (SOFT) {                                              // four soft bytes per word, first byte in the top bits
+            while ((ib >> 2) != wbase) { ++wbase; wcur = wnext; wnext = load_word(wbase + 1); }
+            return (wcur >> (24u - 8u * (ib & 3u))) & 0xffu;
+        }
         while ((ib >> 5) != wbase) { ++wbase; wcur = wnext; wnext = load_word(wbase + 1); }
         return ((wcur >> (31u - (ib & 31u))) & 1u) ? 255u : 0u;
     };
@@ -869,7 +876,11 @@ void launch_viterbi(const PayloadParams &P, const unsigned *list, unsigned n, in
         if (punct) k_viterbi27x4<true><<<(threads + kV4Threads - 1) / kV4Threads, kV4Threads, 0, s>>>(P, list, n, stage, reinterpret_cast<unsigned *>(P.decisions), warm);
         else k_viterbi27x4<false><<<(threads + kV4Threads - 1) / kV4Threads, kV4Threads, 0, s>>>(P, list, n, stage, reinterpret_cast<unsigned *>(P.decisions), warm);
     }
-    else k_viterbi<<<(n + kVitWarps - 1) / kVitWarps, 32 * kVitWarps, 0, s>>>(P, list, n, stage);
+    else k_viterbi<false><<<(n + kVitWarps - 1) / kVitWarps, 32 * kVitWarps, 0, s>>>(P, list, n, stage);
+}
+void launch_viterbi_soft(const PayloadParams &P, const unsigned *list, unsigned n, int stage, cudaStream_t s)
+{
+    if (n) k_viterbi<true><<<(n + kVitWarps - 1) / kVitWarps, 32 * kVitWarps, 0, s>>>(P, list, n, stage);
 }
 void launch_rs(const PayloadParams &P, const unsigned *blocks, unsigned n_blocks, int stage, cudaStream_t s)
 {

@@ -268,6 +268,26 @@ std::vector<uint32_t> ilv_maps(unsigned n)
     return maps;
 }
 
+// The deinterleaver of an n-byte block as a permutation of its 8 n coded bits (MSB-first positions):
+// deinterleaved[i] = interleaved[perm[i]].  The masked byte swaps only move bits, so the passes (3, 2, 1, 0) are run
+// once on position labels.  Used by the soft-decision path, where every coded bit is a byte of its own.
+std::vector<uint32_t> ilv_bit_perm(unsigned n)
+{
+    const unsigned n2 = n / 2, masks[4] = { 0xffu, 0x0fu, 0x55u, 0x33u };
+    std::vector<uint32_t> maps = ilv_maps(n), lab(8 * (size_t)n), perm(8 * (size_t)n);
+    for (size_t i = 0; i < lab.size(); ++i) lab[i] = (uint32_t)i;            // index 8 * byte + b, b counted from the LSB
+    if (n >= 2)
+        for (int pass = 3; pass >= 0; --pass)
+            for (unsigned i = 0; i < n2; ++i) {
+                const unsigned j = maps[(size_t)pass * n2 + i];
+                for (unsigned b = 0; b < 8; ++b)
+                    if ((masks[pass] >> b) & 1u) std::swap(lab[8 * (size_t)(2 * j + 1) + b], lab[8 * (size_t)(2 * i) + b]);
+            }
+    auto flip = [](uint32_t k) { return (k & ~7u) | (7u - (k & 7u)); };      // LSB-based index <-> MSB-first position
+    for (size_t pos = 0; pos < perm.size(); ++pos) perm[pos] = flip(lab[flip((uint32_t)pos)]);
+    return perm;
+}
+
 // ------------------------------------------------------------------ small code tables
 static const uint8_t kH84[16] = { 0x00, 0xd2, 0x55, 0x87, 0x99, 0x4b, 0xcc, 0x1e,
                                   0xe1, 0x33, 0xb4, 0x66, 0x78, 0xaa, 0x2d, 0xff };

@@ -61,6 +61,7 @@ unsigned qpm_frame_len(unsigned n, unsigned check, unsigned fec0, unsigned fec1,
 // ---- interleaver: for pass p (0..3) entry i is the j that byte 2i exchanges bits with byte 2j+1
 void ilv_dims(unsigned n, unsigned &M, unsigned &N);
 std::vector<uint32_t> ilv_maps(unsigned n);              // 4 * (n/2) entries
+std::vector<uint32_t> ilv_bit_perm(unsigned n);          // 8 n entries: deinterleaved bit i = interleaved bit perm[i]
 
 // ---- small code tables
 void hamming_dec_tables(uint8_t h84[256], uint8_t h74[128]);

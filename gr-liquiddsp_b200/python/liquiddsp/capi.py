@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("LQB_LIB") or os.path.normpath(os.path.join(_HERE, "..", "..", "lib", "liblqb200.so"))
 
 MEM_HOST, MEM_DEVICE, MEM_HOST_SC16, MEM_DEVICE_SC16 = 0, 1, 2, 3
-RX_NO_FRAMESYMS, RX_DEVICE_RESULTS = 1, 2
+RX_NO_FRAMESYMS, RX_DEVICE_RESULTS, RX_SOFT = 1, 2, 4
 
 DECLARED_SYMBOLS = [
     "lqb_last_error", "lqb_device_count", "lqb_version",
@@ -25,7 +25,7 @@ DECLARED_SYMBOLS = [
     "lqb_det_create", "lqb_det_destroy", "lqb_det_reset", "lqb_det_execute", "lqb_det_execute_dense",
     "lqb_det_poll", "lqb_det_last_timing", "lqb_det_last_work", "lqb_det_last_search",
     "lqb_tab_interp_taps", "lqb_tab_pfb_banks", "lqb_tab_detector_template", "lqb_tab_nco_sintab",
-    "lqb_tab_packet_len",
+    "lqb_tab_packet_len", "lqb_tab_ilv_bit_perm",
 ]
 
 
@@ -343,6 +343,13 @@ def tab_nco_sintab():
     t = np.zeros(1024, np.float32)
     lib().lqb_tab_nco_sintab(t.ctypes.data)
     return t
+
+
+def tab_ilv_bit_perm(n):
+    p = np.zeros(8 * n, np.uint32)
+    lib().lqb_tab_ilv_bit_perm.argtypes = [C.c_uint32, C.c_void_p]
+    _check(lib().lqb_tab_ilv_bit_perm(n, p.ctypes.data))
+    return p
 
 
 def tab_packet_len(n, check, fec0, fec1, ms):

@@ -119,6 +119,13 @@ typedef struct lqb_rx_s *lqb_rx;
 
 #define LQB_RX_NO_FRAMESYMS  1u   /* do not copy payload constellation points back to the host */
 #define LQB_RX_DEVICE_RESULTS 2u  /* keep payload bytes on the device too (descriptors only are copied) */
+#define LQB_RX_SOFT 4u            /* opt-in extension (not liquid-dsp's default, which the blocks use): frames whose coding
+                                     stage nearest the channel (fec1, or fec0 when fec1 is "none") is convolutional are
+                                     decoded from SOFT decisions -- per coded bit clamp(128 + G (d0 - d1)) from the squared
+                                     distances to the nearest constellation points with that bit 0 / 1, G = 64 / dmin^2 --
+                                     through a soft-input Viterbi decoder (about 2 dB at the same PER).  DPSK frames and
+                                     all other coding chains are decoded as without the flag.  Header decoding, estimates
+                                     and constellation points do not change. */
 
 typedef struct {
     int      device;             /* CUDA device ordinal */
@@ -264,6 +271,7 @@ int lqb_tab_interp_taps(float beta, float *h30);
 int lqb_tab_pfb_banks(float beta, float *banks32x28);
 int lqb_tab_detector_template(float beta, float *s156_complex);
 int lqb_tab_nco_sintab(float *tab1024);
+int lqb_tab_ilv_bit_perm(uint32_t n_bytes, uint32_t *perm /* 8 * n_bytes */);   /* deinterleaved bit i = interleaved bit perm[i] */
 int lqb_tab_packet_len(uint32_t payload_len, uint32_t check, uint32_t fec0, uint32_t fec1,
                        uint32_t mod_scheme, uint32_t *enc_bytes, uint32_t *n_symbols);
 

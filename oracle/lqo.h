@@ -108,6 +108,13 @@ void     lqo_deinterleave(uint8_t *x, unsigned n, int depth); /* in place */
 unsigned lqo_fec_enc_len(int fs, unsigned dec_len);
 void     lqo_fec_encode(int fs, unsigned dec_len, const uint8_t *dec, uint8_t *enc);
 void     lqo_fec_decode(int fs, unsigned dec_len, const uint8_t *enc, uint8_t *dec);
+/* soft-input Viterbi for the convolutional schemes: soft[] holds one byte per coded bit (8 * enc_len of them, in
+ * transmission order), same trellis, metrics and traceback as the hard decoder; returns 0 for other schemes */
+int      lqo_fec_decode_soft(int fs, unsigned dec_len, const uint8_t *soft, uint8_t *dec);
+int      lqo_fec_is_conv(int fs);
+/* the byte interleaver of an n-byte block as a permutation of its 8 n coded bits (MSB-first positions):
+ * deinterleaved[i] = interleaved[perm[i]] */
+void     lqo_deinterleave_bit_perm(unsigned n, uint32_t *perm /* 8 n */);
 /* exposed for KATs */
 int      lqo_rs_decode_block(uint8_t *block /* 255-pad */, unsigned pad); /* returns #corrected or -1 */
 void     lqo_rs_encode_block(const uint8_t *data, unsigned pad, uint8_t *parity32);
@@ -133,6 +140,12 @@ void     lqo_modem_reset(lqo_modem *q);
 lqo_cf   lqo_modem_modulate(lqo_modem *q, unsigned sym);
 unsigned lqo_modem_demodulate(lqo_modem *q, lqo_cf x);
 float    lqo_modem_phase_error(const lqo_modem *q);
+/* Soft decisions (opt-in extension; OUR definition, liquid's own soft demodulator is not
+ * restated): for bit k (MSB first) of the symbol, with d0 / d1 the smallest squared distance from x to a constellation
+ * point whose bit k is 0 / 1 and G = 64 / (smallest squared distance between two points),
+ *     soft[k] = clamp(trunc(128 + G (d0 - d1)), 0, 255)        -- 0 = surely 0, 255 = surely 1 (libfec's convention).
+ * Not defined for DPSK (returns 0: the caller falls back to hard decisions). */
+int      lqo_modem_demodulate_soft(const lqo_modem *q, lqo_cf x, uint8_t *soft /* bps */);
 float    lqo_modem_evm(const lqo_modem *q);
 /* the pinned arg() / exp(j t) of the per-symbol loops (see lqo_modem.c) */
 float    lqo_pm_atan2f(float y, float x);
@@ -142,6 +155,10 @@ void     lqo_pm_sincosf(float t, float *sn, float *cs);
 unsigned lqo_qpm_frame_len(unsigned payload_len, int check, int fec0, int fec1, int ms);
 void     lqo_qpm_encode(unsigned payload_len, int check, int fec0, int fec1, int ms,
                         const uint8_t *payload, lqo_cf *frame);
+/* soft-decision variant: the coding stage nearest the channel (fec1, or fec0 when fec1 is "none") is decoded from soft
+ * bits when it is convolutional and the modem has a soft demodulator; everything else as lqo_qpm_decode */
+int      lqo_qpm_decode_soft(unsigned payload_len, int check, int fec0, int fec1, int ms,
+                             const lqo_cf *frame, uint8_t *payload);
 int      lqo_qpm_decode(unsigned payload_len, int check, int fec0, int fec1, int ms,
                         const lqo_cf *frame, uint8_t *payload);
 
@@ -200,6 +217,7 @@ lqo_flexframesync lqo_flexframesync_create(lqo_framesync_callback cb, void *user
 void     lqo_flexframesync_destroy(lqo_flexframesync q);
 void     lqo_flexframesync_reset(lqo_flexframesync q);
 void     lqo_flexframesync_execute(lqo_flexframesync q, const lqo_cf *x, unsigned n);
+void     lqo_flexframesync_set_soft(lqo_flexframesync q, int soft);   /* payloads through lqo_qpm_decode_soft */
 
 /* ---- convenience collectors for ctypes-driven tests / bench ---- */
 typedef struct {
@@ -218,6 +236,10 @@ unsigned lqo_rx_capture(const lqo_cf *x, uint64_t n, unsigned chunk,
                         lqo_frame_record *recs, unsigned max_frames,
                         uint8_t *payload_pool, uint64_t payload_cap,
                         lqo_cf *sym_pool, uint64_t sym_cap);
+unsigned lqo_rx_capture_soft(const lqo_cf *x, uint64_t n, unsigned chunk,
+                             lqo_frame_record *recs, unsigned max_frames,
+                             uint8_t *payload_pool, uint64_t payload_cap,
+                             lqo_cf *sym_pool, uint64_t sym_cap);
 /* multi-threaded: n_streams captures of n samples each (stride in samples); returns total frames
  * and number of valid payloads through *n_valid; nothing stored (used for CPU timing) */
 uint64_t lqo_rx_many(const lqo_cf *x, unsigned n_streams, uint64_t stride, uint64_t n,

@@ -316,7 +316,11 @@ static void conv_encode_(const conv_t *c, unsigned n, const uint8_t *dec, uint8_
 
 /* hard-input Viterbi: bits expanded to 0/255, punctured positions erased to 127; 32-bit
  * metrics, start state 0 biased (others 63), traceback from state 0 */
-static void conv_decode_(const conv_t *c, unsigned n, const uint8_t *enc, uint8_t *dec)
+static void conv_decode_x_(const conv_t *c, unsigned n, const uint8_t *enc, const uint8_t *soft, uint8_t *dec);
+static void conv_decode_(const conv_t *c, unsigned n, const uint8_t *enc, uint8_t *dec) { conv_decode_x_(c, n, enc, NULL, dec); }
+
+/* soft == NULL: hard input (bits of enc expanded to 0 / 255); else one soft byte per kept coded bit */
+static void conv_decode_x_(const conv_t *c, unsigned n, const uint8_t *enc, const uint8_t *soft, uint8_t *dec)
 {
     unsigned ns = 1u << (c->K - 1), half = ns >> 1, T = n * 8 + c->K - 1;
     unsigned words = ns / 32;
@@ -334,7 +338,7 @@ static void conv_decode_(const conv_t *c, unsigned n, const uint8_t *enc, uint8_
     for (unsigned t = 0; t < T; t++) {
         unsigned sym[2];
         for (unsigned r = 0; r < 2; r++) {
-            if (c->pm[r * c->P + p]) { sym[r] = ((enc[ib >> 3] >> (7 - (ib & 7))) & 1u) ? 255u : 0u; ib++; }
+            if (c->pm[r * c->P + p]) { sym[r] = soft ? soft[ib] : (((enc[ib >> 3] >> (7 - (ib & 7))) & 1u) ? 255u : 0u); ib++; }
             else sym[r] = 127u;
         }
         p = (p + 1) % c->P;
@@ -633,6 +637,39 @@ void lqo_fec_decode(int fs, unsigned n, const uint8_t *enc, uint8_t *dec)
         if (conv_lookup_(fs, &c)) conv_decode_(&c, n, enc, dec);
         return;
     }
+}
+
+int lqo_fec_is_conv(int fs)
+{
+    conv_t c;
+    return conv_lookup_(fs, &c) ? 1 : 0;
+}
+
+int lqo_fec_decode_soft(int fs, unsigned n, const uint8_t *soft, uint8_t *dec)
+{
+    conv_t c;
+    if (!conv_lookup_(fs, &c)) return 0;
+    conv_decode_x_(&c, n, NULL, soft, dec);
+    return 1;
+}
+
+void lqo_deinterleave_bit_perm(unsigned n, uint32_t *perm)
+{
+    /* run the byte deinterleaver on the bit planes of the position labels */
+    uint8_t *buf = (uint8_t *)malloc(n + 8);
+    for (unsigned i = 0; i < 8 * n; i++) perm[i] = 0;
+    unsigned planes = 1;
+    while ((1u << planes) < 8 * n) planes++;
+    for (unsigned p = 0; p < planes; p++) {
+        for (unsigned i = 0; i < n; i++) {
+            unsigned v = 0;
+            for (unsigned q = 0; q < 8; q++) if (((8 * i + q) >> p) & 1u) v |= 0x80u >> q;
+            buf[i] = (uint8_t)v;
+        }
+        lqo_deinterleave(buf, n, 4);
+        for (unsigned i = 0; i < 8 * n; i++) if ((buf[i >> 3] >> (7 - (i & 7))) & 1u) perm[i] |= 1u << p;
+    }
+    free(buf);
 }
 
 /* ================================================================== packetizer */

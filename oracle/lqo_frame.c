@@ -416,7 +416,10 @@ struct lqo_flexframesync_s {
     lqo_cf *payload_sym; uint8_t *payload_dec;
     float evm_acc;
     uint64_t n_consumed, frame_start;
+    int soft;                             /* opt-in: payloads through lqo_qpm_decode_soft */
 };
+
+void lqo_flexframesync_set_soft(lqo_flexframesync q, int soft) { q->soft = soft; }
 
 lqo_flexframesync lqo_flexframesync_create(lqo_framesync_callback cb, void *ud)
 {
@@ -542,7 +545,8 @@ static void fs_rx_(lqo_flexframesync q, lqo_cf x)
     q->evm_acc += evm * evm;
     q->symbol_counter++;
     if (q->symbol_counter < q->payload_sym_len) return;
-    int ok = lqo_qpm_decode(q->payload_dec_len, q->check, q->fec0, q->fec1, q->ms, q->payload_sym, q->payload_dec);
+    int ok = q->soft ? lqo_qpm_decode_soft(q->payload_dec_len, q->check, q->fec0, q->fec1, q->ms, q->payload_sym, q->payload_dec)
+                     : lqo_qpm_decode(q->payload_dec_len, q->check, q->fec0, q->fec1, q->ms, q->payload_sym, q->payload_dec);
     lqo_framesyncstats st;
     fs_stats_(q, &st);
     st.evm = 10.0f * log10f(q->evm_acc / (float)q->payload_sym_len);
@@ -617,12 +621,25 @@ static int collect_cb_(const uint8_t *header, int hv, const uint8_t *payload, un
     return 0;
 }
 
+static unsigned rx_capture_(const lqo_cf *x, uint64_t n, unsigned chunk, lqo_frame_record *recs, unsigned max_frames,
+                            uint8_t *ppool, uint64_t pcap, lqo_cf *spool, uint64_t scap, int soft);
 unsigned lqo_rx_capture(const lqo_cf *x, uint64_t n, unsigned chunk, lqo_frame_record *recs, unsigned max_frames,
                         uint8_t *ppool, uint64_t pcap, lqo_cf *spool, uint64_t scap)
+{
+    return rx_capture_(x, n, chunk, recs, max_frames, ppool, pcap, spool, scap, 0);
+}
+unsigned lqo_rx_capture_soft(const lqo_cf *x, uint64_t n, unsigned chunk, lqo_frame_record *recs, unsigned max_frames,
+                             uint8_t *ppool, uint64_t pcap, lqo_cf *spool, uint64_t scap)
+{
+    return rx_capture_(x, n, chunk, recs, max_frames, ppool, pcap, spool, scap, 1);
+}
+static unsigned rx_capture_(const lqo_cf *x, uint64_t n, unsigned chunk, lqo_frame_record *recs, unsigned max_frames,
+                            uint8_t *ppool, uint64_t pcap, lqo_cf *spool, uint64_t scap, int soft)
 {
     collect_t c; memset(&c, 0, sizeof c);
     c.recs = recs; c.max_frames = max_frames; c.ppool = ppool; c.pcap = pcap; c.spool = spool; c.scap = scap;
     lqo_flexframesync fs = lqo_flexframesync_create(collect_cb_, &c);
+    lqo_flexframesync_set_soft(fs, soft);
     if (!chunk) chunk = 256;
     for (uint64_t i = 0; i < n; i += chunk) {
         unsigned m = (n - i < chunk) ? (unsigned)(n - i) : chunk;

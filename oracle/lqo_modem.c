@@ -202,6 +202,36 @@ unsigned lqo_modem_demodulate(lqo_modem *q, lqo_cf x)
     return sym;
 }
 
+int lqo_modem_demodulate_soft(const lqo_modem *q, lqo_cf x, uint8_t *soft)
+{
+    if (is_dpsk_(q->scheme) || !q->bps) return 0;
+    const unsigned M = 1u << q->bps;
+    /* G = 64 / dmin^2 (every operation a single IEEE operation, in this order: the CUDA kernel repeats it) */
+    float dmin2 = 3.0e38f;
+    for (unsigned a = 0; a < M; a++)
+        for (unsigned b = a + 1; b < M; b++) {
+            float dr = q->map[a].re - q->map[b].re, di = q->map[a].im - q->map[b].im;
+            float d = fmaf(di, di, dr * dr);
+            if (d < dmin2) dmin2 = d;
+        }
+    const float G = 64.0f / dmin2;
+    float d0[8], d1[8];
+    for (unsigned k = 0; k < q->bps; k++) { d0[k] = 3.0e38f; d1[k] = 3.0e38f; }
+    for (unsigned s = 0; s < M; s++) {
+        float dr = x.re - q->map[s].re, di = x.im - q->map[s].im;
+        float d = fmaf(di, di, dr * dr);
+        for (unsigned k = 0; k < q->bps; k++) {
+            if ((s >> (q->bps - 1 - k)) & 1u) { if (d < d1[k]) d1[k] = d; }
+            else { if (d < d0[k]) d0[k] = d; }
+        }
+    }
+    for (unsigned k = 0; k < q->bps; k++) {
+        float t = fmaf(G, d0[k] - d1[k], 128.0f);
+        soft[k] = (uint8_t)(t <= 0.0f ? 0 : t >= 255.0f ? 255 : (int)t);
+    }
+    return 1;
+}
+
 float lqo_modem_phase_error(const lqo_modem *q)
 {   /* imag( r * conj(x_hat) ) */
     return fmaf(q->r.im, q->x_hat.re, -(q->r.re * q->x_hat.im));
@@ -241,6 +271,43 @@ void lqo_qpm_encode(unsigned n, int check, int fec0, int fec1, int ms, const uin
         frame[i] = lqo_modem_modulate(&mod, s);
     }
     free(enc);
+}
+
+int lqo_qpm_decode_soft(unsigned n, int check, int fec0, int fec1, int ms, const lqo_cf *frame, uint8_t *payload)
+{
+    /* the stage nearest the channel */
+    const int stage1 = (fec1 != LQ_FEC_NONE);
+    const int fs = stage1 ? fec1 : fec0;
+    lqo_modem mod;
+    lqo_modem_init(&mod, ms);
+    uint8_t probe[8];
+    lqo_cf zero = { 0.0f, 0.0f };
+    if (!lqo_fec_is_conv(fs) || !lqo_modem_demodulate_soft(&mod, zero, probe))
+        return lqo_qpm_decode(n, check, fec0, fec1, ms, frame, payload);
+    const unsigned cl = lqo_crc_len(check), k0 = n + cl;
+    const unsigned n0 = lqo_fec_enc_len(fec0, k0), n1 = lqo_fec_enc_len(fec1, n0);
+    const unsigned nsym = lqo_qpm_frame_len(n, check, fec0, fec1, ms);
+    const unsigned bps = mod.bps, nbits = 8 * n1;             /* (n1 == n0 when fec1 is "none") */
+    uint8_t *raw = (uint8_t *)calloc((size_t)nsym * bps + 8, 1), *soft = (uint8_t *)calloc(nbits + 8, 1);
+    for (unsigned i = 0; i < nsym; i++) lqo_modem_demodulate_soft(&mod, frame[i], raw + (size_t)i * bps);
+    uint32_t *perm = (uint32_t *)malloc(sizeof(uint32_t) * nbits);
+    lqo_deinterleave_bit_perm(n1, perm);
+    for (unsigned i = 0; i < nbits; i++) soft[i] = raw[perm[i]];
+    const unsigned dec_len = stage1 ? n0 : k0;
+    uint8_t *b0 = (uint8_t *)calloc(dec_len + k0 + 8, 1), *b1 = (uint8_t *)calloc(dec_len + k0 + 8, 1);
+    lqo_fec_decode_soft(fs, dec_len, soft, b0);
+    if (stage1) {                                             /* then fec0, hard */
+        lqo_deinterleave(b0, n0, fec0 == LQ_FEC_NONE ? 0 : 4);
+        lqo_fec_decode(fec0, k0, b0, b1);
+        memcpy(b0, b1, k0);
+    }
+    lqo_scramble(b0, k0);
+    unsigned key = 0;
+    for (unsigned i = 0; i < cl; i++) key = (key << 8) | b0[n + i];
+    memcpy(payload, b0, n);
+    int ok = (lqo_crc_key(check, b0, n) == key);
+    free(raw); free(soft); free(perm); free(b0); free(b1);
+    return ok;
 }
 
 int lqo_qpm_decode(unsigned n, int check, int fec0, int fec1, int ms, const lqo_cf *frame, uint8_t *payload)

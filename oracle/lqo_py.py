@@ -75,6 +75,8 @@ def lib():
         L.lqo_tx_frame.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, C.c_uint, vp, C.c_uint]
         L.lqo_rx_capture.restype = C.c_uint
         L.lqo_rx_capture.argtypes = [vp, C.c_uint64, C.c_uint, vp, C.c_uint, vp, C.c_uint64, vp, C.c_uint64]
+        L.lqo_rx_capture_soft.restype = C.c_uint
+        L.lqo_rx_capture_soft.argtypes = L.lqo_rx_capture.argtypes
         L.lqo_rx_many.restype = C.c_uint64
         L.lqo_rx_many.argtypes = [vp, C.c_uint, C.c_uint64, C.c_uint64, C.c_uint, C.POINTER(C.c_uint64)]
         L.lqo_detect_capture.restype = C.c_uint
@@ -106,8 +108,9 @@ def tx_frame(ms, check, fec0, fec1, payload, header=None):
     return out
 
 
-def rx_capture(x, chunk=256, max_frames=4096):
-    """Run one flexframesync over capture x; returns list of dict frames."""
+def rx_capture(x, chunk=256, max_frames=4096, soft=False):
+    """Run one flexframesync over capture x; returns list of dict frames.  soft=True: soft-decision payloads (opt-in
+    extension: soft demodulation + soft-input Viterbi where the stage nearest the channel is convolutional)."""
     L = lib()
     x = np.ascontiguousarray(x, dtype=np.complex64)
     recs = (FrameRecord * max_frames)()
@@ -115,7 +118,8 @@ def rx_capture(x, chunk=256, max_frames=4096):
     scap = max(1 << 16, len(x))
     ppool = np.zeros(pcap, np.uint8)
     spool = np.zeros(scap, np.complex64)
-    n = L.lqo_rx_capture(_ptr(x), len(x), chunk, C.byref(recs), max_frames, _ptr(ppool), pcap, _ptr(spool), scap)
+    fn = L.lqo_rx_capture_soft if soft else L.lqo_rx_capture
+    n = fn(_ptr(x), len(x), chunk, C.byref(recs), max_frames, _ptr(ppool), pcap, _ptr(spool), scap)
     out = []
     for i in range(min(n, max_frames)):
         r = recs[i]

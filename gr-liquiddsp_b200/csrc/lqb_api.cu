@@ -232,6 +232,7 @@ struct Front {
         StreamState z;
         std::memset(&z, 0, sizeof z);
         z.wstart = -256;           // first window = 256 zeros + first 256 samples (qdetector reset state)
+        z.stop_at = kNoStop; z.mark_at = kNoStop; z.mark_w = kNoMark;
         if (s < 0) {
             for (unsigned i = 0; i < n_streams; ++i) h_states[i] = z;
             CU(cudaMemcpyAsync(d_states, h_states, (size_t)n_streams * sizeof(StreamState), cudaMemcpyHostToDevice, stream));
@@ -1156,6 +1157,11 @@ struct lqb_det_s {
     uint64_t search[4] = {};              // windows, alignments, exact window evaluations, CFO bins those visited
     cudaEvent_t ev[2] = {};
     float ms = 0.0f;
+    // time-sharded search of one capture (lqb_det_execute_sharded)
+    DevBuf<float2> d_capture;             // host captures are staged here
+    std::vector<Detection> merged;        // the sequential detector's list, in order
+    bool use_merged = false;
+    uint64_t shard[4] = {};               // segments, segment runs in all, rounds, launches
 };
 
 extern "C" {
@@ -1177,7 +1183,7 @@ void lqb_det_destroy(lqb_det h)
     if (!h) return;
     cudaSetDevice(h->f.device);
     if (h->f.stream) cudaStreamSynchronize(h->f.stream);
-    h->d_det.release(); h->h_det.release();
+    h->d_det.release(); h->h_det.release(); h->d_capture.release();
     for (auto &ev : h->ev) if (ev) cudaEventDestroy(ev);
     h->f.destroy();
     delete h;
@@ -1190,7 +1196,7 @@ int lqb_det_execute(lqb_det h, uint32_t n, const uint32_t *ids, const float *con
     Front &f = h->f;
     CU(cudaSetDevice(f.device));
     cudaStream_t st = f.stream;
-    h->n_det = 0; h->order.clear();
+    h->n_det = 0; h->order.clear(); h->use_merged = false;
     uint64_t total = 0, max_n = 0;
     if (int e = f.feed(n, ids, iq, ns, mem, &total, &max_n)) return e;
     if (!n) return 0;
@@ -1240,12 +1246,180 @@ int lqb_det_execute_dense(lqb_det h, const float *iq, uint64_t stride, uint64_t 
     return lqb_det_execute(h, n, nullptr, ptr.data(), len.data(), mem);
 }
 
+// One capture, searched as the sequential detector would search it from its reset state, but cut in TIME into segments
+// that run side by side as streams of this handle (the reference's qdetector is strictly serial: its hop grid re-phases
+// at every detection, lib/frame_detector_cc_impl.cc:77).  Exactness does not rest on the cut:
+//   * a segment k >= 1 is first run SPECULATIVELY from `preroll` samples before its boundary b_k = k seg_len, on the
+//     grid that is right when nothing was detected so far; any two walks that detect the same frame are in the same
+//     state from there on, so after a pre-roll that holds a frame the walk usually IS the sequential one;
+//   * every run records the first window start >= b_k it reaches (its ENTRY) and the first one >= b_(k+1) (its EXIT,
+//     where it stops).  Segment 0 starts from the true reset state.  A run is accepted only if its entry equals the
+//     accepted exit of the segment before it; otherwise the segment is run again from exactly that state.  The walk is a
+//     function of its state and of the samples at or after it, so every accepted run is a piece of the sequential walk.
+// Results (lqb_det_poll): stream 0, seq = order of detection, sample_index absolute -- the list qdetector_cccf returns
+// for the whole capture (windows that need samples beyond its end are not evaluated, as in a stream that has not ended).
+// The handle's stream states are consumed: reset before going back to lqb_det_execute.
+int lqb_det_execute_sharded(lqb_det h, const float *iq, uint64_t n_samples, int mem, uint32_t seg_len, uint32_t preroll)
+{
+    if (!h) return fail(LQB_EINVAL, "null handle");
+    if (mem != LQB_MEM_HOST && mem != LQB_MEM_DEVICE) return fail(LQB_EINVAL, "complex64 input only");
+    if (!iq && n_samples) return fail(LQB_EINVAL, "null sample pointer");
+    Front &f = h->f;
+    CU(cudaSetDevice(f.device));
+    cudaStream_t st = f.stream;
+    if (!seg_len) seg_len = 1u << 18;
+    seg_len = std::max(2048u, (seg_len + 255u) & ~255u);
+    preroll = std::min((preroll + 255u) & ~255u, seg_len);
+    h->n_det = 0; h->order.clear(); h->merged.clear(); h->use_merged = true;
+    std::memset(h->shard, 0, sizeof h->shard);
+    h->windows = 0; std::memset(h->search, 0, sizeof h->search);
+    if (n_samples < 512) return 0;
+    const float2 *x = reinterpret_cast<const float2 *>(iq);
+    CU(cudaEventRecord(h->ev[0], st));
+    if (mem == LQB_MEM_HOST) {
+        if (int e = h->d_capture.reserve(n_samples + 2)) return e;
+        CU(cudaMemcpyAsync(h->d_capture.p, iq, n_samples * sizeof(float2), cudaMemcpyHostToDevice, st));
+        x = h->d_capture.p;
+    }
+    const long long N = (long long)n_samples, L = seg_len;
+    const unsigned K = (unsigned)((N + L - 1) / L);
+    struct Seg {
+        long long start = 0;        // window start the current / next run begins at
+        long long entry = 0, exit = 0;
+        bool ran = false, fin = false, todo = true;
+        std::vector<Detection> det;
+    };
+    std::vector<Seg> seg(K);
+    for (unsigned k = 0; k < K; ++k) seg[k].start = k ? std::max<long long>(0, (long long)k * L - (long long)preroll) : -256;
+    h->shard[0] = K;
+    const unsigned W = f.n_streams;
+    std::vector<unsigned> batch;
+    std::vector<const float *> ptr;
+    std::vector<uint64_t> len;
+    while (true) {
+        // ---- run every segment that needs it, W at a time
+        std::vector<unsigned> todo;
+        for (unsigned k = 0; k < K; ++k) if (seg[k].todo) todo.push_back(k);
+        if (todo.empty()) break;
+        h->shard[2]++;
+        for (size_t t0 = 0; t0 < todo.size(); t0 += W) {
+            const unsigned nb = (unsigned)std::min<size_t>(W, todo.size() - t0);
+            ptr.resize(nb); len.resize(nb);
+            size_t max_det = 0;
+            for (unsigned i = 0; i < nb; ++i) {
+                const unsigned k = todo[t0 + i];
+                Seg &sg = seg[k];
+                // samples from 256 before the first window (what the sequential walk has behind it there) up to what a
+                // frame found by the segment's last window needs: start + 355 + 512 < b_(k+1) + 1024
+                const long long base = std::max<long long>(0, sg.start - 256);
+                const long long end = std::min<long long>(N, (long long)(k + 1) * L + 1024);
+                StreamState z;
+                std::memset(&z, 0, sizeof z);
+                z.base = base; z.G = base; z.wstart = sg.start;
+                z.stop_at = (k + 1 < K) ? (long long)(k + 1) * L : kNoStop;
+                z.mark_at = k ? (long long)k * L : -256;
+                z.mark_w = kNoMark;
+                f.h_states[i] = z;
+                ptr[i] = reinterpret_cast<const float *>(x + base);
+                len[i] = (uint64_t)std::max<long long>(0, end - base);
+                max_det += (size_t)(len[i] / 256 + 4);
+            }
+            CU(cudaMemcpyAsync(f.d_states, f.h_states, nb * sizeof(StreamState), cudaMemcpyHostToDevice, st));
+            uint64_t total = 0, max_n = 0;
+            const bool lpt = f.lpt;
+            f.lpt = false;                                   // (segments cost about the same; keep the list in order)
+            const int fe = f.feed(nb, nullptr, ptr.data(), len.data(), LQB_MEM_DEVICE, &total, &max_n);
+            f.lpt = lpt;
+            if (fe) return fe;
+            if (int e = h->d_det.reserve(max_det)) return e;
+            if (int e = h->h_det.reserve(max_det)) return e;
+            SeekParams sp;
+            sp.tables = f.d_tables; sp.states = f.d_states; sp.io = f.io[0].d_io.p;
+            sp.carry[0] = f.d_carry[0]; sp.carry[1] = f.d_carry[1]; sp.carry_cap = f.carry_cap;
+            sp.det_mode = 1; sp.frames = nullptr; sp.detections = h->d_det.p; sp.views = nullptr;
+            sp.n_out = f.io[0].d_count; sp.max_out = (unsigned)max_det;
+            f.set_coarse(sp);
+            CU(cudaMemsetAsync(f.io[0].d_count, 0, 8 * sizeof(unsigned), st));
+            launch_seek(sp, nb, st); f.launches++; h->shard[3]++;
+            CU(cudaMemcpyAsync(f.io[0].h_count, f.io[0].d_count, 8 * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(f.h_states, f.d_states, nb * sizeof(StreamState), cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            const unsigned nd = std::min<unsigned>(f.io[0].h_count[0], (unsigned)max_det);
+            if (nd) {
+                CU(cudaMemcpyAsync(h->h_det.p, h->d_det.p, nd * sizeof(Detection), cudaMemcpyDeviceToHost, st));
+                CU(cudaStreamSynchronize(st));
+            }
+            CU(cudaGetLastError());
+            h->windows += f.io[0].h_count[1];
+            h->search[0] += f.io[0].h_count[1]; h->search[1] += f.io[0].h_count[2]; h->search[2] += f.io[0].h_count[3]; h->search[3] += f.io[0].h_count[5];
+            for (unsigned i = 0; i < nb; ++i) {
+                Seg &sg = seg[todo[t0 + i]];
+                const StreamState &z = f.h_states[i];
+                sg.ran = true; sg.todo = false; sg.det.clear();
+                // a walk that ends with a frame start it cannot align yet (the capture ends there) has no further state
+                sg.exit = (z.mode == 0) ? z.wstart : kNoStop;
+                sg.entry = (z.mark_w == kNoMark) ? kNoStop : z.mark_w;        // (never reached its own boundary: the capture ended)
+                h->shard[1]++;
+            }
+            for (unsigned j = 0; j < nd; ++j) {
+                const Detection &d = h->h_det.p[j];
+                if (d.stream < nb) seg[todo[t0 + d.stream]].det.push_back(d);
+            }
+        }
+        // ---- accept runs whose entry is the accepted exit before them; schedule the others from that exit
+        bool chain = true;                                   // everything before k is accepted
+        for (unsigned k = 0; k < K; ++k) {
+            Seg &sg = seg[k];
+            if (k == 0) { sg.fin = true; continue; }
+            const long long want = seg[k - 1].exit;          // accepted (chain) or merely the best knowledge so far
+            if (want == kNoStop || want < (long long)k * L) {
+                // the walk before never reaches this segment (it ran out of samples, or waits for the rest of a frame,
+                // at the end of the capture): nothing of k belongs to the result
+                if (chain) { sg.fin = true; sg.todo = false; sg.det.clear(); sg.exit = kNoStop; }
+                else chain = false;
+                continue;
+            }
+            if (sg.ran && sg.entry == want) { if (chain) sg.fin = true; }
+            else {
+                // the run has to start exactly in that state (a window start at or beyond the boundary)
+                if (!sg.fin) { sg.start = want; sg.todo = true; }
+                chain = false;
+            }
+            if (!sg.fin) chain = false;
+        }
+    }
+    // ---- the sequential list: each accepted run's detections from windows at or beyond its entry, in walk order
+    for (unsigned k = 0; k < K; ++k) {
+        Seg &sg = seg[k];
+        std::sort(sg.det.begin(), sg.det.end(), [](const Detection &a, const Detection &b) { return a.seq < b.seq; });
+        const long long lo = k ? (long long)k * L : -256;
+        for (const Detection &d : sg.det) {
+            if (d.F - (long long)d.pad < lo) continue;       // found during the pre-roll: the segment before owns it
+            Detection o = d;
+            o.stream = 0; o.seq = (unsigned)h->merged.size(); o.pad = 0;
+            h->merged.push_back(o);
+        }
+    }
+    CU(cudaEventRecord(h->ev[1], st));
+    CU(cudaEventSynchronize(h->ev[1]));
+    cudaEventElapsedTime(&h->ms, h->ev[0], h->ev[1]);
+    h->n_det = (unsigned)h->merged.size();
+    return 0;
+}
+
+int lqb_det_last_shard_info(lqb_det h, uint64_t out[4])
+{
+    if (!h || !out) return fail(LQB_EINVAL, "null handle");
+    std::memcpy(out, h->shard, sizeof h->shard);
+    return 0;
+}
+
 int lqb_det_poll(lqb_det h, lqb_detection *out, uint32_t max_out, uint32_t *n_out)
 {
     if (!h) return fail(LQB_EINVAL, "null handle");
     unsigned n = std::min<unsigned>(h->n_det, max_out);
     for (unsigned k = 0; k < n && out; ++k) {
-        const Detection &d = h->h_det.p[h->order[k]];
+        const Detection &d = h->use_merged ? h->merged[k] : h->h_det.p[h->order[k]];
         out[k].stream = d.stream; out[k].seq = d.seq; out[k].sample_index = d.F;
         out[k].tau_hat = d.tau; out[k].gamma_hat = d.gamma; out[k].dphi_hat = d.dphi; out[k].phi_hat = d.phi; out[k].rxy = d.rxy;
     }

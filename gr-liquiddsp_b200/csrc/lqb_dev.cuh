@@ -51,8 +51,13 @@ struct StreamState {
     unsigned  seq;             // frames emitted since reset
     unsigned  dropped;
     unsigned  carry_sel;       // which of the two carry buffers is current
-    unsigned  pad;
+    unsigned  det_idx;         // PENDING: offset of the frame start in the window that triggered (F = window start + det_idx)
+    // time-sharded search (one capture cut into segments that run as streams of their own, lqb_det_execute_sharded):
+    long long stop_at;         // windows starting at or beyond this index are left alone (kNoStop: none)
+    long long mark_at;         // mark_w <- the first window start >= mark_at this stream's walk reaches (kNoMark: unset)
+    long long mark_w;
 };
+constexpr long long kNoStop = 0x3fffffffffffffffll, kNoMark = -0x3fffffffffffffffll;
 
 struct StreamIO {              // one entry per stream fed by this execute call
     const float2      *in;

@@ -6,6 +6,10 @@
 #include <cuda_fp8.h>
 #include <stdint.h>
 
+#ifndef LQB_MBAR_HINT_NS
+#define LQB_MBAR_HINT_NS 0
+#endif
+
 namespace lqb {
 namespace tc {
 
@@ -56,10 +60,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, uint32
     uint32_t done = 0, polls = 0;
     const uint32_t addr = smem_u32(bar);
     while (true) {
+#if LQB_MBAR_HINT_NS
+        // suspend-time hint: the thread sleeps in hardware until the phase completes or the hint elapses, instead of
+        // returning after the (short) default limit and taking issue slots from the warps it is waiting for
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+                     "selp.b32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(done) : "r"(addr), "r"(parity), "r"((uint32_t)LQB_MBAR_HINT_NS) : "memory");
+#else
         asm volatile("{\n\t.reg .pred p;\n\t"
                      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
                      "selp.b32 %0, 1, 0, p;\n\t}\n"
                      : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+#endif
         if (done) break;
         // back off: a polling warp takes issue slots from the warps it is waiting for (ncu: a third of all executed
         // instructions were this loop before the sleep)

@@ -258,6 +258,16 @@ int     lqb_det_reset(lqb_det h, int stream);
 int     lqb_det_execute(lqb_det h, uint32_t n, const uint32_t *stream_ids,
                         const float *const *iq, const uint64_t *n_samples, int mem);
 int     lqb_det_execute_dense(lqb_det h, const float *iq, uint64_t stride_samples, uint64_t n_samples, int mem);
+/* ONE capture searched as the sequential detector would search it from its reset state (the list qdetector_cccf returns
+ * for the whole capture; reference call site lib/frame_detector_cc_impl.cc:77), but cut in time into segments of seg_len
+ * samples that run side by side as the streams of this handle (n_streams at a time).  A segment is first searched
+ * speculatively from `preroll` samples before its boundary; a run is accepted only if it entered its segment in exactly
+ * the state the accepted run before it left in, otherwise the segment is searched again from that state -- so the
+ * result does not depend on seg_len / preroll, only the time does (preroll should span a frame period).  mem:
+ * LQB_MEM_HOST or LQB_MEM_DEVICE (complex64).  Results: lqb_det_poll (stream 0, seq = order).  Consumes the handle's
+ * stream states: lqb_det_reset before going back to lqb_det_execute.  0 for seg_len: 262144. */
+int     lqb_det_execute_sharded(lqb_det h, const float *iq, uint64_t n_samples, int mem, uint32_t seg_len, uint32_t preroll);
+int     lqb_det_last_shard_info(lqb_det h, uint64_t out[4]);   /* segments, segment runs in all, rounds, launches */
 int     lqb_det_poll(lqb_det h, lqb_detection *out, uint32_t max_out, uint32_t *n_out);
 int     lqb_det_last_timing(lqb_det h, float *ms);
 int     lqb_det_last_work(lqb_det h, uint64_t *windows);   /* detector windows evaluated by the last execute */

@@ -359,6 +359,25 @@ def detector_arm(args, rank, local, world, steps=None, warmup=None, emit=True):
     nd = len(found)
     ms = e0.elapsed_time(e1)
     clk = clocks.stop()
+    # ---- the same samples as ONE capture (row after row), searched by the time-sharded detector: the sequential
+    # qdetector's list, whatever the cut (lqb_det_execute_sharded); checked below against the oracle on a prefix
+    one = None
+    if not os.environ.get("LQB_BENCH_NO_ONE_CAPTURE"):
+        seg_len = int(os.environ.get("LQB_BENCH_SEG_LEN", 1 << 18))
+        preroll = int(os.environ.get("LQB_BENCH_PREROLL", 1 << 14))
+        n_seg = (S * L + seg_len - 1) // seg_len
+        det1 = capi.Det(min(n_seg, 4096), device=local, cuda_stream=cs.cuda_stream)
+        det1.execute_sharded_ptr(cap.data_ptr(), S * L, capi.MEM_DEVICE, seg_len, preroll)      # warm-up (buffers)
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        det1.execute_sharded_ptr(cap.data_ptr(), S * L, capi.MEM_DEVICE, seg_len, preroll)
+        torch.cuda.synchronize(dev)
+        one_s = time.perf_counter() - t0
+        one_found = det1.poll()
+        one = {"samples": S * L, "seg_len": seg_len, "preroll": preroll, "ms": one_s * 1e3, "msps": S * L / one_s / 1e6,
+               "gpu_ms": det1.timing(), "detections": len(one_found), "windows": det1.windows()}
+        one.update(det1.shard_info())
+        det1.close()
     tt = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -367,6 +386,9 @@ def detector_arm(args, rank, local, world, steps=None, warmup=None, emit=True):
     if rank == 0 and not args.no_cpu_baseline:
         sub = list(range(0, S, max(1, S // 16)))[:16]
         cap_sub = {sidx: cap[sidx].cpu().numpy() for sidx in sub}
+        if one is not None:
+            n_pref = min(S * L, 3 << 20)
+            cap_prefix = cap.reshape(-1)[:n_pref].cpu().numpy()
     del cap
     torch.cuda.empty_cache()
     if rank != 0:
@@ -407,6 +429,13 @@ def detector_arm(args, rank, local, world, steps=None, warmup=None, emit=True):
             same += int(ref == mine)
         cpu_s = time.perf_counter() - t0
         agree = {"segments": cnt, "identical_detection_lists": same, "cpu_msps_1_thread": len(sub) * L / cpu_s / 1e6}
+        if one is not None:
+            # the sequential oracle over the first samples of the one-capture run: same list up to where its input ends
+            ref = [int(np.int64(np.uint64(r["sample_index"]))) for r in o.detect_capture(cap_prefix, 0.3, 0.45)]
+            lim = len(cap_prefix) - 2048
+            mine = [d["sample_index"] for d in one_found if d["sample_index"] < lim]
+            ref = [r for r in ref if r < lim]
+            one["oracle_prefix"] = {"samples": len(cap_prefix), "detections": len(ref), "identical": bool(ref == mine)}
     peaks = load_peaks()
     tc_peak = 2.0 * float(peaks.get("bf16_tflops_sustained", 1400.0))   # fp8 operands: twice the measured bf16 rate (see the flex_rx arm)
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
@@ -427,6 +456,7 @@ def detector_arm(args, rank, local, world, steps=None, warmup=None, emit=True):
                      "hbm_gbs": 8.0 * S * L * steps / t_k / 1e9 if t_k else None,
                      "hbm_frac": 8.0 * S * L * steps / t_k / 1e9 / hbm_peak if t_k else None},
         "oracle_agreement": agree,
+        "one_capture_time_sharded": one,
     }
     if emit:
         print(json.dumps(out))

@@ -817,6 +817,37 @@ struct lqb_rx_s {
     std::vector<unsigned> lane_of, local_of;
     std::vector<std::vector<unsigned>> global_of;
     unsigned global_stream(unsigned lane, unsigned local) const { return global_of[lane][local]; }
+    // time-sharded decoding of one capture (lqb_rx_execute_sharded): the accepted frames, owned by the handle
+    struct OwnedFrame {
+        lqb_frame_result r;
+        long long trig_w;                 // start of the window that triggered
+        std::vector<unsigned char> payload;
+        std::vector<float> syms;
+    };
+    std::vector<OwnedFrame> merged;
+    bool use_merged = false;
+    uint64_t merged_valid = 0;
+    uint64_t shard[4] = {};               // segments, segment runs in all, rounds, execute calls
+    DevBuf<float2> d_capture;
+    // stream states of the listed streams <- z[i] (host staging of each lane, then one copy per lane)
+    int put_states(unsigned n, const StreamState *z)
+    {
+        for (unsigned i = 0; i < n; ++i) lanes[lane_of[i]]->f.h_states[local_of[i]] = z[i];
+        for (auto *l : lanes) {
+            CU(cudaMemcpyAsync(l->f.d_states, l->f.h_states, (size_t)l->f.n_streams * sizeof(StreamState), cudaMemcpyHostToDevice, l->f.stream));
+            CU(cudaStreamSynchronize(l->f.stream));
+        }
+        return 0;
+    }
+    int get_states()
+    {
+        for (auto *l : lanes) {
+            CU(cudaStreamSynchronize(l->f.stream));
+            CU(cudaMemcpyAsync(l->f.h_states, l->f.d_states, (size_t)l->f.n_streams * sizeof(StreamState), cudaMemcpyDeviceToHost, l->f.stream));
+            CU(cudaStreamSynchronize(l->f.stream));
+        }
+        return 0;
+    }
     void sync_all()
     {
         for (auto *l : lanes) {
@@ -854,6 +885,7 @@ void lqb_rx_destroy(lqb_rx h)
     cudaSetDevice(h->device);
     h->sync_all();
     for (auto *l : h->lanes) { l->destroy(); delete l; }
+    h->d_capture.release();
     if (h->ev_in) cudaEventDestroy(h->ev_in);
     for (auto &e : h->ev_out) if (e) cudaEventDestroy(e);
     delete h;
@@ -1011,6 +1043,7 @@ int lqb_rx_submit(lqb_rx h, uint32_t n, const uint32_t *ids, const float *const 
     if (!h) return fail(LQB_EINVAL, "null handle");
     if (h->pending >= 2) return fail(LQB_EBUSY, "two submitted calls are waiting for lqb_rx_collect");
     CU(cudaSetDevice(h->device));
+    h->use_merged = false;
     if (n > h->n_streams) return fail(LQB_EINVAL, "more entries than streams");
     for (auto *l : h->lanes) { l->ids.clear(); l->iq.clear(); l->ns.clear(); }
     for (uint32_t i = 0; i < n; ++i) {
@@ -1080,9 +1113,184 @@ int lqb_rx_submit_dense(lqb_rx h, const float *iq, uint64_t stride, uint64_t ns,
     return lqb_rx_submit(h, n, nullptr, ptr.data(), len.data(), mem);
 }
 
+// One capture, decoded as ONE flexframesync would decode it from its reset state (reference call site
+// lib/flex_rx_impl.cc:213), but cut in TIME into segments that run side by side as the streams of this handle.  The seam
+// rule is the detector's (lqb_det_execute_sharded): a segment is first run speculatively from `preroll` samples before
+// its boundary; the state of the walk is (next window start, zero boundary G); a run is accepted only if the first
+// state at or beyond its boundary equals the state the accepted run before it stopped in, else the segment is run again
+// from exactly that state.  A frame belongs to the segment in which the window that triggered it starts; a run is fed
+// max_frame_samples beyond its segment so that such a frame is decoded in full.  Every accepted run is a piece of the
+// sequential walk, so the frames (bytes, flags, estimates) are the sequential receiver's whatever the cut.
+// Results: lqb_rx_poll / lqb_rx_counts (stream 0, seq = order; payload / framesyms owned by the handle until the next
+// call).  Consumes the stream states: lqb_rx_reset before going back to lqb_rx_execute.
+int lqb_rx_execute_sharded(lqb_rx h, const float *iq, uint64_t n_samples, int mem, uint32_t seg_len, uint32_t preroll)
+{
+    if (!h) return fail(LQB_EINVAL, "null handle");
+    if (mem != LQB_MEM_HOST && mem != LQB_MEM_DEVICE) return fail(LQB_EINVAL, "complex64 input only");
+    if (h->flags & LQB_RX_DEVICE_RESULTS) return fail(LQB_EINVAL, "the sharded call returns host results");
+    if (!iq && n_samples) return fail(LQB_EINVAL, "null sample pointer");
+    while (h->pending) if (int e = lqb_rx_collect(h)) return e;
+    CU(cudaSetDevice(h->device));
+    const unsigned cap = h->lanes[0]->f.carry_cap;
+    if (!seg_len) seg_len = 1u << 20;
+    seg_len = std::max(4096u, (seg_len + 255u) & ~255u);
+    preroll = std::min((preroll + 255u) & ~255u, seg_len);
+    h->merged.clear(); h->merged_valid = 0;
+    std::memset(h->shard, 0, sizeof h->shard);
+    if (n_samples < 512) { h->use_merged = true; return 0; }
+    const float2 *x = reinterpret_cast<const float2 *>(iq);
+    if (mem == LQB_MEM_HOST) {
+        if (int e = h->d_capture.reserve(n_samples + 2)) return e;
+        CU(cudaMemcpy(h->d_capture.p, iq, n_samples * sizeof(float2), cudaMemcpyHostToDevice));
+        x = h->d_capture.p;
+    } else if (h->user_stream) CU(cudaStreamSynchronize(h->user_stream));      // the capture is complete before any lane reads it
+    const long long N = (long long)n_samples, L = seg_len;
+    const unsigned K = (unsigned)((N + L - 1) / L);
+    struct Seg {
+        long long start_w = 0, start_G = 0;     // state the current / next run begins in
+        long long entry_w = 0, entry_G = 0, exit_w = 0, exit_G = 0;
+        bool ran = false, fin = false, todo = true;
+        std::vector<lqb_rx_s::OwnedFrame> fr;
+    };
+    // G only matters while it lies above the window start
+    auto norm_G = [](long long w, long long G) { return G > w ? G : w; };
+    std::vector<Seg> seg(K);
+    for (unsigned k = 0; k < K; ++k) {
+        seg[k].start_w = k ? std::max<long long>(0, (long long)k * L - (long long)preroll) : -256;
+        seg[k].start_G = k ? seg[k].start_w : 0;
+    }
+    h->shard[0] = K;
+    const unsigned W = h->n_streams;
+    std::vector<StreamState> zs;
+    std::vector<const float *> ptr;
+    std::vector<uint64_t> len;
+    std::vector<uint32_t> ids;
+    while (true) {
+        std::vector<unsigned> todo;
+        for (unsigned k = 0; k < K; ++k) if (seg[k].todo) todo.push_back(k);
+        if (todo.empty()) break;
+        h->shard[2]++;
+        for (size_t t0 = 0; t0 < todo.size(); t0 += W) {
+            const unsigned nb = (unsigned)std::min<size_t>(W, todo.size() - t0);
+            zs.assign(nb, StreamState{}); ptr.resize(nb); len.resize(nb); ids.resize(nb);
+            for (unsigned i = 0; i < nb; ++i) {
+                const unsigned k = todo[t0 + i];
+                Seg &sg = seg[k];
+                const long long base = std::max<long long>(0, std::min(sg.start_w, sg.start_G) - 256);
+                const long long end = std::min<long long>(N, (long long)(k + 1) * L + (long long)cap + 1024);
+                StreamState &z = zs[i];
+                std::memset(&z, 0, sizeof z);
+                z.base = base; z.G = std::max(sg.start_G > sg.start_w ? sg.start_G : base, k ? base : 0ll); z.wstart = sg.start_w;
+                if (!k && sg.start_w == -256) { z.base = 0; z.G = 0; }
+                z.stop_at = (k + 1 < K) ? (long long)(k + 1) * L : kNoStop;
+                z.mark_at = k ? (long long)k * L : -256;
+                z.mark_w = kNoMark; z.mark_G = 0;
+                ptr[i] = reinterpret_cast<const float *>(x + z.base);
+                len[i] = (uint64_t)std::max<long long>(0, end - z.base);
+                ids[i] = i;
+            }
+            if (int e = h->put_states(nb, zs.data())) return e;
+            if (int e = lqb_rx_execute(h, nb, ids.data(), ptr.data(), len.data(), LQB_MEM_DEVICE)) return e;
+            h->shard[3]++;
+            if (int e = h->get_states()) return e;
+            for (unsigned i = 0; i < nb; ++i) {
+                Seg &sg = seg[todo[t0 + i]];
+                const StreamState &z = h->lanes[h->lane_of[i]]->f.h_states[h->local_of[i]];
+                sg.ran = true; sg.todo = false; sg.fr.clear();
+                // a walk that ends inside a frame it cannot finish (the capture ends there) has no further state
+                if (z.mode == 0) { sg.exit_w = z.wstart; sg.exit_G = norm_G(z.wstart, z.G); } else { sg.exit_w = kNoStop; sg.exit_G = kNoStop; }
+                if (z.mark_w == kNoMark) { sg.entry_w = kNoStop; sg.entry_G = kNoStop; }
+                else { sg.entry_w = z.mark_w; sg.entry_G = norm_G(z.mark_w, z.mark_G); }
+                h->shard[1]++;
+            }
+            // keep this call's frames (the receiver's result arenas are reused by the next call)
+            for (unsigned kf = 0; kf < h->n_frames; ++kf) {
+                const RxLane *ln = h->lanes[h->order[kf].first];
+                const RxGen &G = ln->g[h->cur_gen];
+                const FrameDesc &d = G.h_frames.p[h->order[kf].second];
+                const unsigned gs = h->global_stream(ln->lane, d.stream);
+                if (gs >= nb) continue;
+                lqb_rx_s::OwnedFrame of;
+                lqb_frame_result one;
+                h->use_merged = false;
+                // (the ordinary conversion, one frame at a time)
+                {
+                    lqb_frame_result &r = one;
+                    std::memset(&r, 0, sizeof r);
+                    r.stream = 0; r.seq = d.seq; r.sample_index = d.F;
+                    std::memcpy(r.header, d.header, 20);
+                    r.header_valid = d.header_valid; r.payload_valid = d.payload_valid; r.payload_len = d.payload_len;
+                    if (d.header_valid && !(d.flags & 1u)) {
+                        of.payload.assign(G.h_payload.p + d.pay_off, G.h_payload.p + d.pay_off + d.payload_len);
+                        if (!(h->flags & LQB_RX_NO_FRAMESYMS)) {
+                            const float *sp = reinterpret_cast<const float *>(G.h_syms.p + d.sym_off);
+                            of.syms.assign(sp, sp + 2 * (size_t)d.n_sym);
+                        }
+                        r.num_framesyms = d.n_sym;
+                    }
+                    r.mod_scheme = d.ms; r.mod_bps = d.bps; r.check = d.check; r.fec0 = d.fec0; r.fec1 = d.fec1;
+                    r.evm = d.evm; r.rssi = d.rssi; r.cfo = d.cfo;
+                    r.tau_hat = d.tau; r.gamma_hat = d.gamma; r.dphi_hat = d.dphi; r.phi_hat = d.phi; r.rxy = d.rxy;
+                    r.flags = d.flags;
+                }
+                of.r = one;
+                of.trig_w = d.F - (long long)d.det_idx;
+                seg[todo[t0 + gs]].fr.push_back(std::move(of));
+            }
+        }
+        // accept runs whose entry state is the accepted exit state before them; schedule the others from that state
+        bool chain = true;
+        for (unsigned k = 1; k < K; ++k) {
+            Seg &sg = seg[k];
+            seg[0].fin = true;
+            const long long want_w = seg[k - 1].exit_w, want_G = seg[k - 1].exit_G;
+            if (!seg[k - 1].fin) chain = false;
+            if (want_w == kNoStop || want_w < (long long)k * L) {
+                // the walk before never reaches this segment (the capture ends first): nothing of k belongs to the result
+                if (chain) { sg.fin = true; sg.todo = false; sg.fr.clear(); sg.exit_w = kNoStop; sg.exit_G = kNoStop; }
+                continue;
+            }
+            if (sg.ran && sg.entry_w == want_w && sg.entry_G == want_G) { if (chain) sg.fin = true; }
+            else if (!sg.fin) { sg.start_w = want_w; sg.start_G = want_G; sg.todo = true; }
+        }
+        if (K == 1) seg[0].fin = true;
+    }
+    // the sequential list: every accepted run's frames whose triggering window starts in the run's own segment
+    for (unsigned k = 0; k < K; ++k) {
+        Seg &sg = seg[k];
+        std::sort(sg.fr.begin(), sg.fr.end(), [](const lqb_rx_s::OwnedFrame &a, const lqb_rx_s::OwnedFrame &b) { return a.r.seq < b.r.seq; });
+        const long long lo = k ? (long long)k * L : -256;
+        for (auto &of : sg.fr) {
+            if (of.trig_w < lo) continue;                    // found during the pre-roll: the segment before owns it
+            of.r.stream = 0; of.r.seq = (uint32_t)h->merged.size();
+            h->merged_valid += (of.r.header_valid && of.r.payload_valid) ? 1u : 0u;
+            h->merged.push_back(std::move(of));
+        }
+    }
+    for (auto &of : h->merged) {                             // (pointers into the vectors as they finally lie)
+        of.r.payload = of.payload.empty() ? nullptr : of.payload.data();
+        of.r.framesyms = of.syms.empty() ? nullptr : of.syms.data();
+    }
+    h->use_merged = true;
+    return 0;
+}
+
+int lqb_rx_last_shard_info(lqb_rx h, uint64_t out[4])
+{
+    if (!h || !out) return fail(LQB_EINVAL, "null handle");
+    std::memcpy(out, h->shard, sizeof h->shard);
+    return 0;
+}
+
 int lqb_rx_poll(lqb_rx h, lqb_frame_result *out, uint32_t max_out, uint32_t *n_out)
 {
     if (!h) return fail(LQB_EINVAL, "null handle");
+    if (h->use_merged) {
+        const unsigned nm = std::min<unsigned>((unsigned)h->merged.size(), max_out);
+        for (unsigned k = 0; k < nm && out; ++k) out[k] = h->merged[k].r;
+        if (n_out) *n_out = (uint32_t)h->merged.size();
+        return 0;
+    }
     unsigned n = std::min<unsigned>(h->n_frames, max_out);
     const bool host_res = !(h->flags & LQB_RX_DEVICE_RESULTS);
     for (unsigned k = 0; k < n && out; ++k) {
@@ -1112,8 +1320,8 @@ int lqb_rx_poll(lqb_rx h, lqb_frame_result *out, uint32_t max_out, uint32_t *n_o
 int lqb_rx_counts(lqb_rx h, uint64_t *frames, uint64_t *valid)
 {
     if (!h) return fail(LQB_EINVAL, "null handle");
-    if (frames) *frames = h->n_frames;
-    if (valid) *valid = h->n_valid;
+    if (frames) *frames = h->use_merged ? h->merged.size() : h->n_frames;
+    if (valid) *valid = h->use_merged ? h->merged_valid : h->n_valid;
     return 0;
 }
 int lqb_rx_last_timing(lqb_rx h, float ms[6])

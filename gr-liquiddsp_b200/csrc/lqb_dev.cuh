@@ -55,7 +55,7 @@ struct StreamState {
     // time-sharded search (one capture cut into segments that run as streams of their own, lqb_det_execute_sharded):
     long long stop_at;         // windows starting at or beyond this index are left alone (kNoStop: none)
     long long mark_at;         // mark_w <- the first window start >= mark_at this stream's walk reaches (kNoMark: unset)
-    long long mark_w;
+    long long mark_w, mark_G;  // (the zero boundary G at that point belongs to the state as long as it lies above the window start)
 };
 constexpr long long kNoStop = 0x3fffffffffffffffll, kNoMark = -0x3fffffffffffffffll;
 
@@ -85,7 +85,8 @@ struct FrameDesc {
     float    evm, rssi, cfo, evm_acc;
     unsigned char header[20];
     unsigned ck_off;                 // first PLL checkpoint of this frame (16-byte entries)
-    unsigned pad[2];
+    unsigned det_idx;                // offset of F in the window that triggered (F - det_idx: that window's start)
+    unsigned pad;
 };
 
 struct Detection {

@@ -1110,13 +1110,15 @@ k_seek(SeekParams P)
         if (st.mode == 0) {
             // (sharded search) the first window start at or beyond mark_at that the walk reaches, and the stop boundary
             const long long w_in = st.wstart;
-            if (tid == 0 && st.mark_w == kNoMark && w_in >= st.mark_at) st.mark_w = w_in;
+            if (tid == 0 && st.mark_w == kNoMark && w_in >= st.mark_at) { st.mark_w = w_in; st.mark_G = st.G; }
             if (w_in + 512 > sv.end || w_in >= st.stop_at) break;
             if (fused) {
                 const int hit = fused_scan(sh, sv, T, P.b_err, st, tid, sc_, tc_pre, tc_pre_a0, ph_full, buf_w, n_windows, n_tc_tiles, rxy_q PROF_PASS);
                 // the scan walked the grid w_in, w_in + 256, .. up to st.wstart: if it passed mark_at, the mark is on that grid
-                if (tid == 0 && st.mark_w == kNoMark && st.wstart >= st.mark_at)
+                if (tid == 0 && st.mark_w == kNoMark && st.wstart >= st.mark_at) {
                     st.mark_w = w_in + 256ll * ((st.mark_at - w_in + 255ll) / 256ll);
+                    st.mark_G = st.G;
+                }
                 if (!hit) break;
             } else {
                 ++n_windows;
@@ -1229,7 +1231,7 @@ k_seek(SeekParams P)
                             FrameDesc &d = P.frames[slot];
                             d = FrameDesc{};
                             d.F = F; d.G = sv.G;
-                            d.stream = io.stream; d.seq = st.seq; d.io_index = blockIdx.x; d.flags = 1u;
+                            d.stream = io.stream; d.seq = st.seq; d.io_index = blockIdx.x; d.flags = 1u; d.det_idx = st.det_idx;
                             d.tau = sh.tau; d.gamma = sh.gamma; d.dphi = sh.dphi; d.phi = sh.phi; d.rxy = st.rxy;
                             d.header_valid = 1; d.payload_len = plen; d.ms = ms; d.bps = modem_bps_hd(ms);
                             d.check = check; d.fec0 = fec0; d.fec1 = fec1;
@@ -1256,7 +1258,7 @@ k_seek(SeekParams P)
                 FrameDesc &d = P.frames[slot];
                 d.F = F; d.G = sv.G;
                 d.sym_off = 0; d.buf_off = 0; d.pay_off = 0; d.dec_off = 0;
-                d.stream = io.stream; d.seq = st.seq; d.io_index = blockIdx.x; d.flags = 0;
+                d.stream = io.stream; d.seq = st.seq; d.io_index = blockIdx.x; d.flags = 0; d.det_idx = st.det_idx;
                 d.tau = sh.tau; d.gamma = sh.gamma; d.dphi = sh.dphi; d.phi = sh.phi; d.rxy = st.rxy;
                 d.mf_scale = sh.mf_scale;
                 d.mix_theta0 = sh.theta0; d.mix_dtheta = sh.dtheta;

@@ -24,7 +24,7 @@ DECLARED_SYMBOLS = [
     "lqb_tx_create", "lqb_tx_destroy", "lqb_tx_props_init_default", "lqb_tx_frame_len", "lqb_tx_assemble", "lqb_tx_submit", "lqb_tx_collect", "lqb_tx_last_timing",
     "lqb_det_create", "lqb_det_destroy", "lqb_det_reset", "lqb_det_execute", "lqb_det_execute_dense",
     "lqb_det_poll", "lqb_det_last_timing", "lqb_det_last_work", "lqb_det_last_search",
-    "lqb_det_execute_sharded", "lqb_det_last_shard_info",
+    "lqb_det_execute_sharded", "lqb_det_last_shard_info", "lqb_rx_execute_sharded", "lqb_rx_last_shard_info",
     "lqb_tab_interp_taps", "lqb_tab_pfb_banks", "lqb_tab_detector_template", "lqb_tab_nco_sintab",
     "lqb_tab_packet_len", "lqb_tab_ilv_bit_perm",
 ]
@@ -124,6 +124,8 @@ def lib():
     L.lqb_det_execute_dense.argtypes = [vp, vp, u64, u64, C.c_int]
     L.lqb_det_poll.argtypes = [vp, vp, u32, C.POINTER(u32)]
     L.lqb_det_execute_sharded.argtypes = [vp, vp, u64, C.c_int, u32, u32]
+    L.lqb_rx_execute_sharded.argtypes = [vp, vp, u64, C.c_int, u32, u32]
+    L.lqb_rx_last_shard_info.argtypes = [vp, C.POINTER(u64)]
     L.lqb_det_last_shard_info.argtypes = [vp, C.POINTER(u64)]
     L.lqb_det_last_timing.argtypes = [vp, C.POINTER(C.c_float)]
     L.lqb_tab_interp_taps.argtypes = [C.c_float, vp]
@@ -192,6 +194,20 @@ class Rx:
 
     def execute_dense_ptr(self, ptr, stride, n_samples, mem):
         _check(self._L.lqb_rx_execute_dense(self._h, C.c_void_p(ptr), stride, n_samples, mem))
+
+    def execute_sharded(self, x, seg_len=1 << 20, preroll=1 << 16):
+        """One complex64 capture (host numpy array) decoded as ONE sequential receiver would decode it, cut in time over
+        the handle's streams; the frames do not depend on seg_len / preroll (see lqb_rx_execute_sharded)."""
+        x = np.ascontiguousarray(x, dtype=np.complex64)
+        _check(self._L.lqb_rx_execute_sharded(self._h, C.c_void_p(x.ctypes.data), len(x), MEM_HOST, seg_len, preroll))
+
+    def execute_sharded_ptr(self, ptr, n_samples, mem, seg_len=1 << 20, preroll=1 << 16):
+        _check(self._L.lqb_rx_execute_sharded(self._h, C.c_void_p(ptr), n_samples, mem, seg_len, preroll))
+
+    def shard_info(self):
+        w = (C.c_uint64 * 4)()
+        _check(self._L.lqb_rx_last_shard_info(self._h, w))
+        return dict(segments=int(w[0]), runs=int(w[1]), rounds=int(w[2]), executes=int(w[3]))
 
     def execute_sc16(self, chunks, stream_ids=None):
         """chunks: list of int16 arrays of shape [n, 2] (re, im); a sample is value / 32768 (LQB_MEM_HOST_SC16)."""

@@ -187,6 +187,17 @@ int    lqb_rx_submit(lqb_rx h, uint32_t n, const uint32_t *stream_ids,
                      const float *const *iq, const uint64_t *n_samples, int mem);
 int    lqb_rx_submit_dense(lqb_rx h, const float *iq, uint64_t stride_samples, uint64_t n_samples, int mem);
 int    lqb_rx_collect(lqb_rx h);
+/* ONE capture decoded as one flexframesync would decode it from its reset state (reference call site
+ * lib/flex_rx_impl.cc:213), cut in time into segments of seg_len samples that run side by side as the streams of this
+ * handle (n_streams at a time): the single-stream case at batch speed.  Seam rule as lqb_det_execute_sharded (speculative
+ * start `preroll` samples early; a run is accepted only if it entered its segment in exactly the state -- next window
+ * start and zero boundary -- the accepted run before it stopped in, otherwise the segment is run again from that
+ * state), so frames, bytes, flags and estimates do not depend on the cut.  preroll should span the longest frame plus a
+ * gap.  mem: LQB_MEM_HOST or LQB_MEM_DEVICE (complex64).  Results through lqb_rx_poll / lqb_rx_counts: stream 0, seq =
+ * order, payload / framesyms owned by the handle until its next call.  Not with LQB_RX_DEVICE_RESULTS.  Consumes the
+ * stream states: lqb_rx_reset before going back to lqb_rx_execute.  0 for seg_len: 1048576. */
+int lqb_rx_execute_sharded(lqb_rx h, const float *iq, uint64_t n_samples, int mem, uint32_t seg_len, uint32_t preroll);
+int lqb_rx_last_shard_info(lqb_rx h, uint64_t out[4]);   /* segments, segment runs in all, rounds, execute calls */
 /* Frames completed by the last execute / collect, ordered by (stream, seq). */
 int    lqb_rx_poll(lqb_rx h, lqb_frame_result *out, uint32_t max_out, uint32_t *n_out);
 /* number of frames completed by the last execute / payloads with a passing check */

@@ -1094,6 +1094,41 @@ def main():
         gpu_rec = [(int(r["stream"]), int(r["seq"]), int(r["sample_index"]), int(r["header_valid"]), int(r["payload_valid"]), bytes(r["header"]),
                     _C.string_at(int(r["payload"]), int(r["payload_len"])) if (r["header_valid"] and r["payload"]) else b"") for r in rec]
         rx3.close()
+    # ---- the single-stream case (what ONE flex_rx block instance sees): the whole capture, row after row, as one stream,
+    # decoded by the time-sharded receiver (lqb_rx_execute_sharded: the sequential receiver's frames whatever the cut),
+    # beside the same receiver fed the ordinary way (one CTA walks the stream) on a prefix
+    single = single_prefix = single_rec = None
+    if world == 1 and not args.no_workloads:
+        seg_len, preroll = int(os.environ.get("LQB_BENCH_RX_SEG_LEN", 1 << 20)), int(os.environ.get("LQB_BENCH_RX_PREROLL", 1 << 16))
+        rx4 = capi.Rx(S, device=local, max_frame_samples=65536, flags=capi.RX_NO_FRAMESYMS, cuda_stream=cs.cuda_stream, lanes=args.lanes)
+        rx4.execute_sharded_ptr(cap.data_ptr(), S * N, capi.MEM_DEVICE, seg_len, preroll)           # warm-up (arenas)
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        rx4.execute_sharded_ptr(cap.data_ptr(), S * N, capi.MEM_DEVICE, seg_len, preroll)
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t0
+        f4, v4 = rx4.counts()
+        single = {"samples": S * N, "seg_len": seg_len, "preroll": preroll, "ms": dt * 1e3, "msps": S * N / dt / 1e6,
+                  "frames_found": f4, "frames_valid": v4}
+        single.update(rx4.shard_info())
+        n_pref = min(S * N, 3 << 20)
+        rec4 = rx4.poll_array()
+        rec4 = rec4[rec4["sample_index"] < n_pref - 70000]
+        import ctypes as _C
+        single_rec = [(int(r["sample_index"]), int(r["header_valid"]), int(r["payload_valid"]), bytes(r["header"]),
+                       _C.string_at(int(r["payload"]), int(r["payload_len"])) if (r["header_valid"] and r["payload"]) else b"") for r in rec4]
+        single_prefix = cap.reshape(-1)[:n_pref].cpu().numpy() if not args.no_cpu_baseline else None
+        rx4.close()
+        n_plain = min(S * N, 16 << 20)
+        rx5 = capi.Rx(1, device=local, max_frame_samples=65536, flags=capi.RX_NO_FRAMESYMS, cuda_stream=cs.cuda_stream)
+        rx5.execute_dense_ptr(cap.data_ptr(), n_plain, n_plain, capi.MEM_DEVICE)
+        rx5.reset()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        rx5.execute_dense_ptr(cap.data_ptr(), n_plain, n_plain, capi.MEM_DEVICE)
+        torch.cuda.synchronize(dev)
+        single["plain_one_cta"] = {"samples": n_plain, "msps": n_plain / (time.perf_counter() - t0) / 1e6}
+        rx5.close()
     del cap
     torch.cuda.empty_cache()
 
@@ -1216,6 +1251,21 @@ def main():
         parity = {"streams": Sc, "frames": n_ref, "mismatches": mism,
                   "compared": "sample_index, header_valid, payload_valid, header bytes, payload bytes; oracle vs one full-size GPU step"}
 
+    if single is not None and single_prefix is not None:
+        # ONE sequential oracle receiver over the first samples of the one-stream run
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import lqo_py as o
+        lim = len(single_prefix) - 70000                  # (frames the prefix holds in full)
+        refp = [r for r in o.rx_capture(single_prefix, chunk=4096, max_frames=1 << 16) if r["sample_index"] < lim]
+        same = len(refp) == len(single_rec) and all(
+            x["sample_index"] == y[0] and x["header_valid"] == y[1] and x["payload_valid"] == y[2] and x["header"] == y[3]
+            and (not x["header_valid"] or x["payload"] == y[4]) for x, y in zip(refp, single_rec))
+        single["oracle_prefix"] = {"samples": len(single_prefix), "frames": len(refp), "identical": bool(same)}
+        if workloads is not None:
+            workloads["single_stream"] = single
+    elif single is not None and workloads is not None:
+        workloads["single_stream"] = single
+
     out = {
         "metric": "flex_rx_msps", "value": value, "unit": "Msps", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -1238,6 +1288,8 @@ def main():
         dist.destroy_process_group()
     if parity and parity["mismatches"]:
         raise SystemExit("flex_rx: GPU frames differ from the oracle's on the sampled streams: %r" % (parity,))
+    if single is not None and single.get("oracle_prefix") and not single["oracle_prefix"]["identical"]:
+        raise SystemExit("flex_rx: the time-sharded single-stream run differs from the sequential oracle: %r" % (single,))
     bad = [k for k, v in (workloads or {}).items() if v and v.get("failed")]
     if bad:
         raise SystemExit("workloads failed their oracle check: %s" % ", ".join(bad))

@@ -54,6 +54,25 @@ def replay(captures, chunk=1 << 18, device=0, flags=0, rx=None):
             rx.close()
 
 
+def replay_sharded(capture, workers=512, seg_len=1 << 20, preroll=1 << 16, device=0, flags=0, rx=None):
+    """ONE capture (a single channel: what one flex_rx block instance sees) decoded at batch speed: the capture is cut in
+    time over `workers` streams of a batch receiver inside the library (lqb_rx_execute_sharded) and the frames that come
+    back are those of one sequential receiver, whatever the cut.  Returns the list of frames (dicts, as `capi.Rx.poll`,
+    stream 0, in time order).  `preroll` should span the longest frame plus a gap; seg_len * workers samples are searched
+    per pass."""
+    x = np.ascontiguousarray(np.asarray(capture).reshape(-1), dtype=np.complex64)
+    own = rx is None
+    if own:
+        n_seg = max(1, (len(x) + seg_len - 1) // seg_len)
+        rx = capi.Rx(max(1, min(workers, n_seg)), device=device, flags=flags)
+    try:
+        rx.execute_sharded(x, seg_len=seg_len, preroll=preroll)
+        return rx.poll()
+    finally:
+        if own:
+            rx.close()
+
+
 def to_pdus(frame):
     """The messages `flex_rx` publishes for a frame, in publish order -- ('constellation', (None, complex64[])), then for a
     valid header ('payload_data', (None, bytes)) and ('packet_info', dict) -- lib/flex_rx_impl.cc:218-247."""

@@ -150,6 +150,24 @@ def test_capture_replay_in_chunks_equals_one_shot(gpu_required, tmp_path):
         assert [f["sample_index"] for f in a] == sorted(f["sample_index"] for f in a)
 
 
+@pytest.mark.gpu
+def test_single_capture_replay_sharded_equals_chunked_replay(gpu_required, tmp_path):
+    # one capture file (one channel): the time-sharded replay returns the frames of the chunk-by-chunk replay
+    import lqo_py as o
+    import util
+    from liquiddsp import replay
+    rng = np.random.default_rng(17)
+    frames = [o.tx_frame(util.QAM16, util.CRC24, 11, 1, rng.integers(0, 256, 150 + 60 * (k % 5), dtype=np.uint8)) for k in range(25)]
+    cap = util.build_capture(frames, rng, [600 + 350 * (k % 4) for k in range(25)], snr_db=22.0, cfo=-0.008, tau=0.2)
+    cap.tofile(tmp_path / "one.c32")
+    x = replay.open_capture(str(tmp_path / "one.c32"))[0]
+    ref = list(replay.replay([x], chunk=2048))
+    got = replay.replay_sharded(x, workers=16, seg_len=8192, preroll=4096)
+    assert len(ref) == 25 and all(f["payload_valid"] for f in ref)
+    assert [(f["sample_index"], f["payload"]) for f in got] == [(f["sample_index"], f["payload"]) for f in ref]
+    assert [m[0] for f in got for m in replay.to_pdus(f)] == ["constellation", "payload_data", "packet_info"] * 25
+
+
 def test_pdu_tagged_stream_adapters_round_trip():
     """PDUs -> tagged stream -> PDUs: lengths and contents survive any chunking, tags carry
     absolute offsets, the chunker only produces multiples of 256."""

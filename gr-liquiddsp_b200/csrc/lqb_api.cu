@@ -821,6 +821,7 @@ struct lqb_rx_s {
     struct OwnedFrame {
         lqb_frame_result r;
         long long trig_w;                 // start of the window that triggered
+        long long after_w, after_G;       // the walk's state once this frame is through (time-sharded decoding)
         std::vector<unsigned char> payload;
         std::vector<float> syms;
     };
@@ -1151,6 +1152,11 @@ int lqb_rx_execute_sharded(lqb_rx h, const float *iq, uint64_t n_samples, int me
         long long entry_w = 0, entry_G = 0, exit_w = 0, exit_G = 0;
         bool ran = false, fin = false, todo = true;
         std::vector<lqb_rx_s::OwnedFrame> fr;
+        // a re-run that only goes as far as the first frame of the run before it (old[splice]) and is spliced onto the
+        // rest of that run when it leaves the frame in the same state
+        std::vector<lqb_rx_s::OwnedFrame> old;
+        long long old_exit_w = 0, old_exit_G = 0, partial_stop = 0;
+        int splice = -1;
     };
     // G only matters while it lies above the window start
     auto norm_G = [](long long w, long long G) { return G > w ? G : w; };
@@ -1183,6 +1189,7 @@ int lqb_rx_execute_sharded(lqb_rx h, const float *iq, uint64_t n_samples, int me
                 z.base = base; z.G = std::max(sg.start_G > sg.start_w ? sg.start_G : base, k ? base : 0ll); z.wstart = sg.start_w;
                 if (!k && sg.start_w == -256) { z.base = 0; z.G = 0; }
                 z.stop_at = (k + 1 < K) ? (long long)(k + 1) * L : kNoStop;
+                if (sg.splice >= 0) z.stop_at = std::min(z.stop_at, sg.partial_stop);
                 z.mark_at = k ? (long long)k * L : -256;
                 z.mark_w = kNoMark; z.mark_G = 0;
                 ptr[i] = reinterpret_cast<const float *>(x + z.base);
@@ -1235,7 +1242,28 @@ int lqb_rx_execute_sharded(lqb_rx h, const float *iq, uint64_t n_samples, int me
                 }
                 of.r = one;
                 of.trig_w = d.F - (long long)d.det_idx;
+                // where k_seek leaves the walk behind this frame (lqb_rx_seek.cu: st.G = last + 1, st.wstart = st.G - 256)
+                if (d.flags & 1u) of.after_G = d.F + 512;
+                else if (d.header_valid) of.after_G = d.F + 2ll * (308ll + (long long)d.n_sym) - (long long)d.tau_neg + 1;
+                else of.after_G = d.F + 616 - (long long)d.tau_neg + 1;
+                of.after_w = of.after_G - 256;
                 seg[todo[t0 + gs]].fr.push_back(std::move(of));
+            }
+        }
+        // partial re-runs: spliced onto the rest of the old run if they left its frame in the same state, else run in full
+        for (unsigned k = 1; k < K; ++k) {
+            Seg &sg = seg[k];
+            if (sg.splice < 0 || sg.todo) continue;
+            std::sort(sg.fr.begin(), sg.fr.end(), [](const lqb_rx_s::OwnedFrame &a, const lqb_rx_s::OwnedFrame &b) { return a.r.seq < b.r.seq; });
+            const lqb_rx_s::OwnedFrame &jf = sg.old[(size_t)sg.splice];
+            if (sg.exit_w == jf.after_w && sg.exit_G == norm_G(jf.after_w, jf.after_G)) {
+                for (size_t q = (size_t)sg.splice + 1; q < sg.old.size(); ++q) sg.fr.push_back(std::move(sg.old[q]));
+                for (size_t q = 0; q < sg.fr.size(); ++q) sg.fr[q].r.seq = (uint32_t)q;
+                sg.exit_w = sg.old_exit_w; sg.exit_G = sg.old_exit_G;
+                sg.splice = -1; sg.old.clear();
+            } else {
+                sg.splice = -1; sg.old.clear();
+                sg.ran = false;                              // its frames stop short: the next run of this segment is a full one
             }
         }
         // accept runs whose entry state is the accepted exit state before them; schedule the others from that state
@@ -1251,7 +1279,21 @@ int lqb_rx_execute_sharded(lqb_rx h, const float *iq, uint64_t n_samples, int me
                 continue;
             }
             if (sg.ran && sg.entry_w == want_w && sg.entry_G == want_G) { if (chain) sg.fin = true; }
-            else if (!sg.fin) { sg.start_w = want_w; sg.start_G = want_G; sg.todo = true; }
+            else if (!sg.fin) {
+                sg.start_w = want_w; sg.start_G = want_G; sg.todo = true;
+                // the old run's first frame the true walk can still reach: go that far only, then try to splice
+                if (sg.splice == -1 && sg.ran) {
+                    std::sort(sg.fr.begin(), sg.fr.end(), [](const lqb_rx_s::OwnedFrame &a, const lqb_rx_s::OwnedFrame &b) { return a.r.seq < b.r.seq; });
+                    int j = -1;
+                    for (size_t q = 0; q < sg.fr.size(); ++q)
+                        if (sg.fr[q].trig_w >= (long long)k * L && (long long)sg.fr[q].r.sample_index > std::max(want_w, want_G) + 512) { j = (int)q; break; }
+                    if (j >= 0) {
+                        sg.old = std::move(sg.fr); sg.fr.clear();
+                        sg.old_exit_w = sg.exit_w; sg.old_exit_G = sg.exit_G;
+                        sg.splice = j; sg.partial_stop = (long long)sg.old[(size_t)j].r.sample_index + 1;
+                    }
+                }
+            }
         }
         if (K == 1) seg[0].fin = true;
     }
@@ -1496,6 +1538,11 @@ int lqb_det_execute_sharded(lqb_det h, const float *iq, uint64_t n_samples, int 
         long long entry = 0, exit = 0;
         bool ran = false, fin = false, todo = true;
         std::vector<Detection> det;
+        // a re-run that only goes as far as the first detection of the run before it (old[splice]) and is spliced onto
+        // the rest of that run when it makes the same detection (the walk's state behind a detection at F is F + 256)
+        std::vector<Detection> old;
+        long long old_exit = 0, partial_stop = 0;
+        int splice = -1;
     };
     std::vector<Seg> seg(K);
     for (unsigned k = 0; k < K; ++k) seg[k].start = k ? std::max<long long>(0, (long long)k * L - (long long)preroll) : -256;
@@ -1525,6 +1572,7 @@ int lqb_det_execute_sharded(lqb_det h, const float *iq, uint64_t n_samples, int 
                 std::memset(&z, 0, sizeof z);
                 z.base = base; z.G = base; z.wstart = sg.start;
                 z.stop_at = (k + 1 < K) ? (long long)(k + 1) * L : kNoStop;
+                if (sg.splice >= 0) z.stop_at = std::min(z.stop_at, sg.partial_stop);
                 z.mark_at = k ? (long long)k * L : -256;
                 z.mark_w = kNoMark;
                 f.h_states[i] = z;
@@ -1574,6 +1622,19 @@ int lqb_det_execute_sharded(lqb_det h, const float *iq, uint64_t n_samples, int 
                 if (d.stream < nb) seg[todo[t0 + d.stream]].det.push_back(d);
             }
         }
+        // ---- partial re-runs: spliced onto the rest of the old run if they made its detection, else run in full
+        auto by_seq = [](const Detection &a, const Detection &b) { return a.seq < b.seq; };
+        for (unsigned k = 1; k < K; ++k) {
+            Seg &sg = seg[k];
+            if (sg.splice < 0 || sg.todo) continue;
+            std::sort(sg.det.begin(), sg.det.end(), by_seq);
+            if (sg.exit == sg.old[(size_t)sg.splice].F + 256) {
+                for (size_t q = (size_t)sg.splice + 1; q < sg.old.size(); ++q) sg.det.push_back(sg.old[q]);
+                for (size_t q = 0; q < sg.det.size(); ++q) sg.det[q].seq = (unsigned)q;
+                sg.exit = sg.old_exit;
+            } else sg.ran = false;                           // its list stops short: the next run of this segment is a full one
+            sg.splice = -1; sg.old.clear();
+        }
         // ---- accept runs whose entry is the accepted exit before them; schedule the others from that exit
         bool chain = true;                                   // everything before k is accepted
         for (unsigned k = 0; k < K; ++k) {
@@ -1590,7 +1651,20 @@ int lqb_det_execute_sharded(lqb_det h, const float *iq, uint64_t n_samples, int 
             if (sg.ran && sg.entry == want) { if (chain) sg.fin = true; }
             else {
                 // the run has to start exactly in that state (a window start at or beyond the boundary)
-                if (!sg.fin) { sg.start = want; sg.todo = true; }
+                if (!sg.fin) {
+                    sg.start = want; sg.todo = true;
+                    // the old run's first detection the true walk can still make: go that far only, then try to splice
+                    if (sg.ran) {
+                        std::sort(sg.det.begin(), sg.det.end(), by_seq);
+                        int j = -1;
+                        for (size_t q = 0; q < sg.det.size(); ++q)
+                            if (sg.det[q].F - (long long)sg.det[q].pad >= (long long)k * L && sg.det[q].F > want + 512) { j = (int)q; break; }
+                        if (j >= 0) {
+                            sg.old = std::move(sg.det); sg.det.clear();
+                            sg.old_exit = sg.exit; sg.splice = j; sg.partial_stop = sg.old[(size_t)j].F + 1;
+                        }
+                    }
+                }
                 chain = false;
             }
             if (!sg.fin) chain = false;

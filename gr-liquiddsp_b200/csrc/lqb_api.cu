@@ -596,7 +596,7 @@ struct RxLane {
         g_trace.mark("frame list on host", lane);
         // ---------------- plan
         size_t sym_total = 0, buf_total = 0, pay_total = 0, dec_total = 0, n_tiles = 0, ck_total = 0;
-        std::vector<unsigned> tile_start(nf + 1, 0), valid, deint[2], blk[2], vit[2], vit9[2], rsb[2], softl, vsoft[2];
+        std::vector<unsigned> tile_start(nf + 1, 0), valid, deint[2], blk[2], vit[2], vit9[2], rsb[2], softl, vsoft7[2], vsoft9[2];
         const bool soft_on = (flags & LQB_RX_SOFT) != 0;
         size_t soft_raw_total = 0, soft_d_total = 0;
         unsigned soft_max_syms = 0, soft_max_bits = 0;
@@ -606,8 +606,8 @@ struct RxLane {
             sdesc = G.h_softdesc.p;
             for (unsigned i = 0; i < nf; ++i) { sdesc[i].raw_off = 0; sdesc[i].d_off = 0; sdesc[i].perm_off = 0; sdesc[i].stage = -1; }
         }
-        size_t tmax7[2] = { 0, 0 };
-        bool punct7[2] = { false, false };
+        size_t tmax7[2] = { 0, 0 }, tmax_s7[2] = { 0, 0 };
+        bool punct7[2] = { false, false }, punct_s7[2] = { false, false };
         std::fill(f.est_work.begin(), f.est_work.end(), 0);
         for (unsigned i = 0; i < nf; ++i) {
             FrameDesc &d = fr[i];
@@ -640,9 +640,12 @@ struct RxLane {
                 sd.raw_off = soft_raw_total; soft_raw_total += ((size_t)d.n_sym * d.bps + 31u) & ~(size_t)15u;
                 sd.d_off = soft_d_total; soft_d_total += ((size_t)8 * enc[sstage] + 31u) & ~(size_t)15u;
                 soft_max_syms = std::max(soft_max_syms, d.n_sym); soft_max_bits = std::max(soft_max_bits, 8u * enc[sstage]);
-                softl.push_back(i); vsoft[sstage].push_back(i);
+                softl.push_back(i);
                 const size_t T = (size_t)8 * dl[sstage] + conv_K(fs[sstage]) - 1;
-                need_dec = std::max(need_dec, T * (conv_K(fs[sstage]) == 7 ? 1u : 4u));        // 2 or 8 decision words per step
+                if (conv_K(fs[sstage]) == 7) {                // the packed four-lane decoder, soft input: shared [step][thread] arena
+                    vsoft7[sstage].push_back(i); tmax_s7[sstage] = std::max(tmax_s7[sstage], T);
+                    punct_s7[sstage] = punct_s7[sstage] || fs[sstage] != FEC_CONV_V27;
+                } else { vsoft9[sstage].push_back(i); need_dec = std::max(need_dec, T * 4); }            // 8 words per step
             }
             for (int stg = 1; stg >= 0; --stg) {
                 if (stg == sstage) continue;              // deinterleaved and decoded from soft bytes instead
@@ -667,7 +670,7 @@ struct RxLane {
         }
         tile_start[nf] = (unsigned)n_tiles;
         // K=7 frames share one [step][thread] decision arena at the front; K=9 frames follow with private slices
-        const size_t dec7 = std::max(tmax7[0] * vit[0].size(), tmax7[1] * vit[1].size());
+        const size_t dec7 = std::max(std::max(tmax7[0] * vit[0].size(), tmax7[1] * vit[1].size()), std::max(tmax_s7[0] * vsoft7[0].size(), tmax_s7[1] * vsoft7[1].size()));
         for (unsigned i = 0; i < nf; ++i) fr[i].dec_off += dec7;
         dec_total += dec7;
         G.work[2] = sym_total;
@@ -689,7 +692,7 @@ struct RxLane {
             // one list arena: tile_start | pll | valid | deint1 | blk1 | vit1 | rs1 | deint0 | blk0 | vit0 | rs0
             std::vector<const std::vector<unsigned> *> parts = { &tile_start, &pll, &valid, &deint[1], &blk[1], &vit[1], &rsb[1],
                                                                  &deint[0], &blk[0], &vit[0], &rsb[0], &vit9[1], &vit9[0], &span_start,
-                                                                 &softl, &vsoft[1], &vsoft[0] };
+                                                                 &softl, &vsoft7[1], &vsoft7[0], &vsoft9[1], &vsoft9[0] };
             size_t ltot = 0;
             std::vector<size_t> loff;
             for (auto p : parts) { loff.push_back(ltot); ltot += p->size(); }
@@ -742,7 +745,8 @@ struct RxLane {
             if (!softl.empty()) { launch_soft_demod(pp, G.d_lists.p + loff[14], (unsigned)softl.size(), soft_max_syms, soft_max_bits, ps); f.launches += 2; }
             for (int stg = 1; stg >= 0; --stg) {
                 const size_t base = stg ? 3 : 7;
-                if (!vsoft[stg].empty()) { launch_viterbi_soft(pp, G.d_lists.p + loff[stg ? 15 : 16], (unsigned)vsoft[stg].size(), stg, ps); f.launches++; }
+                if (!vsoft7[stg].empty()) { launch_viterbi_soft(pp, G.d_lists.p + loff[stg ? 15 : 16], (unsigned)vsoft7[stg].size(), stg, 7, punct_s7[stg], ps); f.launches++; }
+                if (!vsoft9[stg].empty()) { launch_viterbi_soft(pp, G.d_lists.p + loff[stg ? 17 : 18], (unsigned)vsoft9[stg].size(), stg, 9, true, ps); f.launches++; }
                 if (!deint[stg].empty()) { launch_deinterleave(pp, G.d_lists.p + loff[base], (unsigned)deint[stg].size(), stg, ps); f.launches++; }
                 if (!blk[stg].empty()) { launch_blockfec(pp, G.d_lists.p + loff[base + 1], (unsigned)blk[stg].size(), stg, ps); f.launches++; }
                 if (!vit[stg].empty()) { launch_viterbi(pp, G.d_lists.p + loff[base + 2], (unsigned)vit[stg].size(), stg, 7, punct7[stg], ps); f.launches++; }

@@ -114,7 +114,7 @@ void launch_crc(const PayloadParams &P, const unsigned *list, unsigned n, cudaSt
 // soft decisions for the listed frames: demodulate the stored constellation points to soft bytes, deinterleave them
 // through the bit permutation, then (launch_viterbi_soft, per stage) the soft-input Viterbi decoder
 void launch_soft_demod(const PayloadParams &P, const unsigned *list, unsigned n, unsigned max_syms, unsigned max_bits, cudaStream_t s);
-void launch_viterbi_soft(const PayloadParams &P, const unsigned *list, unsigned n, int stage, cudaStream_t s);
+void launch_viterbi_soft(const PayloadParams &P, const unsigned *list, unsigned n, int stage, unsigned K, bool punct, cudaStream_t s);
 
 // debug / unit-test hooks (single launches on tiny inputs)
 void launch_dbg_fft512(const DevTables *T, const float2 *in, float2 *out, int dir, cudaStream_t s);

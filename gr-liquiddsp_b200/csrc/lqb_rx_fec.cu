@@ -455,7 +455,10 @@ constexpr int kV4Threads = 64;
 constexpr unsigned kV4Renorm = 96;                    // steps between metric renormalisations (multiple of 6)
 constexpr int kV4Warm = 96;                           // speculative traceback warm-up, steps (debug override: LQB_V4_WARM)
 
-template <bool PUNCT>
+// SOFT: the received values are bytes (one per kept coded bit, deinterleaved: LQB_RX_SOFT, csrc/lqb_rx_soft.cu) instead of
+// bits; the packed branch metrics are then computed per step from the two bytes (v4_metrics is plain arithmetic on them)
+// instead of being looked up by the received pair.  Everything else -- metrics layout, decisions, traceback -- is shared.
+template <bool PUNCT, bool SOFT = false>
 __global__ void __launch_bounds__(kV4Threads)
 k_viterbi27x4(PayloadParams P, const unsigned *__restrict__ list, unsigned n_list, int stage, unsigned *__restrict__ dec, int warm)
 {
@@ -470,7 +473,8 @@ k_viterbi27x4(PayloadParams P, const unsigned *__restrict__ list, unsigned n_lis
     const bool active = gi < n_list;
     if (!active) gi = n_list - 1;
     const FrameDesc &d = P.frames[list[gi]];
-    const StageIO io = stage_io(P, d, stage);
+    StageIO io = stage_io(P, d, stage);
+    if (SOFT) { io.src = P.soft_d + P.soft[list[gi]].d_off; io.enc_len *= 8u; }       // one byte per coded bit
     const ConvSpec cs = conv_spec(io.fs);
     const unsigned nbits = 8 * io.dec_len, T = nbits + 6;          // T is even
     unsigned Tw = T;                                  // longest codeword in this warp
@@ -481,7 +485,14 @@ k_viterbi27x4(PayloadParams P, const unsigned *__restrict__ list, unsigned n_lis
 
     // lane part of the branch labels, as XOR masks on the received symbols, per phase
     auto lane_mask = [](unsigned lane, int r, unsigned poly) { return (__popc((lane << kV4PosBits) & v4_phase_mask(poly, r)) & 1) ? 255u : 0u; };
-    {
+    // SOFT: the twelve lane masks (six phases x two polynomials) as bits 2 r, 2 r + 1 of one word
+    unsigned lmask12 = 0;
+    if (SOFT) {
+#pragma unroll
+        for (int r = 0; r < 6; ++r)
+            lmask12 |= ((lane_mask(l, r, 0x6d) & 1u) << (2 * r)) | ((lane_mask(l, r, 0x4f) & 1u) << (2 * r + 1));
+    }
+    if (!SOFT) {
         const unsigned soft[3] = { 0u, 255u, 127u };
         for (unsigned i = threadIdx.x; i < kV4Lanes * 6 * kPairs; i += kV4Threads) {
             const unsigned ll = i / (6 * kPairs), v = i % kPairs;
@@ -513,10 +524,32 @@ k_viterbi27x4(PayloadParams P, const unsigned *__restrict__ list, unsigned n_lis
     };
     // unpunctured: the window of the next group is fetched one group ahead; punctured: the bit position of the next group
     // depends on the puncturing column, the window is fetched at the group's start
-    unsigned bits = 0, bits_next = PUNCT ? 0u : fetch32(0u);
+    unsigned bits = 0, bits_next = (PUNCT || SOFT) ? 0u : fetch32(0u);
     unsigned bitpos = 0, col = 0;                   // punctured: encoded bits consumed, column t mod P
     const char *lut_l = reinterpret_cast<const char *>(&lut[l][0][0]);
+    // SOFT, unpunctured: the twelve bytes of a group of six steps (three words, byte 0 of the stream in the low byte)
+    unsigned sw0 = 0, sw1 = 0, sw2 = 0;
+    const unsigned soft_words = max((io.enc_len + 3u) / 4u, 1u);
+    auto soft_byte = [&](unsigned i) -> unsigned { return i < io.enc_len ? (unsigned)__ldg(enc + i) : 0u; };
     auto metrics = [&](const int r) -> uint4 {
+        if (SOFT) {
+            unsigned s0, s1;
+            if (PUNCT) {
+                const unsigned k0 = (cs.keep0 >> col) & 1u, k1 = (cs.keep1 >> col) & 1u;
+                s0 = k0 ? soft_byte(bitpos) : 127u;
+                s1 = k1 ? soft_byte(bitpos + k0) : 127u;
+                bitpos += k0 + k1;
+                col = (col + 1u == cs.P) ? 0u : col + 1u;
+            } else {
+                const unsigned w = (r < 2) ? sw0 : (r < 4) ? sw1 : sw2;
+                s0 = (w >> (16 * (r & 1))) & 0xffu;
+                s1 = (w >> (16 * (r & 1) + 8)) & 0xffu;
+            }
+            // (an erased position enters as 127 and takes the label mask like any other value, exactly as in the table of
+            // the hard-input form: soft[] = 0, 255, 127 XOR mask)
+            const unsigned m0 = ((lmask12 >> (2 * r)) & 1u) ? 255u : 0u, m1 = ((lmask12 >> (2 * r + 1)) & 1u) ? 255u : 0u;
+            return v4_metrics(r, s0 ^ m0, s1 ^ m1);
+        }
         if (PUNCT) {
             const unsigned k0 = (cs.keep0 >> col) & 1u, k1 = (cs.keep1 >> col) & 1u;
             const unsigned c0 = k0 ? bits >> 31 : 2u;
@@ -548,7 +581,13 @@ k_viterbi27x4(PayloadParams P, const unsigned *__restrict__ list, unsigned n_lis
     }
     // whole groups of six phases; steps past a codeword's end run on arbitrary symbols and store nothing
     for (; t < Tw; t += 6) {
-        if (!PUNCT) { bits = bits_next; bits_next = fetch32(2u * (t + 6u)); }
+        if (SOFT) {
+            if (!PUNCT) {
+                const unsigned wi = 3u * (t / 6u);            // bytes 2 t .. 2 t + 11
+                sw0 = __ldg(enc32 + min(wi, soft_words - 1u)); sw1 = __ldg(enc32 + min(wi + 1u, soft_words - 1u)); sw2 = __ldg(enc32 + min(wi + 2u, soft_words - 1u));
+            }
+        }
+        else if (!PUNCT) { bits = bits_next; bits_next = fetch32(2u * (t + 6u)); }
         else bits = fetch32(bitpos);
         LQB_V4_PAIR(0, role0, role1, xm0)
         LQB_V4_PAIR(2, 0x00010000u, 0u, xm1)
@@ -878,9 +917,17 @@ void launch_viterbi(const PayloadParams &P, const unsigned *list, unsigned n, in
     }
     else k_viterbi<false><<<(n + kVitWarps - 1) / kVitWarps, 32 * kVitWarps, 0, s>>>(P, list, n, stage);
 }
-void launch_viterbi_soft(const PayloadParams &P, const unsigned *list, unsigned n, int stage, cudaStream_t s)
+void launch_viterbi_soft(const PayloadParams &P, const unsigned *list, unsigned n, int stage, unsigned K, bool punct, cudaStream_t s)
 {
-    if (n) k_viterbi<true><<<(n + kVitWarps - 1) / kVitWarps, 32 * kVitWarps, 0, s>>>(P, list, n, stage);
+    if (!n) return;
+    if (K == 7) {
+        const unsigned threads = n * kV4Lanes;
+        const char *we = std::getenv("LQB_V4_WARM");
+        const int warm = we ? std::max(0, std::atoi(we)) : kV4Warm;
+        if (punct) k_viterbi27x4<true, true><<<(threads + kV4Threads - 1) / kV4Threads, kV4Threads, 0, s>>>(P, list, n, stage, reinterpret_cast<unsigned *>(P.decisions), warm);
+        else k_viterbi27x4<false, true><<<(threads + kV4Threads - 1) / kV4Threads, kV4Threads, 0, s>>>(P, list, n, stage, reinterpret_cast<unsigned *>(P.decisions), warm);
+    }
+    else k_viterbi<true><<<(n + kVitWarps - 1) / kVitWarps, 32 * kVitWarps, 0, s>>>(P, list, n, stage);
 }
 void launch_rs(const PayloadParams &P, const unsigned *blocks, unsigned n_blocks, int stage, cudaStream_t s)
 {

@@ -15,6 +15,12 @@ public:
     typedef boost::shared_ptr<flex_rx> sptr;
     static sptr make();
     static sptr make_multi(unsigned n_channels, int device = 0);
+    // Additive (not in the reference): decode ONE recorded capture of this block's single channel at batch speed and
+    // publish its frames exactly as work() would have, in order.  The capture is cut in time over `workers` GPU
+    // streams with an exact seam rule (lqb_rx_execute_sharded): the messages are those of feeding the capture through
+    // work() chunk by chunk.  Returns the number of frames, -1 on error.  Only for blocks made by make() / n_channels 1.
+    virtual long decode_capture(const gr_complex *samples, size_t n_samples, unsigned workers = 512,
+                                unsigned seg_len = 1u << 20, unsigned preroll = 1u << 16) = 0;
 };
 }}
 #endif

@@ -1,6 +1,7 @@
 // flex_rx block over the B200 receiver (C-ABI in include/lqb200.h).
 #include "flex_rx_impl.h"
 #include "scheme_tables.h"
+#include <algorithm>
 #include <iostream>
 #include <stdexcept>
 
@@ -13,7 +14,7 @@ flex_rx_impl::flex_rx_impl(unsigned n_channels, int device)
     : gr::sync_block("flex_rx",
                      gr::io_signature::make(n_channels == 1 ? 0 : (int)n_channels, (int)n_channels, sizeof(gr_complex)),
                      gr::io_signature::make(0, 0, 0)),
-      d_rx(NULL), d_channels(n_channels), d_num_frames(0)
+      d_rx(NULL), d_bulk(NULL), d_bulk_workers(0), d_device(device), d_channels(n_channels), d_num_frames(0)
 {
     lqb_rx_opts o = { device, n_channels, 0, 0, NULL };
     d_rx = lqb_rx_create(&o);
@@ -24,7 +25,7 @@ flex_rx_impl::flex_rx_impl(unsigned n_channels, int device)
     message_port_register_out(pmt::mp("packet_info"));
 }
 
-flex_rx_impl::~flex_rx_impl() { lqb_rx_destroy(d_rx); }
+flex_rx_impl::~flex_rx_impl() { lqb_rx_destroy(d_rx); if (d_bulk) lqb_rx_destroy(d_bulk); }
 
 int flex_rx_impl::mod_index(unsigned ms)
 {
@@ -67,6 +68,30 @@ void flex_rx_impl::publish(const lqb_frame_result &r)
     info = pmt::dict_add(info, pmt::mp("outer_code"), pmt::from_long((long)outer_index(r.fec1)));
     message_port_pub(pmt::mp("packet_info"), info);
     d_num_frames++;
+}
+
+long flex_rx_impl::decode_capture(const gr_complex *samples, size_t n_samples, unsigned workers, unsigned seg_len, unsigned preroll)
+{
+    if (d_channels != 1 || (!samples && n_samples)) return -1;
+    if (!seg_len) seg_len = 1u << 20;
+    const size_t n_seg = (n_samples + seg_len - 1) / seg_len;
+    workers = (unsigned)std::max<size_t>(1, std::min<size_t>(workers ? workers : 512, n_seg));
+    if (!d_bulk || d_bulk_workers < workers) {
+        if (d_bulk) lqb_rx_destroy(d_bulk);
+        lqb_rx_opts o = { d_device, workers, 0, 0, NULL };
+        d_bulk = lqb_rx_create(&o);
+        d_bulk_workers = d_bulk ? workers : 0;
+        if (!d_bulk) return -1;
+    }
+    if (lqb_rx_execute_sharded(d_bulk, reinterpret_cast<const float *>(samples), n_samples, LQB_MEM_HOST, seg_len, preroll) != 0) return -1;
+    uint64_t frames = 0;
+    lqb_rx_counts(d_bulk, &frames, NULL);
+    d_results.resize((size_t)frames + 1);
+    uint32_t got = 0;
+    lqb_rx_poll(d_bulk, d_results.data(), (uint32_t)frames, &got);
+    for (uint32_t i = 0; i < got && i < frames; ++i) publish(d_results[i]);   // in time order
+    lqb_rx_reset(d_bulk, -1);
+    return (long)frames;
 }
 
 int flex_rx_impl::work(int noutput_items, gr_vector_const_void_star &input_items, gr_vector_void_star &)

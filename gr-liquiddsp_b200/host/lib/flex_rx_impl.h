@@ -15,6 +15,7 @@ public:
     flex_rx_impl(unsigned n_channels, int device);
     ~flex_rx_impl();
     int work(int noutput_items, gr_vector_const_void_star &input_items, gr_vector_void_star &output_items);
+    long decode_capture(const gr_complex *samples, size_t n_samples, unsigned workers, unsigned seg_len, unsigned preroll);
     // liquid enum -> block-API index, -1 (and a note on stdout) when the scheme is outside the tables
     static int mod_index(unsigned mod_scheme);
     static int inner_index(unsigned fec0);
@@ -23,6 +24,9 @@ public:
 private:
     void publish(const lqb_frame_result &r);
     lqb_rx d_rx;
+    lqb_rx d_bulk;            // batch handle of decode_capture (made on first use)
+    unsigned d_bulk_workers;
+    int d_device;
     unsigned d_channels;
     unsigned long d_num_frames;
     std::vector<lqb_frame_result> d_results;

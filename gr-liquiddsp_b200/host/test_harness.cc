@@ -18,6 +18,12 @@ void *blk_make_flex_tx(unsigned m, unsigned i, unsigned o) { try { blk *h = new 
 void *blk_make_flex_rx(void) { try { blk *h = new blk; h->b = flex_rx::make(); return h; } catch (...) { return NULL; } }
 void *blk_make_flex_rx_multi(unsigned n) { try { blk *h = new blk; h->b = flex_rx::make_multi(n); return h; } catch (...) { return NULL; } }
 void *blk_make_frame_detector(void) { try { blk *h = new blk; h->b = frame_detector_cc::make(); return h; } catch (...) { return NULL; } }
+long blk_rx_decode_capture(void *p, const float *iq, unsigned long n, unsigned workers, unsigned seg_len, unsigned preroll)
+{
+    flex_rx *rx = dynamic_cast<flex_rx *>(static_cast<blk *>(p)->b.get());
+    if (!rx) return -2;
+    try { return rx->decode_capture(reinterpret_cast<const gr_complex *>(iq), n, workers, seg_len, preroll); } catch (...) { return -3; }
+}
 void blk_destroy(void *p) { delete static_cast<blk *>(p); }
 const char *blk_name(void *p) { return static_cast<blk *>(p)->b->name().c_str(); }
 int blk_output_multiple(void *p) { return static_cast<blk *>(p)->b->output_multiple(); }

@@ -41,6 +41,8 @@ def _lib():
     L.blk_pop.argtypes = [vp, C.c_char_p, C.c_int, vp, C.c_int, C.POINTER(C.c_int)]
     L.blk_rx_index.argtypes = [C.c_int, C.c_uint]
     L.blk_tx_props.argtypes = [vp, vp]
+    L.blk_rx_decode_capture.restype = C.c_long
+    L.blk_rx_decode_capture.argtypes = [vp, vp, C.c_ulong, C.c_uint, C.c_uint, C.c_uint]
     return L
 
 
@@ -154,6 +156,37 @@ def test_flex_tx_to_flex_rx_loopback_messages(gpu_required):
         assert info == {"header_valid": 1, "payload_valid": 1, "modulation": m, "inner_code": i, "outer_code": oo}
     assert len(msgs[-1][1]) == 0                                              # header invalid: empty constellation only
     L.blk_destroy(rx)
+
+
+@pytest.mark.gpu
+def test_flex_rx_decode_capture_publishes_what_work_publishes(gpu_required):
+    """Additive offline entry of the block: one recorded capture, cut in time over many GPU streams underneath
+    (lqb_rx_execute_sharded), publishes the messages that feeding it through work() in 256-multiples publishes."""
+    L = _lib()
+    rng = np.random.default_rng(21)
+    frames = [o.tx_frame(util.MODS[k % 11], util.CRC24, util.INNER[k % 7], util.OUTER[k % 8], rng.integers(0, 256, 60 + 37 * (k % 9), dtype=np.uint8))
+              for k in range(22)]
+    cap = util.build_capture(frames, rng, [500 + 611 * (k % 5) for k in range(22)], snr_db=28.0, cfo=0.006, tau=-0.15)
+    cap = np.concatenate([cap, np.zeros((-len(cap)) % 256 + 2048, np.complex64)])
+    rx = L.blk_make_flex_rx()
+    ref = []
+    for i in range(0, len(cap), 4096):
+        chunk = np.ascontiguousarray(cap[i:i + 4096])
+        assert L.blk_work(rx, chunk.ctypes.data, 1, len(chunk), None) == len(chunk)
+        ref += pop_all(L, rx)
+    L.blk_destroy(rx)
+    rx = L.blk_make_flex_rx()
+    n = L.blk_rx_decode_capture(rx, cap.ctypes.data, len(cap), 24, 8192, 4096)
+    got = pop_all(L, rx)
+    L.blk_destroy(rx)
+    assert n == 22 and [m[0] for m in ref] == ["constellation", "payload_data", "packet_info"] * 22
+    assert len(got) == len(ref)
+    for a, b in zip(ref, got):
+        assert a[0] == b[0]
+        if a[0] == "constellation":
+            assert np.allclose(a[1], b[1], atol=1e-6)
+        else:
+            assert a[1] == b[1]
 
 
 @pytest.mark.gpu

@@ -49,6 +49,8 @@ namespace {
 #define LQB_TX_THREADS 64
 #endif
 constexpr int kTxThreads = LQB_TX_THREADS;
+constexpr int kTxTile = 4 * LQB_TX_THREADS;          // symbols interpolated per pass (two passes of two symbols per thread)
+constexpr int kTxBytesWords = (kTxTile + 16) * 8 / 32 + 2;   // words that hold the bits of kTxTile + 16 symbols of up to 8 bits from any bit offset
 static_assert(kTxThreads >= 64 && kTxThreads % 32 == 0, "warp 0 encodes the header while warp 1 checks the payload");
 constexpr float kPiF = 3.14159274f;
 constexpr float kTwoPiF = 6.28318548f;
@@ -268,12 +270,13 @@ k_tx(const TxTables *T, const TxFrame *frames, unsigned char *bufA, unsigned cha
     // the frame's symbols in one array: [14 zeros | 64 preamble | 231 header | n_sym payload | 16 zeros], so that the
     // interpolator reads a plain window (it used to pick the source of every tap with a three-way branch: 375
     // instructions per output sample, profiles/r01_notes.md v23)
-    float2 *arr = syms + f.sym_off;
-    float2 *hsym = arr + 14 + 64;
-    float2 *psym = arr + 14 + 64 + 231;
-    for (int i = tid; i < 14; i += kTxThreads) arr[i] = make_float2(0.0f, 0.0f);
-    for (int i = tid; i < 16; i += kTxThreads) psym[f.n_sym + i] = make_float2(0.0f, 0.0f);
-    for (int i = tid; i < 64; i += kTxThreads) arr[14 + i] = T->preamble[i];
+    // The symbols never exist in global memory: they are made tile by tile into shared memory (preamble from the table,
+    // header from `hsym`, payload from the encoded bytes through the symbol map) and interpolated from there.  Only DPSK,
+    // whose modulator carries phase memory from symbol to symbol, still writes its payload symbols to `psym` first.
+    __shared__ float2 hsym[232];
+    __shared__ float2 tile[kTxTile + 16 + (kTxTile + 16) / 16 + 1];   // entry i at i + i / 16: the interpolator's stride-2 reads (8-byte words) would otherwise collide two by two
+    __shared__ unsigned abytes[2][kTxBytesWords];          // the encoded bytes one tile of symbols is cut from (bps <= 8), two tiles in rotation
+    float2 *psym = syms + f.sym_off;
     if (f.check >= 3 && f.check <= 6) {
         const unsigned *tab = T->crc_tab[f.check];
         for (int i = tid; i < 256; i += kTxThreads) {
@@ -435,9 +438,10 @@ k_tx(const TxTables *T, const TxFrame *frames, unsigned char *bufA, unsigned cha
     }
     A = cur;                                              // the encoded message
 
-    // ---------------- bits -> symbols
+    // ---------------- bits -> symbols -> samples, a tile of kTxTile symbols at a time
     const unsigned bps = f.bps, nbits = 8 * f.n1;
-    if (f.ms >= 9 && f.ms <= 16) {          // DPSK carries phase memory: serial
+    const bool dpsk = (f.ms >= 9 && f.ms <= 16);
+    if (dpsk) {                             // DPSK carries phase memory: serial, through global memory
         if (tid == 0) {
             const float alpha = __fdiv_rn(kPiF, (float)(1u << bps));
             float phi = 0.0f;
@@ -451,45 +455,100 @@ k_tx(const TxTables *T, const TxFrame *frames, unsigned char *bufA, unsigned cha
                 psym[i] = make_float2(cs, sn);
             }
         }
-    } else {
-        for (unsigned i = tid; i < f.n_sym; i += kTxThreads) {
-            // bps <= 8 bits starting at bit i * bps: they lie inside the two bytes from pos >> 3 (MSB first); bits past
-            // the end of the encoded message read as zero
-            const unsigned pos = i * bps, byte = pos >> 3;
-            unsigned w = ((unsigned)A[byte] << 8) | (byte + 1 < f.n1 ? (unsigned)A[byte + 1] : 0u);
-            unsigned s = (w >> (16u - (pos & 7u) - bps)) & ((1u << bps) - 1u);
-            if (pos + bps > nbits) s &= ~((1u << (pos + bps - nbits)) - 1u);
-            psym[i] = smap[s];
-        }
+        __syncthreads();
     }
-    __syncthreads();
 
-    // ---------------- 2x interpolation: out[2t+ph] = sum_n h[ph + 2n] sym[t-n], oldest symbol first.
-    // A thread makes the four samples of two neighbouring symbols from a 16-symbol window; FFMA2 with the tap as the
-    // scalar operand is two IEEE fmas, applied in the specification's order (n = 14 first), so the samples are
-    // bit-identical to the per-sample form.
+    // 2x interpolation: out[2t+ph] = sum_n h[ph + 2n] sym[t-n], oldest symbol first.  A thread makes the four samples of
+    // two neighbouring symbols from a 16-symbol window; FFMA2 with the tap as the scalar operand is two IEEE fmas, applied
+    // in the specification's order (n = 14 first), so the samples are bit-identical to the per-sample form.
+    // Symbol index a runs over [14 zeros | 64 preamble | 231 header | n_sym payload | zeros]; tile[j] = symbol a0 + j.
     const int total_syms = 64 + 231 + (int)f.n_sym + 14;
+    const int pay0 = 14 + 64 + 231;
     float2 *o = f.out;
     float h[30];
 #pragma unroll
     for (int i = 0; i < 30; ++i) h[i] = __ldg(T->h + i);
-    for (int t = 2 * tid; t < total_syms; t += 2 * kTxThreads) {
-        const float2 *w = arr + t;                    // w[q] = sym[t - 14 + q]
-        float2 a0 = make_float2(0.0f, 0.0f), a1 = a0, a2 = a0, a3 = a0;
+    const unsigned n1_words = (f.n1 + 3u) >> 2;
+    const unsigned *A32 = reinterpret_cast<const unsigned *>(A);              // buf_off is a multiple of 16
+    // encoded bytes of the payload symbols [p0, p0 + kTxTile + 16) -> abytes[buf]: whole words from the byte p0 * bps / 8 on
+    auto stage_bytes = [&](int a0, int buf) {
+        const int p0 = max(a0 - pay0, 0);
+        const unsigned w0 = ((unsigned)p0 * bps) >> 5;
+        for (int i = tid; i < kTxBytesWords; i += kTxThreads) {
+            const unsigned w = w0 + (unsigned)i;
+            abytes[buf][i] = (!dpsk && w < n1_words) ? __byte_perm(A32[w], 0u, 0x0123) : 0u;     // MSB-first bit order
+        }
+    };
+    const bool al16 = (reinterpret_cast<uintptr_t>(o) & 15u) == 0;
+    __syncthreads();                                      // the encoded message is complete
+    stage_bytes(0, 0);
+    int buf = 0;
+    for (int a0 = 0; a0 < total_syms; a0 += kTxTile, buf ^= 1) {
+        __syncthreads();                                  // abytes[buf] is complete; the previous tile has been read
+        // ---- fill the tile: symbols a0 .. a0 + kTxTile + 15
+        const int p0 = max(a0 - pay0, 0);
+        const unsigned wbase = ((unsigned)p0 * bps) >> 5;
+        // a tile that lies wholly inside the payload (all but the first two and the last of a frame): no case analysis
+        const bool pure = !dpsk && a0 >= pay0 && a0 + kTxTile + 16 <= pay0 + (int)f.n_sym && ((unsigned)(p0 + kTxTile + 16) * bps <= nbits);
+        if (pure) {
+            const unsigned pos0 = (unsigned)p0 * bps - 32u * wbase;           // bit offset of the tile's first symbol in abytes
+            const unsigned *ab = abytes[buf];
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
-            const float2 x = w[q];
-            if (q <= 14) {                            // symbol t: n = 14 - q
-                a0 = __ffma2_rn(make_float2(h[2 * (14 - q)], h[2 * (14 - q)]), x, a0);
-                a1 = __ffma2_rn(make_float2(h[1 + 2 * (14 - q)], h[1 + 2 * (14 - q)]), x, a1);
+            for (int k = 0; k < (kTxTile + 16 + kTxThreads - 1) / kTxThreads; ++k) {
+                const int j = tid + kTxThreads * k;
+                if (j < kTxTile + 16) {
+                    const unsigned pos = pos0 + (unsigned)j * bps, wi = pos >> 5;
+                    tile[j + (j >> 4)] = smap[__funnelshift_l(ab[wi + 1], ab[wi], pos & 31u) >> (32u - bps)];
+                }
             }
-            if (q >= 1) {                             // symbol t + 1: n = 15 - q
-                a2 = __ffma2_rn(make_float2(h[2 * (15 - q)], h[2 * (15 - q)]), x, a2);
-                a3 = __ffma2_rn(make_float2(h[1 + 2 * (15 - q)], h[1 + 2 * (15 - q)]), x, a3);
+        } else
+        for (int j = tid; j < kTxTile + 16; j += kTxThreads) {
+            const int a = a0 + j;
+            float2 v = make_float2(0.0f, 0.0f);
+            if (a >= 14 && a < 14 + 64) v = T->preamble[a - 14];
+            else if (a >= 14 + 64 && a < pay0) v = hsym[a - 14 - 64];
+            else if (a >= pay0 && a < pay0 + (int)f.n_sym) {
+                const unsigned i = (unsigned)(a - pay0);
+                if (dpsk) v = psym[i];
+                else {
+                    // bps <= 8 bits starting at bit i * bps (MSB first); bits past the end of the encoded message read as zero
+                    const unsigned pos = i * bps, wi = (pos >> 5) - wbase, sh = pos & 31u;
+                    const unsigned hi = abytes[buf][wi], lo = abytes[buf][wi + 1];
+                    unsigned sv = __funnelshift_l(lo, hi, sh) >> (32u - bps);
+                    if (pos + bps > nbits) sv &= ~((1u << (pos + bps - nbits)) - 1u);
+                    v = smap[sv];
+                }
+            }
+            tile[j + (j >> 4)] = v;
+        }
+        if (a0 + kTxTile < total_syms) stage_bytes(a0 + kTxTile, buf ^ 1);   // the next tile's bytes travel while this one is interpolated
+        __syncthreads();
+        // ---- interpolate symbols t = a0 .. a0 + kTxTile - 1 (w[q] = sym[t - 14 + q] = tile[t - a0 + q] as a starts 14 early)
+        const int t_end = min(a0 + kTxTile, total_syms);
+        for (int t = a0 + 2 * tid; t < t_end; t += 2 * kTxThreads) {
+            const int j0 = t - a0;
+            float2 a0_ = make_float2(0.0f, 0.0f), a1 = a0_, a2 = a0_, a3 = a0_;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const float2 x = tile[(j0 + q) + ((j0 + q) >> 4)];
+                if (q <= 14) {                            // symbol t: n = 14 - q
+                    a0_ = __ffma2_rn(make_float2(h[2 * (14 - q)], h[2 * (14 - q)]), x, a0_);
+                    a1 = __ffma2_rn(make_float2(h[1 + 2 * (14 - q)], h[1 + 2 * (14 - q)]), x, a1);
+                }
+                if (q >= 1) {                             // symbol t + 1: n = 15 - q
+                    a2 = __ffma2_rn(make_float2(h[2 * (15 - q)], h[2 * (15 - q)]), x, a2);
+                    a3 = __ffma2_rn(make_float2(h[1 + 2 * (15 - q)], h[1 + 2 * (15 - q)]), x, a3);
+                }
+            }
+            // two 16-byte stores per thread when the caller's frame buffer is 16-byte aligned
+            if (al16) {
+                *reinterpret_cast<float4 *>(o + 2 * t) = make_float4(a0_.x, a0_.y, a1.x, a1.y);
+                if (t + 1 < total_syms) *reinterpret_cast<float4 *>(o + 2 * t + 2) = make_float4(a2.x, a2.y, a3.x, a3.y);
+            } else {
+                o[2 * t] = a0_; o[2 * t + 1] = a1;
+                if (t + 1 < total_syms) { o[2 * t + 2] = a2; o[2 * t + 3] = a3; }
             }
         }
-        o[2 * t] = a0; o[2 * t + 1] = a1;
-        if (t + 1 < total_syms) { o[2 * t + 2] = a2; o[2 * t + 3] = a3; }
     }
 }
 

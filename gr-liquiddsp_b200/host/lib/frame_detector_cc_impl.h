@@ -14,8 +14,12 @@ public:
     ~frame_detector_cc_impl();
     int work(int noutput_items, gr_vector_const_void_star &input_items, gr_vector_void_star &output_items);
     unsigned long frames_detected() const { return d_num_frames; }
+    long detect_capture(const gr_complex *samples, size_t n_samples, long long *indices, size_t max_out,
+                        unsigned workers, unsigned seg_len, unsigned preroll);
 private:
     lqb_det d_det;
+    lqb_det d_bulk;           // batch handle of detect_capture (made on first use)
+    unsigned d_bulk_workers;
     unsigned long d_num_frames;
 };
 

@@ -24,6 +24,17 @@ long blk_rx_decode_capture(void *p, const float *iq, unsigned long n, unsigned w
     if (!rx) return -2;
     try { return rx->decode_capture(reinterpret_cast<const gr_complex *>(iq), n, workers, seg_len, preroll); } catch (...) { return -3; }
 }
+long blk_det_detect_capture(void *p, const float *iq, unsigned long n, long long *idx, unsigned long max_out, unsigned workers, unsigned seg_len, unsigned preroll)
+{
+    frame_detector_cc *d = dynamic_cast<frame_detector_cc *>(static_cast<blk *>(p)->b.get());
+    if (!d) return -2;
+    try { return d->detect_capture(reinterpret_cast<const gr_complex *>(iq), n, idx, max_out, workers, seg_len, preroll); } catch (...) { return -3; }
+}
+unsigned long blk_det_frames(void *p)
+{
+    frame_detector_cc *d = dynamic_cast<frame_detector_cc *>(static_cast<blk *>(p)->b.get());
+    return d ? d->frames_detected() : 0;
+}
 void blk_destroy(void *p) { delete static_cast<blk *>(p); }
 const char *blk_name(void *p) { return static_cast<blk *>(p)->b->name().c_str(); }
 int blk_output_multiple(void *p) { return static_cast<blk *>(p)->b->output_multiple(); }

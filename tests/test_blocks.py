@@ -42,6 +42,10 @@ def _lib():
     L.blk_rx_index.argtypes = [C.c_int, C.c_uint]
     L.blk_tx_props.argtypes = [vp, vp]
     L.blk_rx_decode_capture.restype = C.c_long
+    L.blk_det_detect_capture.restype = C.c_long
+    L.blk_det_detect_capture.argtypes = [vp, vp, C.c_ulong, vp, C.c_ulong, C.c_uint, C.c_uint, C.c_uint]
+    L.blk_det_frames.restype = C.c_ulong
+    L.blk_det_frames.argtypes = [vp]
     L.blk_rx_decode_capture.argtypes = [vp, vp, C.c_ulong, C.c_uint, C.c_uint, C.c_uint]
     return L
 
@@ -222,9 +226,13 @@ def test_frame_detector_block_passthrough_and_count(gpu_required):
         assert L.blk_work(det, chunk.ctypes.data, 1, len(chunk), out[i:i + 1000].ctypes.data) == len(chunk)
     assert np.array_equal(out, cap)
     ref = o.detect_capture(cap, 0.3, 0.45)
-    # the block only counts: compare with the oracle's count over the part both have fully seen
-    lib2 = C.CDLL(BLK)
-    assert len(ref) >= 6
+    # the block only counts: the streamed work() calls counted what the sequential oracle finds
+    assert len(ref) >= 6 and L.blk_det_frames(det) == len(ref)
+    # additive offline entry: the same capture in one call, cut in time over GPU streams underneath
+    idx = np.zeros(64, np.int64)
+    n = L.blk_det_detect_capture(det, cap.ctypes.data, len(cap), idx.ctypes.data, 64, 16, 4096, 2048)
+    assert n == len(ref) and L.blk_det_frames(det) == 2 * len(ref)
+    assert list(idx[:n]) == [int(np.int64(np.uint64(r["sample_index"]))) for r in ref]
     L.blk_destroy(det)
 
 

@@ -654,7 +654,9 @@ def mixed_mod_arm(args, rank, local, world, steps=None, warmup=None, emit=True):
         t0 = time.perf_counter()
         m, i, o_ = pol.choose_arrays()
         ms_a, f0_a, f1_a = np.asarray(MODULATION)[m], np.asarray(INNER_CODE)[i], np.asarray(OUTER_CODE)[o_]
-        L = np.array([frame_len((int(a), int(b), int(c))) for a, b, c in zip(ms_a, f0_a, f1_a)], np.int64)
+        key = ms_a.astype(np.int64) * 4096 + f0_a.astype(np.int64) * 64 + f1_a.astype(np.int64)
+        uk, inv = np.unique(key, return_inverse=True)         # frame lengths per distinct configuration, not per channel
+        L = np.array([frame_len((int(k >> 12), int((k >> 6) & 63), int(k & 63))) for k in uk], np.int64)[inv]
         nfr = np.maximum(0, (NM - LEAD - 700) // (L + GAP))           # whole frames only; 700 samples of tail for the last one
         tot = int(nfr.sum())
         ch_of = np.repeat(np.arange(S), nfr)

@@ -501,25 +501,27 @@ k_tx(const TxTables *T, const TxFrame *frames, unsigned char *bufA, unsigned cha
                     tile[j + (j >> 4)] = smap[__funnelshift_l(ab[wi + 1], ab[wi], pos & 31u) >> (32u - bps)];
                 }
             }
-        } else
-        for (int j = tid; j < kTxTile + 16; j += kTxThreads) {
-            const int a = a0 + j;
-            float2 v = make_float2(0.0f, 0.0f);
-            if (a >= 14 && a < 14 + 64) v = T->preamble[a - 14];
-            else if (a >= 14 + 64 && a < pay0) v = hsym[a - 14 - 64];
-            else if (a >= pay0 && a < pay0 + (int)f.n_sym) {
-                const unsigned i = (unsigned)(a - pay0);
-                if (dpsk) v = psym[i];
-                else {
+        } else {
+            // region by region (zeros | preamble | header | payload | zeros), each a plain strided loop over its part of the tile
+            constexpr int kJ = kTxTile + 16;
+            const int pay1 = pay0 + (int)f.n_sym;
+            auto lo = [&](int ra) { return min(max(ra - a0, 0), kJ); };
+            for (int j = lo(0) + tid; j < lo(14); j += kTxThreads) tile[j + (j >> 4)] = make_float2(0.0f, 0.0f);
+            for (int j = lo(14) + tid; j < lo(14 + 64); j += kTxThreads) tile[j + (j >> 4)] = T->preamble[a0 + j - 14];
+            for (int j = lo(14 + 64) + tid; j < lo(pay0); j += kTxThreads) tile[j + (j >> 4)] = hsym[a0 + j - 14 - 64];
+            if (dpsk) {
+                for (int j = lo(pay0) + tid; j < lo(pay1); j += kTxThreads) tile[j + (j >> 4)] = psym[a0 + j - pay0];
+            } else {
+                const unsigned *ab = abytes[buf];
+                for (int j = lo(pay0) + tid; j < lo(pay1); j += kTxThreads) {
                     // bps <= 8 bits starting at bit i * bps (MSB first); bits past the end of the encoded message read as zero
-                    const unsigned pos = i * bps, wi = (pos >> 5) - wbase, sh = pos & 31u;
-                    const unsigned hi = abytes[buf][wi], lo = abytes[buf][wi + 1];
-                    unsigned sv = __funnelshift_l(lo, hi, sh) >> (32u - bps);
+                    const unsigned i = (unsigned)(a0 + j - pay0), pos = i * bps, wi = (pos >> 5) - wbase;
+                    unsigned sv = __funnelshift_l(ab[wi + 1], ab[wi], pos & 31u) >> (32u - bps);
                     if (pos + bps > nbits) sv &= ~((1u << (pos + bps - nbits)) - 1u);
-                    v = smap[sv];
+                    tile[j + (j >> 4)] = smap[sv];
                 }
             }
-            tile[j + (j >> 4)] = v;
+            for (int j = lo(pay1) + tid; j < kJ; j += kTxThreads) tile[j + (j >> 4)] = make_float2(0.0f, 0.0f);
         }
         if (a0 + kTxTile < total_syms) stage_bytes(a0 + kTxTile, buf ^ 1);   // the next tile's bytes travel while this one is interpolated
         __syncthreads();

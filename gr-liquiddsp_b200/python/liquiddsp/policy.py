@@ -56,7 +56,14 @@ class EpsilonGreedy(object):
         self._lut[self.cfg_m, self.cfg_i, self.cfg_o] = np.arange(self.n_cfg)
         self.trials = np.zeros((n_channels, self.n_cfg), np.int64)
         self.reward = np.zeros((n_channels, self.n_cfg), np.float64)
+        # mean reward per (channel, configuration), +inf while untried: kept up to date entry by entry in update_arrays, so
+        # that a choice is one argmax per channel instead of a pass of divisions over the whole table
+        self.mean = np.full((n_channels, self.n_cfg), np.inf, np.float64)
         self.rng = np.random.default_rng(seed)
+
+    def recompute(self):
+        """Rebuild the cached means from `trials` / `reward` (only needed after writing to those arrays directly)."""
+        self.mean = np.where(self.trials > 0, self.reward / np.maximum(self.trials, 1), np.inf)
 
     def update_arrays(self, channels, modulation, inner_code, outer_code, payload_valid):
         """One entry per received packet (arrays of equal length); schemes outside the tables (-1) are not learned from."""
@@ -67,8 +74,14 @@ class EpsilonGreedy(object):
         col = np.where(ok, self._lut[np.where(ok, m, 0), np.where(ok, i, 0), np.where(ok, o, 0)], -1)
         ok &= col >= 0
         ch, col, m, i, o, pv = ch[ok], col[ok], m[ok], i[ok], o[ok], pv[ok]
-        np.add.at(self.trials, (ch, col), 1)
-        np.add.at(self.reward, (ch, col), goodput(m, i, o, pv))
+        # (bincount over the flat index: the same sums as np.add.at, an order of magnitude faster)
+        flat = ch * self.n_cfg + col
+        uniq, inv = np.unique(flat, return_inverse=True)
+        t = self.trials.reshape(-1)
+        r = self.reward.reshape(-1)
+        t[uniq] += np.bincount(inv, minlength=len(uniq))
+        r[uniq] += np.bincount(inv, weights=goodput(m, i, o, pv), minlength=len(uniq))
+        self.mean.reshape(-1)[uniq] = r[uniq] / t[uniq]
 
     def update(self, channels, packet_infos):
         """packet_infos: dicts as published on flex_rx's packet_info port."""
@@ -79,8 +92,7 @@ class EpsilonGreedy(object):
 
     def choose_arrays(self):
         """Per-channel (modulation, inner_code, outer_code) index arrays."""
-        mean = np.where(self.trials > 0, self.reward / np.maximum(self.trials, 1), np.inf)   # untried first
-        best = mean.argmax(axis=1)
+        best = self.mean.argmax(axis=1)                   # untried (+inf) first, then the best mean; first index on ties
         explore = self.rng.random(self.n) < self.eps
         pick = np.where(explore, self.rng.integers(0, self.n_cfg, self.n), best)
         return self.cfg_m[pick], self.cfg_i[pick], self.cfg_o[pick]

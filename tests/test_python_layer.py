@@ -17,6 +17,7 @@ def test_policy_numbering_matches_cognitive_engine():
     assert np.array_equal(policy.config_id(m, i, oo), np.arange(1, 617))
     p = policy.EpsilonGreedy(3, epsilon=0.0, seed=1)
     p.trials[:] = 1                                   # everything tried once with zero reward ...
+    p.recompute()                                     # (the state arrays were written directly)
     p.update([0, 1, 2], [{"modulation": 8, "inner_code": 0, "outer_code": 0, "payload_valid": 1, "header_valid": 1}] * 3)
     assert p.choose() == [{"modulation": 8, "inner_code": 0, "outer_code": 0}] * 3   # ... so the rewarded one wins
     p.update([0], [{"modulation": -1, "inner_code": 0, "outer_code": 0, "payload_valid": 1, "header_valid": 1}])   # ignored

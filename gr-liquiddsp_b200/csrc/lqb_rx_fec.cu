@@ -692,6 +692,160 @@ k_viterbi27x4(PayloadParams P, const unsigned *__restrict__ list, unsigned n_lis
     }
 }
 
+// ------------------------------------------------------------------ Viterbi K=9, sixteen lanes per codeword
+// The 256 path metrics of a codeword sit in 16 lanes x 8 registers of packed 16-bit pairs: lane l holds the OLD states
+// 16 q + l (low half of word q) and 16 (q + 8) + l (high half), q = 0 .. 7 -- the two predecessors i and i + 128 of
+// butterfly i = 16 q + l share a word, so the add-compare-select is lane-local:
+//   X = W + (m | 510 - m << 16),  Y = W + (510 - m | m << 16)      candidate sums into new states 2 i and 2 i + 1
+//   Z1 = (X.lo | Y.lo << 16), Z2 = (X.hi | Y.hi << 16)             the first / second candidate of both
+//   N = min16x2(Z1, Z2),  decision = Z1 > Z2 (sign of Z1 - Z2 - 1, per half)
+// with m the branch metric of the butterfly's label: label(i) = label(16 q) ^ label(l), the lane part XORed into the
+// received values once per step, the register part a compile-time constant.  The new states 32 q + 2 l + x then move to
+// where the next step wants them (lane 2 (l & 7) + x, register 2 q + (l >> 3)): sixteen shuffles and eight byte permutes.
+// 16 bits suffice: the metric spread of a K = 9 trellis is at most 8 * 510 and the common minimum is subtracted every 96
+// steps (4080 + 96 * 510 < 65536); relative metrics, comparisons and tie-breaks are the specification's.
+// Decisions: one 32-bit word per lane and PAIR of steps (even step in the high nibbles of the four bytes, odd step in
+// the low ones; the bit of new state 32 q + 2 l + x: byte 2 (q & 1) + x, bit 7 - (q >> 1)), [pair][lane] in the frame's
+// private slice of the decision arena.  Traceback: the sixteen lanes walk the state together, the lane that owns it
+// hands its bit over by shuffle.  Hard or SOFT input, punctured or not (the generic symbol fetch).  Two codewords per warp.
+constexpr int kV9Lanes = 16;
+constexpr int kV9Threads = 128;
+
+__host__ __device__ constexpr unsigned v9_par(unsigned x) { x ^= x >> 8; x ^= x >> 4; x ^= x >> 2; x ^= x >> 1; return x & 1u; }
+// label of butterfly i: bit 0 = parity(2 i & poly0), bit 1 = parity(2 i & poly1)   (K = 9: 0x1af, 0x11d)
+__host__ __device__ constexpr unsigned v9_label(unsigned i) { return v9_par((2u * i) & 0x1afu) | (v9_par((2u * i) & 0x11du) << 1); }
+
+template <bool SOFT>
+__global__ void __launch_bounds__(kV9Threads)
+k_viterbi29x16(PayloadParams P, const unsigned *__restrict__ list, unsigned n_list, int stage)
+{
+    const unsigned lane = threadIdx.x & 31u, l = lane & 15u, grp_base = lane & 16u;
+    unsigned gi = (blockIdx.x * kV9Threads + threadIdx.x) / kV9Lanes;
+    // a group past the end of the list shadows the last codeword without storing anything (full-mask shuffles)
+    const bool active = gi < n_list;
+    if (!active) gi = n_list - 1;
+    const FrameDesc &d = P.frames[list[gi]];
+    StageIO io = stage_io(P, d, stage);
+    if (SOFT) { io.src = P.soft_d + P.soft[list[gi]].d_off; io.enc_len *= 8u; }     // one byte per coded bit
+    const ConvSpec cs = conv_spec(io.fs);
+    const unsigned nbits = 8 * io.dec_len, T = nbits + 8;          // T is even
+    unsigned Tw = T;                                  // longest codeword in this warp
+    Tw = max(Tw, __shfl_xor_sync(0xffffffffu, Tw, 16));
+    unsigned *dec = reinterpret_cast<unsigned *>(P.decisions + d.dec_off);        // [pair][lane]
+
+    // received values, in order (as the warp-per-codeword kernel reads them: words, one ahead)
+    unsigned per = 0, pre[8];
+    for (unsigned c = 0; c < cs.P; ++c) { pre[c] = per; per += ((cs.keep0 >> c) & 1u) + ((cs.keep1 >> c) & 1u); }
+    const unsigned enc_words = (io.enc_len + 3u) >> 2;
+    auto load_word = [&](unsigned w) -> unsigned {
+        if (w >= enc_words) return 0u;
+        const unsigned char *p = io.src + 4u * w;
+        unsigned v = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v = (v << 8) | ((4u * w + k < io.enc_len) ? (unsigned)p[k] : 0u);
+        return v;
+    };
+    unsigned wbase = 0, wcur = load_word(0), wnext = load_word(1);
+    auto take = [&](unsigned ib) -> unsigned {                   // ib never decreases
+        if (SOFT) {
+            while ((ib >> 2) != wbase) { ++wbase; wcur = wnext; wnext = load_word(wbase + 1); }
+            return (wcur >> (24u - 8u * (ib & 3u))) & 0xffu;
+        }
+        while ((ib >> 5) != wbase) { ++wbase; wcur = wnext; wnext = load_word(wbase + 1); }
+        return ((wcur >> (31u - (ib & 31u))) & 1u) ? 255u : 0u;
+    };
+    const unsigned lab_l = v9_label(l);
+    const unsigned lm0 = (lab_l & 1u) ? 255u : 0u, lm1 = (lab_l & 2u) ? 255u : 0u;
+
+    unsigned W[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) W[q] = 63u | (63u << 16);
+    if (l == 0) W[0] = 63u << 16;                    // state 0 starts at 0
+    const unsigned src0 = grp_base | (l >> 1), src1 = src0 + 8u;     // the two lanes this lane's next states come from
+    const unsigned sel = (l & 1u) ? 0x7632u : 0x5410u;               // their half: x = l & 1
+    unsigned col = 0, tcol = 0, since = 0, pair_word = 0;
+    for (unsigned t = 0; t < Tw; ++t) {
+        // ---- received pair and the four packed branch metrics
+        unsigned ib = tcol * per + pre[col];
+        unsigned sym0 = 127u, sym1 = 127u;
+        if (t < T) {
+            if ((cs.keep0 >> col) & 1u) { sym0 = take(ib); ++ib; }
+            if ((cs.keep1 >> col) & 1u) { sym1 = take(ib); }
+        }
+        if (++col == cs.P) { col = 0; ++tcol; }
+        const unsigned s0 = sym0 ^ lm0, s1 = sym1 ^ lm1;
+        unsigned M[4];
+        M[0] = s0 + s1; M[1] = (s0 ^ 255u) + s1; M[2] = s0 + (s1 ^ 255u); M[3] = 510u - M[0];
+        const unsigned A[4] = { M[0] | (M[3] << 16), M[1] | (M[2] << 16), M[2] | (M[1] << 16), M[3] | (M[0] << 16) };
+        // ---- add-compare-select, lane-local
+        unsigned N[8], G[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            constexpr unsigned kLab[8] = { v9_label(0), v9_label(16), v9_label(32), v9_label(48), v9_label(64), v9_label(80), v9_label(96), v9_label(112) };
+            const unsigned X = W[q] + A[kLab[q]], Y = W[q] + A[3u - kLab[q]];
+            const unsigned Z1 = __byte_perm(X, Y, 0x5410), Z2 = __byte_perm(X, Y, 0x7632);
+            G[q] = v2_add(Z1, ~Z2);                  // sign clear <=> Z1 > Z2 <=> the predecessor i + 128 wins
+            N[q] = v2_min(Z1, Z2);                   // new states 2 i (low) and 2 i + 1 (high)
+        }
+        // ---- decisions: sign bits of the eight words -> the high nibbles of four bytes (byte 2 (q & 1) + x, bit 7 - (q >> 1))
+        {
+            const unsigned p0 = __byte_perm(G[0], G[1], 0x7531), p1 = __byte_perm(G[2], G[3], 0x7531);
+            const unsigned p2 = __byte_perm(G[4], G[5], 0x7531), p3 = __byte_perm(G[6], G[7], 0x7531);
+            unsigned r = (p0 & 0x80808080u) | ((p1 >> 1) & 0x40404040u) | ((p2 >> 2) & 0x20202020u) | ((p3 >> 3) & 0x10101010u);
+            r ^= 0xf0f0f0f0u;                        // stored sense: 1 = the predecessor i + 128 wins
+            if (t & 1u) {
+                pair_word |= r >> 4;
+                if (active && t < T) dec[(size_t)(t >> 1) * kV9Lanes + l] = pair_word;
+            } else pair_word = r;
+        }
+        // ---- the new states go where the next step reads them
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const unsigned a0 = __shfl_sync(0xffffffffu, N[j], src0), a4 = __shfl_sync(0xffffffffu, N[j + 4], src0);
+            const unsigned b0 = __shfl_sync(0xffffffffu, N[j], src1), b4 = __shfl_sync(0xffffffffu, N[j + 4], src1);
+            W[2 * j] = __byte_perm(a0, a4, sel);     // register 2 j     <- butterflies j, j + 4 of lane (l >> 1)
+            W[2 * j + 1] = __byte_perm(b0, b4, sel); // register 2 j + 1 <- the same of lane (l >> 1) + 8
+        }
+        if (++since == 96u) {
+            since = 0;
+            unsigned mn = v2_min(v2_min(v2_min(W[0], W[1]), v2_min(W[2], W[3])), v2_min(v2_min(W[4], W[5]), v2_min(W[6], W[7])));
+            mn = v2_min(mn, __byte_perm(mn, 0u, 0x1032));
+#pragma unroll
+            for (int m = 1; m <= 8; m <<= 1) mn = v2_min(mn, __shfl_xor_sync(0xffffffffu, mn, m));
+            const unsigned neg = __vsub2(0u, mn);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) W[q] = v2_add(W[q], neg);
+        }
+    }
+    __syncwarp();
+    __threadfence_block();
+
+    // ---- traceback from state 0: the sixteen lanes track the state, the owner of its bit hands it over
+    unsigned char *out = io.dst;
+    unsigned state = 0, acc = 0;
+    const int pairs = (int)(T >> 1);
+    unsigned w_cur = active ? dec[(size_t)(pairs - 1) * kV9Lanes + l] : 0u;
+    for (int pr = pairs - 1; pr >= 0; --pr) {
+        const unsigned w_next = (active && pr > 0) ? dec[(size_t)(pr - 1) * kV9Lanes + l] : 0u;     // (requested one pair ahead)
+#pragma unroll
+        for (int odd = 1; odd >= 0; --odd) {
+            const unsigned t = 2u * (unsigned)pr + (unsigned)odd;
+            // new state `state` after step t = 32 q + 2 l' + x
+            const unsigned x = state & 1u, owner = (state >> 1) & 15u, q = state >> 5;
+            const unsigned byte = (w_cur >> (8u * (2u * (q & 1u) + x))) & 0xffu;
+            const unsigned mine = (byte >> ((odd ? 3u : 7u) - (q >> 1))) & 1u;
+            const unsigned k = __shfl_sync(0xffffffffu, mine, grp_base | owner);
+            if (t >= 8u) {
+                const unsigned bi = t - 8u;          // the bit shifted out at step t entered at t - 8
+                acc |= k << (7u - (bi & 7u));
+                if ((bi & 7u) == 0u) { if (active && l == 0) out[bi >> 3] = (unsigned char)acc; acc = 0; }
+            }
+            state = (state >> 1) | (k << 7);
+        }
+        w_cur = w_next;
+    }
+}
+
 // ------------------------------------------------------------------ Reed-Solomon (warp per 255-byte block)
 constexpr int kRsWarps = 4;
 constexpr int kRsSynBytes = 256 * 32 * 4;
@@ -915,7 +1069,8 @@ void launch_viterbi(const PayloadParams &P, const unsigned *list, unsigned n, in
         if (punct) k_viterbi27x4<true><<<(threads + kV4Threads - 1) / kV4Threads, kV4Threads, 0, s>>>(P, list, n, stage, reinterpret_cast<unsigned *>(P.decisions), warm);
         else k_viterbi27x4<false><<<(threads + kV4Threads - 1) / kV4Threads, kV4Threads, 0, s>>>(P, list, n, stage, reinterpret_cast<unsigned *>(P.decisions), warm);
     }
-    else k_viterbi<false><<<(n + kVitWarps - 1) / kVitWarps, 32 * kVitWarps, 0, s>>>(P, list, n, stage);
+    else if (!std::getenv("LQB_V9_GENERIC")) k_viterbi29x16<false><<<(n * kV9Lanes + kV9Threads - 1) / kV9Threads, kV9Threads, 0, s>>>(P, list, n, stage);
+    else k_viterbi<false><<<(n + kVitWarps - 1) / kVitWarps, 32 * kVitWarps, 0, s>>>(P, list, n, stage);      // (the warp-per-codeword form, kept for A/B)
 }
 void launch_viterbi_soft(const PayloadParams &P, const unsigned *list, unsigned n, int stage, unsigned K, bool punct, cudaStream_t s)
 {
@@ -927,6 +1082,7 @@ void launch_viterbi_soft(const PayloadParams &P, const unsigned *list, unsigned 
         if (punct) k_viterbi27x4<true, true><<<(threads + kV4Threads - 1) / kV4Threads, kV4Threads, 0, s>>>(P, list, n, stage, reinterpret_cast<unsigned *>(P.decisions), warm);
         else k_viterbi27x4<false, true><<<(threads + kV4Threads - 1) / kV4Threads, kV4Threads, 0, s>>>(P, list, n, stage, reinterpret_cast<unsigned *>(P.decisions), warm);
     }
+    else if (!std::getenv("LQB_V9_GENERIC")) k_viterbi29x16<true><<<(n * kV9Lanes + kV9Threads - 1) / kV9Threads, kV9Threads, 0, s>>>(P, list, n, stage);
     else k_viterbi<true><<<(n + kVitWarps - 1) / kVitWarps, 32 * kVitWarps, 0, s>>>(P, list, n, stage);
 }
 void launch_rs(const PayloadParams &P, const unsigned *blocks, unsigned n_blocks, int stage, cudaStream_t s)

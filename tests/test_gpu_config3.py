@@ -161,3 +161,24 @@ def test_sc16_input_equals_the_widened_floats():
         rx3.execute_sc16([q[i:i + 3001]])
         got3 += rx3.poll()
     assert_frames_match(ref, got3)
+
+
+@pytest.mark.parametrize("fec", [12, 21, 22, 23, 24, 25, 26])
+def test_k9_codes_sixteen_lane_viterbi_matches_oracle(fec):
+    """v29 and its punctured rates on the sixteen-lane K = 9 decoder (k_viterbi29x16): ragged lengths (two codewords share a
+    warp and run to the longer one), a 1500-byte frame, a one-byte frame, as inner code alone and under RS(255,223), near
+    the knee so that decisions carry errors."""
+    rng = np.random.default_rng(900 + fec)
+    lens = [1500, 1, 333, 64, 257, 9, 800]
+    pls = [rng.integers(0, 256, n, dtype=np.uint8) for n in lens]
+    frames = [o.tx_frame(util.PSK4, util.CRC24, fec, 27 if k % 2 else 1, p) for k, p in enumerate(pls)]
+    cap = util.build_capture(frames, rng, [700] * len(frames), snr_db=5.5, cfo=0.011, tau=0.2)
+    ref = o.rx_capture(cap)
+    rx = capi.Rx(1)
+    rx.execute([cap])
+    got = rx.poll()
+    assert len(ref) == len(got) == len(lens)
+    for r, g in zip(ref, got):
+        assert r["sample_index"] == g["sample_index"] and r["header_valid"] == g["header_valid"] == 1
+        assert r["payload_valid"] == g["payload_valid"] and r["payload"] == g["payload"]      # the decoded bytes, right or wrong
+    assert sum(r["payload_valid"] for r in ref) >= 3

@@ -1736,6 +1736,14 @@ int lqb_tab_interp_taps(float beta, float *h30) { auto h = interp_taps(beta); st
 int lqb_tab_pfb_banks(float beta, float *b) { auto v = pfb_banks(beta); std::memcpy(b, v.data(), v.size() * sizeof(float)); return 0; }
 int lqb_tab_detector_template(float beta, float *s) { auto v = detector_template(beta); std::memcpy(s, v.data(), v.size() * sizeof(cf)); return 0; }
 int lqb_tab_nco_sintab(float *t) { std::memcpy(t, nco_sintab(), 1024 * sizeof(float)); return 0; }
+int lqb_tab_secded_columns(uint32_t data_bytes, uint8_t *col)
+{
+    if (!col || (data_bytes != 2 && data_bytes != 4 && data_bytes != 8)) return fail(LQB_EINVAL, "data_bytes is 2, 4 or 8");
+    uint8_t c[3][64];
+    secded_cols(c);
+    std::memcpy(col, c[data_bytes == 2 ? 0 : data_bytes == 4 ? 1 : 2], 8 * data_bytes);
+    return 0;
+}
 int lqb_tab_ilv_bit_perm(uint32_t n, uint32_t *perm)
 {
     if (!perm) return fail(LQB_EINVAL, "null pointer");

@@ -29,7 +29,7 @@ struct DevTables {
     uint16_t hperm27[216];     // (bit b of byte i has index 8 i + b, b = 0 the least significant bit)
     uint8_t  h84_dec[256];
     uint8_t  h74_dec[128];
-    uint8_t  secded_col[64];
+    uint8_t  secded_col[3][64]; // liquid's Hsiao codes, by code (0: (22,16), 1: (39,32), 2: (72,64)) and data bit: parity-byte contribution
     uint8_t  gf_exp[512];
     uint8_t  gf_log[256];
     uint8_t  rs_gen[64];       // 33 used

@@ -111,22 +111,21 @@ __device__ unsigned h128_decode(unsigned r)
     return r & 0xffu;
 }
 
-__device__ void secded_block(const DevTables *T, const unsigned char *src, unsigned char *dst, unsigned nb, unsigned nc, unsigned r)
+__device__ void secded_block(const DevTables *T, const unsigned char *src, unsigned char *dst, unsigned nb, unsigned R, unsigned r)
 {
-    // src: [parity][r data bytes], block of nb data bytes (missing ones are zero); writes r bytes
+    // src: [parity][r data bytes], block of nb data bytes (missing ones are zero), R parity bits; writes r bytes.
+    // Syndrome = parity of the data XOR the received parity bits: zero: nothing; a column of P: that data bit is
+    // flipped back; anything else (a parity bit, or two or more errors): left as received.
+    const unsigned char *col = T->secded_col[nb == 2 ? 0 : nb == 4 ? 1 : 2];
     unsigned char blk[8];
-    const unsigned rp = src[0];
-    unsigned p = 0, all = 0, tot = 0;
-    for (unsigned q = 0; q < nb; ++q) { blk[q] = q < r ? src[1 + q] : 0; tot ^= (unsigned)__popc(blk[q]) & 1u; }
+    unsigned p = 0;
+    for (unsigned q = 0; q < nb; ++q) blk[q] = q < r ? src[1 + q] : 0;
     for (unsigned bit = 0; bit < nb * 8; ++bit)
-        if ((blk[bit >> 3] >> (7 - (bit & 7))) & 1u) { p ^= T->secded_col[bit]; all ^= 1u; }
-    all ^= (unsigned)__popc(p) & 1u;
-    const unsigned calc = p | (all << nc);
-    const unsigned syn = (calc ^ rp) & ((1u << nc) - 1u);
-    tot ^= (unsigned)__popc(rp & ((1u << (nc + 1)) - 1u)) & 1u;
-    if (tot && syn && (syn & (syn - 1)))
+        if ((blk[bit >> 3] >> (7 - (bit & 7))) & 1u) p ^= col[bit];
+    const unsigned syn = p ^ (src[0] & ((1u << R) - 1u));
+    if (syn)
         for (unsigned bit = 0; bit < nb * 8; ++bit)
-            if (T->secded_col[bit] == syn) { blk[bit >> 3] ^= (unsigned char)(0x80u >> (bit & 7)); break; }
+            if (col[bit] == syn) { blk[bit >> 3] ^= (unsigned char)(0x80u >> (bit & 7)); break; }
     for (unsigned q = 0; q < r; ++q) dst[q] = blk[q];
 }
 
@@ -181,7 +180,7 @@ k_blockfec(PayloadParams P, const unsigned *__restrict__ list, int stage)
         break;
     }
     case 8: case 9: case 10: {
-        const unsigned nb = io.fs == 8 ? 2u : io.fs == 9 ? 4u : 8u, nc = io.fs == 8 ? 5u : io.fs == 9 ? 6u : 7u;
+        const unsigned nb = io.fs == 8 ? 2u : io.fs == 9 ? 4u : 8u, nc = io.fs == 8 ? 6u : io.fs == 9 ? 7u : 8u;      // data bytes, parity bits
         const unsigned blocks = (n + nb - 1) / nb;
         for (unsigned b = tid; b < blocks; b += nt) {
             unsigned r = (n - b * nb >= nb) ? nb : (n - b * nb);

@@ -995,18 +995,18 @@ __device__ void decode_header(SeekShared &sh, const DevTables *T, const StreamVi
         if (tid < 3) {
             const int blk = tid;
             const unsigned char *src = d27b + 9 * blk;
-            unsigned rp = src[0], p = 0, all = 0, tot = 0;
+            // liquid's Hsiao (72,64) code: syndrome = parity of the data XOR the received parity byte; a syndrome that
+            // equals a column of P is that data bit (flipped back), anything else is left as received
+            const unsigned char *col = T->secded_col[2];
+            unsigned p = 0;
             unsigned char b8[8];
-            for (int q = 0; q < 8; ++q) { b8[q] = src[1 + q]; tot ^= (unsigned)__popc(b8[q]) & 1u; }
+            for (int q = 0; q < 8; ++q) b8[q] = src[1 + q];
             for (int bit = 0; bit < 64; ++bit)
-                if ((b8[bit >> 3] >> (7 - (bit & 7))) & 1u) { p ^= T->secded_col[bit]; all ^= 1u; }
-            all ^= (unsigned)__popc(p) & 1u;
-            unsigned calc = p | (all << 7);
-            unsigned syn = (calc ^ rp) & 0x7fu;
-            tot ^= (unsigned)__popc(rp & 0xffu) & 1u;
-            if (tot && syn && (syn & (syn - 1)))
+                if ((b8[bit >> 3] >> (7 - (bit & 7))) & 1u) p ^= col[bit];
+            const unsigned syn = (p ^ src[0]) & 0xffu;
+            if (syn)
                 for (int bit = 0; bit < 64; ++bit)
-                    if (T->secded_col[bit] == syn) { b8[bit >> 3] ^= (unsigned char)(0x80u >> (bit & 7)); break; }
+                    if (col[bit] == syn) { b8[bit >> 3] ^= (unsigned char)(0x80u >> (bit & 7)); break; }
             const unsigned char mask[4] = { 0xb4, 0x6a, 0x8b, 0xc5 };
             for (int q = 0; q < 8; ++q) d[8 * blk + q] = b8[q] ^ mask[q & 3];      // 8 blk is a multiple of 4: unscramble in place
         }

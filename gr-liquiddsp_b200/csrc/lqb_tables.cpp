@@ -312,14 +312,27 @@ void hamming_dec_tables(uint8_t h84[256], uint8_t h74[128])
     }
 }
 
-void secded_cols(uint8_t col[64])
+// liquid-dsp's Hsiao SEC-DED codes (fec_secded2216 / 3932 / 7264): parity matrices [R x C], row 0 = the most significant
+// parity bit; col[c][i] = contribution of data bit i (0 = MSB of the first data byte) to the parity byte of code c
+// (0: (22,16), 1: (39,32), 2: (72,64)).  Every column is distinct and of odd weight.
+static const uint8_t kSecded2216P[12] = { 0x99, 0x3c, 0x3e, 0x8a, 0xee, 0x60, 0xe1, 0xd1, 0x13, 0xc7, 0x44, 0x3f };
+static const uint8_t kSecded3932P[28] = { 0x8a, 0x82, 0x0f, 0x1b, 0x10, 0x1f, 0x71, 0x61, 0x16, 0xf0, 0x92, 0xa6, 0xff, 0x01, 0xa4, 0x44,
+                                          0x6c, 0xff, 0x08, 0x08, 0x21, 0x24, 0xff, 0x90, 0xc1, 0x48, 0x40, 0xff };
+static const uint8_t kSecded7264P[64] = { 0xff, 0x0f, 0x0f, 0x0c, 0x68, 0x88, 0x88, 0x80, 0xf0, 0xff, 0x00, 0xf3, 0x64, 0x44, 0x44, 0x40,
+                                          0x30, 0xf0, 0xff, 0x0f, 0x02, 0x22, 0x22, 0x26, 0xcf, 0x00, 0xf0, 0xff, 0x01, 0x11, 0x11, 0x16,
+                                          0x68, 0x88, 0x88, 0x80, 0xff, 0x0f, 0x00, 0xf3, 0x64, 0x44, 0x44, 0x40, 0xf0, 0xff, 0x0f, 0x0c,
+                                          0x02, 0x22, 0x22, 0x26, 0xcf, 0x00, 0xff, 0x0f, 0x01, 0x11, 0x11, 0x16, 0x30, 0xf0, 0xf0, 0xff };
+void secded_cols(uint8_t col[3][64])
 {
-    unsigned c = 2;
-    for (unsigned i = 0; i < 64; ++i) {
-        ++c;
-        while ((c & (c - 1)) == 0) ++c;
-        col[i] = (uint8_t)c;
-    }
+    const uint8_t *P[3] = { kSecded2216P, kSecded3932P, kSecded7264P };
+    const unsigned nb[3] = { 2, 4, 8 }, R[3] = { 6, 7, 8 };
+    for (unsigned c = 0; c < 3; ++c)
+        for (unsigned i = 0; i < 64; ++i) {
+            unsigned v = 0;
+            if (i < 8 * nb[c])
+                for (unsigned r = 0; r < R[c]; ++r) v |= ((P[c][r * nb[c] + (i >> 3)] >> (7 - (i & 7))) & 1u) << (R[c] - 1 - r);
+            col[c][i] = (uint8_t)v;
+        }
 }
 
 void gf256_tables(uint8_t gf_exp[512], uint8_t gf_log[256], uint8_t rs_gen[33])

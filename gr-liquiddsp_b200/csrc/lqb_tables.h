@@ -65,7 +65,7 @@ std::vector<uint32_t> ilv_bit_perm(unsigned n);          // 8 n entries: deinter
 
 // ---- small code tables
 void hamming_dec_tables(uint8_t h84[256], uint8_t h74[128]);
-void secded_cols(uint8_t col[64]);
+void secded_cols(uint8_t col[3][64]);   // [code 0: (22,16), 1: (39,32), 2: (72,64)][data bit]
 void gf256_tables(uint8_t gf_exp[512], uint8_t gf_log[256], uint8_t rs_gen[33]);
 void crc_table(unsigned check, uint32_t tab[256]);
 

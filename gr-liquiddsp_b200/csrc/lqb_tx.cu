@@ -28,7 +28,7 @@ struct TxTables {
     uint32_t crc_tab[8][256];
     uint16_t ilv54[4][28], ilv27[4][16];
     uint16_t hperm27f[216], hperm54f[432];   // the header's two interleavers as bit gathers: out bit i = in bit perm[i]
-    uint8_t  secded_col[64];
+    uint8_t  secded_col[3][64];
     uint8_t  gf_exp[512], gf_log[256], rs_gen[64];
 };
 
@@ -85,13 +85,14 @@ __device__ void ilv_small(unsigned char *x, const uint16_t *map, unsigned n2, un
     }
 }
 
-__device__ unsigned secded_parity(const TxTables *T, const unsigned char *blk, unsigned nb, unsigned nc)
+// parity byte of liquid's Hsiao SEC-DED code with nb data bytes: XOR of the columns of the set data bits
+__device__ unsigned secded_parity(const TxTables *T, const unsigned char *blk, unsigned nb)
 {
-    unsigned p = 0, all = 0;
+    const unsigned char *col = T->secded_col[nb == 2 ? 0 : nb == 4 ? 1 : 2];
+    unsigned p = 0;
     for (unsigned bit = 0; bit < nb * 8; ++bit)
-        if ((blk[bit >> 3] >> (7 - (bit & 7))) & 1u) { p ^= T->secded_col[bit]; all ^= 1u; }
-    all ^= (unsigned)__popc(p) & 1u;
-    return p | (all << nc);
+        if ((blk[bit >> 3] >> (7 - (bit & 7))) & 1u) p ^= col[bit];
+    return p;
 }
 
 __constant__ unsigned char c_h84[16] = { 0x00, 0xd2, 0x55, 0x87, 0x99, 0x4b, 0xcc, 0x1e, 0xe1, 0x33, 0xb4, 0x66, 0x78, 0xaa, 0x2d, 0xff };
@@ -165,14 +166,14 @@ __device__ void fec_encode(const TxTables *T, unsigned fs, unsigned n, unsigned 
         break;
     }
     case 8: case 9: case 10: {
-        const unsigned nb = fs == 8 ? 2u : fs == 9 ? 4u : 8u, nc = fs == 8 ? 5u : fs == 9 ? 6u : 7u;
+        const unsigned nb = fs == 8 ? 2u : fs == 9 ? 4u : 8u;
         const unsigned blocks = (n + nb - 1) / nb;
         for (unsigned b = tid; b < blocks; b += kTxThreads) {
             unsigned r = (n - b * nb >= nb) ? nb : (n - b * nb);
             unsigned char blk[8];
             for (unsigned q = 0; q < nb; ++q) blk[q] = q < r ? src[b * nb + q] : 0;
             unsigned char *d = dst + b * (nb + 1);
-            d[0] = (unsigned char)secded_parity(T, blk, nb, nc);
+            d[0] = (unsigned char)secded_parity(T, blk, nb);
             for (unsigned q = 0; q < r; ++q) d[1 + q] = blk[q];
         }
         break;
@@ -325,16 +326,15 @@ k_tx(const TxTables *T, const TxFrame *frames, unsigned char *bufA, unsigned cha
         __syncwarp();
         // SECDED(72,64): parity of block b = XOR of the columns of its set bits; lane handles bits lane and lane + 32
         for (unsigned b = 0; b < 3; ++b) {
-            unsigned p = 0, ones = 0;
+            unsigned p = 0;
 #pragma unroll
             for (unsigned h2 = 0; h2 < 2; ++h2) {
                 const unsigned bit = lane + 32u * h2;
-                if ((hd[8 * b + (bit >> 3)] >> (7 - (bit & 7))) & 1u) { p ^= T->secded_col[bit]; ones ^= 1u; }
+                if ((hd[8 * b + (bit >> 3)] >> (7 - (bit & 7))) & 1u) p ^= T->secded_col[2][bit];
             }
 #pragma unroll
-            for (int m = 16; m >= 1; m >>= 1) { p ^= __shfl_xor_sync(0xffffffffu, p, m); ones ^= __shfl_xor_sync(0xffffffffu, ones, m); }
-            ones ^= (unsigned)__popc(p) & 1u;
-            if (lane == 0) he[9 * b] = (unsigned char)(p | (ones << 7));
+            for (int m = 16; m >= 1; m >>= 1) p ^= __shfl_xor_sync(0xffffffffu, p, m);
+            if (lane == 0) he[9 * b] = (unsigned char)p;
             if (lane < 8) he[9 * b + 1 + lane] = hd[8 * b + lane];
         }
         __syncwarp();

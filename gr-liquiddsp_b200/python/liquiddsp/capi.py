@@ -26,7 +26,7 @@ DECLARED_SYMBOLS = [
     "lqb_det_poll", "lqb_det_last_timing", "lqb_det_last_work", "lqb_det_last_search",
     "lqb_det_execute_sharded", "lqb_det_last_shard_info", "lqb_rx_execute_sharded", "lqb_rx_last_shard_info",
     "lqb_tab_interp_taps", "lqb_tab_pfb_banks", "lqb_tab_detector_template", "lqb_tab_nco_sintab",
-    "lqb_tab_packet_len", "lqb_tab_ilv_bit_perm",
+    "lqb_tab_packet_len", "lqb_tab_ilv_bit_perm", "lqb_tab_secded_columns",
 ]
 
 
@@ -376,6 +376,13 @@ def tab_nco_sintab():
     t = np.zeros(1024, np.float32)
     lib().lqb_tab_nco_sintab(t.ctypes.data)
     return t
+
+
+def tab_secded_columns(data_bytes):
+    c = np.zeros(8 * data_bytes, np.uint8)
+    lib().lqb_tab_secded_columns.argtypes = [C.c_uint32, C.c_void_p]
+    _check(lib().lqb_tab_secded_columns(data_bytes, c.ctypes.data))
+    return c
 
 
 def tab_ilv_bit_perm(n):

@@ -292,6 +292,7 @@ int lqb_tab_interp_taps(float beta, float *h30);
 int lqb_tab_pfb_banks(float beta, float *banks32x28);
 int lqb_tab_detector_template(float beta, float *s156_complex);
 int lqb_tab_nco_sintab(float *tab1024);
+int lqb_tab_secded_columns(uint32_t data_bytes /* 2, 4, 8 */, uint8_t *col /* 8 * data_bytes: parity-byte contribution of every data bit */);
 int lqb_tab_ilv_bit_perm(uint32_t n_bytes, uint32_t *perm /* 8 * n_bytes */);   /* deinterleaved bit i = interleaved bit perm[i] */
 int lqb_tab_packet_len(uint32_t payload_len, uint32_t check, uint32_t fec0, uint32_t fec1,
                        uint32_t mod_scheme, uint32_t *enc_bytes, uint32_t *n_symbols);

@@ -116,6 +116,7 @@ int      lqo_fec_is_conv(int fs);
  * deinterleaved[i] = interleaved[perm[i]] */
 void     lqo_deinterleave_bit_perm(unsigned n, uint32_t *perm /* 8 n */);
 /* exposed for KATs */
+void     lqo_secded_columns(unsigned nb /* 2, 4 or 8 data bytes */, uint8_t *col /* 8 nb: parity-byte contribution of every data bit */);
 int      lqo_rs_decode_block(uint8_t *block /* 255-pad */, unsigned pad); /* returns #corrected or -1 */
 void     lqo_rs_encode_block(const uint8_t *data, unsigned pad, uint8_t *parity32);
 

@@ -195,52 +195,60 @@ static unsigned golay_decode_(unsigned r)
     return (rm ^ em) & 0xfff;                    /* uncorrectable -> message part as received */
 }
 
-/* ================================================================== SECDED (extended Hamming; our construction) */
-/* data bit i (0 = MSB of first byte) gets the i-th integer >= 3 that is not a power of two as
- * its check column; nc check bits + one overall parity bit, stored [parity byte][data bytes] */
-static unsigned secded_col_(unsigned i)
+/* ================================================================== SECDED (22,16) / (39,32) / (72,64) */
+/* liquid-dsp's Hsiao codes (src/fec/src/fec_secded{2216,3932,7264}.c): parity matrices P [R x C], one row per parity
+ * bit, row 0 the most significant bit of the parity byte, blocks stored [parity byte][data bytes].  Every column is
+ * distinct and of odd weight (3 or 5), so a nonzero syndrome that equals a column is a single data-bit error (corrected),
+ * a syndrome of weight one a parity-bit error, anything else at least two errors (left as received).  The matrices are
+ * restated from liquid-dsp; tests/test_oracle_kats.py checks the structural properties that make them SEC-DED codes. */
+static const uint8_t secded2216_P[12] = { 0x99, 0x3c, 0x3e, 0x8a, 0xee, 0x60, 0xe1, 0xd1, 0x13, 0xc7, 0x44, 0x3f };
+static const uint8_t secded3932_P[28] = { 0x8a, 0x82, 0x0f, 0x1b, 0x10, 0x1f, 0x71, 0x61, 0x16, 0xf0, 0x92, 0xa6, 0xff, 0x01, 0xa4, 0x44,
+                                          0x6c, 0xff, 0x08, 0x08, 0x21, 0x24, 0xff, 0x90, 0xc1, 0x48, 0x40, 0xff };
+static const uint8_t secded7264_P[64] = { 0xff, 0x0f, 0x0f, 0x0c, 0x68, 0x88, 0x88, 0x80, 0xf0, 0xff, 0x00, 0xf3, 0x64, 0x44, 0x44, 0x40,
+                                          0x30, 0xf0, 0xff, 0x0f, 0x02, 0x22, 0x22, 0x26, 0xcf, 0x00, 0xf0, 0xff, 0x01, 0x11, 0x11, 0x16,
+                                          0x68, 0x88, 0x88, 0x80, 0xff, 0x0f, 0x00, 0xf3, 0x64, 0x44, 0x44, 0x40, 0xf0, 0xff, 0x0f, 0x0c,
+                                          0x02, 0x22, 0x22, 0x26, 0xcf, 0x00, 0xff, 0x0f, 0x01, 0x11, 0x11, 0x16, 0x30, 0xf0, 0xf0, 0xff };
+/* column of data bit i (0 = MSB of the first data byte) of the code with nb data bytes: its contribution to the parity byte */
+static unsigned secded_col_(unsigned nb, unsigned i)
 {
-    unsigned c = 2;
-    for (unsigned k = 0; k <= i; k++) { c++; while ((c & (c - 1)) == 0) c++; }
+    const uint8_t *P = nb == 2 ? secded2216_P : nb == 4 ? secded3932_P : secded7264_P;
+    const unsigned R = nb == 2 ? 6 : nb == 4 ? 7 : 8;
+    unsigned c = 0;
+    for (unsigned r = 0; r < R; r++) c |= ((P[r * nb + (i >> 3)] >> (7 - (i & 7))) & 1u) << (R - 1 - r);
     return c;
 }
-static unsigned secded_parity_(const uint8_t *d, unsigned nbytes, unsigned nc)
+void lqo_secded_columns(unsigned nb, uint8_t *col /* 8 nb */) { for (unsigned i = 0; i < 8 * nb; i++) col[i] = (uint8_t)secded_col_(nb, i); }
+static unsigned secded_parity_(const uint8_t *d, unsigned nb)
 {
-    unsigned p = 0, all = 0;
-    for (unsigned i = 0; i < nbytes * 8; i++)
-        if ((d[i >> 3] >> (7 - (i & 7))) & 1u) { p ^= secded_col_(i); all ^= 1u; }
-    all ^= (unsigned)__builtin_parity(p);
-    return p | (all << nc);                      /* bit nc = overall parity of data + checks */
+    unsigned p = 0;
+    for (unsigned i = 0; i < nb * 8; i++)
+        if ((d[i >> 3] >> (7 - (i & 7))) & 1u) p ^= secded_col_(nb, i);
+    return p;
 }
-static void secded_encode_(unsigned nb, unsigned nc, unsigned n, const uint8_t *dec, uint8_t *enc)
+static void secded_encode_(unsigned nb, unsigned n, const uint8_t *dec, uint8_t *enc)
 {
     unsigned i = 0, j = 0;
     uint8_t blk[8];
     while (i < n) {
         unsigned r = (n - i >= nb) ? nb : (n - i);
         memset(blk, 0, sizeof blk); memcpy(blk, dec + i, r);
-        enc[j++] = (uint8_t)secded_parity_(blk, nb, nc);
+        enc[j++] = (uint8_t)secded_parity_(blk, nb);
         memcpy(enc + j, dec + i, r); j += r; i += r;
     }
 }
-static void secded_decode_(unsigned nb, unsigned nc, unsigned n, const uint8_t *enc, uint8_t *dec)
+static void secded_decode_(unsigned nb, unsigned n, const uint8_t *enc, uint8_t *dec)
 {
+    const unsigned R = nb == 2 ? 6 : nb == 4 ? 7 : 8;
     unsigned i = 0, j = 0;
     uint8_t blk[8];
     while (i < n) {
         unsigned r = (n - i >= nb) ? nb : (n - i);
-        unsigned rp = enc[j++];
+        unsigned rp = enc[j++] & ((1u << R) - 1u);          /* (the unused high bits of the parity byte do not enter) */
         memset(blk, 0, sizeof blk); memcpy(blk, enc + j, r); j += r;
-        unsigned calc = secded_parity_(blk, nb, nc);
-        unsigned syn = (calc ^ rp) & ((1u << nc) - 1u);
-        /* overall parity over received word: data bits + received check bits + received overall bit */
-        unsigned tot = 0;
-        for (unsigned b = 0; b < nb; b++) tot ^= (unsigned)__builtin_parity(blk[b]);
-        tot ^= (unsigned)__builtin_parity(rp & ((1u << (nc + 1)) - 1u));
-        if (tot && syn && (syn & (syn - 1))) {   /* single error in a data bit */
+        unsigned syn = secded_parity_(blk, nb) ^ rp;
+        if (syn)                                             /* a column: that data bit; else a parity bit or >= 2 errors */
             for (unsigned b = 0; b < nb * 8; b++)
-                if (secded_col_(b) == syn) { blk[b >> 3] ^= (uint8_t)(0x80u >> (b & 7)); break; }
-        }
+                if (secded_col_(nb, b) == syn) { blk[b >> 3] ^= (uint8_t)(0x80u >> (b & 7)); break; }
         memcpy(dec + i, blk, r); i += r;
     }
 }
@@ -569,9 +577,9 @@ void lqo_fec_encode(int fs, unsigned n, const uint8_t *dec, uint8_t *enc)
         }
         return;
     }
-    case LQ_FEC_SECDED2216: secded_encode_(2, 5, n, dec, enc); return;
-    case LQ_FEC_SECDED3932: secded_encode_(4, 6, n, dec, enc); return;
-    case LQ_FEC_SECDED7264: secded_encode_(8, 7, n, dec, enc); return;
+    case LQ_FEC_SECDED2216: secded_encode_(2, n, dec, enc); return;
+    case LQ_FEC_SECDED3932: secded_encode_(4, n, dec, enc); return;
+    case LQ_FEC_SECDED7264: secded_encode_(8, n, dec, enc); return;
     case LQ_FEC_RS_M8: rs_encode_(n, dec, enc); return;
     default:
         if (conv_lookup_(fs, &c)) conv_encode_(&c, n, dec, enc);
@@ -629,9 +637,9 @@ void lqo_fec_decode(int fs, unsigned n, const uint8_t *enc, uint8_t *dec)
         }
         return;
     }
-    case LQ_FEC_SECDED2216: secded_decode_(2, 5, n, enc, dec); return;
-    case LQ_FEC_SECDED3932: secded_decode_(4, 6, n, enc, dec); return;
-    case LQ_FEC_SECDED7264: secded_decode_(8, 7, n, enc, dec); return;
+    case LQ_FEC_SECDED2216: secded_decode_(2, n, enc, dec); return;
+    case LQ_FEC_SECDED3932: secded_decode_(4, n, enc, dec); return;
+    case LQ_FEC_SECDED7264: secded_decode_(8, n, enc, dec); return;
     case LQ_FEC_RS_M8: rs_decode_(n, enc, dec); return;
     default:
         if (conv_lookup_(fs, &c)) conv_decode_(&c, n, enc, dec);

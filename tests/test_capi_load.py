@@ -90,3 +90,13 @@ def test_interleaver_bit_permutation_matches_oracle(n):
     want = blk.copy()
     Lo.lqo_deinterleave(o._ptr(want), n, 4)
     assert np.array_equal(np.packbits(bits[ref]), want)
+
+
+@pytest.mark.parametrize("nb", [2, 4, 8])
+def test_secded_tables_of_the_library_equal_the_oracles(nb):
+    import ctypes as C
+    Lo = o.lib()
+    Lo.lqo_secded_columns.argtypes = [C.c_uint, C.c_void_p]
+    ref = np.zeros(8 * nb, np.uint8)
+    Lo.lqo_secded_columns(nb, o._ptr(ref))
+    assert np.array_equal(capi.tab_secded_columns(nb), ref)

@@ -35,7 +35,7 @@ def test_cfg3_size_snr_sweep_matches_oracle():
     """15 streams, one per SNR point -2 .. +12 dB, three 1500-byte v27 + RS8 frames each, CFO within +-0.02 rad/sample,
     timing offset within +-0.5 sample, gain 0.5 .. 1.5: every frame record (position, header, flags, payload bytes,
     estimates, constellation) equals the oracle's -- decodable, CRC-failed and header-failed frames alike."""
-    rng = np.random.default_rng(303)
+    rng = np.random.default_rng(306)                 # (a seed whose sweep holds all three outcomes)
     caps, refs = [], []
     for k in range(15):
         snr = -2.0 + k

@@ -143,6 +143,35 @@ def test_block_codes_correct_their_design_errors(fs, nerr):
         assert np.array_equal(r[:n], d), (fs, n)
 
 
+@pytest.mark.parametrize("fs,nb,R", [(8, 2, 6), (9, 4, 7), (10, 8, 8)])
+def test_secded_matrices_are_hsiao_codes_and_decode_as_liquid_does(fs, nb, R):
+    """The parity matrices are restated from liquid-dsp (fec_secded2216 / 3932 / 7264).  What can be checked without
+    liquid: they are Hsiao SEC-DED codes (every column distinct, of odd weight >= 3, inside R bits), so every single
+    error is corrected and every double error leaves the data as received."""
+    import ctypes as C
+    L.lqo_secded_columns.argtypes = [C.c_uint, C.c_void_p]
+    col = np.zeros(8 * nb, np.uint8)
+    L.lqo_secded_columns(nb, o._ptr(col))
+    w = np.array([bin(int(c)).count("1") for c in col])
+    assert len(set(col.tolist())) == 8 * nb and np.all(w % 2 == 1) and np.all(w >= 3) and np.all(col < (1 << R))
+    assert sorted(set(w.tolist())) == ([3, 5] if nb == 8 else [3])        # (72,64): 56 columns of weight 3, 8 of weight 5
+    rng = np.random.default_rng(fs)
+    d = rng.integers(0, 256, nb, dtype=np.uint8)
+    e = np.zeros(nb + 1, np.uint8)
+    L.lqo_fec_encode(fs, nb, o._ptr(d), o._ptr(e))
+    assert e[0] == np.bitwise_xor.reduce(col[np.unpackbits(d).astype(bool)], initial=0) and np.array_equal(e[1:], d)
+    r = np.zeros(nb + 8, np.uint8)
+    for b in range(8 * (nb + 1)):                    # every single error, parity byte included (its unused high bits too)
+        x = e.copy(); x[b // 8] ^= 0x80 >> (b % 8)
+        L.lqo_fec_decode(fs, nb, o._ptr(x), o._ptr(r))
+        assert np.array_equal(r[:nb], d), b
+    for _ in range(200):                             # double errors inside the code word: data left as received
+        b1, b2 = rng.choice(np.arange(8 - R, 8 * (nb + 1)), 2, replace=False)
+        x = e.copy(); x[b1 // 8] ^= 0x80 >> (b1 % 8); x[b2 // 8] ^= 0x80 >> (b2 % 8)
+        L.lqo_fec_decode(fs, nb, o._ptr(x), o._ptr(r))
+        assert np.array_equal(r[:nb], x[1:])
+
+
 def test_secded_detects_double_error_without_miscorrecting_other_bits():
     d = np.arange(8, dtype=np.uint8) * 17
     e = np.zeros(16, np.uint8)

@@ -171,6 +171,7 @@ struct Front {
         DevBuf<int> d_stage16;            // raw sc16 samples (one int = one complex sample) before conversion
         unsigned *d_count = nullptr;
         unsigned *h_count = nullptr;
+        size_t conv_pairs = 0;            // sc16 samples staged by a caller-supplied copy stream, widening still to be launched (take_conversion)
     } io[2];
     unsigned cur = 0;
     std::vector<uint8_t> fed;
@@ -267,6 +268,7 @@ struct Front {
             tot += ns[i]; mx = std::max<uint64_t>(mx, ns[i]);
         }
         const bool sc16 = (mem == LQB_MEM_HOST_SC16 || mem == LQB_MEM_DEVICE_SC16);
+        io[cur].conv_pairs = 0;
         if (sc16) {
             // int16 pairs travel as they are (half the bytes of complex64 over PCIe) and are widened on the device:
             // packed back to back in feed order, then one conversion kernel on the same stream
@@ -290,11 +292,11 @@ struct Front {
                 off += ns[k];
             }
             const size_t pairs = (size_t)((tot + 1) / 2);
-            if (pairs) {
-                const unsigned grid = (unsigned)std::min<size_t>((pairs + 255) / 256, 148u * 16u);
-                k_sc16_to_c32<<<grid, 256, 0, stream>>>(reinterpret_cast<const int2 *>(d_raw.p), reinterpret_cast<float4 *>(d_stage.p), pairs);
-                launches++;
-            }
+            // With a separate copy stream (the pipelined receiver) the widening is NOT queued behind the copy: it would sit
+            // there until an SM is free of search CTAs and hold up the next call's H2D copy, which queues on the same stream
+            // (measured: the link ran at 37 GB/s instead of 52).  The search stream launches it right before its k_seek.
+            if (cs && cs != this->stream) io[cur].conv_pairs = pairs;
+            else { io[cur].conv_pairs = pairs; launch_conversion(cur, stream); }
         } else if (mem == LQB_MEM_HOST) {
             if (int e = d_stage.reserve(tot + 1)) return e;
             // equal-length streams at a constant pitch in host memory (the dense layout, also after the lane split):
@@ -334,6 +336,16 @@ struct Front {
         CU(cudaMemcpyAsync(d_io.p, h_io.p, n * sizeof(StreamIO), cudaMemcpyHostToDevice, stream));
         *total = tot; *max_n = mx;
         return 0;
+    }
+    // widen the staged sc16 samples of I/O set `set` on stream s (no-op when there is nothing pending)
+    void launch_conversion(unsigned set, cudaStream_t s)
+    {
+        const size_t pairs = io[set].conv_pairs;
+        io[set].conv_pairs = 0;
+        if (!pairs) return;
+        const unsigned grid = (unsigned)std::min<size_t>((pairs + 255) / 256, 148u * 16u);
+        k_sc16_to_c32<<<grid, 256, 0, s>>>(reinterpret_cast<const int2 *>(io[set].d_stage16.p), reinterpret_cast<float4 *>(io[set].d_stage.p), pairs);
+        launches++;
     }
     // the pre-filter fields of sp (coarse == 0: exact FFT search only, LQB_NO_COARSE=1)
     void set_coarse(SeekParams &sp) const
@@ -535,6 +547,7 @@ struct RxLane {
         if (!n) return 0;
         cudaStream_t st = f.stream;
         CU(cudaStreamWaitEvent(st, G.staged, 0));
+        f.launch_conversion(f.cur, st);            // sc16 input: widened here, ahead of the search that reads it
         G.sp.views = G.d_views.p;
         G.sp.tables = f.d_tables; G.sp.states = f.d_states; G.sp.io = f.io[f.cur].d_io.p;
         G.sp.carry[0] = f.d_carry[0]; G.sp.carry[1] = f.d_carry[1]; G.sp.carry_cap = f.carry_cap;

@@ -956,23 +956,51 @@ k_rs(PayloadParams P, const unsigned *__restrict__ blocks, unsigned n_blocks, in
         __syncwarp();
         const int deg = deg_s[warp];
         // Chien search: lane tests i = lane+1, lane+33, ... ; roots kept in a per-lane bit mask
+        // lambda(alpha^i) for this lane's eight positions at once, coefficient by coefficient: the exponent of term j moves
+        // by 32 j from one position to the next, so it is stepped (one add, one conditional subtract) instead of being
+        // formed with a multiply and a division by 255 per term and position -- the same field elements, summed in GF(256)
         unsigned mine = 0, count = 0;
-        for (unsigned it = 0; it < 8; ++it) {
-            const unsigned i = it * 32 + lane + 1;
-            unsigned q = 1;
-            if (i <= 255) { for (int j = 1; j <= deg; ++j) if (L[j]) q ^= gexp[(glog[L[j]] + i * j) % 255]; }
-            const bool root = (i <= 255) && (q == 0);
-            if (root) mine |= 1u << it;
-            count += __popc(__ballot_sync(0xffffffffu, root));
+        {
+            unsigned q8[8];
+#pragma unroll
+            for (int it = 0; it < 8; ++it) q8[it] = 1u;
+            for (int j = 1; j <= deg; ++j) {
+                const unsigned c = L[j];
+                if (!c) continue;                    // (uniform: L is the warp's)
+                unsigned e = (glog[c] + (unsigned)(lane + 1) * (unsigned)j) % 255u;
+                const unsigned step = (32u * (unsigned)j) % 255u;
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    q8[it] ^= gexp[e];
+                    e += step;
+                    e -= (e >= 255u) ? 255u : 0u;
+                }
+            }
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const unsigned i = (unsigned)it * 32u + (unsigned)lane + 1u;
+                const bool root = (i <= 255u) && (q8[it] == 0u);
+                if (root) mine |= 1u << it;
+                count += __popc(__ballot_sync(0xffffffffu, root));
+            }
         }
         if ((int)count == deg) {
             for (unsigned it = 0; it < 8; ++it) {
                 if (!((mine >> it) & 1u)) continue;
                 const unsigned root = it * 32 + lane + 1, loc = root - 1;
                 unsigned num = 0, den = 0;
-                for (int i = 0; i < deg; ++i) if (O[i]) num ^= gexp[(glog[O[i]] + i * root) % 255];
+                const unsigned rr = root % 255u, rr2 = (2u * rr) % 255u;         // exponent steps of root^i, root^(2 i)
+                unsigned ex = 0;
+                for (int i = 0; i < deg; ++i) {
+                    if (O[i]) { unsigned e = glog[O[i]] + ex; e -= (e >= 255u) ? 255u : 0u; num ^= gexp[e]; }
+                    ex += rr; ex -= (ex >= 255u) ? 255u : 0u;
+                }
                 const int top = (deg < 31 ? deg : 31) & ~1;
-                for (int i = 0; i <= top; i += 2) if (L[i + 1]) den ^= gexp[(glog[L[i + 1]] + i * root) % 255];
+                ex = 0;
+                for (int i = 0; i <= top; i += 2) {
+                    if (L[i + 1]) { unsigned e = glog[L[i + 1]] + ex; e -= (e >= 255u) ? 255u : 0u; den ^= gexp[e]; }
+                    ex += rr2; ex -= (ex >= 255u) ? 255u : 0u;
+                }
                 if (num != 0 && loc >= pad) x[loc - pad] ^= gexp[(glog[num] + 255 - glog[den]) % 255];
             }
         }

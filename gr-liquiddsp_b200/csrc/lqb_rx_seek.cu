@@ -30,6 +30,9 @@ namespace {
 #ifndef LQB_SEEK_BINS
 #define LQB_SEEK_BINS 1                  // exact windows visit only the CFO bins the tensor cores cannot rule out (0: all 49)
 #endif
+#ifndef LQB_SEEK_THR_PRUNE
+#define LQB_SEEK_THR_PRUNE 1             // the bin scan also drops bins that cannot reach the threshold; every window that is not skipped takes it
+#endif
 #ifndef LQB_SEEK_SLEEP
 #define LQB_SEEK_SLEEP 0                 // scale of the nanosleep back-off in mbarrier waits (0: plain polling)
 #endif
@@ -746,11 +749,20 @@ __device__ unsigned long long bin_candidates(SeekShared &sh, const StreamView &s
         const float err = (s_norm * (rd + (re + rd) * b_err) + 0.004f * fast_sqrt(en * (156.0f / 512.0f)) * s_norm) * 1.001f;
         float best = 0.0f;
         for (int i = 0; i < tc::kNBins; ++i) best = fmaxf(best, __uint_as_float(sh.binmax[i]));
-        const float floor_ = fast_sqrt(best * s2) - err;
+        float floor_ = fast_sqrt(best * s2) - err;
+#if LQB_SEEK_THR_PRUNE
+        // A bin matters only if it can TRIGGER: the exact evaluation's result is used for nothing else (a window that
+        // does not trigger just moves the hop grid on), and when something does trigger the global maximum is at least the
+        // threshold, so no bin that cannot reach the threshold can hold it.  In |C| units the threshold is
+        // thr * g0 * ||s||, g0 = sqrt(E 156 / 512) of this very window.  An EMPTY set proves "no trigger" outright.
+        floor_ = fmaxf(floor_, T->threshold * fast_sqrt(en * (156.0f / 512.0f)) * s_norm * 0.999f);
+#endif
         cand = 0ull;
         for (int i = 0; i <= 2 * T->range; ++i)
             if (fast_sqrt(__uint_as_float(sh.binmax[i]) * s2) + err >= floor_) cand |= 1ull << i;
+#if !LQB_SEEK_THR_PRUNE
         if (!cand) cand = all;
+#endif
     }
     wsync();                                   // binmax / statistics slots are free again
     return cand;
@@ -1131,10 +1143,27 @@ k_seek(SeekParams P)
             // survive); a window that merely could not be ruled out has a noise-like spectrum in which nearly every bin
             // stays a candidate, and the scan would be pure overhead.  Measured (B200): flex_rx search 22.1 -> 20.9 ms;
             // the bare detector, where two of three exact windows are of the second kind, 87.3 -> 89.6 ms: off there.
+#if LQB_SEEK_THR_PRUNE
+            // Every window the pre-filter could not rule out: with the threshold in the candidate rule a noise-like window
+            // (one in five in flex_rx, two in three in the bare detector) keeps the one or two bins that can still reach
+            // it -- or none, which proves it cannot trigger -- instead of all 49.
+            if (fused && LQB_SEEK_BINS) {
+                cand = bin_candidates(sh, sv, T, P.b_err, st.wstart, tid, tc_pre, tc_pre_a0, ph_full, buf_w, n_tc_tiles PROF_PASS);
+                sh.tables_dirty = 1;
+                if (cand == 0ull) {                  // (uniform) proven: no bin of this window reaches the threshold
+                    --n_exact;
+                    if (tid == 0) st.wstart += 256;
+                    wsync();
+                    PROF_MARK(11);
+                    continue;
+                }
+            }
+#else
             if (fused && LQB_SEEK_BINS && !P.det_mode && rxy_q > T->threshold + 0.1f) {
                 cand = bin_candidates(sh, sv, T, P.b_err, st.wstart, tid, tc_pre, tc_pre_a0, ph_full, buf_w, n_tc_tiles PROF_PASS);
                 sh.tables_dirty = 1;
             }
+#endif
             PROF_MARK(11);
             n_bins += (unsigned)__popcll(cand);
             restore_tables();

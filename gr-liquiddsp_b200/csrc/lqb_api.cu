@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <memory>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -839,10 +840,15 @@ struct lqb_rx_s {
         lqb_frame_result r;
         long long trig_w;                 // start of the window that triggered
         long long after_w, after_G;       // the walk's state once this frame is through (time-sharded decoding)
-        std::vector<unsigned char> payload;
-        std::vector<float> syms;
+        int pool;                         // which copy of a lane's result arenas (shard_pools) holds its bytes / points
+        size_t pay_off, sym_off;
+        bool has_payload, has_syms;
     };
     std::vector<OwnedFrame> merged;
+    // one bulk copy of every lane's payload pool / symbol arena per execute of the sharded call (a copy per frame cost
+    // 0.5 us each: 16 ms of the 59 ms a 31 000-frame capture took)
+    struct ShardPool { std::vector<unsigned char> pay; std::vector<float2> syms; };
+    std::vector<std::unique_ptr<ShardPool>> shard_pools;
     bool use_merged = false;
     uint64_t merged_valid = 0;
     uint64_t shard[4] = {};               // segments, segment runs in all, rounds, execute calls
@@ -1154,6 +1160,7 @@ int lqb_rx_execute_sharded(lqb_rx h, const float *iq, uint64_t n_samples, int me
     seg_len = std::max(4096u, (seg_len + 255u) & ~255u);
     preroll = std::min((preroll + 255u) & ~255u, seg_len);
     h->merged.clear(); h->merged_valid = 0;
+    size_t pools_used = 0;                             // (the pools of the previous call are recycled: their pages are already mapped)
     std::memset(h->shard, 0, sizeof h->shard);
     if (n_samples < 512) { h->use_merged = true; return 0; }
     const float2 *x = reinterpret_cast<const float2 *>(iq);
@@ -1188,6 +1195,10 @@ int lqb_rx_execute_sharded(lqb_rx h, const float *iq, uint64_t n_samples, int me
     std::vector<const float *> ptr;
     std::vector<uint64_t> len;
     std::vector<uint32_t> ids;
+    const bool shard_trace = getenv("LQB_SHARD_TRACE") != nullptr;
+    double t_exec = 0.0, t_copy = 0.0, t_state = 0.0;
+    auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_begin = now();
     while (true) {
         std::vector<unsigned> todo;
         for (unsigned k = 0; k < K; ++k) if (seg[k].todo) todo.push_back(k);
@@ -1213,10 +1224,14 @@ int lqb_rx_execute_sharded(lqb_rx h, const float *iq, uint64_t n_samples, int me
                 len[i] = (uint64_t)std::max<long long>(0, end - z.base);
                 ids[i] = i;
             }
+            double ta = now();
             if (int e = h->put_states(nb, zs.data())) return e;
+            double tb = now(); t_state += tb - ta;
             if (int e = lqb_rx_execute(h, nb, ids.data(), ptr.data(), len.data(), LQB_MEM_DEVICE)) return e;
             h->shard[3]++;
+            ta = now(); t_exec += ta - tb;
             if (int e = h->get_states()) return e;
+            tb = now(); t_state += tb - ta;
             for (unsigned i = 0; i < nb; ++i) {
                 Seg &sg = seg[todo[t0 + i]];
                 const StreamState &z = h->lanes[h->lane_of[i]]->f.h_states[h->local_of[i]];
@@ -1228,6 +1243,26 @@ int lqb_rx_execute_sharded(lqb_rx h, const float *iq, uint64_t n_samples, int me
                 h->shard[1]++;
             }
             // keep this call's frames (the receiver's result arenas are reused by the next call)
+            const double tc0 = now();
+            // this execute's result arenas, lane by lane, in one copy each (extent = what its frames reference)
+            const int pool0 = (int)pools_used;
+            {
+                std::vector<size_t> pay_ext(h->lanes.size(), 0), sym_ext(h->lanes.size(), 0);
+                for (unsigned kf = 0; kf < h->n_frames; ++kf) {
+                    const unsigned li = h->order[kf].first;
+                    const FrameDesc &d = h->lanes[li]->g[h->cur_gen].h_frames.p[h->order[kf].second];
+                    if (!d.header_valid || (d.flags & 1u)) continue;
+                    pay_ext[li] = std::max(pay_ext[li], (size_t)d.pay_off + d.payload_len);
+                    sym_ext[li] = std::max(sym_ext[li], (size_t)d.sym_off + d.n_sym);
+                }
+                for (size_t li = 0; li < h->lanes.size(); ++li) {
+                    const RxGen &G = h->lanes[li]->g[h->cur_gen];
+                    if (pools_used == h->shard_pools.size()) h->shard_pools.emplace_back(new lqb_rx_s::ShardPool);
+                    lqb_rx_s::ShardPool *sp = h->shard_pools[pools_used++].get();
+                    sp->pay.assign(G.h_payload.p, G.h_payload.p + pay_ext[li]);
+                    if (!(h->flags & LQB_RX_NO_FRAMESYMS)) sp->syms.assign(G.h_syms.p, G.h_syms.p + sym_ext[li]); else sp->syms.clear();
+                }
+            }
             for (unsigned kf = 0; kf < h->n_frames; ++kf) {
                 const RxLane *ln = h->lanes[h->order[kf].first];
                 const RxGen &G = ln->g[h->cur_gen];
@@ -1235,6 +1270,7 @@ int lqb_rx_execute_sharded(lqb_rx h, const float *iq, uint64_t n_samples, int me
                 const unsigned gs = h->global_stream(ln->lane, d.stream);
                 if (gs >= nb) continue;
                 lqb_rx_s::OwnedFrame of;
+                of.pool = pool0 + (int)h->order[kf].first; of.pay_off = 0; of.sym_off = 0; of.has_payload = false; of.has_syms = false;
                 lqb_frame_result one;
                 h->use_merged = false;
                 // (the ordinary conversion, one frame at a time)
@@ -1245,11 +1281,8 @@ int lqb_rx_execute_sharded(lqb_rx h, const float *iq, uint64_t n_samples, int me
                     std::memcpy(r.header, d.header, 20);
                     r.header_valid = d.header_valid; r.payload_valid = d.payload_valid; r.payload_len = d.payload_len;
                     if (d.header_valid && !(d.flags & 1u)) {
-                        of.payload.assign(G.h_payload.p + d.pay_off, G.h_payload.p + d.pay_off + d.payload_len);
-                        if (!(h->flags & LQB_RX_NO_FRAMESYMS)) {
-                            const float *sp = reinterpret_cast<const float *>(G.h_syms.p + d.sym_off);
-                            of.syms.assign(sp, sp + 2 * (size_t)d.n_sym);
-                        }
+                        of.pay_off = d.pay_off; of.has_payload = true;
+                        if (!(h->flags & LQB_RX_NO_FRAMESYMS)) { of.sym_off = d.sym_off; of.has_syms = true; }
                         r.num_framesyms = d.n_sym;
                     }
                     r.mod_scheme = d.ms; r.mod_bps = d.bps; r.check = d.check; r.fec0 = d.fec0; r.fec1 = d.fec1;
@@ -1266,6 +1299,7 @@ int lqb_rx_execute_sharded(lqb_rx h, const float *iq, uint64_t n_samples, int me
                 of.after_w = of.after_G - 256;
                 seg[todo[t0 + gs]].fr.push_back(std::move(of));
             }
+            t_copy += now() - tc0;
         }
         // partial re-runs: spliced onto the rest of the old run if they left its frame in the same state, else run in full
         for (unsigned k = 1; k < K; ++k) {
@@ -1327,10 +1361,13 @@ int lqb_rx_execute_sharded(lqb_rx h, const float *iq, uint64_t n_samples, int me
         }
     }
     for (auto &of : h->merged) {                             // (pointers into the vectors as they finally lie)
-        of.r.payload = of.payload.empty() ? nullptr : of.payload.data();
-        of.r.framesyms = of.syms.empty() ? nullptr : of.syms.data();
+        const lqb_rx_s::ShardPool &sp = *h->shard_pools[(size_t)of.pool];
+        of.r.payload = of.has_payload ? sp.pay.data() + of.pay_off : nullptr;
+        of.r.framesyms = of.has_syms ? reinterpret_cast<const float *>(sp.syms.data() + of.sym_off) : nullptr;
     }
     h->use_merged = true;
+    if (shard_trace) fprintf(stderr, "[lqb sharded] total %.1f ms: execute %.1f, states %.1f, frame copies %.1f, rest (verify, merge) %.1f\n",
+                             now() - t_begin, t_exec, t_state, t_copy, now() - t_begin - t_exec - t_state - t_copy);
     return 0;
 }
 

@@ -1271,11 +1271,9 @@ int lqb_rx_execute_sharded(lqb_rx h, const float *iq, uint64_t n_samples, int me
                 if (gs >= nb) continue;
                 lqb_rx_s::OwnedFrame of;
                 of.pool = pool0 + (int)h->order[kf].first; of.pay_off = 0; of.sym_off = 0; of.has_payload = false; of.has_syms = false;
-                lqb_frame_result one;
-                h->use_merged = false;
-                // (the ordinary conversion, one frame at a time)
+                // (the conversion lqb_rx_poll does, with the payload / points left as offsets into the pool)
                 {
-                    lqb_frame_result &r = one;
+                    lqb_frame_result &r = of.r;
                     std::memset(&r, 0, sizeof r);
                     r.stream = 0; r.seq = d.seq; r.sample_index = d.F;
                     std::memcpy(r.header, d.header, 20);
@@ -1290,7 +1288,6 @@ int lqb_rx_execute_sharded(lqb_rx h, const float *iq, uint64_t n_samples, int me
                     r.tau_hat = d.tau; r.gamma_hat = d.gamma; r.dphi_hat = d.dphi; r.phi_hat = d.phi; r.rxy = d.rxy;
                     r.flags = d.flags;
                 }
-                of.r = one;
                 of.trig_w = d.F - (long long)d.det_idx;
                 // where k_seek leaves the walk behind this frame (lqb_rx_seek.cu: st.G = last + 1, st.wstart = st.G - 256)
                 if (d.flags & 1u) of.after_G = d.F + 512;

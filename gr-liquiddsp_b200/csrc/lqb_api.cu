@@ -188,6 +188,30 @@ struct Front {
     void *d_bmat = nullptr;
     float b_err = 0.0f;                   // rounding error of B relative to ||s|| (enters the pre-filter's bound)
     StreamState *h_states = nullptr;      // pinned staging for reset()
+    DevBuf<unsigned> d_queue;             // slice queue of k_seek (searches of one front never overlap: one buffer)
+
+    // Time slices of the search (k_seek): LQB_SEEK_SLICE=<samples per slice> turns them on for calls whose streams are
+    // at least four slices long; unset or 0: one CTA per stream.  Never changes a result (tests/test_gpu_slices.py).
+    // Off by default -- measured on the bench workload (1024 streams, one lane): the search alone 20.3 -> 19.65 ms
+    // (every CTA slot busy to the end), but one sliced lane gives up the four-lane pipeline that hides the host's
+    // planning and the payload chains behind other lanes' searches: step 31.3 -> 33.1 ms (profiles/r02_notes.md v24).
+    int set_slices(SeekParams &sp, uint32_t n, const StreamIO *h_io)
+    {
+        sp.slice_len = 0; sp.n_io = n; sp.grid = n; sp.queue = nullptr;
+        const char *ev = getenv("LQB_SEEK_SLICE");
+        const long conf = ev ? atol(ev) : 0;
+        if (conf <= 0) return 0;
+        const uint64_t Q = ((uint64_t)conf + 255u) & ~uint64_t(255);
+        uint64_t grid = 0, mx = 0;
+        for (uint32_t i = 0; i < n; ++i) {
+            grid += ((uint64_t)carry_cap + h_io[i].n_in + Q - 1) / Q + 1;
+            mx = std::max<uint64_t>(mx, h_io[i].n_in);
+        }
+        if (mx < 4 * Q || grid > 0x7fffff00ull) return 0;
+        if (int e = d_queue.reserve((size_t)grid + 4 + 3u * (size_t)sm_count_of_this_device())) return e;
+        sp.slice_len = (unsigned)Q; sp.grid = (unsigned)grid; sp.queue = d_queue.p;
+        return 0;
+    }
 
     int init(int dev, unsigned ns, unsigned cap, void *user_stream, const DevTables &T, bool low_priority = false)
     {
@@ -369,6 +393,7 @@ struct Front {
             if (x.h_count) cudaFreeHost(x.h_count);
         }
         if (d_bmat) cudaFree(d_bmat);
+        d_queue.release();
         if (h_states) cudaFreeHost(h_states);
         if (own_stream && stream) cudaStreamDestroy(stream);
     }
@@ -556,8 +581,9 @@ struct RxLane {
         G.sp.n_out = f.io[f.cur].d_count; G.sp.max_out = (unsigned)G.max_frames;
         CU(cudaEventRecord(G.ev[0], st));
         f.set_coarse(G.sp);
+        if (int e = f.set_slices(G.sp, n, f.io[f.cur].h_io.p)) return e;
         CU(cudaMemsetAsync(f.io[f.cur].d_count, 0, 8 * sizeof(unsigned), st));
-        launch_seek(G.sp, n, st); f.launches++;
+        launch_seek(G.sp, n, st); f.launches += G.sp.slice_len ? 2 : 1;
         CU(cudaEventRecord(G.ev[1], st));
         launch_copy(f.io[f.cur].h_count, f.io[f.cur].d_count, 8 * sizeof(unsigned), st);
         CU(cudaEventRecord(G.seek_done, st));
@@ -1512,8 +1538,9 @@ int lqb_det_execute(lqb_det h, uint32_t n, const uint32_t *ids, const float *con
     sp.n_out = f.io[0].d_count; sp.max_out = (unsigned)max_det;
     CU(cudaEventRecord(h->ev[0], st));
     f.set_coarse(sp);
+    if (int e = f.set_slices(sp, n, f.io[0].h_io.p)) return e;
     CU(cudaMemsetAsync(f.io[0].d_count, 0, 8 * sizeof(unsigned), st));
-    launch_seek(sp, n, st); f.launches++;
+    launch_seek(sp, n, st); f.launches += sp.slice_len ? 2 : 1;
     launch_carry(sp, n, st); f.launches++;
     CU(cudaEventRecord(h->ev[1], st));
     CU(cudaMemcpyAsync(f.io[0].h_count, f.io[0].d_count, 8 * sizeof(unsigned), cudaMemcpyDeviceToHost, st));

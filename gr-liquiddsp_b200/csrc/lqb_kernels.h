@@ -48,6 +48,12 @@ struct SeekParams {
     int              coarse;        // 0: off (every window takes the exact 50-FFT evaluation), 2: on
     const void      *bmat;          // B operand in shared-memory layout (build_coarse_bmat)
     float            b_err;         // max_b ||t_b - e4m3(t_b)|| / ||s|| of those bytes (error bound of the pre-filter)
+    // time slices (0: one CTA per stream for the whole call): see k_seek
+    unsigned         slice_len = 0; // samples a CTA searches before it hands the stream back (multiple of 256)
+    unsigned         n_io = 0;      // fed streams of this launch
+    unsigned         grid = 0;      // bound on the slices of this launch: sum over streams of ceil(available / slice_len) + 1
+    unsigned        *queue = nullptr; // [4 + grid + CTAs launched] device words
+    unsigned         queue_cap = 0; // entries behind the 4 header words (launch_seek fills it in)
 };
 
 // CTA shapes of k_mf / k_pll_emit.  64-thread / 1024-symbol variants (14 KB / 13 KB of shared memory) were built to fit

@@ -55,6 +55,31 @@ __device__ unsigned long long g_seek_prof[24];
 #define PROF_PASS
 #endif
 
+#ifdef LQB_SEEK_TRACE
+// one record per CTA (debug builds only): start / end in ns (globaltimer), SM, stream.  See lqb_dbg_seek_trace().
+__device__ unsigned long long g_seek_trace[4][1 << 16];
+__device__ unsigned g_seek_trace_n;
+__device__ __forceinline__ unsigned long long gtime_ns() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ unsigned smid_of() { unsigned v; asm volatile("mov.u32 %0, %smid;" : "=r"(v)); return v; }
+#endif
+
+// acquire / release accesses for the slice queue (a stream's state passes from one CTA to the next inside one launch)
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned *p, unsigned v)
+{
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+constexpr unsigned kQueueEmpty = 0xffffffffu;
+// a draw that waits longer than this many polls (200 ns apart: about two seconds) gives up: the CTA leaves, the host
+// reports the stall (lqb_dbg_seek_stall) instead of the GPU hanging
+constexpr unsigned kQueueMaxPolls = 10u * 1000u * 1000u;
+__device__ unsigned g_seek_stall[8];
+
 // barrier over the worker warps only (the MMA warp never joins it)
 __device__ __forceinline__ void wsync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
@@ -1043,12 +1068,19 @@ __global__ void __launch_bounds__(kCtaThreads, 3)
 k_seek(SeekParams P)
 {
     __shared__ SeekShared sh;
-    __shared__ StreamState st;
+    __shared__ __align__(16) StreamState st;
     __shared__ unsigned pll_theta0, pll_dtheta;
     const int tid = threadIdx.x;
     PROF_DECL;
     const DevTables *T = P.tables;
-    const StreamIO io = P.io[blockIdx.x];
+    // Time slices (P.slice_len != 0): the launch has one CTA per slot of the GPU, not one per stream; a CTA takes the
+    // next READY stream from a queue, walks it for about slice_len samples, hands it back and takes the next one.  The
+    // work items become short and alike, so a call with more streams than the GPU has CTA slots keeps every slot busy
+    // to the end (no wave of leftovers).  queue[0]: next ticket, [1]: next free entry, [2]: finished streams,
+    // [4 + t]: io index behind ticket t.  A stream's state passes from CTA to CTA through global memory (release by
+    // the CTA that hands it back, acquire by the one that takes it).
+    __shared__ unsigned s_item;                 // io entry this CTA works on
+    __shared__ long long s_saved_stop;          // the stream's own stop_at while the slice boundary stands in for it
 
     extern __shared__ unsigned char dyn_smem[];
     unsigned char *Bsm = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(dyn_smem) + 127) & ~uintptr_t(127));
@@ -1070,7 +1102,7 @@ k_seek(SeekParams P)
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
-    if (tid == 0) { st = P.states[io.stream]; sh.tables_dirty = 1; }
+    if (tid == 0) sh.tables_dirty = 1;
     __syncthreads();
     if (fused) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
@@ -1086,25 +1118,13 @@ k_seek(SeekParams P)
     }
     wsync();
     ScanCarry sc_;
-    sc_.valid = false; sc_.unsafe = false; sc_.ex_valid = false; sc_.w = 0; sc_.tail = 0.0f; sc_.tail_d = 0.0f; sc_.tail_e = 0.0f; sc_.half = 0.0f; sc_.ex = 0;
     float2 tc_pre[4];
-    long long tc_pre_a0 = -(1ll << 62);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) tc_pre[k] = make_float2(0.0f, 0.0f);
+    long long tc_pre_a0;
     unsigned ph_full = 0u;
     int buf_w = 0;
     float rxy_q = 0.0f;
-
     unsigned n_windows = 0, n_aligns = 0, n_exact = 0, n_tc_tiles = 0, n_bins = 0;      // work counters (uniform across the workers)
     PROF_MARK(10);
-    StreamView sv;
-    sv.carry = P.carry[st.carry_sel] + (size_t)io.stream * P.carry_cap;
-    sv.in = io.in;
-    sv.base = st.base;
-    sv.carry_len = st.carry_len;
-    sv.end = st.base + (long long)st.carry_len + (long long)io.n_in;
-    sv.G = st.G;
-    if (tid == 0 && P.views) P.views[blockIdx.x] = sv;
 
     // make Sc / W valid again after a strip overwrote them
     auto restore_tables = [&]() {
@@ -1116,6 +1136,68 @@ k_seek(SeekParams P)
             wsync();
         }
     };
+
+    for (;;) {       // one pass (a CTA per stream) or one pass per slice taken from the queue
+#ifdef LQB_SEEK_TRACE
+    const unsigned long long trace_t0 = gtime_ns();
+    const unsigned trace_w0 = n_windows;
+#endif
+    if (tid == 0) {
+        unsigned v = blockIdx.x;
+        if (P.slice_len) {
+            const unsigned t = atomicAdd(P.queue + 0, 1u);
+            unsigned polls = 0;
+            if (t >= P.queue_cap) { atomicAdd(&g_seek_stall[0], 1u << 16); v = kQueueEmpty; }       // cannot happen: see launch_seek
+            else
+            while ((v = ld_acquire_u32(P.queue + 4 + t)) == kQueueEmpty) {
+                if (ld_acquire_u32(P.queue + 2) >= P.n_io) break;       // every stream is through
+                __nanosleep(200);
+                if (++polls > kQueueMaxPolls) {
+                    if (atomicAdd(&g_seek_stall[0], 1u) == 0u) {
+                        g_seek_stall[1] = t; g_seek_stall[2] = ld_acquire_u32(P.queue + 0); g_seek_stall[3] = ld_acquire_u32(P.queue + 1);
+                        g_seek_stall[4] = ld_acquire_u32(P.queue + 2); g_seek_stall[5] = P.n_io; g_seek_stall[6] = P.grid; g_seek_stall[7] = blockIdx.x;
+                    }
+                    break;
+                }
+            }
+        }
+        s_item = v;
+        if (v != kQueueEmpty) {
+            if (P.slice_len) {
+                // the state was written by another CTA of this launch: nothing of it may come from this SM's L1
+                __threadfence();
+                const uint4 *gs = reinterpret_cast<const uint4 *>(P.states + P.io[v].stream);
+                uint4 *ss = reinterpret_cast<uint4 *>(&st);
+                static_assert(sizeof(StreamState) % 16 == 0, "StreamState is copied in 16-byte words");
+#pragma unroll
+                for (unsigned k = 0; k < sizeof(StreamState) / 16; ++k) ss[k] = __ldcg(gs + k);
+            } else
+            st = P.states[P.io[v].stream];
+            s_saved_stop = st.stop_at;
+            if (P.slice_len) {
+                // the slice ends at the first window start slice_len beyond where this CTA picks the stream up (only
+                // the search stops there: a frame in progress is finished first)
+                const long long lim = (st.mode == 0 ? st.wstart : st.F) + (long long)P.slice_len;
+                if (lim < st.stop_at) st.stop_at = lim;
+            }
+        }
+    }
+    wsync();
+    if (s_item == kQueueEmpty) break;
+    const StreamIO io = P.io[s_item];
+    sc_.valid = false; sc_.unsafe = false; sc_.ex_valid = false; sc_.w = 0; sc_.tail = 0.0f; sc_.tail_d = 0.0f; sc_.tail_e = 0.0f; sc_.half = 0.0f; sc_.ex = 0;
+    tc_pre_a0 = -(1ll << 62);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) tc_pre[k] = make_float2(0.0f, 0.0f);
+    StreamView sv;
+    sv.carry = P.carry[st.carry_sel] + (size_t)io.stream * P.carry_cap;
+    sv.in = io.in;
+    sv.base = st.base;
+    sv.carry_len = st.carry_len;
+    sv.end = st.base + (long long)st.carry_len + (long long)io.n_in;
+    sv.G = st.G;
+    if (tid == 0 && P.views) P.views[s_item] = sv;
+    PROF_MARK(10);
 
     while (true) {
         // ---------------- SEEK
@@ -1260,7 +1342,7 @@ k_seek(SeekParams P)
                             FrameDesc &d = P.frames[slot];
                             d = FrameDesc{};
                             d.F = F; d.G = sv.G;
-                            d.stream = io.stream; d.seq = st.seq; d.io_index = blockIdx.x; d.flags = 1u; d.det_idx = st.det_idx;
+                            d.stream = io.stream; d.seq = st.seq; d.io_index = s_item; d.flags = 1u; d.det_idx = st.det_idx;
                             d.tau = sh.tau; d.gamma = sh.gamma; d.dphi = sh.dphi; d.phi = sh.phi; d.rxy = st.rxy;
                             d.header_valid = 1; d.payload_len = plen; d.ms = ms; d.bps = modem_bps_hd(ms);
                             d.check = check; d.fec0 = fec0; d.fec1 = fec1;
@@ -1287,7 +1369,7 @@ k_seek(SeekParams P)
                 FrameDesc &d = P.frames[slot];
                 d.F = F; d.G = sv.G;
                 d.sym_off = 0; d.buf_off = 0; d.pay_off = 0; d.dec_off = 0;
-                d.stream = io.stream; d.seq = st.seq; d.io_index = blockIdx.x; d.flags = 0; d.det_idx = st.det_idx;
+                d.stream = io.stream; d.seq = st.seq; d.io_index = s_item; d.flags = 0; d.det_idx = st.det_idx;
                 d.tau = sh.tau; d.gamma = sh.gamma; d.dphi = sh.dphi; d.phi = sh.phi; d.rxy = st.rxy;
                 d.mf_scale = sh.mf_scale;
                 d.mix_theta0 = sh.theta0; d.mix_dtheta = sh.dtheta;
@@ -1313,6 +1395,33 @@ k_seek(SeekParams P)
         PROF_MARK(9);
     }
     PROF_MARK(7);
+    if (tid == 0) {
+        long long r = (st.mode == 0) ? st.wstart : st.F;
+        if (r < st.G) r = st.G;
+        if (r > sv.end) r = sv.end;
+        if (r < sv.base) r = sv.base;
+        st.resume = r;
+        // (time slices) the stream goes back into the queue when this CTA stopped at its slice boundary only
+        const bool again = P.slice_len && st.mode == 0 && st.wstart + 512 <= sv.end && st.wstart < s_saved_stop;
+        st.stop_at = s_saved_stop;
+        P.states[io.stream] = st;
+        if (P.slice_len) {
+            __threadfence();                                             // state and frame descriptors before the hand-over
+            if (again) {
+                const unsigned p_ = atomicAdd(P.queue + 1, 1u);
+                if (p_ < P.queue_cap) st_release_u32(P.queue + 4 + p_, s_item);
+                else { atomicAdd(&g_seek_stall[0], 1u << 24); atomicAdd(P.queue + 2, 1u); }            // cannot happen: see launch_seek
+            } else atomicAdd(P.queue + 2, 1u);
+        }
+#ifdef LQB_SEEK_TRACE
+        const unsigned slot_ = atomicAdd(&g_seek_trace_n, 1u) & 0xffffu;
+        g_seek_trace[0][slot_] = trace_t0; g_seek_trace[1][slot_] = gtime_ns();
+        g_seek_trace[2][slot_] = smid_of(); g_seek_trace[3][slot_] = ((unsigned long long)(n_windows - trace_w0) << 32) | io.stream;
+#endif
+    }
+    if (!P.slice_len) break;
+    wsync();                      // (st and s_item are rewritten by the next pass)
+    }   // passes
 
     if (fused) {
         // tell the MMA warp to leave (the pipeline is empty here)
@@ -1320,12 +1429,6 @@ k_seek(SeekParams P)
         mbar_arrive(&sh.z_full[buf_w]);
     }
     if (tid == 0) {
-        long long r = (st.mode == 0) ? st.wstart : st.F;
-        if (r < st.G) r = st.G;
-        if (r > sv.end) r = sv.end;
-        if (r < sv.base) r = sv.base;
-        st.resume = r;
-        P.states[io.stream] = st;
         atomicAdd(P.n_out + 1, n_windows);
         atomicAdd(P.n_out + 2, n_aligns);
         atomicAdd(P.n_out + 3, n_exact);
@@ -1370,12 +1473,29 @@ __global__ void k_carry(SeekParams P)
     }
 }
 
+__global__ void k_seek_queue_init(unsigned *q, unsigned n_io, unsigned cap)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < cap) q[4 + i] = i < n_io ? i : kQueueEmpty;
+    if (i == 0) { q[0] = 0; q[1] = n_io; q[2] = 0; q[3] = 0; }
+}
+
 void launch_seek(const SeekParams &P, unsigned n_io, cudaStream_t s)
 {
     static std::atomic<unsigned long long> attr_seen{ 0 };
     const int dyn = tc::kBBytes + 256;       // three CTAs per SM: 3 x (34 KB static + 35 KB B) fits 227 KB
     if (first_launch_on_this_device(attr_seen)) cudaFuncSetAttribute(k_seek, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
-    k_seek<<<n_io, kCtaThreads, P.coarse == 2 ? dyn : 0, s>>>(P);
+    if (P.slice_len) {
+        // one CTA per slot of the GPU (three per SM); P.grid bounds the tickets they can draw: the slices the fed
+        // streams can take plus one failed draw per CTA
+        const unsigned ctas = std::min<unsigned>(3u * (unsigned)sm_count_of_this_device(), P.grid);
+        SeekParams Q = P;
+        Q.queue_cap = P.grid + ctas;
+        k_seek_queue_init<<<(Q.queue_cap + 255) / 256, 256, 0, s>>>(Q.queue, n_io, Q.queue_cap);
+        k_seek<<<ctas, kCtaThreads, P.coarse == 2 ? dyn : 0, s>>>(Q);
+    } else {
+        k_seek<<<n_io, kCtaThreads, P.coarse == 2 ? dyn : 0, s>>>(P);
+    }
 }
 void launch_carry(const SeekParams &P, unsigned n_io, cudaStream_t s) { k_carry<<<n_io, 256, 0, s>>>(P); }
 
@@ -1415,6 +1535,31 @@ float build_coarse_bmat(const float *s_re, const float *s_im, int range, std::ve
     }
     return (float)(std::sqrt(worst / s2) * 1.0001);
 }
+
+// [0] draws that gave up since the last reset, then the first one's ticket, queue head / tail / finished count, streams, slice bound, CTA
+extern "C" int lqb_dbg_seek_stall(unsigned *out8, int reset)
+{
+    cudaDeviceSynchronize();
+    if (cudaMemcpyFromSymbol(out8, g_seek_stall, sizeof(unsigned) * 8) != cudaSuccess) return -5;
+    if (reset) { unsigned z[8] = {}; cudaMemcpyToSymbol(g_seek_stall, z, sizeof z); }
+    return 0;
+}
+
+#ifdef LQB_SEEK_TRACE
+extern "C" int lqb_dbg_seek_trace(unsigned long long *out /* [4][cap] */, unsigned cap, unsigned *n, int reset)
+{
+    cudaDeviceSynchronize();
+    unsigned cnt = 0;
+    if (cudaMemcpyFromSymbol(&cnt, g_seek_trace_n, sizeof cnt) != cudaSuccess) return -5;
+    if (cnt > 65536u) cnt = 65536u;
+    if (cnt > cap) cnt = cap;
+    for (int k = 0; k < 4; ++k)
+        if (out && cudaMemcpyFromSymbol(out + (size_t)k * cap, g_seek_trace, sizeof(unsigned long long) * cnt, sizeof(unsigned long long) * 65536 * k) != cudaSuccess) return -5;
+    if (n) *n = cnt;
+    if (reset) { unsigned z = 0; cudaMemcpyToSymbol(g_seek_trace_n, &z, sizeof z); }
+    return 0;
+}
+#endif
 
 #ifdef LQB_SEEK_PROF
 extern "C" int lqb_dbg_seek_prof(unsigned long long *out24, int reset)

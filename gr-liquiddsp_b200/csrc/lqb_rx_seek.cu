@@ -1064,7 +1064,10 @@ __device__ void decode_header(SeekShared &sh, const DevTables *T, const StreamVi
 // ------------------------------------------------------------------ the kernel
 // 4 worker warps walk the stream's state machine; a fifth warp only issues tcgen05.mma for the
 // pre-filter pipeline (fused mode) and otherwise idles until the end of the CTA.
-__global__ void __launch_bounds__(kCtaThreads, 3)
+#ifndef LQB_SEEK_CTAS_PER_SM
+#define LQB_SEEK_CTAS_PER_SM 3
+#endif
+__global__ void __launch_bounds__(kCtaThreads, LQB_SEEK_CTAS_PER_SM)
 k_seek(SeekParams P)
 {
     __shared__ SeekShared sh;

@@ -259,7 +259,12 @@ __device__ float2 modulate(const TxTables *T, unsigned ms, unsigned bps, unsigne
     return make_float2((s & 1u) ? -0.707106769f : 0.707106769f, (s & 2u) ? -0.707106769f : 0.707106769f);
 }
 
-__global__ void __launch_bounds__(kTxThreads)
+// 20 CTAs per SM is what the 11 KB of shared memory allow; asking for it caps the registers at 48 (56 without: 18 CTAs
+// per SM and 3.08 waves for 8192 frames instead of 2.77).  Measured: 0.241 -> 0.231 ms (profiles/r02_notes.md v26).
+#ifndef LQB_TX_CTAS_PER_SM
+#define LQB_TX_CTAS_PER_SM 20
+#endif
+__global__ void __launch_bounds__(kTxThreads, LQB_TX_CTAS_PER_SM)
 k_tx(const TxTables *T, const TxFrame *frames, unsigned char *bufA, unsigned char *bufB, const unsigned *ilv, float2 *syms)
 {
     __shared__ unsigned char hb[64], hd[32], he[32], hraw[64];  // header: 54 coded bytes; 24 data bytes; 27 SECDED bytes; 54 before the last interleaver
